@@ -1,0 +1,199 @@
+/*
+ * psnode_b200.h -- C ABI of the B200-native fixed-grid neural ODE/DAE integrator.
+ *
+ * The reference (xxh0523/Py_PSNODE @ d366e75) has NO native / FFI boundary: its hot path is a Python
+ * loop (neural_dae/my_solvers.py:52-131) calling Python nn.Modules.  This header is therefore the
+ * boundary a maintainer would bind *underneath* the reference's Python call surface; every entry
+ * point cites the reference code whose work it takes over.  The binding itself (ctypes, because the
+ * reference is Python) is py_psnode_b200/_native.py and is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every pointer is a DEVICE pointer unless the function name ends in _host.
+ *   - all floating point data is IEEE fp32 (the reference runs nn.Linear default dtype everywhere).
+ *   - functions return PSNODE_OK (0) or a negative PSNODE_E* code; they never throw, never allocate
+ *     device memory (the caller owns outputs and workspace), are stream-ordered on `stream`
+ *     (a cudaStream_t passed as void*) and never synchronise the device.
+ *   - time series are passed as strided views: element (j, b, c) of a series lives at
+ *     p[j*st + b*sb + c] (unit stride over the feature index c).  This honours the reference's
+ *     `x.permute(1,0,2)` views of batch-major storage (neural_00_ODE_01_no_encode.py:82-84)
+ *     without a copy.
+ */
+#ifndef PSNODE_B200_H
+#define PSNODE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSNODE_ABI_VERSION 1
+#define PSNODE_MAX_LAYERS 8
+
+/* status codes */
+#define PSNODE_OK 0
+#define PSNODE_EINVAL (-1)      /* inconsistent dimensions / null pointers                      */
+#define PSNODE_EUNSUPPORTED (-2) /* legal problem this build has no kernel for                   */
+#define PSNODE_EWORKSPACE (-3)  /* workspace pointer null or too small                           */
+#define PSNODE_ECUDA (-4)       /* a CUDA runtime call failed (see psnode_last_cuda_error)       */
+#define PSNODE_ENODEVICE (-5)   /* no sm_100 device                                              */
+
+/* integration scheme: neural_dae/my_fixed_grid.py:12-59 (Euler :15-18, Midpoint :23-32, RK4 3/8-rule :38-59) */
+#define PSNODE_EULER 0
+#define PSNODE_MIDPOINT 1
+#define PSNODE_RK4 2
+
+/* problem kind: integrate_ODE (my_solvers.py:52-80) or integrate_DAE (my_solvers.py:82-131) */
+#define PSNODE_ODE 0
+#define PSNODE_DAE 1
+
+/* kernel selection for psnode_forward / psnode_backward (`impl` field) */
+#define PSNODE_IMPL_AUTO 0     /* fastest kernel that supports the problem                       */
+#define PSNODE_IMPL_GENERIC 1  /* shared-memory-weight kernel, reference formulation of layer 1  */
+#define PSNODE_IMPL_FUSED 2    /* register-resident-weight kernel, folded layer 1 (H = 64 nets)  */
+
+/* A small ELU MLP: Linear -> ELU -> ... -> Linear, weights in nn.Linear layout W[out][in] (row major,
+ * contiguous), as built by the script-local DE_Func / AE_Func classes
+ * (neural_00_ODE_01_no_encode.py:61-64, neural_00_ODE_02_direct_encode.py:52-53,
+ *  neural_01_DAE_01_no_encode.py:64-67 and :77-80, neural_01_DAE_02_direct_encode.py:73-80 and :90-97). */
+typedef struct psnode_mlp {
+    int32_t n_layers;                      /* number of Linear layers, 1..PSNODE_MAX_LAYERS       */
+    int32_t in_dim[PSNODE_MAX_LAYERS];
+    int32_t out_dim[PSNODE_MAX_LAYERS];
+    const float* W[PSNODE_MAX_LAYERS];
+    const float* b[PSNODE_MAX_LAYERS];
+} psnode_mlp;
+
+/* strided (T, B, width) view, unit stride over the feature index */
+typedef struct psnode_series {
+    const float* p;
+    int64_t st;     /* element stride between consecutive grid points */
+    int64_t sb;     /* element stride between consecutive trajectories */
+} psnode_series;
+
+typedef struct psnode_series_out {
+    float* p;
+    int64_t st;
+    int64_t sb;
+} psnode_series_out;
+
+/*
+ * One integrate_ODE / integrate_DAE call.
+ *   S = X + Z (+ V + I for a DAE) is the width of `all_initial` and of s = cat(x, held inputs).
+ *   de : dx/dt network, input cat(a0, s - a0, s) (width 3S), output width X     (DE_Func.forward)
+ *   ae : algebraic network, input cat(a0, x, z, v) (width S + X + Z + V), output width I (AE_Func.forward); DAE only
+ *   ODE: initial state is x[0]; DAE: initial state is x_init, i_0 = ae(x_init, z[0], v[0]) (my_solvers.py:94-95).
+ *   teacher_x / teacher_i reproduce input_true_x / input_true_i (my_solvers.py:72-74, 111-119, 121).
+ *   event_idx[j] (j = 0..T-2) is the index k of the event that fires when LEAVING grid point j, or -1; it
+ *   replaces the per-step host callback ODE_Event/DAE_Event.event_fn (neural_base.py:52-57, 180-185);
+ *   the held inputs of that step are then z_jump[:,k] (and v_jump[:,k]) as in jump_change_fn (:59-65, :187-196).
+ *   event_idx == NULL means "no event callbacks were given".
+ */
+typedef struct psnode_problem {
+    int32_t kind;        /* PSNODE_ODE | PSNODE_DAE */
+    int32_t method;      /* PSNODE_EULER | PSNODE_MIDPOINT | PSNODE_RK4 */
+    int32_t impl;        /* PSNODE_IMPL_* */
+    int32_t B;           /* trajectories */
+    int32_t T;           /* grid points (N = T-1 steps) */
+    int32_t X, Z, V, I;  /* widths; V = I = 0 for an ODE; Z may be 0 */
+    int32_t teacher_x, teacher_i;
+    int32_t E;           /* events per trajectory (second dim of z_jump / v_jump); 0 if none */
+    psnode_series t;     /* (T,B,1) */
+    psnode_series x;     /* (T,B,X): ODE initial state x[0]; teacher-forcing series when teacher_x */
+    psnode_series z;     /* (T,B,Z) */
+    psnode_series v;     /* (T,B,V)  DAE */
+    psnode_series i;     /* (T,B,I)  DAE, read only when teacher_i */
+    const float* x_init; /* (B,X)    DAE */
+    int64_t x_init_sb;
+    const float* a0;     /* (B,S) all_initial */
+    int64_t a0_sb;
+    const int32_t* event_idx;   /* [T-1] or NULL */
+    const float* z_jump; /* (B,E,Z) */
+    int64_t zj_sb, zj_se;
+    const float* v_jump; /* (B,E,V) */
+    int64_t vj_sb, vj_se;
+    psnode_mlp de;
+    psnode_mlp ae;
+    psnode_series_out x_sol;    /* (T,B,X) */
+    psnode_series_out i_sol;    /* (T,B,I)  DAE */
+} psnode_problem;
+
+/*
+ * Reverse sweep (discrete adjoint = exact reverse mode of the unrolled loop; replaces the autograd graph
+ * the reference builds and replays at loss.backward(), neural_00_ODE_01_no_encode.py:359 etc.).
+ * `p` must describe the SAME problem as the forward call, with p->x_sol / p->i_sol holding the forward result
+ * (they are the checkpoints the sweep restarts every step from).
+ * Upstream gradients gx = dL/dx_sol (T,B,X) and gi = dL/di_sol (T,B,I) are strided views.
+ * Outputs (any may be NULL = not wanted, except d_theta):
+ *   d_theta   : flat fp32 vector, layout = for net in (de, ae): for layer: W (out*in, row major) then b (out)
+ *   d_x0      : (B,X)  grad of x[0] (ODE) / x_init (DAE) as the INITIAL STATE
+ *   d_a0      : (B,S)
+ *   d_z, d_v  : (T,B,Z) / (T,B,V) grads of the held-input series (encoded variants: they carry grad)
+ *   d_zjump, d_vjump : (B,E,Z) / (B,E,V)
+ *   d_xteach, d_iteach : (T,B,X) / (T,B,I) grads of the teacher-forcing series (only with teacher_x / teacher_i)
+ * All outputs are OVERWRITTEN (not accumulated).
+ */
+typedef struct psnode_adjoint {
+    psnode_series gx;
+    psnode_series gi;
+    float* d_theta;
+    int64_t n_theta;
+    float* d_x0;      int64_t d_x0_sb;
+    float* d_a0;      int64_t d_a0_sb;
+    psnode_series_out d_z;
+    psnode_series_out d_v;
+    float* d_zjump;   int64_t d_zj_sb, d_zj_se;
+    float* d_vjump;   int64_t d_vj_sb, d_vj_se;
+    psnode_series_out d_xteach;
+    psnode_series_out d_iteach;
+} psnode_adjoint;
+
+/* library / device introspection */
+int psnode_abi_version(void);
+const char* psnode_status_string(int status);
+const char* psnode_last_cuda_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches counter) */
+int64_t psnode_launch_count(void);
+/* name of the kernel variant the last psnode_forward / psnode_backward call dispatched to */
+const char* psnode_last_kernel(void);
+
+/* number of parameters of a net = sum(out*in + out) */
+int64_t psnode_mlp_param_count(const psnode_mlp* m);
+
+/*
+ * Build the per-step event table on the device (no host sync).
+ *   t0      : times of SAMPLE 0, element j at t0[j*t_st]          (reference looks at sample 0 only: neural_base.py:54)
+ *   ev0     : event times of SAMPLE 0, element k at ev0[k*ev_se]  (event_t[0], shape (E,1))
+ *   event_idx[j] = k if t0[j] == ev0[k] (exact float equality) else -1, for j = 0..T-2
+ *   err[0] is set to 1 if some grid point matches more than one event (the reference raises there), else 0.
+ * Replaces ODE_Event.event_fn / DAE_Event.event_fn being called from the hot loop every step (my_solvers.py:70, :108).
+ */
+int psnode_event_table(const float* t0, int64_t t_st, int32_t T, const float* ev0, int64_t ev_se, int32_t E,
+                       int32_t* event_idx, int32_t* err, void* stream);
+
+/* workspace sizes in bytes (0 is possible) */
+int64_t psnode_forward_workspace(const psnode_problem* p);
+int64_t psnode_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);
+
+/* forward integration: FixedGridODESolver.integrate_ODE / integrate_DAE (my_solvers.py:52-80, 82-131) incl. the
+ * per-step step_integrate (:48-50) -> _step_func (my_fixed_grid.py) -> DE_Func/AE_Func forward evaluations. */
+int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* reverse sweep, see psnode_adjoint */
+int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* workspace, int64_t workspace_bytes,
+                    void* stream);
+
+/*
+ * Host-buffer convenience entry (the end-to-end path bench.py times as `e2e`): every data pointer in `p`
+ * (series, x_init, a0, jumps, weights, outputs) is a HOST pointer, event_idx is a HOST table or NULL.  Inputs
+ * are staged to the device with cudaMemcpyAsync on `stream`, the problem is integrated, and x_sol / i_sol are copied
+ * back; the call returns after the stream has drained.  `h2d_bytes` / `d2h_bytes` receive the bytes moved.
+ * This is the only entry point that allocates (device scratch, cached across calls) and synchronises.
+ */
+int psnode_forward_host(const psnode_problem* p, void* stream, int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSNODE_B200_H */

@@ -1,0 +1,150 @@
+// psnode_api.cu -- the extern "C" surface declared in include/psnode_b200.h: validation, kernel dispatch,
+// the device-side event table, launch accounting and the host-buffer convenience entry.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include "psnode_internal.cuh"
+
+namespace {
+std::atomic<int64_t> g_launches{0};
+char g_last_kernel[128] = "none";
+char g_last_cuda_error[256] = "";
+}  // namespace
+
+void psn_count_launch(const char* kernel_name) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    std::snprintf(g_last_kernel, sizeof(g_last_kernel), "%s", kernel_name);
+}
+
+int psn_cuda_fail(cudaError_t e, const char* where) {
+    std::snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", where, cudaGetErrorString(e));
+    return PSNODE_ECUDA;
+}
+
+namespace {
+
+bool mlp_ok(const psnode_mlp& m, int in0, int out_last) {
+    if (m.n_layers < 1 || m.n_layers > PSNODE_MAX_LAYERS) return false;
+    if (m.in_dim[0] != in0 || m.out_dim[m.n_layers - 1] != out_last) return false;
+    for (int l = 0; l < m.n_layers; l++) {
+        if (m.in_dim[l] < 1 || m.out_dim[l] < 1 || !m.W[l] || !m.b[l]) return false;
+        if (l > 0 && m.in_dim[l] != m.out_dim[l - 1]) return false;
+    }
+    return true;
+}
+
+int validate(const psnode_problem* p) {
+    if (!p) return PSNODE_EINVAL;
+    if (p->kind != PSNODE_ODE && p->kind != PSNODE_DAE) return PSNODE_EINVAL;
+    if (p->method < PSNODE_EULER || p->method > PSNODE_RK4) return PSNODE_EINVAL;
+    if (p->B < 1 || p->T < 1 || p->X < 1 || p->Z < 0 || p->V < 0 || p->I < 0) return PSNODE_EINVAL;
+    const bool dae = p->kind == PSNODE_DAE;
+    if (!dae && (p->V != 0 || p->I != 0)) return PSNODE_EINVAL;
+    if (dae && p->I < 1) return PSNODE_EINVAL;
+    const int S = psn_S(p);
+    if (!mlp_ok(p->de, 3 * S, p->X)) return PSNODE_EINVAL;
+    if (dae && !mlp_ok(p->ae, S + p->X + p->Z + p->V, p->I)) return PSNODE_EINVAL;
+    if (!p->t.p || !p->a0 || !p->x_sol.p) return PSNODE_EINVAL;
+    if (p->Z > 0 && !p->z.p) return PSNODE_EINVAL;
+    if (dae) {
+        if (!p->x_init || !p->i_sol.p) return PSNODE_EINVAL;
+        if (p->V > 0 && !p->v.p) return PSNODE_EINVAL;
+        if (p->teacher_i && !p->i.p) return PSNODE_EINVAL;
+    }
+    if ((!dae || p->teacher_x) && !p->x.p) return PSNODE_EINVAL;
+    if (p->event_idx) {
+        if (p->E < 1) return PSNODE_EINVAL;
+        if (p->Z > 0 && !p->z_jump) return PSNODE_EINVAL;
+        if (dae && p->V > 0 && !p->v_jump) return PSNODE_EINVAL;
+    }
+    return PSNODE_OK;
+}
+
+__global__ void psn_event_table_kernel(const float* __restrict__ t0, int64_t t_st, int T, const float* __restrict__ ev0,
+                                       int64_t ev_se, int E, int* __restrict__ event_idx, int* __restrict__ err) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) err[0] = 0;
+    __syncthreads();   // only orders block 0; other blocks can only ever write 1
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < T - 1; j += gridDim.x * blockDim.x) {
+        const float tj = t0[(int64_t)j * t_st];
+        int hit = -1, nhit = 0;
+        for (int k = 0; k < E; k++)
+            if (ev0[(int64_t)k * ev_se] == tj) { if (hit < 0) hit = k; nhit++; }
+        event_idx[j] = hit;
+        if (nhit > 1) atomicExch(err, 1);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int psnode_abi_version(void) { return PSNODE_ABI_VERSION; }
+
+const char* psnode_status_string(int status) {
+    switch (status) {
+        case PSNODE_OK: return "ok";
+        case PSNODE_EINVAL: return "invalid problem description (dimensions / null pointers)";
+        case PSNODE_EUNSUPPORTED: return "problem shape not supported by the requested kernel";
+        case PSNODE_EWORKSPACE: return "workspace missing or too small";
+        case PSNODE_ECUDA: return "CUDA runtime error (see psnode_last_cuda_error)";
+        case PSNODE_ENODEVICE: return "no sm_100 CUDA device";
+        default: return "unknown status";
+    }
+}
+
+const char* psnode_last_cuda_error(void) { return g_last_cuda_error; }
+int64_t psnode_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+const char* psnode_last_kernel(void) { return g_last_kernel; }
+
+int64_t psnode_mlp_param_count(const psnode_mlp* m) {
+    if (!m) return 0;
+    int64_t n = 0;
+    for (int l = 0; l < m->n_layers; l++) n += (int64_t)m->out_dim[l] * m->in_dim[l] + m->out_dim[l];
+    return n;
+}
+
+int psnode_event_table(const float* t0, int64_t t_st, int32_t T, const float* ev0, int64_t ev_se, int32_t E,
+                       int32_t* event_idx, int32_t* err, void* stream) {
+    if (!t0 || !ev0 || !event_idx || !err || T < 1 || E < 1) return PSNODE_EINVAL;
+    if (T == 1) return PSNODE_OK;
+    // a single block keeps the err[0] = 0 initialisation ordered before every write of 1
+    psn_event_table_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(t0, t_st, T, ev0, ev_se, E, event_idx, err);
+    psn_count_launch("psn_event_table_kernel");
+    PSN_CUDA(cudaGetLastError());
+    return PSNODE_OK;
+}
+
+int64_t psnode_forward_workspace(const psnode_problem* p) {
+    if (validate(p) != PSNODE_OK) return 0;
+    int64_t g = psn_generic_forward_workspace(p);
+    int64_t f = psn_fused_supports(p) ? psn_fused_forward_workspace(p) : 0;
+    return g > f ? g : f;
+}
+
+int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_bytes, void* stream) {
+    const int st = validate(p);
+    if (st != PSNODE_OK) return st;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (p->impl == PSNODE_IMPL_FUSED) {
+        if (!psn_fused_supports(p)) return PSNODE_EUNSUPPORTED;
+        return psn_fused_forward(p, workspace, workspace_bytes, s);
+    }
+    if (p->impl == PSNODE_IMPL_AUTO && psn_fused_supports(p)) return psn_fused_forward(p, workspace, workspace_bytes, s);
+    return psn_generic_forward(p, workspace, workspace_bytes, s);
+}
+
+int64_t psnode_backward_workspace(const psnode_problem* p, const psnode_adjoint* a) {
+    if (validate(p) != PSNODE_OK || !a) return 0;
+    return psn_generic_backward_workspace(p, a);
+}
+
+int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* workspace, int64_t workspace_bytes,
+                    void* stream) {
+    const int st = validate(p);
+    if (st != PSNODE_OK) return st;
+    if (!a || !a->d_theta) return PSNODE_EINVAL;
+    return psn_generic_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,298 @@
+"""Host-side glue between torch tensors and the C ABI: builds `psnode_problem`, owns the workspace, launches the
+forward kernel and the reverse sweep, and exposes both as one `torch.autograd.Function`.
+
+torch is plumbing here (device memory, streams, autograd bookkeeping); every FLOP of the integration runs in
+libpsnode_b200.so.  If the library is missing or the tensors are not CUDA fp32 the call raises.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+_workspaces = {}      # device index -> uint8 tensor
+
+
+def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ws = _workspaces.get(key)
+    need = max(int(nbytes), 256)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _require_cuda_f32(name: str, ten: torch.Tensor) -> None:
+    if not ten.is_cuda:
+        raise RuntimeError(
+            f"py_psnode_b200: `{name}` lives on {ten.device}; the fused integrator runs on CUDA (sm_100a) only and has "
+            "no CPU fallback.  Move the batch and the model to a CUDA device (or construct the solver with eager=True "
+            "to run the plain PyTorch loop).")
+    if ten.dtype != torch.float32:
+        raise TypeError(f"py_psnode_b200: `{name}` has dtype {ten.dtype}; the integrator computes in float32 like the reference")
+
+
+def _series(ten: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    """(T,B,W) view with unit stride over W (copy only if the feature stride is not 1); None for zero width."""
+    if ten is None or ten.shape[-1] == 0:
+        return None
+    _require_cuda_f32(name, ten)
+    if ten.dim() != 3:
+        raise ValueError(f"`{name}` must be (T,B,width), got {tuple(ten.shape)}")
+    if ten.stride(2) != 1 and ten.shape[2] != 1:
+        ten = ten.contiguous()
+    return ten
+
+
+def _rows(ten: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    """(B,W) matrix with unit stride over W."""
+    if ten is None or ten.shape[-1] == 0:
+        return None
+    _require_cuda_f32(name, ten)
+    if ten.stride(-1) != 1 and ten.shape[-1] != 1:
+        ten = ten.contiguous()
+    return ten
+
+
+def _set_series(dst: N.Series, ten: Optional[torch.Tensor]) -> None:
+    if ten is None:
+        dst.p, dst.st, dst.sb = None, 0, 0
+    else:
+        dst.p, dst.st, dst.sb = ten.data_ptr(), ten.stride(0), ten.stride(1)
+
+
+def _fill_mlp(dst: N.Mlp, params: Sequence[torch.Tensor], keep: list) -> None:
+    """params = [W0, b0, W1, b1, ...] (nn.Linear layout)."""
+    n = len(params) // 2
+    dst.n_layers = n
+    for l in range(n):
+        W, b = params[2 * l], params[2 * l + 1]
+        _require_cuda_f32("weight", W)
+        Wc, bc = W.detach().contiguous(), b.detach().contiguous()
+        keep.extend((Wc, bc))
+        dst.in_dim[l], dst.out_dim[l] = Wc.shape[1], Wc.shape[0]
+        dst.W[l], dst.b[l] = Wc.data_ptr(), bc.data_ptr()
+
+
+@dataclass
+class Config:
+    """Static (non-tensor) description of one integrate_* call."""
+    kind: int
+    method: int
+    impl: int
+    X: int
+    Z: int
+    V: int
+    I: int
+    teacher_x: bool
+    teacher_i: bool
+    n_de: int                       # number of Linear layers of the DE net
+    n_ae: int
+    has_event: bool
+    check_events: bool = False
+
+
+# fixed positional layout of the tensor arguments of _Integrate.apply
+_T, _X, _Zs, _Vs, _Is, _XINIT, _A0, _EVT, _ZJ, _VJ, _NFIXED = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+
+
+def _build_problem(cfg: Config, tens: Sequence[Optional[torch.Tensor]], x_sol, i_sol, keep: list) -> N.Problem:
+    t = _series(tens[_T], "t")
+    T, B = t.shape[0], t.shape[1]
+    x = _series(tens[_X], "x")
+    z = _series(tens[_Zs], "z")
+    v = _series(tens[_Vs], "v")
+    i = _series(tens[_Is], "i")
+    x_init = _rows(tens[_XINIT], "x_init")
+    a0 = _rows(tens[_A0], "all_initial")
+    keep.extend((t, x, z, v, i, x_init, a0))
+    p = N.Problem()
+    p.kind, p.method, p.impl = cfg.kind, cfg.method, cfg.impl
+    p.B, p.T = B, T
+    p.X, p.Z, p.V, p.I = cfg.X, cfg.Z, cfg.V, cfg.I
+    p.teacher_x, p.teacher_i = int(cfg.teacher_x), int(cfg.teacher_i)
+    _set_series(p.t, t)
+    _set_series(p.x, x if (cfg.kind == N.ODE or cfg.teacher_x) else None)
+    _set_series(p.z, z)
+    _set_series(p.v, v)
+    _set_series(p.i, i if cfg.teacher_i else None)
+    if x_init is not None:
+        p.x_init, p.x_init_sb = x_init.data_ptr(), x_init.stride(0)
+    S = cfg.X + cfg.Z + cfg.V + cfg.I
+    if a0 is None or a0.shape[-1] != S or a0.shape[0] != B:
+        raise ValueError(f"all_initial must be (B, X+Z+V+I) = ({B}, {S}), got {None if a0 is None else tuple(a0.shape)}")
+    p.a0, p.a0_sb = a0.data_ptr(), a0.stride(0)
+    p.E = 0
+    if cfg.has_event:
+        ev_t = tens[_EVT]
+        _require_cuda_f32("event_t", ev_t)
+        E = ev_t.shape[1]
+        ev0 = ev_t[0].reshape(E)                    # event times of sample 0 (the only sample the reference inspects)
+        idx = torch.empty(max(T - 1, 1), dtype=torch.int32, device=t.device)
+        err = torch.empty(1, dtype=torch.int32, device=t.device)
+        keep.extend((ev0, idx, err))
+        t00 = t[:, 0, 0]
+        N.check(N.lib().psnode_event_table(t00.data_ptr(), t00.stride(0), T, ev0.data_ptr(), ev0.stride(0), E,
+                                           idx.data_ptr(), err.data_ptr(), torch.cuda.current_stream(t.device).cuda_stream),
+                "psnode_event_table")
+        if cfg.check_events and int(err.item()) != 0:
+            raise RuntimeError("more than one event matches the same grid time (the reference raises here too)")
+        p.event_idx, p.E = idx.data_ptr(), E
+        zj = tens[_ZJ]
+        if cfg.Z > 0:
+            _require_cuda_f32("z_jump", zj)
+            if zj.stride(-1) != 1 and zj.shape[-1] != 1:
+                zj = zj.contiguous()
+            keep.append(zj)
+            p.z_jump, p.zj_sb, p.zj_se = zj.data_ptr(), zj.stride(0), zj.stride(1)
+        if cfg.kind == N.DAE and cfg.V > 0:
+            vj = tens[_VJ]
+            _require_cuda_f32("v_jump", vj)
+            if vj.stride(-1) != 1 and vj.shape[-1] != 1:
+                vj = vj.contiguous()
+            keep.append(vj)
+            p.v_jump, p.vj_sb, p.vj_se = vj.data_ptr(), vj.stride(0), vj.stride(1)
+    params = tens[_NFIXED:]
+    _fill_mlp(p.de, params[:2 * cfg.n_de], keep)
+    if cfg.kind == N.DAE:
+        _fill_mlp(p.ae, params[2 * cfg.n_de:2 * (cfg.n_de + cfg.n_ae)], keep)
+    _set_series(p.x_sol, x_sol)
+    _set_series(p.i_sol, i_sol)
+    return p
+
+
+def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Run the forward kernel; returns time-major contiguous (x_sol, i_sol)."""
+    t = tens[_T]
+    _require_cuda_f32("t", t)
+    L = N.lib()
+    T, B = t.shape[0], t.shape[1]
+    with torch.cuda.device(t.device):
+        x_sol = torch.empty((T, B, cfg.X), dtype=torch.float32, device=t.device)
+        i_sol = torch.empty((T, B, cfg.I), dtype=torch.float32, device=t.device) if cfg.kind == N.DAE else None
+        keep: list = []
+        p = _build_problem(cfg, tens, x_sol, i_sol, keep)
+        ws = _workspace(t.device, L.psnode_forward_workspace(C.byref(p)))
+        stream = torch.cuda.current_stream(t.device).cuda_stream
+        N.check(L.psnode_forward(C.byref(p), ws.data_ptr(), ws.numel(), stream), "psnode_forward")
+    return x_sol, i_sol
+
+
+def _theta_sizes(params: Sequence[torch.Tensor]) -> List[int]:
+    return [int(q.numel()) for q in params]
+
+
+class _Integrate(torch.autograd.Function):
+    """x_sol, i_sol = integrate(cfg, t, x, z, v, i, x_init, a0, event_t, z_jump, v_jump, *weights)."""
+
+    @staticmethod
+    def forward(ctx, cfg: Config, *tens):
+        x_sol, i_sol = forward_raw(cfg, tens)
+        ctx.cfg = cfg
+        ctx.n_in = len(tens)
+        ctx.save_for_backward(*[q for q in tens if q is not None], x_sol, *( [i_sol] if i_sol is not None else []))
+        ctx.present = [q is not None for q in tens]
+        if i_sol is None:
+            i_sol = x_sol.new_empty(0)
+            ctx.mark_non_differentiable(i_sol)
+        return x_sol, i_sol
+
+    @staticmethod
+    def backward(ctx, gx, gi):
+        cfg: Config = ctx.cfg
+        saved = list(ctx.saved_tensors)
+        tens: List[Optional[torch.Tensor]] = []
+        it = iter(saved)
+        for present in ctx.present:
+            tens.append(next(it) if present else None)
+        x_sol = next(it)
+        i_sol = next(it) if cfg.kind == N.DAE else None
+        grads = backward_raw(cfg, tens, x_sol, i_sol, gx, gi if cfg.kind == N.DAE else None, ctx.needs_input_grad[1:])
+        return (None, *grads)
+
+
+def backward_raw(cfg: Config, tens, x_sol, i_sol, gx, gi, needs) -> List[Optional[torch.Tensor]]:
+    """Reverse sweep through the native library.  `needs[k]` says whether tens[k] wants a gradient."""
+    L = N.lib()
+    t = tens[_T]
+    dev = t.device
+    T, B = t.shape[0], t.shape[1]
+    X, Z, V, I = cfg.X, cfg.Z, cfg.V, cfg.I
+    S = X + Z + V + I
+    dae = cfg.kind == N.DAE
+    out: List[Optional[torch.Tensor]] = [None] * len(tens)
+    with torch.cuda.device(dev):
+        keep: list = []
+        p = _build_problem(cfg, tens, x_sol, i_sol, keep)
+        a = N.Adjoint()
+        gx = torch.zeros_like(x_sol) if gx is None else _series(gx, "grad x_sol")
+        _set_series(a.gx, gx)
+        if dae:
+            gi = torch.zeros_like(i_sol) if gi is None else _series(gi, "grad i_sol")
+            _set_series(a.gi, gi)
+        params = tens[_NFIXED:]
+        sizes = _theta_sizes(params)
+        d_theta = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        a.d_theta, a.n_theta = d_theta.data_ptr(), d_theta.numel()
+        d_x0 = torch.empty((B, X), dtype=torch.float32, device=dev)
+        a.d_x0, a.d_x0_sb = d_x0.data_ptr(), X
+        d_a0 = None
+        if needs[_A0]:
+            d_a0 = torch.empty((B, S), dtype=torch.float32, device=dev)
+            a.d_a0, a.d_a0_sb = d_a0.data_ptr(), S
+        d_z = d_v = d_zj = d_vj = d_xt = d_it = None
+        if Z > 0 and needs[_Zs]:
+            d_z = torch.empty((T, B, Z), dtype=torch.float32, device=dev)
+            _set_series(a.d_z, d_z)
+        if dae and V > 0 and needs[_Vs]:
+            d_v = torch.empty((T, B, V), dtype=torch.float32, device=dev)
+            _set_series(a.d_v, d_v)
+        if cfg.has_event and Z > 0 and needs[_ZJ]:
+            E = tens[_ZJ].shape[1]
+            d_zj = torch.empty((B, E, Z), dtype=torch.float32, device=dev)
+            a.d_zjump, a.d_zj_sb, a.d_zj_se = d_zj.data_ptr(), E * Z, Z
+        if cfg.has_event and dae and V > 0 and needs[_VJ]:
+            E = tens[_VJ].shape[1]
+            d_vj = torch.empty((B, E, V), dtype=torch.float32, device=dev)
+            a.d_vjump, a.d_vj_sb, a.d_vj_se = d_vj.data_ptr(), E * V, V
+        if cfg.teacher_x and needs[_X]:
+            d_xt = torch.empty((T, B, X), dtype=torch.float32, device=dev)
+            _set_series(a.d_xteach, d_xt)
+        if cfg.teacher_i and needs[_Is]:
+            d_it = torch.empty((T, B, I), dtype=torch.float32, device=dev)
+            _set_series(a.d_iteach, d_it)
+        ws = _workspace(dev, L.psnode_backward_workspace(C.byref(p), C.byref(a)))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        N.check(L.psnode_backward(C.byref(p), C.byref(a), ws.data_ptr(), ws.numel(), stream), "psnode_backward")
+    # ---- route the native outputs to the autograd inputs -------------------------------------------
+    if dae:
+        if needs[_XINIT]:
+            out[_XINIT] = d_x0
+        if needs[_X] and tens[_X] is not None and tens[_X].shape[-1] != 0:
+            out[_X] = d_xt if d_xt is not None else torch.zeros_like(tens[_X])
+    else:
+        if needs[_X]:
+            g = d_xt if d_xt is not None else torch.zeros((T, B, X), dtype=torch.float32, device=dev)
+            g[0] += d_x0                       # x[0] is the initial state (and x_sol[0])
+            out[_X] = g
+    out[_Zs], out[_Vs], out[_Is] = d_z, d_v, d_it
+    out[_A0], out[_ZJ], out[_VJ] = d_a0, d_zj, d_vj
+    off = 0
+    for k, n in enumerate(sizes):
+        if needs[_NFIXED + k]:
+            out[_NFIXED + k] = d_theta[off:off + n].view_as(params[k])
+        off += n
+    return out
+
+
+def integrate(cfg: Config, tens: Sequence[Optional[torch.Tensor]]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Autograd-aware entry used by the solver classes."""
+    needs_grad = torch.is_grad_enabled() and any(q is not None and q.requires_grad for q in tens)
+    if not needs_grad:
+        return forward_raw(cfg, tens)
+    x_sol, i_sol = _Integrate.apply(cfg, *tens)
+    return x_sol, (i_sol if cfg.kind == N.DAE else None)

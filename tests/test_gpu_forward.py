@@ -1,0 +1,77 @@
+"""GPU parity: the CUDA path (through the Python call surface -> C ABI) against the reference's own outputs
+(tests/golden/*.npz, produced by the unmodified reference) at rtol=1e-5 / atol=1e-6."""
+import pytest
+import torch
+
+from helpers import AE, DE, ATOL, RTOL, golden_names, load_golden, params_of, tm, tol_report
+
+pytestmark = pytest.mark.gpu
+
+SOLVERS = {}
+
+
+def _solver(name, impl):
+    from py_psnode_b200 import Euler, Midpoint, RK4
+    return {"euler": Euler, "midpoint": Midpoint, "rk4": RK4}[name](impl=impl)
+
+
+def run_ode_case(d, impl, dev="cuda:0", requires_grad=False):
+    from py_psnode_b200 import ODE_Event
+    de = DE(params_of(d, "de")).to(dev)
+    t, x, z = tm(d["t"], dev), tm(d["x"], dev), tm(d["z"], dev)
+    name = str(d["_name"])
+    ev = ODE_Event()
+    event_fn = jump_fn = None
+    if "noevent" not in name:
+        ev.set_event(t=torch.from_numpy(d["event_t"]).to(dev), z=torch.from_numpy(d["z_jump"]).to(dev))
+        event_fn, jump_fn = ev.event_fn, ev.jump_change_fn
+    a0 = torch.cat((x[0], z[0]), dim=-1)
+    sol = _solver(str(d["solver"]), impl).integrate_ODE(x_func=de, t=t, x=x, z=z, all_initial=a0, event_fn=event_fn,
+                                                        jump_change_fn=jump_fn, input_true_x=bool(d["teacher_x"]))
+    return sol
+
+
+def run_dae_case(d, impl, dev="cuda:0"):
+    from py_psnode_b200 import DAE_Event
+    de, ae = DE(params_of(d, "de")).to(dev), AE(params_of(d, "ae")).to(dev)
+    t, x, z, v, i = (tm(d[k], dev) for k in ("t", "x", "z", "v", "i"))
+    name = str(d["_name"])
+    ev = DAE_Event()
+    event_fn = jump_fn = None
+    if "noevent" not in name:
+        ev.set_event(t=torch.from_numpy(d["event_t"]).to(dev), z=torch.from_numpy(d["z_jump"]).to(dev),
+                     v=torch.from_numpy(d["v_jump"]).to(dev))
+        event_fn, jump_fn = ev.event_fn, ev.jump_change_fn
+    x_init = torch.from_numpy(d["x_init"]).to(dev)
+    a0 = torch.cat((x_init, z[0], v[0], i[0]), dim=-1)
+    return _solver(str(d["solver"]), impl).integrate_DAE(
+        x_init=x_init, x_func=de, i_func=ae, t=t, x=x, z=z, v=v, i=i, all_initial=a0, event_fn=event_fn,
+        jump_change_fn=jump_fn, input_true_x=bool(d["teacher_x"]), input_true_i=bool(d["teacher_i"]))
+
+
+@pytest.mark.parametrize("impl", ["generic", "auto"])
+@pytest.mark.parametrize("name", [n for n in golden_names("ode0") if "model" not in n])
+def test_ode_forward_matches_reference(native_lib, name, impl):
+    d = load_golden(name)
+    d["_name"] = name
+    with torch.no_grad():
+        got = run_ode_case(d, impl).cpu()
+    want = torch.from_numpy(d["x_sol"])
+    want64 = torch.from_numpy(d["x_sol64"])
+    assert got.shape == want.shape
+    assert torch.equal(got[0], want[0]), "x_sol[0] must equal the given initial state exactly"
+    assert torch.allclose(got, want, rtol=RTOL, atol=ATOL), tol_report(got, want, want64)
+
+
+@pytest.mark.parametrize("impl", ["generic", "auto"])
+@pytest.mark.parametrize("name", golden_names("dae0"))
+def test_dae_forward_matches_reference(native_lib, name, impl):
+    d = load_golden(name)
+    d["_name"] = name
+    with torch.no_grad():
+        gx, gi = run_dae_case(d, impl)
+    gx, gi = gx.cpu(), gi.cpu()
+    wx, wi = torch.from_numpy(d["x_sol"]), torch.from_numpy(d["i_sol"])
+    assert gx.shape == wx.shape and gi.shape == wi.shape
+    assert torch.allclose(gx, wx, rtol=RTOL, atol=ATOL), "x: " + tol_report(gx, wx, torch.from_numpy(d["x_sol64"]))
+    assert torch.allclose(gi, wi, rtol=RTOL, atol=ATOL), "i: " + tol_report(gi, wi, torch.from_numpy(d["i_sol64"]))
