@@ -52,7 +52,7 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
                                       const float* __restrict__ src, int ss, float* __restrict__ dst, int ds, int dcols,
                                       bool elu) {
     constexpr int NG = G_TB / G_TM;
-    for (int it = threadIdx.x; it < nout * NG; it += G_NT) {
+    for (int it = threadIdx.x; it < nout * NG; it += blockDim.x) {
         const int g = it / nout, n = it - g * nout;
         const float* wrow = W + (size_t)n * kpad;
         const float* arow = src + g * G_TM * ss;
@@ -78,7 +78,7 @@ __device__ __forceinline__ void layer(const float* __restrict__ W, const float* 
     }
     const int padc = dcols - nout;   // keep the next layer's zero-padded input tail clean
     if (padc > 0)
-        for (int e = threadIdx.x; e < G_TB * padc; e += G_NT) dst[(e / padc) * ds + nout + (e % padc)] = 0.0f;
+        for (int e = threadIdx.x; e < G_TB * padc; e += blockDim.x) dst[(e / padc) * ds + nout + (e % padc)] = 0.0f;
 }
 
 // whole net; every layer ends with a CTA barrier, so `out` is visible to all threads on return
