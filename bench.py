@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--cpu-sample-steps", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the forward+reverse-sweep(+grad all-reduce) leg")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -287,6 +288,48 @@ def main():
         e2e = {"value": units * world / (e2e_ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
 
+    # ---- training step: forward + reverse sweep (discrete adjoint) + ONE gradient all-reduce ---------------------
+    train = None
+    if not args.no_train:
+        from py_psnode_b200 import parallel
+        T = w["N"] + 1
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        x_target = torch.randn((T, w["B"], w["X"]), device=dev, generator=gen) * 0.1
+        mask = torch.ones((T, w["B"], w["X"]), device=dev)
+        i_target = torch.randn((T, w["B"], w["I"]), device=dev, generator=gen) * 0.1 if w["kind"] == "dae" else None
+        plist = list(de.parameters()) + (list(ae.parameters()) if ae is not None else [])
+        bucket = parallel.GradBucket(plist, n_extras=2)
+
+        def numden(out):
+            xs, is_ = out
+            num, den = parallel.masked_mse_sum(xs, x_target, mask)
+            if is_ is not None:
+                num = num + parallel.masked_mse_sum(is_, i_target, mask[..., :1].expand_as(is_))[0]
+            return num, den
+
+        def train_step():
+            return parallel.sharded_training_step(lambda: call_integrate(w, solver, de, ae, resident), plist, bucket, numden)
+
+        for _ in range(2):
+            train_step()
+        bwd_kernel = _native.last_kernel()
+        barrier()
+        l0 = _native.launch_count()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            loss_val = train_step()
+        b.record()
+        barrier()
+        tt = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tr_ms = float(tt.item()) / args.steps
+        train = {"value": units * world / (tr_ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": tr_ms,
+                 "what": "forward + reverse sweep (discrete adjoint, all parameter grads) + masked-MSE + one flat gradient all-reduce",
+                 "allreduce_bytes": bucket.nbytes, "kernel": bwd_kernel, "gpu_launches": int(_native.launch_count() - l0),
+                 "loss": loss_val}
+
     if rank == 0:
         peaks = {}
         try:
@@ -319,6 +362,8 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if train is not None:
+            line["train"] = train
         if not args.no_cpu and world >= 1:
             v, threads, secs = cpu_baseline(w, args.cpu_sample_steps)
             line["cpu_baseline"] = {"value": v, "unit": "traj-steps/s", "cores": threads, "kind": "port",

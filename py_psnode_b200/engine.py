@@ -30,8 +30,7 @@ def _require_cuda_f32(name: str, ten: torch.Tensor) -> None:
     if not ten.is_cuda:
         raise RuntimeError(
             f"py_psnode_b200: `{name}` lives on {ten.device}; the fused integrator runs on CUDA (sm_100a) only and has "
-            "no CPU fallback.  Move the batch and the model to a CUDA device (or construct the solver with eager=True "
-            "to run the plain PyTorch loop).")
+            "no CPU fallback.  Move the batch and the model to a CUDA device.")
     if ten.dtype != torch.float32:
         raise TypeError(f"py_psnode_b200: `{name}` has dtype {ten.dtype}; the integrator computes in float32 like the reference")
 
@@ -94,6 +93,7 @@ class Config:
     n_ae: int
     has_event: bool
     check_events: bool = False
+    event_ref: Optional[tuple] = None   # (t_row (T,), ev_row (E,)) of the GLOBAL sample 0 in batch-sharded runs
 
 
 # fixed positional layout of the tensor arguments of _Integrate.apply
@@ -132,10 +132,16 @@ def _build_problem(cfg: Config, tens: Sequence[Optional[torch.Tensor]], x_sol, i
         _require_cuda_f32("event_t", ev_t)
         E = ev_t.shape[1]
         ev0 = ev_t[0].reshape(E)                    # event times of sample 0 (the only sample the reference inspects)
+        t00 = t[:, 0, 0]
+        if cfg.event_ref is not None:               # batch-sharded: the global batch's sample 0, pinned by parallel.py
+            t00, ev0 = cfg.event_ref
+            _require_cuda_f32("event reference t row", t00)
+            _require_cuda_f32("event reference event row", ev0)
+            if t00.numel() != T or ev0.numel() != E:
+                raise ValueError("pinned event reference rows do not match (T,) / (E,)")
         idx = torch.empty(max(T - 1, 1), dtype=torch.int32, device=t.device)
         err = torch.empty(1, dtype=torch.int32, device=t.device)
-        keep.extend((ev0, idx, err))
-        t00 = t[:, 0, 0]
+        keep.extend((ev0, t00, idx, err))
         N.check(N.lib().psnode_event_table(t00.data_ptr(), t00.stride(0), T, ev0.data_ptr(), ev0.stride(0), E,
                                            idx.data_ptr(), err.data_ptr(), torch.cuda.current_stream(t.device).cuda_stream),
                 "psnode_event_table")

@@ -18,8 +18,8 @@ class _EventBase:
 
     `event_t` is (B, E, 1); event k of EVERY sample fires when the grid time of SAMPLE 0 equals event_t[0, k]
     exactly.  The fused integrator never calls these methods: it reads `event_t` / `*_jump` off the object
-    (pattern.match_event) and builds a per-step table on the device.  They remain callable for user code and
-    for the eager loop.
+    (pattern.match_event) and builds a per-step table on the device.  They remain callable for user code (the
+    reference's public callback contract), nothing on the integration path uses them.
     """
     _jump_names = ()
 

@@ -150,3 +150,11 @@ def match_event(event_fn, jump_change_fn, dae: bool) -> Optional[Tuple[torch.Ten
             raise UnsupportedModuleError("DAE integration needs a DAE_Event (z_jump and v_jump)")
         return owner.event_t, owner.z_jump, owner.v_jump
     return owner.event_t, owner.z_jump
+
+
+def event_reference(event_fn):
+    """(t_row, ev_row) pinned on the event object by `parallel.pin_event_reference` (batch-sharded runs: every rank must
+    test the GLOBAL sample 0, because the reference's predicate looks at sample 0 of the whole batch, neural_base.py:54),
+    or None -> use sample 0 of the tensors passed to the call."""
+    owner = getattr(event_fn, "__self__", None)
+    return getattr(owner, "_psn_event_ref", None) if owner is not None else None

@@ -13,7 +13,7 @@ What is kept from the reference, deliberately:
   * the event predicate looks at sample 0 only, with exact float equality (neural_base.py:54).
 What differs: x_func / i_func must be Linear/ELU chains of the reference's DE_Func / AE_Func shape and the event
 callbacks must be bound methods of an ODE_Event / DAE_Event (see pattern.py); anything else raises
-UnsupportedModuleError unless the solver was built with `eager=True`, which runs the plain PyTorch loop.
+UnsupportedModuleError -- there is no Python-loop or CPU fallback for integrate_ODE / integrate_DAE.
 """
 import abc
 from typing import Optional
@@ -38,7 +38,7 @@ class FixedGridODESolver(metaclass=abc.ABCMeta):
     order: int
     _method: int
 
-    def __init__(self, step_size=None, grid_constructor=None, interp="linear", impl: str = "auto", eager: bool = False,
+    def __init__(self, step_size=None, grid_constructor=None, interp="linear", impl: str = "auto",
                  check_events: bool = False):
         if step_size is not None and grid_constructor is not None:
             raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
@@ -53,7 +53,6 @@ class FixedGridODESolver(metaclass=abc.ABCMeta):
         if impl not in N.IMPL_BY_NAME:
             raise ValueError(f"impl must be one of {sorted(N.IMPL_BY_NAME)}")
         self.impl = impl
-        self.eager = eager
         self.check_events = check_events
 
     # ------------------------------------------------------------------ single step (public in the reference)
@@ -76,8 +75,6 @@ class FixedGridODESolver(metaclass=abc.ABCMeta):
     def integrate_ODE(self, x_func: nn.Module, t: torch.Tensor, x: torch.Tensor, z: torch.Tensor, all_initial: torch.Tensor,
                       event_fn=None, jump_change_fn=None, input_true_x=False):
         """x_solution (T,B,X) for dx/dt = x_func(x, z held, all_initial) on the fixed grid t (my_solvers.py:52-80)."""
-        if self.eager:
-            return self._eager_ode(x_func, t, x, z, all_initial, event_fn, jump_change_fn, input_true_x)
         X, Z = x.shape[-1], z.shape[-1]
         de = pattern.match_de(x_func, X=X, Z=Z, dae=False)
         ev = pattern.match_event(event_fn, jump_change_fn, dae=False)
@@ -86,6 +83,7 @@ class FixedGridODESolver(metaclass=abc.ABCMeta):
                             has_event=ev is not None, check_events=self.check_events)
         tens = [t, x, z, None, None, None, all_initial,
                 ev[0] if ev else None, ev[1] if ev else None, None, *_params(de)]
+        cfg.event_ref = pattern.event_reference(event_fn)
         x_sol, _ = engine.integrate(cfg, tens)
         return x_sol
 
@@ -94,9 +92,6 @@ class FixedGridODESolver(metaclass=abc.ABCMeta):
                       jump_change_fn=None, input_true_x=False, input_true_i=False):
         """(x_solution (T,B,X), i_solution (T,B,I)); i = i_func(x, z, v) evaluated explicitly once per step
         (my_solvers.py:82-131 -- the reference has no Newton iteration)."""
-        if self.eager:
-            return self._eager_dae(x_init, x_func, i_func, t, x, z, v, i, all_initial, event_fn, jump_change_fn,
-                                   input_true_x, input_true_i)
         X, Z, V, I = x_init.shape[-1], z.shape[-1], v.shape[-1], i.shape[-1]
         if input_true_x and x.shape[-1] != X:
             raise ValueError("input_true_x needs a ground-truth x series of the state width")
@@ -108,39 +103,8 @@ class FixedGridODESolver(metaclass=abc.ABCMeta):
                             has_event=ev is not None, check_events=self.check_events)
         tens = [t, x if x.shape[-1] != 0 else None, z, v, i, x_init, all_initial,
                 ev[0] if ev else None, ev[1] if ev else None, ev[2] if ev else None, *_params(de), *_params(ae)]
+        cfg.event_ref = pattern.event_reference(event_fn)
         return engine.integrate(cfg, tens)
-
-    # ------------------------------------------------------------------ opt-in eager loop (never chosen automatically)
-    def _eager_ode(self, x_func, t, x, z, all_initial, event_fn, jump_change_fn, input_true_x):
-        rows = [x[0]]
-        prev = x[0]
-        for j in range(1, t.shape[0]):
-            t0, t1, z0 = t[j - 1], t[j], z[j - 1]
-            if event_fn is not None and event_fn(t0) == True:   # noqa: E712  (callbacks may return tensors)
-                z0 = jump_change_fn(t0, z0)
-            start = x[j - 1] if input_true_x else prev
-            prev, _ = self.step_integrate(func=x_func, t0=t0, dt=t1 - t0, t1=t1, x0=start, z0=z0, all_initial=all_initial)
-            rows.append(prev)
-        return torch.stack(rows, dim=0)
-
-    def _eager_dae(self, x_init, x_func, i_func, t, x, z, v, i, all_initial, event_fn, jump_change_fn, input_true_x,
-                   input_true_i):
-        x_prev = x_init
-        i_prev = i_func(xt=x[0] if input_true_x else x_prev, zt=z[0], vt=v[0], all_initial=all_initial)
-        xr, ir = [x_prev], [i_prev]
-        for j in range(1, t.shape[0]):
-            t0, t1, z0, v0 = t[j - 1], t[j], z[j - 1], v[j - 1]
-            if event_fn is not None and event_fn(t0) == True:   # noqa: E712
-                z0, v0 = jump_change_fn(t0, z0, v0)
-                i_prev = i_func(xt=x_prev, zt=z0, vt=v0, all_initial=all_initial)
-            start = x[j - 1] if input_true_x else x_prev
-            held = i[j - 1] if input_true_i else i_prev
-            x_prev, _ = self.step_integrate(func=x_func, t0=t0, dt=t1 - t0, t1=t1, x0=start, z0=z0, v0=v0, i0=held,
-                                            all_initial=all_initial)
-            i_prev = i_func(xt=x[j] if input_true_x else x_prev, zt=z[j], vt=v[j], all_initial=all_initial)
-            xr.append(x_prev)
-            ir.append(i_prev)
-        return torch.stack(xr, dim=0), torch.stack(ir, dim=0)
 
 
 class Euler(FixedGridODESolver):
