@@ -74,7 +74,8 @@ SYMBOLS = [
     ("psnode_forward_host", C.c_int, [C.POINTER(Problem), C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 ]
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libpsnode_b200.so")
+# PSNODE_B200_LIB selects an alternative build of the SAME library (A/B kernel experiments); never a different backend.
+LIB_PATH = os.environ.get("PSNODE_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libpsnode_b200.so")
 
 _lib = None
 _lock = threading.Lock()

@@ -39,6 +39,10 @@ __device__ __forceinline__ u64 pack2(float x, float y) {
     return r;
 }
 
+#ifndef PSN_STAGE_UNROLL
+#define PSN_STAGE_UNROLL 1
+#endif
+constexpr int kStageUnroll = PSN_STAGE_UNROLL;   // 1 = stage loop rolled: the fully unrolled body (4) overflowed the instruction cache (ncu: no_instruction 1.2 warps/issue); rolled is 15 % faster (A/B on B200: 181 -> 209 M traj-steps/s)
 constexpr int FH = 64;     // hidden width
 constexpr int FX = 16;     // state width
 constexpr int FU = 8;      // held-input width (padded)
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(F_NT, 4) psn_fused_ode_kernel(const __grid_con
             h = fmaf(w1u[4], u1.x, h); h = fmaf(w1u[5], u1.y, h); h = fmaf(w1u[6], u1.z, h); h = fmaf(w1u[7], u1.w, h);
             hz[i] = h;
         }
-#pragma unroll
+#pragma unroll kStageUnroll
         for (int e = 0; e < NST; e++) {
             // ---- layer 1 (folded): thread = neuron tid, 16 state columns ----
 #pragma unroll
