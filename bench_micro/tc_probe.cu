@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ W,
         *reinterpret_cast<float*>(alo + tile_byte(n, k, LBO_B, SBO_B)) = lo;
     }
     if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar4, 4); fence_mbar_init(); }
-    if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -53,6 +53,24 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ W,
     const uint64_t dwhi = make_desc(smem_u32(whi), LBO_A, SBO_A), dwlo = make_desc(smem_u32(wlo), LBO_A, SBO_A);
     const uint64_t dahi = make_desc(smem_u32(ahi), LBO_B, SBO_B), dalo = make_desc(smem_u32(alo), LBO_B, SBO_B);
     const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16);
+    {   // weights -> TMEM columns [128,192) = hi, [192,256) = lo ; thread t of warp w owns rows 16w + t/4 (+8), cols 2(t%4)+{0,1} (+8)
+        const int r0 = 16 * warp + lane / 4, c0 = 2 * (lane % 4);
+        for (int half = 0; half < 2; half++)
+            for (int cb = 0; cb < K / 16; cb++) {
+                float w8[8];
+                for (int i = 0; i < 8; i++) {
+                    const int row = r0 + ((i >> 1) & 1) * 8, col = 16 * cb + c0 + (i & 1) + (i >> 2) * 8;
+                    float hi, lo;
+                    split_tf32(W[row * K + col], hi, lo);
+                    w8[i] = half ? lo : hi;
+                }
+                tmem_st_16x256b_x2(taddr + 128 + 64 * half + 16 * cb, w8);
+            }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
     uint32_t phase = 0;
     bool ok = true;
     float v[N / 2 < 4 ? 4 : N / 2];
@@ -112,7 +130,23 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ W,
     long long t0 = clock64();
     for (int it = 0; it < iters && ok; it++) {
         const long long s0 = clock64();
-        if (nacc == -4) {       // every warp issues its own 2 k-steps x 3 terms into its own accumulator; bar expects 4 commits
+        if (nacc == -5) {       // as -4, but the weights (A operand) live in TMEM: only B is fetched from shared memory
+            if (elect_one()) {
+                tc_fence_after();
+#pragma unroll
+                for (int term = 0; term < 3; term++) {
+                    const uint32_t ta = tmem + 128 + (term == 0 ? 64 : 0);
+                    const uint64_t db = term == 1 ? dalo : dahi;
+#pragma unroll
+                    for (int kk = 0; kk < 2; kk++) {
+                        const int ks = 2 * warp + kk;
+                        mma_tf32_ts(tmem + warp * N, ta + 8 * ks, db + (uint64_t)((ks * 2 * LBO_B) >> 4), idesc, (term | kk) ? 1 : 0);
+                    }
+                }
+                mma_commit(&bar4);
+            }
+            __syncwarp();
+        } else if (nacc == -4) {       // every warp issues its own 2 k-steps x 3 terms into its own accumulator; bar expects 4 commits
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
@@ -138,11 +172,11 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ W,
             }
         }
         const long long s1 = clock64();
-        ok = mbar_wait(nacc == -4 ? &bar4 : &bar, phase); phase ^= 1;
+        ok = mbar_wait(nacc <= -4 ? &bar4 : &bar, phase); phase ^= 1;
         tc_fence_after();
         const long long s2 = clock64();
         load_d();
-        if (nacc == -4) {       // sum the 4 partial accumulators
+        if (nacc <= -4) {       // sum the 4 partial accumulators
             float vv[N / 2 < 4 ? 4 : N / 2];
             for (int i = 0; i < (N / 2 < 4 ? 4 : N / 2); i++) vv[i] = v[i];
             for (int a = 1; a < 4; a++) {
@@ -179,7 +213,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ W,
     long long t1 = clock64();
     if (tid == 0) { cycles[0] = t1 - t0; for (int i = 0; i < 6; i++) cycles[1 + i] = acc[i]; if (!ok) err[0] = 1; }
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 template <int N>
@@ -225,5 +259,8 @@ int main() {
     run<8>(2000, 3, -4);
     run<16>(2000, 3, -4);
     run<32>(2000, 3, -4);
+    run<8>(2000, 3, -5);
+    run<16>(2000, 3, -5);
+    run<32>(2000, 3, -5);
     return 0;
 }

@@ -119,13 +119,19 @@ int64_t psnode_forward_workspace(const psnode_problem* p) {
     if (validate(p) != PSNODE_OK) return 0;
     int64_t g = psn_generic_forward_workspace(p);
     int64_t f = psn_fused_supports(p) ? psn_fused_forward_workspace(p) : 0;
-    return g > f ? g : f;
+    int64_t t = psn_tc_supports(p) ? psn_tc_forward_workspace(p) : 0;
+    if (f > g) g = f;
+    return g > t ? g : t;
 }
 
 int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_bytes, void* stream) {
     const int st = validate(p);
     if (st != PSNODE_OK) return st;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (p->impl == PSNODE_IMPL_TC) {
+        if (!psn_tc_supports(p)) return PSNODE_EUNSUPPORTED;
+        return psn_tc_forward(p, workspace, workspace_bytes, s);
+    }
     if (p->impl == PSNODE_IMPL_FUSED) {
         if (!psn_fused_supports(p)) return PSNODE_EUNSUPPORTED;
         return psn_fused_forward(p, workspace, workspace_bytes, s);

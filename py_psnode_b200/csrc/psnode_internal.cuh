@@ -48,3 +48,7 @@ int64_t psn_generic_backward_workspace(const psnode_problem* p, const psnode_adj
 bool psn_fused_supports(const psnode_problem* p);
 int psn_fused_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream);
 int64_t psn_fused_forward_workspace(const psnode_problem* p);
+
+bool psn_tc_supports(const psnode_problem* p);
+int psn_tc_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream);
+int64_t psn_tc_forward_workspace(const psnode_problem* p);

@@ -1,0 +1,443 @@
+// psnode_tc_fwd.cu -- tensor-core forward integrator for the reference's H = 64 ODE nets (BASELINE configs[1]):
+// integrate_ODE (neural_dae/my_solvers.py:52-80) with the 4-layer DE_Func of neural_00_ODE_01_no_encode.py:58-68
+// (3S -> 64 -> 64 -> 64 -> 16, ELU), Euler / Midpoint / RK4-3/8 (neural_dae/my_fixed_grid.py:15-59), event jumps.
+//
+// Every stage MLP layer is a genuine 64 x 16 x K GEMM per group of 16 trajectories, so it runs on the 5th-generation
+// tensor cores: tcgen05.mma kind::tf32 with fp32 accumulation in TMEM.  The reference is fp32 and the parity tolerance
+// (rtol 1e-5 / atol 1e-6 over 1000 steps) leaves no room for plain TF32 (measured 3e-4 per dot product), so every
+// product is formed as 3xTF32:  W a ~= W_lo a_hi + W_hi a_lo + W_hi a_hi  with round-to-nearest hi/lo splits -- measured
+// 1.4e-7 max error per 64-term dot product on B200, the same as an fp32 FMA chain (bench_micro/tc_probe.cu).
+//
+// Mapping (measured design points in profiles/r01_tc_probe_*.log):
+//   * D[neuron m][trajectory n] = W[m][:] . act[n][:]: the WEIGHTS are the A operand and stay resident in TMEM for the whole
+//     kernel (hi and lo copies of the folded layer 1, layer 2 and layer 3: 304 of the 512 columns); only the 16-row
+//     activation tile (B operand, 512 B per MMA) is fetched from shared memory.  With A in shared memory the MMA rate was
+//     bound by the 2 KB operand fetch (27-50 cycles per MMA); from TMEM the issue overhead (~60 cycles per MMA and warp)
+//     dominates, so the 24 MMAs of a layer are issued by all 4 warps of the group in parallel, each into its own
+//     accumulator (6 MMAs per warp, K-split), and the 4 partial accumulators are summed in the epilogue.
+//   * A group = 128 threads = 16 trajectories.  Warp w reads accumulator rows 16w..16w+15 with tcgen05.ld.16x256b (thread t:
+//     rows 16w + t/4 (+8), trajectories 2(t%4) (+1) (+8)), adds the bias, applies ELU, splits hi/lo and writes the next
+//     layer's B tile (K-major, no swizzle, 144-byte K-chunk stride -> conflict-free transposed stores).
+//   * Two groups per CTA (one CTA per SM) run staggered, so one group's epilogue overlaps the other's MMA round trip.
+//   * Layer 1 is folded as in the CUDA-core kernel: W1 [a0; s-a0; s] + b1 = (Wb+Wc) [x; u] + c1, c1 = (Wa-Wb) a0 + b1 is a
+//     per-(neuron, trajectory) register constant; the B tile of layer 1 is [x (16) | held inputs (8)].
+//   * Layer 4 (64 -> 16) uses shared-memory weights (M padded to 64); warp 0 owns its 16 valid rows = the state, keeps
+//     x, k1..k3 in registers, does the stage algebra in the reference's operation order and writes the next stage's x
+//     columns; trajectory rows go out as 1 KB contiguous, 128-bit stores per step and group.
+#include <cstddef>
+#include "psnode_internal.cuh"
+#include "psnode_tc.cuh"
+
+namespace {
+using namespace psn_tc;
+
+constexpr int TN = 16;                 // trajectories per group (MMA N)
+constexpr int TH = 64, TX = 16, TU = 8;
+constexpr int TK1 = TX + TU;           // layer-1 K after folding
+constexpr int LBO = 144;               // K-chunk stride of the activation tiles (16 B chunk + 128 B row block, padded)
+constexpr int SBO_ACT = (TH / 4) * LBO;
+constexpr int SBO_B1 = (TK1 / 4) * LBO;
+constexpr int ACT_TILE = (TN / 8) * SBO_ACT;
+constexpr int B1_TILE = (TN / 8) * SBO_B1;
+constexpr int LBO_W = 128, SBO_W = (TH / 4) * LBO_W;     // layer-4 weight tiles in shared memory (64 rows x K = 64)
+constexpr int W4_TILE = (TH / 8) * SBO_W;
+// TMEM columns: accumulators first (2 groups x 4 warps x 16), then the resident weights
+constexpr int TM_ACC = 0;
+constexpr int TM_W2 = 128, TM_W3 = 256, TM_W1 = 384;     // hi at +0, lo at +64 (layer 1: lo at +32)
+constexpr int TM_COLS = 512;
+constexpr int GROUP_THREADS = 128;
+
+struct TcParams {
+    int B, T, Z, S, groups;
+    psnode_series t, x, z;
+    const float* a0; int64_t a0_sb;
+    const int32_t* event_idx;
+    const float* z_jump; int64_t zj_sb, zj_se;
+    psnode_series_out x_sol;
+    const float* W1; const float* b1; const float* W2; const float* b2;
+    const float* W3; const float* b3; const float* W4; const float* b4;
+    int vec_out;
+    int* err;
+};
+
+struct __align__(128) GroupSmem {
+    unsigned char act_hi[ACT_TILE];
+    unsigned char act_lo[ACT_TILE];
+    unsigned char b1_hi[B1_TILE + 64];
+    unsigned char b1_lo[B1_TILE + 64];
+    float ostage[TN][TX];
+    float dts[2][TN];
+    uint64_t bar;
+};
+
+struct __align__(128) CtaSmem {
+    float w4_hi[W4_TILE / 4];
+    float w4_lo[W4_TILE / 4];
+    GroupSmem g[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float ldser(const psnode_series& s, int j, int b, int c) {
+    return __ldg(s.p + (int64_t)j * s.st + (int64_t)b * s.sb + c);
+}
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(GROUP_THREADS) : "memory"); }
+
+template <int METHOD>
+__global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const __grid_constant__ TcParams q) {
+    constexpr int NST = METHOD == PSNODE_EULER ? 1 : (METHOD == PSNODE_MIDPOINT ? 2 : 4);
+    extern __shared__ unsigned char smem_raw[];
+    CtaSmem& sm = *reinterpret_cast<CtaSmem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+    const int tid = threadIdx.x;
+    const int g = tid >> 7;                    // group
+    const int gt = tid & 127;                  // thread within the group
+    const int warp = gt >> 5, lane = gt & 31;  // warp within the group == TMEM sub-partition (CTA warp index % 4)
+    GroupSmem& gs = sm.g[g];
+    const int B = q.B, T = q.T, Z = q.Z, S = q.S;
+    const int b0 = (blockIdx.x * q.groups + g) * TN;
+    const bool live = g < q.groups && b0 < B;          // whole group has at least one trajectory
+
+    // ---- one-time setup -------------------------------------------------------------------------------
+    if (tid == 0) { mbar_init(&sm.g[0].bar, 4); mbar_init(&sm.g[1].bar, 4); fence_mbar_init(); }
+    if ((tid >> 5) == 0) tmem_alloc(&sm.tmem_base, TM_COLS);
+    // layer-4 weights -> shared-memory tiles (rows >= 16 are zero)
+    for (int e = tid; e < TH * TH; e += 2 * GROUP_THREADS) {
+        const int m = e >> 6, k = e & 63;
+        float hi = 0.0f, lo = 0.0f;
+        if (m < TX) split_tf32(__ldg(q.W4 + m * TH + k), hi, lo);
+        sm.w4_hi[tile_byte(m, k, LBO_W, SBO_W) >> 2] = hi;
+        sm.w4_lo[tile_byte(m, k, LBO_W, SBO_W) >> 2] = lo;
+    }
+    for (int e = gt; e < (int)(offsetof(GroupSmem, bar) / 4); e += GROUP_THREADS) reinterpret_cast<float*>(&gs)[e] = 0.0f;
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+    // this thread's accumulator fragment: element i <-> (row m0 + 8*((i>>1)&1), trajectory c0 + (i&1) + 8*(i>>2))
+    const int m0 = 16 * warp + (lane >> 2), c0 = 2 * (lane & 3);
+    auto frag_row = [&](int i) { return m0 + ((i >> 1) & 1) * 8; };
+    auto frag_col = [&](int i) { return c0 + (i & 1) + (i >> 2) * 8; };
+
+    // resident weights -> TMEM (group 0 writes; both groups read them through the tensor core only)
+    if (g == 0) {
+        const int K1 = 3 * S;
+        auto w1_folded = [&](int m, int c) -> float {      // (Wb + Wc) restricted to [x | held inputs], zero padded
+            int k;
+            if (c < TX) k = c; else if (c - TX < Z) k = TX + (c - TX); else return 0.0f;
+            return __ldg(q.W1 + m * K1 + S + k) + __ldg(q.W1 + m * K1 + 2 * S + k);
+        };
+        for (int half = 0; half < 2; half++) {
+            for (int cb = 0; cb < 4; cb++) {               // layers 2 and 3: 64 columns = 4 x 16
+                float w2[8], w3[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int row = frag_row(i), col = 16 * cb + frag_col(i);
+                    float hi, lo;
+                    split_tf32(__ldg(q.W2 + row * TH + col), hi, lo); w2[i] = half ? lo : hi;
+                    split_tf32(__ldg(q.W3 + row * TH + col), hi, lo); w3[i] = half ? lo : hi;
+                }
+                tmem_st_16x256b_x2(tmem + lane_base + TM_W2 + 64 * half + 16 * cb, w2);
+                tmem_st_16x256b_x2(tmem + lane_base + TM_W3 + 64 * half + 16 * cb, w3);
+            }
+            for (int cb = 0; cb < 2; cb++) {               // layer 1: 24 columns stored as 2 x 16 (tail zero)
+                float w1[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int row = frag_row(i), col = 16 * cb + frag_col(i);
+                    float hi = 0.0f, lo = 0.0f;
+                    if (col < TK1) split_tf32(w1_folded(row, col), hi, lo);
+                    w1[i] = half ? lo : hi;
+                }
+                tmem_st_16x256b_x2(tmem + lane_base + TM_W1 + 32 * half + 16 * cb, w1);
+            }
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();            // resident weights visible to both groups' MMAs
+    tc_fence_after();
+    // per-thread constants: biases of its two rows, c1 of its 8 (row, trajectory) elements
+    float bias2[2], bias3[2], bias4[2], c1[8];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        bias2[r] = __ldg(q.b2 + m0 + 8 * r);
+        bias3[r] = __ldg(q.b3 + m0 + 8 * r);
+        bias4[r] = warp == 0 ? __ldg(q.b4 + m0 + 8 * r) : 0.0f;
+    }
+    {
+        const int K1 = 3 * S;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int row = frag_row(i), bb = min(b0 + frag_col(i), B - 1);
+            float acc = __ldg(q.b1 + row);
+            if (live)
+                for (int k = 0; k < S; k++)
+                    acc = fmaf(__ldg(q.W1 + row * K1 + k) - __ldg(q.W1 + row * K1 + S + k), __ldg(q.a0 + (int64_t)bb * q.a0_sb + k), acc);
+            c1[i] = acc;
+        }
+    }
+    // activation-tile byte offsets of this thread's 8 elements (row = K index of the next layer, column = trajectory)
+    int off_act[8], off_b1[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        off_act[i] = tile_byte(frag_col(i), frag_row(i), LBO, SBO_ACT);
+        off_b1[i] = tile_byte(frag_col(i), frag_row(i) & 15, LBO, SBO_B1);
+    }
+    // descriptors
+    const uint32_t idesc = make_idesc_tf32(TH, TN);
+    const uint64_t d_act_hi = make_desc(smem_u32(gs.act_hi), LBO, SBO_ACT), d_act_lo = make_desc(smem_u32(gs.act_lo), LBO, SBO_ACT);
+    const uint64_t d_b1_hi = make_desc(smem_u32(gs.b1_hi), LBO, SBO_B1), d_b1_lo = make_desc(smem_u32(gs.b1_lo), LBO, SBO_B1);
+    const uint64_t d_w4_hi = make_desc(smem_u32(sm.w4_hi), LBO_W, SBO_W), d_w4_lo = make_desc(smem_u32(sm.w4_lo), LBO_W, SBO_W);
+    const uint32_t acc_base = tmem + TM_ACC + (uint32_t)(g * 4) * TN;      // 4 partial accumulators of this group
+    const uint32_t my_acc = acc_base + (uint32_t)warp * TN;                // the one this warp's MMAs write
+    constexpr uint64_t KSTEP_B = (uint64_t)((2 * LBO) >> 4), KSTEP_W = (uint64_t)((2 * LBO_W) >> 4);
+    uint32_t phase = 0;
+
+    // ---- helpers ---------------------------------------------------------------------------------------
+    // TS layers (weights in TMEM): this warp's K-steps [ks0, ks0 + nks) for the three 3xTF32 terms, small terms first
+    auto issue_ts = [&](uint32_t w_hi, uint32_t w_lo, uint64_t b_hi, uint64_t b_lo, int ks0, int nks) {
+        if (elect_one()) {
+            tc_fence_after();
+            uint32_t accumulate = 0;
+            for (int term = 0; term < 3; term++) {
+                const uint32_t wa = term == 0 ? w_lo : w_hi;
+                const uint64_t bd = term == 1 ? b_lo : b_hi;
+                for (int kk = 0; kk < nks; kk++) {
+                    const int ks = ks0 + kk;
+                    mma_tf32_ts(my_acc, tmem + wa + 8 * ks, bd + KSTEP_B * ks, idesc, accumulate);
+                    accumulate = 1;
+                }
+            }
+            mma_commit(&gs.bar);
+        }
+        __syncwarp();
+    };
+    auto issue_ss = [&](uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, int ks0, int nks) {
+        if (elect_one()) {
+            tc_fence_after();
+            uint32_t accumulate = 0;
+            for (int term = 0; term < 3; term++) {
+                const uint64_t ad = term == 0 ? a_lo : a_hi;
+                const uint64_t bd = term == 1 ? b_lo : b_hi;
+                for (int kk = 0; kk < nks; kk++) {
+                    const int ks = ks0 + kk;
+                    mma_tf32(my_acc, ad + KSTEP_W * ks, bd + KSTEP_B * ks, idesc, accumulate);
+                    accumulate = 1;
+                }
+            }
+            mma_commit(&gs.bar);
+        }
+        __syncwarp();
+    };
+    // wait for the group's 4 commits, then (if `want`) sum the first `nacc` partial accumulators into d[8]
+    auto collect = [&](float (&d)[8], int nacc, bool want) {
+        if (!mbar_wait(&gs.bar, phase)) { atomicExch(q.err, 1); __trap(); }
+        phase ^= 1;
+        tc_fence_after();
+        if (!want) return;
+        float t0[8], t1[8], t2[8], t3[8];
+        tmem_ld_16x256b_x2(acc_base + lane_base + 0 * TN, t0);
+        tmem_ld_16x256b_x2(acc_base + lane_base + 1 * TN, t1);
+        tmem_ld_16x256b_x2(acc_base + lane_base + 2 * TN, t2);
+        if (nacc == 4) tmem_ld_16x256b_x2(acc_base + lane_base + 3 * TN, t3);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; i++) d[i] = nacc == 4 ? (t0[i] + t1[i]) + (t2[i] + t3[i]) : (t0[i] + t1[i]) + t2[i];
+    };
+    // publish freshly written B-tile data to the tensor core and line the group up for the next layer's MMAs
+    auto publish = [&]() {
+        fence_async_smem();
+        tc_fence_before();
+        group_sync(g);
+    };
+    auto store_hidden = [&](const float (&d)[8], const float (&bias)[2], const float* cadd) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            float v = d[i] + bias[(i >> 1) & 1];
+            if (cadd) v = d[i] + cadd[i];
+            float hi, lo;
+            split_tf32(psn_elu(v), hi, lo);
+            *reinterpret_cast<float*>(gs.act_hi + off_act[i]) = hi;
+            *reinterpret_cast<float*>(gs.act_lo + off_act[i]) = lo;
+        }
+    };
+    // held inputs / dt of the step that ENDS at grid point j -> B1 tile columns 16.., dts[j & 1]; done by warp 1, lane = trajectory
+    auto load_step_inputs = [&](int j, float (&u)[TU], float& dt) {
+        const int bb = min(b0 + (lane & 15), B - 1);
+        dt = __fsub_rn(ldser(q.t, j, bb, 0), ldser(q.t, j - 1, bb, 0));
+        const int k = q.event_idx ? __ldg(q.event_idx + (j - 1)) : -1;
+#pragma unroll
+        for (int c = 0; c < TU; c++) {
+            u[c] = 0.0f;
+            if (c < Z) u[c] = k >= 0 ? __ldg(q.z_jump + (int64_t)bb * q.zj_sb + (int64_t)k * q.zj_se + c) : ldser(q.z, j - 1, bb, c);
+        }
+    };
+    auto store_step_inputs = [&](int j, const float (&u)[TU], float dt) {
+        if (lane < TN) {
+            gs.dts[j & 1][lane] = dt;
+#pragma unroll
+            for (int c = 0; c < TU; c++) {
+                float hi, lo;
+                split_tf32(u[c], hi, lo);
+                const int o = tile_byte(lane, TX + c, LBO, SBO_B1);
+                *reinterpret_cast<float*>(gs.b1_hi + o) = hi;
+                *reinterpret_cast<float*>(gs.b1_lo + o) = lo;
+            }
+        }
+    };
+
+    if (live) {
+        // ---- initial state: warp 0 owns the state elements (row = state index m0 (+8), column = trajectory) ------
+        float x0[8], k1[8], k2[8], k3[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { x0[i] = 0.f; k1[i] = 0.f; k2[i] = 0.f; k3[i] = 0.f; }
+        if (warp == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int n = frag_col(i), m = frag_row(i), b = b0 + n, bb = min(b, B - 1);
+                const float xv = ldser(q.x, 0, bb, m);
+                x0[i] = xv;
+                if (b < B) q.x_sol.p[(int64_t)b * q.x_sol.sb + m] = xv;
+                float hi, lo;
+                split_tf32(xv, hi, lo);
+                *reinterpret_cast<float*>(gs.b1_hi + off_b1[i]) = hi;
+                *reinterpret_cast<float*>(gs.b1_lo + off_b1[i]) = lo;
+            }
+        }
+        if (warp == 1 && T > 1) {
+            float u[TU], dt;
+            load_step_inputs(1, u, dt);
+            store_step_inputs(1, u, dt);
+        }
+        publish();
+
+        const float c13 = (float)(1.0 / 3.0);
+        for (int j = 1; j < T; j++) {
+            float un[TU], dtn = 0.0f;                       // next step's inputs, prefetched by warp 1 during stage 0
+            const bool have_next = j + 1 < T;
+#pragma unroll 1
+            for (int e = 0; e < NST; e++) {
+                float d[8];
+                // ---- layer 1: K = 24 -> warps 0..2 take one K-step each; warp 3 only commits ----
+                issue_ts(TM_W1, TM_W1 + 32, d_b1_hi, d_b1_lo, warp, warp < 3 ? 1 : 0);
+                if (e == 0 && warp == 1 && have_next) load_step_inputs(j + 1, un, dtn);
+                collect(d, 3, true);
+                store_hidden(d, bias2, c1);
+                publish();
+                // ---- layer 2 ----
+                issue_ts(TM_W2, TM_W2 + 64, d_act_hi, d_act_lo, 2 * warp, 2);
+                collect(d, 4, true);
+                store_hidden(d, bias2, nullptr);
+                publish();
+                // ---- layer 3 ----
+                issue_ts(TM_W3, TM_W3 + 64, d_act_hi, d_act_lo, 2 * warp, 2);
+                collect(d, 4, true);
+                store_hidden(d, bias3, nullptr);
+                publish();
+                // ---- layer 4 (shared-memory weights) + stage algebra on warp 0 ----
+                issue_ss(d_w4_hi, d_w4_lo, d_act_hi, d_act_lo, 2 * warp, 2);
+                collect(d, 4, warp == 0);
+                if (warp == 0) {
+                    const bool last = e == NST - 1;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const float kv = d[i] + bias4[(i >> 1) & 1];
+                        const float dt = gs.dts[j & 1][frag_col(i)];
+                        float xn;
+                        if (METHOD == PSNODE_EULER) {
+                            xn = __fadd_rn(x0[i], __fmul_rn(dt, kv));
+                        } else if (METHOD == PSNODE_MIDPOINT) {
+                            if (e == 0) xn = __fadd_rn(x0[i], __fmul_rn(kv, __fmul_rn(0.5f, dt)));
+                            else xn = __fadd_rn(x0[i], __fmul_rn(dt, kv));
+                        } else {
+                            if (e == 0) { k1[i] = kv; xn = __fadd_rn(x0[i], __fmul_rn(__fmul_rn(dt, kv), c13)); }
+                            else if (e == 1) { k2[i] = kv; xn = __fadd_rn(x0[i], __fmul_rn(dt, __fsub_rn(kv, __fmul_rn(k1[i], c13)))); }
+                            else if (e == 2) { k3[i] = kv; xn = __fadd_rn(x0[i], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[i], k2[i]), kv))); }
+                            else {
+                                const float ksum = __fadd_rn(__fadd_rn(k1[i], __fmul_rn(3.0f, __fadd_rn(k2[i], k3[i]))), kv);
+                                xn = __fadd_rn(x0[i], __fmul_rn(__fmul_rn(ksum, dt), 0.125f));
+                            }
+                        }
+                        float hi, lo;
+                        split_tf32(xn, hi, lo);
+                        *reinterpret_cast<float*>(gs.b1_hi + off_b1[i]) = hi;
+                        *reinterpret_cast<float*>(gs.b1_lo + off_b1[i]) = lo;
+                        if (last) { x0[i] = xn; gs.ostage[frag_col(i)][frag_row(i)] = xn; }
+                    }
+                    if (last) {     // trajectory row j: 16 x 16 floats, contiguous for contiguous outputs
+                        __syncwarp();
+                        if (q.vec_out) {
+#pragma unroll
+                            for (int r = 0; r < 2; r++) {
+                                const int idx = lane + 32 * r, n = idx >> 2, c4 = idx & 3, b = b0 + n;
+                                if (b < B)
+                                    *reinterpret_cast<float4*>(q.x_sol.p + (int64_t)j * q.x_sol.st + (int64_t)b * q.x_sol.sb + 4 * c4) =
+                                        *reinterpret_cast<const float4*>(&gs.ostage[n][4 * c4]);
+                            }
+                        } else {
+                            for (int idx = lane; idx < TN * TX; idx += 32) {
+                                const int n = idx >> 4, c = idx & 15, b = b0 + n;
+                                if (b < B) q.x_sol.p[(int64_t)j * q.x_sol.st + (int64_t)b * q.x_sol.sb + c] = gs.ostage[n][c];
+                            }
+                        }
+                        __syncwarp();
+                    }
+                } else if (warp == 1 && e == NST - 1 && have_next) {
+                    store_step_inputs(j + 1, un, dtn);      // every layer-1 MMA of this step has completed: the u columns are free
+                }
+                publish();
+            }
+        }
+    }
+    // ---- teardown --------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if ((tid >> 5) == 0) tmem_dealloc(tmem, TM_COLS);
+}
+
+}  // namespace
+
+bool psn_tc_supports(const psnode_problem* p) {
+    if (p->kind != PSNODE_ODE || p->teacher_x) return false;
+    if (p->X != TX || p->Z < 0 || p->Z > TU) return false;
+    const psnode_mlp& m = p->de;
+    if (m.n_layers != 4) return false;
+    const int S = p->X + p->Z;
+    return m.in_dim[0] == 3 * S && m.out_dim[0] == TH && m.out_dim[1] == TH && m.out_dim[2] == TH && m.out_dim[3] == TX;
+}
+
+int64_t psn_tc_forward_workspace(const psnode_problem*) { return 256; }
+
+int psn_tc_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    if (ws == nullptr || ws_bytes < 4) return PSNODE_EWORKSPACE;
+    TcParams q;
+    q.B = p->B; q.T = p->T; q.Z = p->Z; q.S = p->X + p->Z;
+    q.t = p->t; q.x = p->x; q.z = p->z;
+    q.a0 = p->a0; q.a0_sb = p->a0_sb;
+    q.event_idx = p->event_idx;
+    q.z_jump = p->z_jump; q.zj_sb = p->zj_sb; q.zj_se = p->zj_se;
+    q.x_sol = p->x_sol;
+    q.W1 = p->de.W[0]; q.b1 = p->de.b[0]; q.W2 = p->de.W[1]; q.b2 = p->de.b[1];
+    q.W3 = p->de.W[2]; q.b3 = p->de.b[2]; q.W4 = p->de.W[3]; q.b4 = p->de.b[3];
+    q.vec_out = ((reinterpret_cast<uintptr_t>(p->x_sol.p) & 15) == 0 && (p->x_sol.st & 3) == 0 && (p->x_sol.sb & 3) == 0) ? 1 : 0;
+    q.err = static_cast<int*>(ws);
+    PSN_CUDA(cudaMemsetAsync(q.err, 0, 4, stream));
+    // two groups of 16 trajectories per CTA once there are enough trajectories to give every SM a CTA
+    const int ngroups = (p->B + TN - 1) / TN;
+    q.groups = ngroups > 148 ? 2 : 1;
+    const int grid = (ngroups + q.groups - 1) / q.groups;
+    const int smem = (int)sizeof(CtaSmem) + 128;
+    auto launch = [&](auto kern, const char* name) -> int {
+        PSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, 2 * GROUP_THREADS, smem, stream>>>(q);
+        psn_count_launch(name);
+        PSN_CUDA(cudaGetLastError());
+        return PSNODE_OK;
+    };
+    switch (p->method) {
+        case PSNODE_EULER: return launch(psn_tc_ode_kernel<PSNODE_EULER>, "psn_tc_ode_kernel<euler>");
+        case PSNODE_MIDPOINT: return launch(psn_tc_ode_kernel<PSNODE_MIDPOINT>, "psn_tc_ode_kernel<midpoint>");
+        default: return launch(psn_tc_ode_kernel<PSNODE_RK4>, "psn_tc_ode_kernel<rk4>");
+    }
+}

@@ -75,3 +75,44 @@ def test_dae_forward_matches_reference(native_lib, name, impl):
     assert gx.shape == wx.shape and gi.shape == wi.shape
     assert torch.allclose(gx, wx, rtol=RTOL, atol=ATOL), "x: " + tol_report(gx, wx, torch.from_numpy(d["x_sol64"]))
     assert torch.allclose(gi, wi, rtol=RTOL, atol=ATOL), "i: " + tol_report(gi, wi, torch.from_numpy(d["i_sol64"]))
+
+
+TC_CASES = ["ode01_rk4_small", "ode01_midpoint_small", "ode01_rk4_noevent", "ode01_rk4_nomatch", "ode01_rk4_2events_pad",
+            "ode01_rk4_long"]
+
+
+@pytest.mark.parametrize("name", TC_CASES)
+def test_ode_forward_tensor_core_matches_reference(native_lib, name):
+    """tcgen05 3xTF32 kernel (impl="tc") against the reference's fp32 output at the same rtol=1e-5 / atol=1e-6."""
+    from py_psnode_b200 import _native
+    d = load_golden(name)
+    d["_name"] = name
+    with torch.no_grad():
+        got = run_ode_case(d, "tc").cpu()
+    assert _native.last_kernel().startswith("psn_tc_ode_kernel")
+    want = torch.from_numpy(d["x_sol"])
+    want64 = torch.from_numpy(d["x_sol64"])
+    assert torch.equal(got[0], want[0])
+    assert torch.allclose(got, want, rtol=RTOL, atol=ATOL), tol_report(got, want, want64)
+
+
+def test_tensor_core_matches_fused_at_scale(native_lib):
+    """B = 600 trajectories (ragged last group, two groups per CTA), 200 steps: tensor-core vs CUDA-core fused kernel."""
+    from py_psnode_b200 import DE_Func, ODE_Event, RK4
+    torch.manual_seed(3)
+    dev = "cuda:0"
+    B, N, X, Z, H = 5000, 200, 16, 2, 64
+    T = N + 1
+    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H).to(dev)
+    t = (torch.arange(T, dtype=torch.float32, device=dev) * 0.01).view(T, 1, 1).repeat(1, B, 1)
+    x = torch.randn(T, B, X, device=dev) * 0.1
+    z = torch.randn(T, B, Z, device=dev) * 0.1
+    ev = ODE_Event()
+    ev.set_event(t=t[N // 3].view(B, 1, 1).clone(), z=torch.randn(B, 1, Z, device=dev) * 0.1)
+    a0 = torch.cat((x[0], z[0]), dim=-1)
+    outs = {}
+    with torch.no_grad():
+        for impl in ("fused", "tc"):
+            outs[impl] = RK4(impl=impl).integrate_ODE(x_func=de, t=t, x=x, z=z, all_initial=a0, event_fn=ev.event_fn,
+                                                      jump_change_fn=ev.jump_change_fn)
+    assert torch.allclose(outs["tc"], outs["fused"], rtol=RTOL, atol=ATOL), tol_report(outs["tc"].cpu(), outs["fused"].cpu())
