@@ -143,5 +143,12 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     hi = tf32_rn(v);
     lo = tf32_rn(v - hi);
 }
+// Same split in 3 instructions for finite inputs (cvt.rna.tf32.f32 is expanded by ptxas into ~8 integer instructions with
+// NaN/Inf handling): hi = magnitude rounded half-up to 10 mantissa bits, lo = v - hi exactly (<= 13 significant bits; the
+// tensor core ignores the low 13 mantissa bits of a tf32 operand, i.e. truncates lo: |error| <= 2^-21 |v|, sign-symmetric).
+__device__ __forceinline__ void split_tf32_fast(float v, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+    lo = v - hi;
+}
 
 }  // namespace psn_tc

@@ -10,8 +10,8 @@
 //
 // Mapping (measured design points in profiles/r01_tc_probe_*.log):
 //   * D[neuron m][trajectory n] = W[m][:] . act[n][:]: the WEIGHTS are the A operand and stay resident in TMEM for the whole
-//     kernel (hi and lo copies of the folded layer 1, layer 2 and layer 3: 304 of the 512 columns); only the 16-row
-//     activation tile (B operand, 512 B per MMA) is fetched from shared memory.  With A in shared memory the MMA rate was
+//     kernel (hi and lo copies of layers 2, 3 and 4: 384 of the 512 columns, the other 128 are the accumulators); only the
+//     16-row activation tile (B operand, 512 B per MMA) is fetched from shared memory.  With A in shared memory the MMA rate was
 //     bound by the 2 KB operand fetch (27-50 cycles per MMA); from TMEM the issue overhead (~60 cycles per MMA and warp)
 //     dominates, so the 24 MMAs of a layer are issued by all 4 warps of the group in parallel, each into its own
 //     accumulator (6 MMAs per warp, K-split), and the 4 partial accumulators are summed in the epilogue.
@@ -21,9 +21,11 @@
 //   * Two groups per CTA (one CTA per SM) run staggered, so one group's epilogue overlaps the other's MMA round trip.
 //   * Layer 1 is folded as in the CUDA-core kernel: W1 [a0; s-a0; s] + b1 = (Wb+Wc) [x; u] + c1, c1 = (Wa-Wb) a0 + b1 is a
 //     per-(neuron, trajectory) register constant; the B tile of layer 1 is [x (16) | held inputs (8)].
-//   * Layer 4 (64 -> 16) uses shared-memory weights (M padded to 64); warp 0 owns its 16 valid rows = the state, keeps
-//     x, k1..k3 in registers, does the stage algebra in the reference's operation order and writes the next stage's x
-//     columns; trajectory rows go out as 1 KB contiguous, 128-bit stores per step and group.
+//     The folded layer 1 (K = 24, 9 MMAs) keeps its weights in shared memory.
+//   * Layer 4 (64 -> 16): W4 is replicated into all four 16-row blocks of the M = 64 operand, so every warp receives the
+//     whole 16 x 16 slope tile and processes one quarter of it (2 elements per thread: rows t/4 and t/4+8 of one trajectory
+//     column) -- x, k1..k3 live in registers, the stage algebra follows the reference's operation order, the next stage's
+//     x columns are written straight into the layer-1 B tile; trajectory rows leave as 1 KB contiguous 128-bit stores.
 #include <cstddef>
 #include "psnode_internal.cuh"
 #include "psnode_tc.cuh"
@@ -39,11 +41,11 @@ constexpr int SBO_ACT = (TH / 4) * LBO;
 constexpr int SBO_B1 = (TK1 / 4) * LBO;
 constexpr int ACT_TILE = (TN / 8) * SBO_ACT;
 constexpr int B1_TILE = (TN / 8) * SBO_B1;
-constexpr int LBO_W = 128, SBO_W = (TH / 4) * LBO_W;     // layer-4 weight tiles in shared memory (64 rows x K = 64)
-constexpr int W4_TILE = (TH / 8) * SBO_W;
+constexpr int LBO_W = 128, SBO_W = (TK1 / 4) * LBO_W;    // folded layer-1 weight tiles in shared memory (64 rows x K = 24)
+constexpr int W1_TILE = (TH / 8) * SBO_W;
 // TMEM columns: accumulators first (2 groups x 4 warps x 16), then the resident weights
 constexpr int TM_ACC = 0;
-constexpr int TM_W2 = 128, TM_W3 = 256, TM_W1 = 384;     // hi at +0, lo at +64 (layer 1: lo at +32)
+constexpr int TM_W2 = 128, TM_W3 = 256, TM_W4 = 384;     // hi at +0, lo at +64
 constexpr int TM_COLS = 512;
 constexpr int GROUP_THREADS = 128;
 
@@ -71,8 +73,8 @@ struct __align__(128) GroupSmem {
 };
 
 struct __align__(128) CtaSmem {
-    float w4_hi[W4_TILE / 4];
-    float w4_lo[W4_TILE / 4];
+    float w1_hi[W1_TILE / 4];
+    float w1_lo[W1_TILE / 4];
     GroupSmem g[2];
     uint32_t tmem_base;
 };
@@ -99,13 +101,17 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
     // ---- one-time setup -------------------------------------------------------------------------------
     if (tid == 0) { mbar_init(&sm.g[0].bar, 4); mbar_init(&sm.g[1].bar, 4); fence_mbar_init(); }
     if ((tid >> 5) == 0) tmem_alloc(&sm.tmem_base, TM_COLS);
-    // layer-4 weights -> shared-memory tiles (rows >= 16 are zero)
-    for (int e = tid; e < TH * TH; e += 2 * GROUP_THREADS) {
-        const int m = e >> 6, k = e & 63;
-        float hi = 0.0f, lo = 0.0f;
-        if (m < TX) split_tf32(__ldg(q.W4 + m * TH + k), hi, lo);
-        sm.w4_hi[tile_byte(m, k, LBO_W, SBO_W) >> 2] = hi;
-        sm.w4_lo[tile_byte(m, k, LBO_W, SBO_W) >> 2] = lo;
+    // folded layer-1 weights (Wb + Wc restricted to [x | held inputs], zero padded to K = 24) -> shared-memory tiles
+    {
+        const int K1 = 3 * S;
+        for (int e = tid; e < TH * TK1; e += 2 * GROUP_THREADS) {
+            const int m = e / TK1, c = e - m * TK1;
+            const int k = c < TX ? c : (c - TX < Z ? c : -1);
+            float hi = 0.0f, lo = 0.0f;
+            if (k >= 0) split_tf32(__ldg(q.W1 + m * K1 + S + k) + __ldg(q.W1 + m * K1 + 2 * S + k), hi, lo);
+            sm.w1_hi[tile_byte(m, c, LBO_W, SBO_W) >> 2] = hi;
+            sm.w1_lo[tile_byte(m, c, LBO_W, SBO_W) >> 2] = lo;
+        }
     }
     for (int e = gt; e < (int)(offsetof(GroupSmem, bar) / 4); e += GROUP_THREADS) reinterpret_cast<float*>(&gs)[e] = 0.0f;
     fence_async_smem();
@@ -119,37 +125,23 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
     auto frag_row = [&](int i) { return m0 + ((i >> 1) & 1) * 8; };
     auto frag_col = [&](int i) { return c0 + (i & 1) + (i >> 2) * 8; };
 
-    // resident weights -> TMEM (group 0 writes; both groups read them through the tensor core only)
+    // resident weights -> TMEM (group 0 writes; both groups read them through the tensor core only).  W4 (16 rows) is
+    // replicated into every 16-row block: row r of the operand holds W4[r & 15].
     if (g == 0) {
-        const int K1 = 3 * S;
-        auto w1_folded = [&](int m, int c) -> float {      // (Wb + Wc) restricted to [x | held inputs], zero padded
-            int k;
-            if (c < TX) k = c; else if (c - TX < Z) k = TX + (c - TX); else return 0.0f;
-            return __ldg(q.W1 + m * K1 + S + k) + __ldg(q.W1 + m * K1 + 2 * S + k);
-        };
         for (int half = 0; half < 2; half++) {
-            for (int cb = 0; cb < 4; cb++) {               // layers 2 and 3: 64 columns = 4 x 16
-                float w2[8], w3[8];
+            for (int cb = 0; cb < 4; cb++) {               // 64 columns = 4 x 16
+                float w2[8], w3[8], w4[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int row = frag_row(i), col = 16 * cb + frag_col(i);
                     float hi, lo;
                     split_tf32(__ldg(q.W2 + row * TH + col), hi, lo); w2[i] = half ? lo : hi;
                     split_tf32(__ldg(q.W3 + row * TH + col), hi, lo); w3[i] = half ? lo : hi;
+                    split_tf32(__ldg(q.W4 + (row & 15) * TH + col), hi, lo); w4[i] = half ? lo : hi;
                 }
                 tmem_st_16x256b_x2(tmem + lane_base + TM_W2 + 64 * half + 16 * cb, w2);
                 tmem_st_16x256b_x2(tmem + lane_base + TM_W3 + 64 * half + 16 * cb, w3);
-            }
-            for (int cb = 0; cb < 2; cb++) {               // layer 1: 24 columns stored as 2 x 16 (tail zero)
-                float w1[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int row = frag_row(i), col = 16 * cb + frag_col(i);
-                    float hi = 0.0f, lo = 0.0f;
-                    if (col < TK1) split_tf32(w1_folded(row, col), hi, lo);
-                    w1[i] = half ? lo : hi;
-                }
-                tmem_st_16x256b_x2(tmem + lane_base + TM_W1 + 32 * half + 16 * cb, w1);
+                tmem_st_16x256b_x2(tmem + lane_base + TM_W4 + 64 * half + 16 * cb, w4);
             }
         }
         tmem_st_wait();
@@ -158,12 +150,12 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
     __syncthreads();            // resident weights visible to both groups' MMAs
     tc_fence_after();
     // per-thread constants: biases of its two rows, c1 of its 8 (row, trajectory) elements
-    float bias2[2], bias3[2], bias4[2], c1[8];
+    float bias2[2], bias3[2], bias4[2], c1[8];   // bias2 doubles as a dummy for layer 1 (c1 carries b1)
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         bias2[r] = __ldg(q.b2 + m0 + 8 * r);
         bias3[r] = __ldg(q.b3 + m0 + 8 * r);
-        bias4[r] = warp == 0 ? __ldg(q.b4 + m0 + 8 * r) : 0.0f;
+        bias4[r] = __ldg(q.b4 + ((m0 + 8 * r) & 15));
     }
     {
         const int K1 = 3 * S;
@@ -178,17 +170,17 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
         }
     }
     // activation-tile byte offsets of this thread's 8 elements (row = K index of the next layer, column = trajectory)
-    int off_act[8], off_b1[8];
+    int off_act[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        off_act[i] = tile_byte(frag_col(i), frag_row(i), LBO, SBO_ACT);
-        off_b1[i] = tile_byte(frag_col(i), frag_row(i) & 15, LBO, SBO_B1);
-    }
+    for (int i = 0; i < 8; i++) off_act[i] = tile_byte(frag_col(i), frag_row(i), LBO, SBO_ACT);
+    // the two state elements this thread owns in the layer-4 epilogue: states sm0, sm0 + 8 of trajectory column sn
+    const int sm0 = lane >> 2, sn = c0 + (warp & 1) + 8 * (warp >> 1);
+    const int off_x[2] = {(int)tile_byte(sn, sm0, LBO, SBO_B1), (int)tile_byte(sn, sm0 + 8, LBO, SBO_B1)};
     // descriptors
     const uint32_t idesc = make_idesc_tf32(TH, TN);
     const uint64_t d_act_hi = make_desc(smem_u32(gs.act_hi), LBO, SBO_ACT), d_act_lo = make_desc(smem_u32(gs.act_lo), LBO, SBO_ACT);
     const uint64_t d_b1_hi = make_desc(smem_u32(gs.b1_hi), LBO, SBO_B1), d_b1_lo = make_desc(smem_u32(gs.b1_lo), LBO, SBO_B1);
-    const uint64_t d_w4_hi = make_desc(smem_u32(sm.w4_hi), LBO_W, SBO_W), d_w4_lo = make_desc(smem_u32(sm.w4_lo), LBO_W, SBO_W);
+    const uint64_t d_w1_hi = make_desc(smem_u32(sm.w1_hi), LBO_W, SBO_W), d_w1_lo = make_desc(smem_u32(sm.w1_lo), LBO_W, SBO_W);
     const uint32_t acc_base = tmem + TM_ACC + (uint32_t)(g * 4) * TN;      // 4 partial accumulators of this group
     const uint32_t my_acc = acc_base + (uint32_t)warp * TN;                // the one this warp's MMAs write
     constexpr uint64_t KSTEP_B = (uint64_t)((2 * LBO) >> 4), KSTEP_W = (uint64_t)((2 * LBO_W) >> 4);
@@ -230,12 +222,15 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
         }
         __syncwarp();
     };
-    // wait for the group's 4 commits, then (if `want`) sum the first `nacc` partial accumulators into d[8]
-    auto collect = [&](float (&d)[8], int nacc, bool want) {
+    // wait for the group's 4 commits
+    auto wait_mma = [&]() {
         if (!mbar_wait(&gs.bar, phase)) { atomicExch(q.err, 1); __trap(); }
         phase ^= 1;
         tc_fence_after();
-        if (!want) return;
+    };
+    // sum the first `nacc` partial accumulators into d[8] (this thread's 2 rows x 4 trajectory columns)
+    auto collect = [&](float (&d)[8], int nacc) {
+        wait_mma();
         float t0[8], t1[8], t2[8], t3[8];
         tmem_ld_16x256b_x2(acc_base + lane_base + 0 * TN, t0);
         tmem_ld_16x256b_x2(acc_base + lane_base + 1 * TN, t1);
@@ -244,6 +239,20 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; i++) d[i] = nacc == 4 ? (t0[i] + t1[i]) + (t2[i] + t3[i]) : (t0[i] + t1[i]) + t2[i];
+    };
+    // layer 4: the slope elements (state sm0 / sm0 + 8, trajectory sn) of this thread; every 16-row block holds the same tile
+    auto collect_slopes = [&](float (&kv)[2]) {
+        wait_mma();
+        float t0[4], t1[4], t2[4], t3[4];
+        const uint32_t a = acc_base + lane_base + 8 * (warp >> 1);
+        tmem_ld_16x256b_x1(a + 0 * TN, t0);
+        tmem_ld_16x256b_x1(a + 1 * TN, t1);
+        tmem_ld_16x256b_x1(a + 2 * TN, t2);
+        tmem_ld_16x256b_x1(a + 3 * TN, t3);
+        tmem_ld_wait();
+        const bool o = (warp & 1) != 0;
+        kv[0] = ((o ? t0[1] : t0[0]) + (o ? t1[1] : t1[0])) + ((o ? t2[1] : t2[0]) + (o ? t3[1] : t3[0]));
+        kv[1] = ((o ? t0[3] : t0[2]) + (o ? t1[3] : t1[2])) + ((o ? t2[3] : t2[2]) + (o ? t3[3] : t3[2]));
     };
     // publish freshly written B-tile data to the tensor core and line the group up for the next layer's MMAs
     auto publish = [&]() {
@@ -257,7 +266,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
             float v = d[i] + bias[(i >> 1) & 1];
             if (cadd) v = d[i] + cadd[i];
             float hi, lo;
-            split_tf32(psn_elu(v), hi, lo);
+            split_tf32_fast(psn_elu(v), hi, lo);
             *reinterpret_cast<float*>(gs.act_hi + off_act[i]) = hi;
             *reinterpret_cast<float*>(gs.act_lo + off_act[i]) = lo;
         }
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
 #pragma unroll
             for (int c = 0; c < TU; c++) {
                 float hi, lo;
-                split_tf32(u[c], hi, lo);
+                split_tf32_fast(u[c], hi, lo);
                 const int o = tile_byte(lane, TX + c, LBO, SBO_B1);
                 *reinterpret_cast<float*>(gs.b1_hi + o) = hi;
                 *reinterpret_cast<float*>(gs.b1_lo + o) = lo;
@@ -288,21 +297,19 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
     };
 
     if (live) {
-        // ---- initial state: warp 0 owns the state elements (row = state index m0 (+8), column = trajectory) ------
-        float x0[8], k1[8], k2[8], k3[8];
+        // ---- initial state: every thread owns two state elements (states sm0, sm0 + 8 of trajectory column sn) -------
+        float x0[2], k1[2] = {0.f, 0.f}, k2[2] = {0.f, 0.f}, k3[2] = {0.f, 0.f};
+        {
+            const int b = b0 + sn, bb = min(b, B - 1);
 #pragma unroll
-        for (int i = 0; i < 8; i++) { x0[i] = 0.f; k1[i] = 0.f; k2[i] = 0.f; k3[i] = 0.f; }
-        if (warp == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int n = frag_col(i), m = frag_row(i), b = b0 + n, bb = min(b, B - 1);
-                const float xv = ldser(q.x, 0, bb, m);
-                x0[i] = xv;
-                if (b < B) q.x_sol.p[(int64_t)b * q.x_sol.sb + m] = xv;
+            for (int r = 0; r < 2; r++) {
+                const float xv = ldser(q.x, 0, bb, sm0 + 8 * r);
+                x0[r] = xv;
+                if (b < B) q.x_sol.p[(int64_t)b * q.x_sol.sb + sm0 + 8 * r] = xv;
                 float hi, lo;
-                split_tf32(xv, hi, lo);
-                *reinterpret_cast<float*>(gs.b1_hi + off_b1[i]) = hi;
-                *reinterpret_cast<float*>(gs.b1_lo + off_b1[i]) = lo;
+                split_tf32_fast(xv, hi, lo);
+                *reinterpret_cast<float*>(gs.b1_hi + off_x[r]) = hi;
+                *reinterpret_cast<float*>(gs.b1_lo + off_x[r]) = lo;
             }
         }
         if (warp == 1 && T > 1) {
@@ -316,77 +323,75 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
         for (int j = 1; j < T; j++) {
             float un[TU], dtn = 0.0f;                       // next step's inputs, prefetched by warp 1 during stage 0
             const bool have_next = j + 1 < T;
+            const float dt = gs.dts[j & 1][sn];
 #pragma unroll 1
             for (int e = 0; e < NST; e++) {
                 float d[8];
-                // ---- layer 1: K = 24 -> warps 0..2 take one K-step each; warp 3 only commits ----
-                issue_ts(TM_W1, TM_W1 + 32, d_b1_hi, d_b1_lo, warp, warp < 3 ? 1 : 0);
+                // ---- layer 1 (shared-memory weights): K = 24 -> warps 0..2 take one K-step each; warp 3 only commits ----
+                issue_ss(d_w1_hi, d_w1_lo, d_b1_hi, d_b1_lo, warp, warp < 3 ? 1 : 0);
                 if (e == 0 && warp == 1 && have_next) load_step_inputs(j + 1, un, dtn);
-                collect(d, 3, true);
+                if (e == 0 && j > 1 && gt < 64) {           // trajectory row j-1 (staged by the previous step's last stage)
+                    const int n = gt >> 2, c4 = gt & 3, b = b0 + n;
+                    if (b < B) {
+                        float* dst = q.x_sol.p + (int64_t)(j - 1) * q.x_sol.st + (int64_t)b * q.x_sol.sb + 4 * c4;
+                        const float4 v = *reinterpret_cast<const float4*>(&gs.ostage[n][4 * c4]);
+                        if (q.vec_out) *reinterpret_cast<float4*>(dst) = v;
+                        else { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w; }
+                    }
+                }
+                collect(d, 3);
                 store_hidden(d, bias2, c1);
                 publish();
                 // ---- layer 2 ----
                 issue_ts(TM_W2, TM_W2 + 64, d_act_hi, d_act_lo, 2 * warp, 2);
-                collect(d, 4, true);
+                collect(d, 4);
                 store_hidden(d, bias2, nullptr);
                 publish();
                 // ---- layer 3 ----
                 issue_ts(TM_W3, TM_W3 + 64, d_act_hi, d_act_lo, 2 * warp, 2);
-                collect(d, 4, true);
+                collect(d, 4);
                 store_hidden(d, bias3, nullptr);
                 publish();
-                // ---- layer 4 (shared-memory weights) + stage algebra on warp 0 ----
-                issue_ss(d_w4_hi, d_w4_lo, d_act_hi, d_act_lo, 2 * warp, 2);
-                collect(d, 4, warp == 0);
-                if (warp == 0) {
-                    const bool last = e == NST - 1;
+                // ---- layer 4 + stage algebra: 2 state elements per thread ----
+                issue_ts(TM_W4, TM_W4 + 64, d_act_hi, d_act_lo, 2 * warp, 2);
+                float kv[2];
+                collect_slopes(kv);
+                const bool last = e == NST - 1;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const float kv = d[i] + bias4[(i >> 1) & 1];
-                        const float dt = gs.dts[j & 1][frag_col(i)];
-                        float xn;
-                        if (METHOD == PSNODE_EULER) {
-                            xn = __fadd_rn(x0[i], __fmul_rn(dt, kv));
-                        } else if (METHOD == PSNODE_MIDPOINT) {
-                            if (e == 0) xn = __fadd_rn(x0[i], __fmul_rn(kv, __fmul_rn(0.5f, dt)));
-                            else xn = __fadd_rn(x0[i], __fmul_rn(dt, kv));
-                        } else {
-                            if (e == 0) { k1[i] = kv; xn = __fadd_rn(x0[i], __fmul_rn(__fmul_rn(dt, kv), c13)); }
-                            else if (e == 1) { k2[i] = kv; xn = __fadd_rn(x0[i], __fmul_rn(dt, __fsub_rn(kv, __fmul_rn(k1[i], c13)))); }
-                            else if (e == 2) { k3[i] = kv; xn = __fadd_rn(x0[i], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[i], k2[i]), kv))); }
-                            else {
-                                const float ksum = __fadd_rn(__fadd_rn(k1[i], __fmul_rn(3.0f, __fadd_rn(k2[i], k3[i]))), kv);
-                                xn = __fadd_rn(x0[i], __fmul_rn(__fmul_rn(ksum, dt), 0.125f));
-                            }
+                for (int r = 0; r < 2; r++) {
+                    const float kk = kv[r] + bias4[r];
+                    float xn;
+                    if (METHOD == PSNODE_EULER) {
+                        xn = __fadd_rn(x0[r], __fmul_rn(dt, kk));
+                    } else if (METHOD == PSNODE_MIDPOINT) {
+                        if (e == 0) xn = __fadd_rn(x0[r], __fmul_rn(kk, __fmul_rn(0.5f, dt)));
+                        else xn = __fadd_rn(x0[r], __fmul_rn(dt, kk));
+                    } else {
+                        if (e == 0) { k1[r] = kk; xn = __fadd_rn(x0[r], __fmul_rn(__fmul_rn(dt, kk), c13)); }
+                        else if (e == 1) { k2[r] = kk; xn = __fadd_rn(x0[r], __fmul_rn(dt, __fsub_rn(kk, __fmul_rn(k1[r], c13)))); }
+                        else if (e == 2) { k3[r] = kk; xn = __fadd_rn(x0[r], __fmul_rn(dt, __fadd_rn(__fsub_rn(k1[r], k2[r]), kk))); }
+                        else {
+                            const float ksum = __fadd_rn(__fadd_rn(k1[r], __fmul_rn(3.0f, __fadd_rn(k2[r], k3[r]))), kk);
+                            xn = __fadd_rn(x0[r], __fmul_rn(__fmul_rn(ksum, dt), 0.125f));
                         }
-                        float hi, lo;
-                        split_tf32(xn, hi, lo);
-                        *reinterpret_cast<float*>(gs.b1_hi + off_b1[i]) = hi;
-                        *reinterpret_cast<float*>(gs.b1_lo + off_b1[i]) = lo;
-                        if (last) { x0[i] = xn; gs.ostage[frag_col(i)][frag_row(i)] = xn; }
                     }
-                    if (last) {     // trajectory row j: 16 x 16 floats, contiguous for contiguous outputs
-                        __syncwarp();
-                        if (q.vec_out) {
-#pragma unroll
-                            for (int r = 0; r < 2; r++) {
-                                const int idx = lane + 32 * r, n = idx >> 2, c4 = idx & 3, b = b0 + n;
-                                if (b < B)
-                                    *reinterpret_cast<float4*>(q.x_sol.p + (int64_t)j * q.x_sol.st + (int64_t)b * q.x_sol.sb + 4 * c4) =
-                                        *reinterpret_cast<const float4*>(&gs.ostage[n][4 * c4]);
-                            }
-                        } else {
-                            for (int idx = lane; idx < TN * TX; idx += 32) {
-                                const int n = idx >> 4, c = idx & 15, b = b0 + n;
-                                if (b < B) q.x_sol.p[(int64_t)j * q.x_sol.st + (int64_t)b * q.x_sol.sb + c] = gs.ostage[n][c];
-                            }
-                        }
-                        __syncwarp();
-                    }
-                } else if (warp == 1 && e == NST - 1 && have_next) {
-                    store_step_inputs(j + 1, un, dtn);      // every layer-1 MMA of this step has completed: the u columns are free
+                    float hi, lo;
+                    split_tf32_fast(xn, hi, lo);
+                    *reinterpret_cast<float*>(gs.b1_hi + off_x[r]) = hi;
+                    *reinterpret_cast<float*>(gs.b1_lo + off_x[r]) = lo;
+                    if (last) { x0[r] = xn; gs.ostage[sn][sm0 + 8 * r] = xn; }
                 }
+                if (warp == 1 && last && have_next) store_step_inputs(j + 1, un, dtn);   // all layer-1 MMAs of this step are done
                 publish();
+            }
+        }
+        if (T > 1 && gt < 64) {                             // last trajectory row
+            const int n = gt >> 2, c4 = gt & 3, b = b0 + n;
+            if (b < B) {
+                float* dst = q.x_sol.p + (int64_t)(T - 1) * q.x_sol.st + (int64_t)b * q.x_sol.sb + 4 * c4;
+                const float4 v = *reinterpret_cast<const float4*>(&gs.ostage[n][4 * c4]);
+                if (q.vec_out) *reinterpret_cast<float4*>(dst) = v;
+                else { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w; }
             }
         }
     }

@@ -56,5 +56,38 @@ def raw(path):
             print(f"    {name:28s} {val:8.3f}")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] in ("launches", "raw"):
     {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+
+
+def hot(path, top=40):
+    """Top stall-sample SASS instructions (ncu --page source) with their dominant stall reason."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    start = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    hdr = rows[start]
+    ci = {h: i for i, h in enumerate(hdr)}
+    stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    data = []
+    for idx, r in enumerate(rows[start + 1:]):
+        if len(r) < len(hdr) or r[0] == "Address" or r[0] == "Kernel Name":
+            continue
+        try:
+            s = int(r[ci["# Samples"]])
+        except ValueError:
+            continue
+        data.append((idx, s, r))
+    tot = sum(s for _, s, _ in data)
+    print(f"# {path}: {tot} stall samples over {len(data)} SASS instructions")
+    agg = collections.Counter()
+    for _, s, r in data:
+        for h in stall_cols:
+            agg[h] += int(r[ci[h]] or 0)
+    print("# totals by reason: " + ", ".join(f"{k[6:]} {v}" for k, v in agg.most_common(8)))
+    for idx, s, r in sorted(data, key=lambda x: -x[1])[:top]:
+        reasons = sorted(((int(r[ci[h]] or 0), h[6:]) for h in stall_cols), reverse=True)[:2]
+        print(f"{s:7d} {100 * s / tot:5.1f}%  #{idx:5d}  {r[ci['Source']].strip()[:90]:90s}  {reasons[0][1]}:{reasons[0][0]} {reasons[1][1]}:{reasons[1][0]}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "hot":
+    hot(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40)
