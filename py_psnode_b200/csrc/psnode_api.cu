@@ -136,6 +136,7 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
         if (!psn_fused_supports(p)) return PSNODE_EUNSUPPORTED;
         return psn_fused_forward(p, workspace, workspace_bytes, s);
     }
+    if (p->impl == PSNODE_IMPL_AUTO && psn_tc_supports(p)) return psn_tc_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_fused_supports(p)) return psn_fused_forward(p, workspace, workspace_bytes, s);
     return psn_generic_forward(p, workspace, workspace_bytes, s);
 }

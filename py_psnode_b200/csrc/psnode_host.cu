@@ -1,4 +1,13 @@
-// psnode_host.cu -- psnode_forward_host: host-buffer entry point (stages inputs, integrates, copies results back).
+// psnode_host.cu -- psnode_forward_host: the host-buffer entry point (what a maintainer binds when the batch lives in host
+// memory, e.g. straight out of the reference's DataLoader): inputs reach the device, the problem is integrated, and the
+// trajectory lands in the caller's host buffers before the call returns.
+//
+// Two transfer modes, chosen per buffer:
+//   * pinned (cudaHostAlloc / cudaHostRegister'ed / torch pin_memory) buffers are mapped into the device address space, so
+//     the integrator reads its inputs and writes its trajectory there directly ("zero copy"): the PCIe transfer is fused
+//     into the kernel and overlaps it completely -- per step the kernel touches ~50 KB of inputs, prefetched one step
+//     ahead, and writes 1 KB per 16 trajectories as full 128-byte lines;
+//   * ordinary pageable buffers are staged through a cached device arena with cudaMemcpyAsync on `stream`.
 #include <vector>
 #include "psnode_internal.cuh"
 
@@ -18,7 +27,20 @@ struct Scratch {
 };
 Scratch g_scratch;
 
-// dense (rows, width) span covered by a strided (T,B,width) view: we copy the covering contiguous range
+// device alias of a device-visible pointer (pinned host, device or managed memory), nullptr for pageable host memory.
+// Small pinned buffers (weights, all_initial, jump tables: read by every CTA in its prologue) are staged instead: one
+// async copy is cheaper than hundreds of PCIe round trips.
+constexpr size_t kZeroCopyMinBytes = size_t(1) << 20;
+void* mapped_alias(const void* p, size_t bytes) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return at.devicePointer;
+    if (at.type == cudaMemoryTypeHost && bytes >= kZeroCopyMinBytes) return at.devicePointer;
+    return nullptr;
+}
+
+// contiguous element range [lo, hi) covered by a strided (T,B,width) view
 struct Span { int64_t lo, hi; };
 Span span_of(int64_t st, int64_t sb, int T, int B, int w) {
     int64_t lo = 0, hi = 0;
@@ -28,6 +50,22 @@ Span span_of(int64_t st, int64_t sb, int T, int B, int w) {
     hi += w;
     return {lo, hi};
 }
+
+struct Plan {
+    struct Item { const char* src; size_t bytes; size_t off; char* alias; };
+    std::vector<Item> items;
+    size_t cur = 0;
+    int64_t staged = 0, direct = 0;
+    size_t reserve(size_t bytes) { size_t o = cur; cur += (bytes + 255) & ~size_t(255); return o; }
+    // returns the item index; resolve() turns it into a device pointer once the arena exists
+    int add(const void* src, size_t bytes) {
+        Item it{static_cast<const char*>(src), bytes, 0, static_cast<char*>(mapped_alias(src, bytes))};
+        if (it.alias) direct += (int64_t)bytes; else { it.off = reserve(bytes); staged += (int64_t)bytes; }
+        items.push_back(it);
+        return (int)items.size() - 1;
+    }
+    char* resolve(int idx, char* base) const { return items[idx].alias ? items[idx].alias : base + items[idx].off; }
+};
 }  // namespace
 
 extern "C" int psnode_forward_host(const psnode_problem* hp, void* stream, int64_t* h2d_bytes, int64_t* d2h_bytes) {
@@ -36,108 +74,109 @@ extern "C" int psnode_forward_host(const psnode_problem* hp, void* stream, int64
     psnode_problem p = *hp;
     const bool dae = p.kind == PSNODE_DAE;
     const int S = psn_S(&p);
-    // 1. plan the device arena
-    struct Item { const void* src; size_t bytes; size_t off; };
-    std::vector<Item> in;
-    size_t cur = 0;
-    auto reserve = [&](size_t bytes) { size_t o = cur; cur += (bytes + 255) & ~size_t(255); return o; };
-    auto add_in = [&](const void* src, size_t bytes) { in.push_back({src, bytes, reserve(bytes)}); return in.back().off; };
-    auto add_series = [&](const psnode_series& sr, int w, bool needed, size_t& off, int64_t& lo) {
-        off = 0; lo = 0;
-        if (!needed || !sr.p || w == 0) return;
-        Span sp = span_of(sr.st, sr.sb, p.T, p.B, w);
-        lo = sp.lo;
-        off = add_in(sr.p + sp.lo, (size_t)(sp.hi - sp.lo) * 4);
+    if (p.B < 1 || p.T < 1 || p.X < 1) return PSNODE_EINVAL;
+    Plan plan;
+    // ---- inputs ----------------------------------------------------------------------------------------
+    struct SeriesRef { int idx = -1; int64_t lo = 0; };
+    auto add_series = [&](const psnode_series& sr, int w, int T, bool needed) {
+        SeriesRef r;
+        if (!needed || !sr.p || w == 0) return r;
+        const Span sp = span_of(sr.st, sr.sb, T, p.B, w);
+        r.lo = sp.lo;
+        r.idx = plan.add(sr.p + sp.lo, (size_t)(sp.hi - sp.lo) * 4);
+        return r;
     };
-    size_t o_t, o_x, o_z, o_v, o_i; int64_t l_t, l_x, l_z, l_v, l_i;
-    add_series(p.t, 1, true, o_t, l_t);
-    // ODE needs only x[0] unless teacher forcing: stage the single initial row in that case
-    psnode_series xs = p.x;
-    int xT = p.T;
-    if (!p.teacher_x) xT = 1;
-    {
-        o_x = 0; l_x = 0;
-        if (xs.p && (!dae || p.teacher_x)) {
-            Span sp = span_of(xs.st, xs.sb, xT, p.B, p.X);
-            l_x = sp.lo; o_x = add_in(xs.p + sp.lo, (size_t)(sp.hi - sp.lo) * 4);
-        }
-    }
-    add_series(p.z, p.Z, true, o_z, l_z);
-    add_series(p.v, p.V, dae, o_v, l_v);
-    add_series(p.i, p.I, dae && p.teacher_i, o_i, l_i);
-    size_t o_xinit = 0, o_a0 = 0, o_ev = 0, o_zj = 0, o_vj = 0;
-    if (dae) o_xinit = add_in(p.x_init, ((size_t)(p.B - 1) * p.x_init_sb + p.X) * 4);
-    o_a0 = add_in(p.a0, ((size_t)(p.B - 1) * p.a0_sb + S) * 4);
+    const SeriesRef r_t = add_series(p.t, 1, p.T, true);
+    const SeriesRef r_x = add_series(p.x, p.X, p.teacher_x ? p.T : 1, !dae || p.teacher_x);   // ODE reads only x[0] unless teacher forcing
+    const SeriesRef r_z = add_series(p.z, p.Z, p.T, true);
+    const SeriesRef r_v = add_series(p.v, p.V, p.T, dae);
+    const SeriesRef r_i = add_series(p.i, p.I, p.T, dae && p.teacher_i);
+    if (!p.a0 || (dae && !p.x_init)) return PSNODE_EINVAL;
+    const int i_xinit = dae ? plan.add(p.x_init, ((size_t)(p.B - 1) * p.x_init_sb + p.X) * 4) : -1;
+    const int i_a0 = plan.add(p.a0, ((size_t)(p.B - 1) * p.a0_sb + S) * 4);
+    int i_ev = -1, i_zj = -1, i_vj = -1;
     if (p.event_idx) {
-        o_ev = add_in(p.event_idx, (size_t)(p.T - 1) * 4);
-        if (p.Z) o_zj = add_in(p.z_jump, ((size_t)(p.B - 1) * p.zj_sb + (size_t)(p.E - 1) * p.zj_se + p.Z) * 4);
-        if (dae && p.V) o_vj = add_in(p.v_jump, ((size_t)(p.B - 1) * p.vj_sb + (size_t)(p.E - 1) * p.vj_se + p.V) * 4);
+        i_ev = plan.add(p.event_idx, (size_t)(p.T > 1 ? p.T - 1 : 1) * 4);
+        if (p.Z) i_zj = plan.add(p.z_jump, ((size_t)(p.B - 1) * p.zj_sb + (size_t)(p.E - 1) * p.zj_se + p.Z) * 4);
+        if (dae && p.V) i_vj = plan.add(p.v_jump, ((size_t)(p.B - 1) * p.vj_sb + (size_t)(p.E - 1) * p.vj_se + p.V) * 4);
     }
-    size_t o_W[2][PSNODE_MAX_LAYERS], o_b[2][PSNODE_MAX_LAYERS];
+    int i_W[2][PSNODE_MAX_LAYERS], i_b[2][PSNODE_MAX_LAYERS];
     for (int net = 0; net < (dae ? 2 : 1); net++) {
         const psnode_mlp& m = net ? p.ae : p.de;
+        if (m.n_layers < 1 || m.n_layers > PSNODE_MAX_LAYERS) return PSNODE_EINVAL;
         for (int l = 0; l < m.n_layers; l++) {
-            o_W[net][l] = add_in(m.W[l], (size_t)m.out_dim[l] * m.in_dim[l] * 4);
-            o_b[net][l] = add_in(m.b[l], (size_t)m.out_dim[l] * 4);
+            if (!m.W[l] || !m.b[l]) return PSNODE_EINVAL;
+            i_W[net][l] = plan.add(m.W[l], (size_t)m.out_dim[l] * m.in_dim[l] * 4);
+            i_b[net][l] = plan.add(m.b[l], (size_t)m.out_dim[l] * 4);
         }
     }
-    // outputs: dense time-major on the device, copied back row by row into the caller's strided view
+    // ---- outputs: written in place when the caller's buffer is device visible, else dense time-major in the arena -------
+    if (!hp->x_sol.p || (dae && !hp->i_sol.p)) return PSNODE_EINVAL;
     const size_t xs_bytes = (size_t)p.T * p.B * p.X * 4, is_bytes = dae ? (size_t)p.T * p.B * p.I * 4 : 0;
-    const size_t o_xsol = reserve(xs_bytes), o_isol = reserve(is_bytes ? is_bytes : 4);
-    const size_t o_ws = reserve(0);
-    // workspace size needs device-pointer-free info only
+    float* x_alias = static_cast<float*>(mapped_alias(hp->x_sol.p, xs_bytes));
+    float* i_alias = dae ? static_cast<float*>(mapped_alias(hp->i_sol.p, is_bytes)) : nullptr;
+    const size_t o_xsol = x_alias ? 0 : plan.reserve(xs_bytes);
+    const size_t o_isol = (!dae || i_alias) ? 0 : plan.reserve(is_bytes);
+    // ---- device problem ------------------------------------------------------------------------------------
+    // The workspace size depends on shapes only, never on the pointer values.
     const int64_t ws_bytes = psnode_forward_workspace(&p);
-    cur += (size_t)ws_bytes;
-    char* base = g_scratch.get(cur);
+    const size_t o_ws = plan.reserve((size_t)(ws_bytes > 0 ? ws_bytes : 256));
+    char* base = g_scratch.get(plan.cur);
     if (!base) return psn_cuda_fail(cudaErrorMemoryAllocation, "psnode_forward_host scratch");
-    int64_t up = 0;
-    for (const Item& it : in) {
-        PSN_CUDA(cudaMemcpyAsync(base + it.off, it.src, it.bytes, cudaMemcpyHostToDevice, s));
-        up += (int64_t)it.bytes;
-    }
-    auto dev_series = [&](psnode_series& sr, size_t off, int64_t lo) { if (sr.p) sr.p = reinterpret_cast<const float*>(base + off) - lo; };
-    dev_series(p.t, o_t, l_t);
-    if (p.x.p && (!dae || p.teacher_x)) p.x.p = reinterpret_cast<const float*>(base + o_x) - l_x; else p.x.p = nullptr;
-    if (p.Z) dev_series(p.z, o_z, l_z);
-    if (dae && p.V) dev_series(p.v, o_v, l_v);
-    if (dae && p.teacher_i) dev_series(p.i, o_i, l_i); else p.i.p = nullptr;
-    if (dae) p.x_init = reinterpret_cast<const float*>(base + o_xinit);
-    p.a0 = reinterpret_cast<const float*>(base + o_a0);
+    for (const Plan::Item& it : plan.items)
+        if (!it.alias) PSN_CUDA(cudaMemcpyAsync(base + it.off, it.src, it.bytes, cudaMemcpyDefault, s));
+    auto dev_series = [&](psnode_series& sr, const SeriesRef& r) {
+        sr.p = r.idx >= 0 ? reinterpret_cast<const float*>(plan.resolve(r.idx, base)) - r.lo : nullptr;
+    };
+    dev_series(p.t, r_t);
+    dev_series(p.x, r_x);
+    dev_series(p.z, r_z);
+    dev_series(p.v, r_v);
+    dev_series(p.i, r_i);
+    if (dae) p.x_init = reinterpret_cast<const float*>(plan.resolve(i_xinit, base));
+    p.a0 = reinterpret_cast<const float*>(plan.resolve(i_a0, base));
     if (p.event_idx) {
-        p.event_idx = reinterpret_cast<const int32_t*>(base + o_ev);
-        if (p.Z) p.z_jump = reinterpret_cast<const float*>(base + o_zj);
-        if (dae && p.V) p.v_jump = reinterpret_cast<const float*>(base + o_vj);
+        p.event_idx = reinterpret_cast<const int32_t*>(plan.resolve(i_ev, base));
+        if (i_zj >= 0) p.z_jump = reinterpret_cast<const float*>(plan.resolve(i_zj, base));
+        if (i_vj >= 0) p.v_jump = reinterpret_cast<const float*>(plan.resolve(i_vj, base));
     }
     for (int net = 0; net < (dae ? 2 : 1); net++) {
         psnode_mlp& m = net ? p.ae : p.de;
         for (int l = 0; l < m.n_layers; l++) {
-            m.W[l] = reinterpret_cast<const float*>(base + o_W[net][l]);
-            m.b[l] = reinterpret_cast<const float*>(base + o_b[net][l]);
+            m.W[l] = reinterpret_cast<const float*>(plan.resolve(i_W[net][l], base));
+            m.b[l] = reinterpret_cast<const float*>(plan.resolve(i_b[net][l], base));
         }
     }
-    p.x_sol = {reinterpret_cast<float*>(base + o_xsol), (int64_t)p.B * p.X, (int64_t)p.X};
-    if (dae) p.i_sol = {reinterpret_cast<float*>(base + o_isol), (int64_t)p.B * p.I, (int64_t)p.I};
+    if (x_alias) p.x_sol.p = x_alias;     // strides stay the caller's
+    else p.x_sol = {reinterpret_cast<float*>(base + o_xsol), (int64_t)p.B * p.X, (int64_t)p.X};
+    if (dae) {
+        if (i_alias) p.i_sol.p = i_alias;
+        else p.i_sol = {reinterpret_cast<float*>(base + o_isol), (int64_t)p.B * p.I, (int64_t)p.I};
+    }
     const int st = psnode_forward(&p, base + o_ws, ws_bytes, stream);
     if (st != PSNODE_OK) return st;
+    // ---- results back ------------------------------------------------------------------------------------
     int64_t down = 0;
     auto copy_back = [&](const psnode_series_out& dst, const float* src, int w) -> int {
         if (dst.sb == w && dst.st == (int64_t)p.B * w) {
             PSN_CUDA(cudaMemcpyAsync(dst.p, src, (size_t)p.T * p.B * w * 4, cudaMemcpyDeviceToHost, s));
-        } else if (dst.st == w && dst.sb == (int64_t)p.T * w) {   // batch-major destination: 2-D copy per trajectory block
+        } else if (dst.st == w && dst.sb == (int64_t)p.T * w) {   // batch-major destination: one 2-D copy per trajectory
             for (int b = 0; b < p.B; b++)
                 PSN_CUDA(cudaMemcpy2DAsync(dst.p + (int64_t)b * dst.sb, (size_t)w * 4, src + (size_t)b * w, (size_t)p.B * w * 4,
                                            (size_t)w * 4, p.T, cudaMemcpyDeviceToHost, s));
         } else {
             return PSNODE_EUNSUPPORTED;
         }
-        down += (int64_t)p.T * p.B * w * 4;
         return PSNODE_OK;
     };
-    int r = copy_back(hp->x_sol, p.x_sol.p, p.X);
-    if (r != PSNODE_OK) return r;
-    if (dae) { r = copy_back(hp->i_sol, p.i_sol.p, p.I); if (r != PSNODE_OK) return r; }
+    if (!x_alias) { const int r = copy_back(hp->x_sol, p.x_sol.p, p.X); if (r != PSNODE_OK) return r; }
+    down += (int64_t)xs_bytes;
+    if (dae) {
+        if (!i_alias) { const int r = copy_back(hp->i_sol, p.i_sol.p, p.I); if (r != PSNODE_OK) return r; }
+        down += (int64_t)is_bytes;
+    }
     PSN_CUDA(cudaStreamSynchronize(s));
-    if (h2d_bytes) *h2d_bytes = up;
+    if (h2d_bytes) *h2d_bytes = plan.staged + plan.direct;     // bytes that crossed the bus host -> device (copied or read in place)
     if (d2h_bytes) *d2h_bytes = down;
     return PSNODE_OK;
 }

@@ -302,3 +302,97 @@ def integrate(cfg: Config, tens: Sequence[Optional[torch.Tensor]]) -> Tuple[torc
         return forward_raw(cfg, tens)
     x_sol, i_sol = _Integrate.apply(cfg, *tens)
     return x_sol, (i_sol if cfg.kind == N.DAE else None)
+
+
+# ------------------------------------------------------------------------------------------------ host-buffer entry
+def _host_series(ten: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if ten is None or ten.shape[-1] == 0:
+        return None
+    if ten.is_cuda or ten.dtype != torch.float32:
+        raise TypeError(f"forward_host: `{name}` must be a CPU float32 tensor")
+    if ten.dim() == 3 and ten.stride(2) != 1 and ten.shape[2] != 1:
+        ten = ten.contiguous()
+    return ten
+
+
+def forward_host(cfg: Config, tens: Sequence[Optional[torch.Tensor]], out_x: Optional[torch.Tensor] = None,
+                 out_i: Optional[torch.Tensor] = None, device: Optional[torch.device] = None):
+    """`psnode_forward_host`: every tensor (series, all_initial, jumps, weights, outputs) lives in HOST memory.
+
+    Pinned tensors (`.pin_memory()`) of >= 1 MB are read / written in place by the kernel over PCIe (zero copy, fused with
+    the integration); pageable ones are staged with cudaMemcpyAsync.  Returns (x_sol, i_sol, h2d_bytes, d2h_bytes) with
+    time-major (T,B,.) CPU outputs (pinned unless the caller passed its own)."""
+    L = N.lib()
+    t = _host_series(tens[_T], "t")
+    T, B = t.shape[0], t.shape[1]
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    keep: list = []
+    host = [t] + [_host_series(tens[k], n) for k, n in ((_X, "x"), (_Zs, "z"), (_Vs, "v"), (_Is, "i"))]
+    x_init = tens[_XINIT]
+    a0 = tens[_A0]
+    for name, ten in (("x_init", x_init), ("all_initial", a0)):
+        if ten is not None and (ten.is_cuda or ten.dtype != torch.float32):
+            raise TypeError(f"forward_host: `{name}` must be a CPU float32 tensor")
+    if out_x is None:
+        out_x = torch.empty((T, B, cfg.X), dtype=torch.float32).pin_memory()
+    if cfg.kind == N.DAE and out_i is None:
+        out_i = torch.empty((T, B, cfg.I), dtype=torch.float32).pin_memory()
+    p = N.Problem()
+    p.kind, p.method, p.impl = cfg.kind, cfg.method, cfg.impl
+    p.B, p.T = B, T
+    p.X, p.Z, p.V, p.I = cfg.X, cfg.Z, cfg.V, cfg.I
+    p.teacher_x, p.teacher_i = int(cfg.teacher_x), int(cfg.teacher_i)
+    _set_series(p.t, host[0])
+    _set_series(p.x, host[1] if (cfg.kind == N.ODE or cfg.teacher_x) else None)
+    _set_series(p.z, host[2])
+    _set_series(p.v, host[3])
+    _set_series(p.i, host[4] if cfg.teacher_i else None)
+    if x_init is not None and x_init.shape[-1] != 0:
+        x_init = x_init if x_init.stride(-1) == 1 else x_init.contiguous()
+        p.x_init, p.x_init_sb = x_init.data_ptr(), x_init.stride(0)
+    a0 = a0 if a0.stride(-1) == 1 else a0.contiguous()
+    p.a0, p.a0_sb = a0.data_ptr(), a0.stride(0)
+    keep.extend(host + [x_init, a0])
+    p.E = 0
+    if cfg.has_event:
+        ev_t, zj, vj = tens[_EVT], tens[_ZJ], tens[_VJ]
+        E = ev_t.shape[1]
+        t00, ev0 = (cfg.event_ref if cfg.event_ref is not None else (t[:, 0, 0], ev_t[0].reshape(E)))
+        hit = t00[:-1].reshape(-1, 1) == ev0.reshape(1, -1)                       # (T-1, E), exact float equality
+        if cfg.check_events and bool((hit.sum(dim=1) > 1).any()):
+            raise RuntimeError("more than one event matches the same grid time (the reference raises here too)")
+        idx = torch.where(hit.any(dim=1), hit.float().argmax(dim=1), torch.full((max(T - 1, 0),), -1)).to(torch.int32).contiguous()
+        if idx.numel() == 0:
+            idx = torch.full((1,), -1, dtype=torch.int32)
+        keep.append(idx)
+        p.event_idx, p.E = idx.data_ptr(), E
+        if cfg.Z > 0:
+            zj = zj if zj.stride(-1) == 1 else zj.contiguous()
+            keep.append(zj)
+            p.z_jump, p.zj_sb, p.zj_se = zj.data_ptr(), zj.stride(0), zj.stride(1)
+        if cfg.kind == N.DAE and cfg.V > 0:
+            vj = vj if vj.stride(-1) == 1 else vj.contiguous()
+            keep.append(vj)
+            p.v_jump, p.vj_sb, p.vj_se = vj.data_ptr(), vj.stride(0), vj.stride(1)
+    params = tens[_NFIXED:]
+
+    def fill(dst, plist):
+        dst.n_layers = len(plist) // 2
+        for l in range(dst.n_layers):
+            W, b = plist[2 * l].detach(), plist[2 * l + 1].detach()
+            if W.is_cuda:
+                raise TypeError("forward_host: weights must be CPU tensors")
+            W, b = W.contiguous(), b.contiguous()
+            keep.extend((W, b))
+            dst.in_dim[l], dst.out_dim[l] = W.shape[1], W.shape[0]
+            dst.W[l], dst.b[l] = W.data_ptr(), b.data_ptr()
+    fill(p.de, params[:2 * cfg.n_de])
+    if cfg.kind == N.DAE:
+        fill(p.ae, params[2 * cfg.n_de:2 * (cfg.n_de + cfg.n_ae)])
+    _set_series(p.x_sol, out_x)
+    _set_series(p.i_sol, out_i)
+    up, down = C.c_int64(0), C.c_int64(0)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        N.check(L.psnode_forward_host(C.byref(p), stream, C.byref(up), C.byref(down)), "psnode_forward_host")
+    return out_x, out_i, int(up.value), int(down.value)

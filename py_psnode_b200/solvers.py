@@ -107,6 +107,43 @@ class FixedGridODESolver(metaclass=abc.ABCMeta):
         return engine.integrate(cfg, tens)
 
 
+    # ------------------------------------------------------------------ host-buffer variants (C ABI psnode_forward_host)
+    def integrate_ODE_host(self, x_func: nn.Module, t, x, z, all_initial, event_fn=None, jump_change_fn=None, input_true_x=False,
+                           out=None):
+        """integrate_ODE for a batch that lives in HOST memory (CPU tensors, CPU module): the library moves the data --
+        zero-copy over PCIe for pinned tensors, staged copies otherwise -- integrates on the GPU and returns the
+        trajectory in host memory (`out`, or a new pinned tensor).  Forward only (no autograd)."""
+        X, Z = x.shape[-1], z.shape[-1]
+        de = pattern.match_de(x_func, X=X, Z=Z, dae=False)
+        ev = pattern.match_event(event_fn, jump_change_fn, dae=False)
+        cfg = engine.Config(kind=N.ODE, method=self._method, impl=N.IMPL_BY_NAME[self.impl], X=X, Z=Z, V=0, I=0,
+                            teacher_x=bool(input_true_x), teacher_i=False, n_de=len(de), n_ae=0,
+                            has_event=ev is not None, check_events=self.check_events)
+        cfg.event_ref = pattern.event_reference(event_fn)
+        tens = [t, x, z, None, None, None, all_initial, ev[0] if ev else None, ev[1] if ev else None, None, *_params(de)]
+        x_sol, _, up, down = engine.forward_host(cfg, tens, out_x=out)
+        self.last_host_bytes = (up, down)
+        return x_sol
+
+    def integrate_DAE_host(self, x_init, x_func: nn.Module, i_func: nn.Module, t, x, z, v, i, all_initial, event_fn=None,
+                           jump_change_fn=None, input_true_x=False, input_true_i=False, out=None):
+        """Host-memory variant of integrate_DAE (see integrate_ODE_host); `out` = (x_sol, i_sol) buffers or None."""
+        X, Z, V, I = x_init.shape[-1], z.shape[-1], v.shape[-1], i.shape[-1]
+        de = pattern.match_de(x_func, X=X, Z=Z, V=V, I=I, dae=True)
+        ae = pattern.match_ae(i_func, X=X, Z=Z, V=V, I=I)
+        ev = pattern.match_event(event_fn, jump_change_fn, dae=True)
+        cfg = engine.Config(kind=N.DAE, method=self._method, impl=N.IMPL_BY_NAME[self.impl], X=X, Z=Z, V=V, I=I,
+                            teacher_x=bool(input_true_x), teacher_i=bool(input_true_i), n_de=len(de), n_ae=len(ae),
+                            has_event=ev is not None, check_events=self.check_events)
+        cfg.event_ref = pattern.event_reference(event_fn)
+        tens = [t, x if x.shape[-1] != 0 else None, z, v, i, x_init, all_initial,
+                ev[0] if ev else None, ev[1] if ev else None, ev[2] if ev else None, *_params(de), *_params(ae)]
+        ox, oi = out if out is not None else (None, None)
+        x_sol, i_sol, up, down = engine.forward_host(cfg, tens, out_x=ox, out_i=oi)
+        self.last_host_bytes = (up, down)
+        return x_sol, i_sol
+
+
 class Euler(FixedGridODESolver):
     order = 1
     _method = N.EULER

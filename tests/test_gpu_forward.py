@@ -97,7 +97,7 @@ def test_ode_forward_tensor_core_matches_reference(native_lib, name):
 
 
 def test_tensor_core_matches_fused_at_scale(native_lib):
-    """B = 600 trajectories (ragged last group, two groups per CTA), 200 steps: tensor-core vs CUDA-core fused kernel."""
+    """B = 5000 trajectories (ragged last group, two groups per CTA), 200 steps: tensor-core vs CUDA-core fused kernel."""
     from py_psnode_b200 import DE_Func, ODE_Event, RK4
     torch.manual_seed(3)
     dev = "cuda:0"
@@ -116,3 +116,35 @@ def test_tensor_core_matches_fused_at_scale(native_lib):
             outs[impl] = RK4(impl=impl).integrate_ODE(x_func=de, t=t, x=x, z=z, all_initial=a0, event_fn=ev.event_fn,
                                                       jump_change_fn=ev.jump_change_fn)
     assert torch.allclose(outs["tc"], outs["fused"], rtol=RTOL, atol=ATOL), tol_report(outs["tc"].cpu(), outs["fused"].cpu())
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("name", ["ode01_rk4_small", "ode01_rk4_2events_pad", "dae01_rk4_small", "ode01_euler_cfg1"])
+def test_host_buffer_entry_matches_reference(native_lib, name, pinned):
+    """C ABI `psnode_forward_host` (HOST pointers; staged copies for pageable memory, zero-copy for pinned >= 1 MB)."""
+    from py_psnode_b200 import _native as N, engine
+    d = load_golden(name)
+    dae = str(d["kind"]) == "dae"
+    fix = (lambda q: q.pin_memory()) if pinned else (lambda q: q)
+    t, x, z = (fix(torch.from_numpy(d[k]).permute(1, 0, 2).contiguous()) for k in ("t", "x", "z"))
+    de = [q for wb in params_of(d, "de") for q in wb]
+    method = {"euler": N.EULER, "midpoint": N.MIDPOINT, "rk4": N.RK4}[str(d["solver"])]
+    ev_t, zj = torch.from_numpy(d["event_t"]), torch.from_numpy(d["z_jump"])
+    if dae:
+        v, i = (fix(torch.from_numpy(d[k]).permute(1, 0, 2).contiguous()) for k in ("v", "i"))
+        ae = [q for wb in params_of(d, "ae") for q in wb]
+        x_init = torch.from_numpy(d["x_init"])
+        a0 = torch.cat((x_init, z[0], v[0], i[0]), dim=-1)
+        cfg = engine.Config(kind=N.DAE, method=method, impl=N.IMPL_AUTO, X=x_init.shape[1], Z=z.shape[2], V=v.shape[2], I=i.shape[2],
+                            teacher_x=False, teacher_i=False, n_de=len(de) // 2, n_ae=len(ae) // 2, has_event=True)
+        tens = [t, None, z, v, i, x_init, a0, ev_t, zj, torch.from_numpy(d["v_jump"]), *de, *ae]
+    else:
+        a0 = torch.cat((x[0], z[0]), dim=-1)
+        cfg = engine.Config(kind=N.ODE, method=method, impl=N.IMPL_AUTO, X=x.shape[2], Z=z.shape[2], V=0, I=0, teacher_x=False,
+                            teacher_i=False, n_de=len(de) // 2, n_ae=0, has_event=True)
+        tens = [t, x, z, None, None, None, a0, ev_t, zj, None, *de]
+    xs, is_, up, down = engine.forward_host(cfg, tens)
+    assert up > 0 and down == xs.numel() * 4 + (is_.numel() * 4 if is_ is not None else 0)
+    assert torch.allclose(xs, torch.from_numpy(d["x_sol"]), rtol=RTOL, atol=ATOL), tol_report(xs, torch.from_numpy(d["x_sol"]))
+    if dae:
+        assert torch.allclose(is_, torch.from_numpy(d["i_sol"]), rtol=RTOL, atol=ATOL)
