@@ -358,6 +358,21 @@ def main():
         except Exception:
             pass
         tflops = w["flop_per_unit"] * units / (kern_ms * 1e-3) / 1e12
+        hbm = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+               "traffic": traffic, "peak_source": peak_src,
+               "note": "algorithmic (compulsory) bytes per traj-step x units / kernel time; the path is ~1300 FLOP/byte, i.e. compute/latency bound"}
+        if kernel_name.startswith("psn_tc_"):
+            tc_peak = peaks.get("bf16_tflops", 1590.0)
+            tc_src = ("measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" if "bf16_tflops" in peaks
+                      else "fallback 1590 TFLOP/s dense bf16 (B200_PROFILING.md)")
+            roofline = {"bound": "tensor", "achieved": tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": tflops / tc_peak,
+                        "traffic": traffic, "peak_source": tc_src,
+                        "note": "achieved = algorithmic FLOPs of the reference formulation (101376 per traj-step at cfg2) / kernel time. The kernel "
+                                "runs tcgen05 kind::tf32 (dense peak = half the bf16 figure) and needs 3 MMAs per product (3xTF32) to hold the "
+                                "reference's fp32 accuracy, with N = 16 trajectories per MMA (4096 trajectories / 148 SMs): it is bound by the "
+                                "serial layer chain (16000 dependent layers per trajectory), not by tensor throughput"}
+        else:
+            roofline = hbm
         line = {
             "metric": "rk4_traj_steps_per_sec", "value": value, "unit": "traj-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -365,11 +380,9 @@ def main():
             "config": {"workload": args.workload + ": " + w["desc"], "batch_per_gpu": w["B"], "global_batch": w["B"] * world,
                        "grid_steps": w["N"], "state_dim": w["X"], "hidden": w["H"], "parallelism": f"batch-shard x{world}",
                        "kernel": kernel_name, "l2": "working set per call (inputs 49 MB + trajectory 262 MB) exceeds the 126 MB L2"},
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "note": "compulsory bytes only; the path is fp32-FMA bound (see fp32)"},
+            "roofline": roofline, "roofline_hbm": hbm,
             "fp32": {"achieved_tflops_reference_formulation": tflops, "peak_tflops_nominal": FP32_PEAK_TFLOPS,
-                     "frac": tflops / FP32_PEAK_TFLOPS},
+                     "frac": tflops / FP32_PEAK_TFLOPS, "note": "CUDA-core fp32 FMA peak, for scale"},
             "kernel_ms": kern_ms, "gpu_launches": int(launches), "clocks": clocks,
         }
         if e2e is not None:

@@ -1,0 +1,114 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol include/psnode_b200.h declares, the
+ctypes structures match the header, the product never imports the oracle, and the product path fails LOUDLY without CUDA
+(no CPU / Python-loop fallback).  No compute calls: there is no GPU here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header():
+    return open(os.path.join(ROOT, "include", "psnode_b200.h")).read()
+
+
+def test_library_exports_every_declared_symbol(native_lib):
+    from py_psnode_b200 import _native
+    text = re.sub(r"/\*.*?\*/", "", _header(), flags=re.S)
+    declared = set(re.findall(r"\b(psnode_[a-z_0-9]+)\s*\(", text))
+    assert declared, "no function declarations found in the header"
+    bound = {name for name, _, _ in _native.SYMBOLS}
+    assert declared == bound, f"header vs binding mismatch: {sorted(declared ^ bound)}"
+    for name in declared:
+        assert hasattr(native_lib, name), f"{name} not exported by libpsnode_b200.so"
+    assert native_lib.psnode_abi_version() == _native.ABI_VERSION
+    assert native_lib.psnode_status_string(-2).decode().startswith("problem shape not supported")
+    assert native_lib.psnode_launch_count() >= 0
+
+
+def test_ctypes_structs_match_header_sizes():
+    """Compile a tiny C program against the header and compare sizeof() with the ctypes mirrors."""
+    import subprocess
+    import tempfile
+    from py_psnode_b200 import _native
+    src = ('#include <stdio.h>\n#include "psnode_b200.h"\nint main(void){printf("%zu %zu %zu %zu %d %d\\n", sizeof(psnode_mlp), '
+           'sizeof(psnode_series), sizeof(psnode_problem), sizeof(psnode_adjoint), PSNODE_IMPL_TC, PSNODE_MAX_LAYERS);return 0;}\n')
+    with tempfile.TemporaryDirectory() as td:
+        cfile, exe = os.path.join(td, "s.c"), os.path.join(td, "s")
+        open(cfile, "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), cfile, "-o", exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    sizes = [int(q) for q in out]
+    assert sizes[:4] == [C.sizeof(_native.Mlp), C.sizeof(_native.Series), C.sizeof(_native.Problem), C.sizeof(_native.Adjoint)]
+    assert sizes[4] == _native.IMPL_TC and sizes[5] == _native.PSNODE_MAX_LAYERS
+
+
+def test_param_count_helper(native_lib):
+    from py_psnode_b200 import _native
+    m = _native.Mlp()
+    m.n_layers = 2
+    m.in_dim[0], m.out_dim[0], m.in_dim[1], m.out_dim[1] = 54, 64, 64, 16
+    assert native_lib.psnode_mlp_param_count(C.byref(m)) == 54 * 64 + 64 + 64 * 16 + 16
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for base in ("py_psnode_b200", "neural_dae"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "psnode_oracle" in text:
+                        bad.append(os.path.join(dirpath, f))
+    for f in ("utils.py",):
+        if "oracle" in open(os.path.join(ROOT, f)).read():
+            bad.append(f)
+    assert not bad, f"product code references the oracle: {bad}"
+
+
+def test_cpu_tensors_fail_loudly():
+    """integrate_ODE on CPU tensors must raise (no CPU fallback); so must a module the kernel cannot represent."""
+    from py_psnode_b200 import DE_Func, RK4, UnsupportedModuleError
+    de = DE_Func(x_dim=4, z_dim=1, hidden_dim=8)
+    T, B = 5, 3
+    t = torch.zeros(T, B, 1)
+    x, z = torch.zeros(T, B, 4), torch.zeros(T, B, 1)
+    a0 = torch.zeros(B, 5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        RK4().integrate_ODE(x_func=de, t=t, x=x, z=z, all_initial=a0)
+
+    class Weird(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.x_dot = torch.nn.Sequential(torch.nn.Linear(15, 8), torch.nn.Tanh(), torch.nn.Linear(8, 4))
+
+        def forward(self, t0, xt, zt, all_initial):
+            return xt
+    with pytest.raises(UnsupportedModuleError):
+        RK4().integrate_ODE(x_func=Weird(), t=t, x=x, z=z, all_initial=a0)
+    with pytest.raises(ValueError):
+        RK4(step_size=0.1, grid_constructor=lambda *a: None)
+
+
+def test_missing_library_is_an_error(monkeypatch, tmp_path):
+    from py_psnode_b200 import _native
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_native.NativeLibraryError):
+        _native.lib()
+
+
+def test_step_integrate_contract_on_cpu():
+    """step_integrate is the reference's public single-step API with an arbitrary module (my_solvers.py:48-50)."""
+    from py_psnode_b200 import Euler, Midpoint, RK4
+    f = lambda t0, xt, zt, all_initial: -xt
+    x0 = torch.ones(2, 3)
+    dt = torch.full((2, 1), 0.1)
+    for cls, want in ((Euler, 0.9), (Midpoint, 1 - 0.1 + 0.005), (RK4, 0.9048375)):
+        x1, f0 = cls().step_integrate(func=f, t0=torch.zeros(2, 1), dt=dt, t1=dt, x0=x0, z0=None, all_initial=None)
+        assert torch.allclose(x1, torch.full_like(x0, want), atol=1e-6)
+        assert torch.equal(f0, -x0)
+    assert (Euler.order, Midpoint.order, RK4.order) == (1, 2, 4)
