@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PSNODE_ABI_VERSION 1
+#define PSNODE_ABI_VERSION 2
 #define PSNODE_MAX_LAYERS 8
 
 /* status codes */
@@ -118,6 +118,13 @@ typedef struct psnode_problem {
     psnode_mlp ae;
     psnode_series_out x_sol;    /* (T,B,X) */
     psnode_series_out i_sol;    /* (T,B,I)  DAE */
+    /* Optional activation tape (caller-owned scratch, psnode_tape_floats(p) floats; NULL = none).  When given to
+     * psnode_forward, the tensor-core kernel records the hidden activations of every RK stage -- what the reference's
+     * autograd graph keeps alive between forward and loss.backward() (neural_00_ODE_01_no_encode.py:350-359) -- and
+     * psnode_backward, given the SAME buffer, runs the tensor-core reverse sweep on it instead of recomputing the
+     * stages from x_sol.  Results are identical up to fp32 rounding; without a tape nothing changes. */
+    float* tape;
+    int64_t tape_floats;
 } psnode_problem;
 
 /*
@@ -172,6 +179,10 @@ int64_t psnode_mlp_param_count(const psnode_mlp* m);
  */
 int psnode_event_table(const float* t0, int64_t t_st, int32_t T, const float* ev0, int64_t ev_se, int32_t E,
                        int32_t* event_idx, int32_t* err, void* stream);
+
+/* floats of activation tape psnode_forward can record for this problem (0: this problem has no tape-based reverse
+ * sweep, psnode_backward recomputes from x_sol) */
+int64_t psnode_tape_floats(const psnode_problem* p);
 
 /* workspace sizes in bytes (0 is possible) */
 int64_t psnode_forward_workspace(const psnode_problem* p);

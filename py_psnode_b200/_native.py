@@ -8,7 +8,7 @@ import os
 import threading
 
 PSNODE_MAX_LAYERS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, EINVAL, EUNSUPPORTED, EWORKSPACE, ECUDA, ENODEVICE = 0, -1, -2, -3, -4, -5
 EULER, MIDPOINT, RK4 = 0, 1, 2
@@ -43,7 +43,8 @@ class Problem(C.Structure):
                 ("z_jump", C.c_void_p), ("zj_sb", C.c_int64), ("zj_se", C.c_int64),
                 ("v_jump", C.c_void_p), ("vj_sb", C.c_int64), ("vj_se", C.c_int64),
                 ("de", Mlp), ("ae", Mlp),
-                ("x_sol", Series), ("i_sol", Series)]
+                ("x_sol", Series), ("i_sol", Series),
+                ("tape", C.c_void_p), ("tape_floats", C.c_int64)]
 
 
 class Adjoint(C.Structure):
@@ -67,6 +68,7 @@ SYMBOLS = [
     ("psnode_mlp_param_count", C.c_int64, [C.POINTER(Mlp)]),
     ("psnode_event_table", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("psnode_tape_floats", C.c_int64, [C.POINTER(Problem)]),
     ("psnode_forward_workspace", C.c_int64, [C.POINTER(Problem)]),
     ("psnode_backward_workspace", C.c_int64, [C.POINTER(Problem), C.POINTER(Adjoint)]),
     ("psnode_forward", C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_int64, C.c_void_p]),

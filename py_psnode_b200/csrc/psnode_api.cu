@@ -5,6 +5,7 @@
 #include <cstring>
 #include <mutex>
 #include "psnode_internal.cuh"
+#include "psnode_tc_tape.cuh"
 
 namespace {
 std::atomic<int64_t> g_launches{0};
@@ -115,6 +116,13 @@ int psnode_event_table(const float* t0, int64_t t_st, int32_t T, const float* ev
     return PSNODE_OK;
 }
 
+int64_t psnode_tape_floats(const psnode_problem* p) {
+    if (validate(p) != PSNODE_OK) return 0;
+    if (p->impl != PSNODE_IMPL_AUTO && p->impl != PSNODE_IMPL_TC) return 0;
+    if (!psn_tc_supports(p)) return 0;
+    return psn_tc_tape_floats(p->B, p->T, p->method);
+}
+
 int64_t psnode_forward_workspace(const psnode_problem* p) {
     if (validate(p) != PSNODE_OK) return 0;
     int64_t g = psn_generic_forward_workspace(p);
@@ -143,7 +151,9 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
 
 int64_t psnode_backward_workspace(const psnode_problem* p, const psnode_adjoint* a) {
     if (validate(p) != PSNODE_OK || !a) return 0;
-    return psn_generic_backward_workspace(p, a);
+    const int64_t g = psn_generic_backward_workspace(p, a);
+    const int64_t t = psn_tc_supports(p) ? psn_tc_backward_workspace(p, a) : 0;
+    return g > t ? g : t;
 }
 
 int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* workspace, int64_t workspace_bytes,
@@ -151,6 +161,8 @@ int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* work
     const int st = validate(p);
     if (st != PSNODE_OK) return st;
     if (!a || !a->d_theta) return PSNODE_EINVAL;
+    if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC) && psn_tc_bwd_supports(p, a))
+        return psn_tc_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     return psn_generic_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 

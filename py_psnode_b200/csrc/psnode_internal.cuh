@@ -52,3 +52,8 @@ int64_t psn_fused_forward_workspace(const psnode_problem* p);
 bool psn_tc_supports(const psnode_problem* p);
 int psn_tc_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream);
 int64_t psn_tc_forward_workspace(const psnode_problem* p);
+
+// tape-based tensor-core reverse sweep (psnode_tc_bwd.cu)
+bool psn_tc_bwd_supports(const psnode_problem* p, const psnode_adjoint* a);
+int psn_tc_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
+int64_t psn_tc_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);

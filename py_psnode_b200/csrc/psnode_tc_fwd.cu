@@ -29,6 +29,7 @@
 #include <cstddef>
 #include "psnode_internal.cuh"
 #include "psnode_tc.cuh"
+#include "psnode_tc_tape.cuh"
 
 namespace {
 using namespace psn_tc;
@@ -59,6 +60,7 @@ struct TcParams {
     const float* W1; const float* b1; const float* W2; const float* b2;
     const float* W3; const float* b3; const float* W4; const float* b4;
     int vec_out;
+    float* tape;            // activation tape for the tensor-core reverse sweep (psnode_tc_tape.cuh) or nullptr
     int* err;
 };
 
@@ -260,15 +262,21 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
         tc_fence_before();
         group_sync(g);
     };
-    auto store_hidden = [&](const float (&d)[8], const float (&bias)[2], const float* cadd) {
+    auto store_hidden = [&](const float (&d)[8], const float (&bias)[2], const float* cadd, float* trec) {
+        float a[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             float v = d[i] + bias[(i >> 1) & 1];
             if (cadd) v = d[i] + cadd[i];
+            a[i] = psn_elu(v);
             float hi, lo;
-            split_tf32_fast(psn_elu(v), hi, lo);
+            split_tf32_fast(a[i], hi, lo);
             *reinterpret_cast<float*>(gs.act_hi + off_act[i]) = hi;
             *reinterpret_cast<float*>(gs.act_lo + off_act[i]) = lo;
+        }
+        if (trec) {   // thread-private, coalesced: 32 contiguous bytes per thread
+            __stcs(reinterpret_cast<float4*>(trec + gt * 8), make_float4(a[0], a[1], a[2], a[3]));
+            __stcs(reinterpret_cast<float4*>(trec + gt * 8) + 1, make_float4(a[4], a[5], a[6], a[7]));
         }
     };
     // held inputs / dt of the step that ENDS at grid point j -> B1 tile columns 16.., dts[j & 1]; done by warp 1, lane = trajectory
@@ -320,6 +328,8 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
         publish();
 
         const float c13 = (float)(1.0 / 3.0);
+        float* trec = q.tape ? q.tape + (int64_t)(blockIdx.x * q.groups + g) * (T - 1) * NST * PSN_TAPE_STAGE : nullptr;
+        float ycur[2] = {x0[0], x0[1]};                     // input of the current stage (recorded on the tape)
         for (int j = 1; j < T; j++) {
             float un[TU], dtn = 0.0f;                       // next step's inputs, prefetched by warp 1 during stage 0
             const bool have_next = j + 1 < T;
@@ -327,6 +337,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
 #pragma unroll 1
             for (int e = 0; e < NST; e++) {
                 float d[8];
+                if (trec) __stcs(reinterpret_cast<float2*>(trec + 3 * PSN_TAPE_FRAG + gt * 2), make_float2(ycur[0], ycur[1]));
                 // ---- layer 1 (shared-memory weights): K = 24 -> warps 0..2 take one K-step each; warp 3 only commits ----
                 issue_ss(d_w1_hi, d_w1_lo, d_b1_hi, d_b1_lo, warp, warp < 3 ? 1 : 0);
                 if (e == 0 && warp == 1 && have_next) load_step_inputs(j + 1, un, dtn);
@@ -340,17 +351,17 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
                     }
                 }
                 collect(d, 3);
-                store_hidden(d, bias2, c1);
+                store_hidden(d, bias2, c1, trec);
                 publish();
                 // ---- layer 2 ----
                 issue_ts(TM_W2, TM_W2 + 64, d_act_hi, d_act_lo, 2 * warp, 2);
                 collect(d, 4);
-                store_hidden(d, bias2, nullptr);
+                store_hidden(d, bias2, nullptr, trec ? trec + PSN_TAPE_FRAG : nullptr);
                 publish();
                 // ---- layer 3 ----
                 issue_ts(TM_W3, TM_W3 + 64, d_act_hi, d_act_lo, 2 * warp, 2);
                 collect(d, 4);
-                store_hidden(d, bias3, nullptr);
+                store_hidden(d, bias3, nullptr, trec ? trec + 2 * PSN_TAPE_FRAG : nullptr);
                 publish();
                 // ---- layer 4 + stage algebra: 2 state elements per thread ----
                 issue_ts(TM_W4, TM_W4 + 64, d_act_hi, d_act_lo, 2 * warp, 2);
@@ -379,8 +390,10 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_ode_kernel(const 
                     split_tf32_fast(xn, hi, lo);
                     *reinterpret_cast<float*>(gs.b1_hi + off_x[r]) = hi;
                     *reinterpret_cast<float*>(gs.b1_lo + off_x[r]) = lo;
+                    ycur[r] = xn;
                     if (last) { x0[r] = xn; gs.ostage[sn][sm0 + 8 * r] = xn; }
                 }
+                if (trec) trec += PSN_TAPE_STAGE;
                 if (warp == 1 && last && have_next) store_step_inputs(j + 1, un, dtn);   // all layer-1 MMAs of this step are done
                 publish();
             }
@@ -426,11 +439,12 @@ int psn_tc_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
     q.W1 = p->de.W[0]; q.b1 = p->de.b[0]; q.W2 = p->de.W[1]; q.b2 = p->de.b[1];
     q.W3 = p->de.W[2]; q.b3 = p->de.b[2]; q.W4 = p->de.W[3]; q.b4 = p->de.b[3];
     q.vec_out = ((reinterpret_cast<uintptr_t>(p->x_sol.p) & 15) == 0 && (p->x_sol.st & 3) == 0 && (p->x_sol.sb & 3) == 0) ? 1 : 0;
+    q.tape = (p->tape && p->tape_floats >= psn_tc_tape_floats(p->B, p->T, p->method)) ? p->tape : nullptr;
     q.err = static_cast<int*>(ws);
     PSN_CUDA(cudaMemsetAsync(q.err, 0, 4, stream));
     // two groups of 16 trajectories per CTA once there are enough trajectories to give every SM a CTA
-    const int ngroups = (p->B + TN - 1) / TN;
-    q.groups = ngroups > 148 ? 2 : 1;
+    const int ngroups = psn_tc_ngroups(p->B);
+    q.groups = psn_tc_groups_per_cta(p->B);
     const int grid = (ngroups + q.groups - 1) / q.groups;
     const int smem = (int)sizeof(CtaSmem) + 128;
     auto launch = [&](auto kern, const char* name) -> int {

@@ -5,6 +5,7 @@ torch is plumbing here (device memory, streams, autograd bookkeeping); every FLO
 libpsnode_b200.so.  If the library is missing or the tensors are not CUDA fp32 the call raises.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -100,7 +101,8 @@ class Config:
 _T, _X, _Zs, _Vs, _Is, _XINIT, _A0, _EVT, _ZJ, _VJ, _NFIXED = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 
 
-def _build_problem(cfg: Config, tens: Sequence[Optional[torch.Tensor]], x_sol, i_sol, keep: list) -> N.Problem:
+def _build_problem(cfg: Config, tens: Sequence[Optional[torch.Tensor]], x_sol, i_sol, keep: list,
+                   tape: Optional[torch.Tensor] = None) -> N.Problem:
     t = _series(tens[_T], "t")
     T, B = t.shape[0], t.shape[1]
     x = _series(tens[_X], "x")
@@ -168,11 +170,25 @@ def _build_problem(cfg: Config, tens: Sequence[Optional[torch.Tensor]], x_sol, i
         _fill_mlp(p.ae, params[2 * cfg.n_de:2 * (cfg.n_de + cfg.n_ae)], keep)
     _set_series(p.x_sol, x_sol)
     _set_series(p.i_sol, i_sol)
+    if tape is not None:
+        p.tape, p.tape_floats = tape.data_ptr(), tape.numel()
     return p
 
 
-def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """Run the forward kernel; returns time-major contiguous (x_sol, i_sol)."""
+def _tape_budget_bytes(device: torch.device) -> int:
+    """How much HBM one call may spend on the activation tape (psnode_b200.h `tape`): PSNODE_TAPE_MAX_GB, default 60 % of
+    the memory that is free right now (B200: 180 GB; the cfg2 tape is 13.6 GB)."""
+    env = os.environ.get("PSNODE_TAPE_MAX_GB")
+    if env is not None:
+        return int(float(env) * 2 ** 30)
+    free, _total = torch.cuda.mem_get_info(device)
+    reusable = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return int(0.6 * (free + reusable))
+
+
+def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]], want_tape: bool = False):
+    """Run the forward kernel; returns time-major contiguous (x_sol, i_sol) -- and, with `want_tape`, the activation tape
+    the tensor-core reverse sweep consumes (None when the problem has no tape-based sweep or the tape would not fit)."""
     t = tens[_T]
     _require_cuda_f32("t", t)
     L = N.lib()
@@ -182,10 +198,16 @@ def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]]) -> Tuple[to
         i_sol = torch.empty((T, B, cfg.I), dtype=torch.float32, device=t.device) if cfg.kind == N.DAE else None
         keep: list = []
         p = _build_problem(cfg, tens, x_sol, i_sol, keep)
+        tape = None
+        if want_tape:
+            n_tape = int(L.psnode_tape_floats(C.byref(p)))
+            if 0 < n_tape * 4 <= _tape_budget_bytes(t.device):
+                tape = torch.empty(n_tape, dtype=torch.float32, device=t.device)
+                p.tape, p.tape_floats = tape.data_ptr(), n_tape
         ws = _workspace(t.device, L.psnode_forward_workspace(C.byref(p)))
         stream = torch.cuda.current_stream(t.device).cuda_stream
         N.check(L.psnode_forward(C.byref(p), ws.data_ptr(), ws.numel(), stream), "psnode_forward")
-    return x_sol, i_sol
+    return x_sol, i_sol, tape
 
 
 def _theta_sizes(params: Sequence[torch.Tensor]) -> List[int]:
@@ -197,7 +219,11 @@ class _Integrate(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cfg: Config, *tens):
-        x_sol, i_sol = forward_raw(cfg, tens)
+        needs = ctx.needs_input_grad[1:]
+        # the tape-based reverse sweep produces parameter, x0 and all_initial gradients; anything else is recomputed
+        want_tape = not (cfg.teacher_x or cfg.teacher_i or any(needs[k] for k in (_Zs, _Vs, _Is, _ZJ, _VJ)))
+        x_sol, i_sol, tape = forward_raw(cfg, tens, want_tape=want_tape)
+        ctx.tape = tape
         ctx.cfg = cfg
         ctx.n_in = len(tens)
         ctx.save_for_backward(*[q for q in tens if q is not None], x_sol, *( [i_sol] if i_sol is not None else []))
@@ -217,12 +243,14 @@ class _Integrate(torch.autograd.Function):
             tens.append(next(it) if present else None)
         x_sol = next(it)
         i_sol = next(it) if cfg.kind == N.DAE else None
-        grads = backward_raw(cfg, tens, x_sol, i_sol, gx, gi if cfg.kind == N.DAE else None, ctx.needs_input_grad[1:])
+        tape, ctx.tape = ctx.tape, None
+        grads = backward_raw(cfg, tens, x_sol, i_sol, gx, gi if cfg.kind == N.DAE else None, ctx.needs_input_grad[1:], tape)
         return (None, *grads)
 
 
-def backward_raw(cfg: Config, tens, x_sol, i_sol, gx, gi, needs) -> List[Optional[torch.Tensor]]:
-    """Reverse sweep through the native library.  `needs[k]` says whether tens[k] wants a gradient."""
+def backward_raw(cfg: Config, tens, x_sol, i_sol, gx, gi, needs, tape=None) -> List[Optional[torch.Tensor]]:
+    """Reverse sweep through the native library.  `needs[k]` says whether tens[k] wants a gradient; `tape` is what
+    forward_raw(..., want_tape=True) recorded (None: the sweep recomputes the stages from x_sol)."""
     L = N.lib()
     t = tens[_T]
     dev = t.device
@@ -233,7 +261,7 @@ def backward_raw(cfg: Config, tens, x_sol, i_sol, gx, gi, needs) -> List[Optiona
     out: List[Optional[torch.Tensor]] = [None] * len(tens)
     with torch.cuda.device(dev):
         keep: list = []
-        p = _build_problem(cfg, tens, x_sol, i_sol, keep)
+        p = _build_problem(cfg, tens, x_sol, i_sol, keep, tape)
         a = N.Adjoint()
         gx = torch.zeros_like(x_sol) if gx is None else _series(gx, "grad x_sol")
         _set_series(a.gx, gx)
@@ -299,7 +327,7 @@ def integrate(cfg: Config, tens: Sequence[Optional[torch.Tensor]]) -> Tuple[torc
     """Autograd-aware entry used by the solver classes."""
     needs_grad = torch.is_grad_enabled() and any(q is not None and q.requires_grad for q in tens)
     if not needs_grad:
-        return forward_raw(cfg, tens)
+        return forward_raw(cfg, tens)[:2]
     x_sol, i_sol = _Integrate.apply(cfg, *tens)
     return x_sol, (i_sol if cfg.kind == N.DAE else None)
 

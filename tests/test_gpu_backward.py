@@ -104,12 +104,34 @@ def grad_errors(d, got):
 CASES = [n for n in golden_names() if "model" not in n and "long" not in n]
 
 
+def _tape_sweep_expected(d):
+    """True when the tensor-core reverse sweep (activation tape) must be the kernel that runs: H = 64 4-layer ODE net,
+    X = 16, no teacher forcing, no input-series gradients."""
+    if str(d["kind"]) != "ode" or bool(d["teacher_x"]) or ("g_z" in d) or ("g_x" in d):
+        return False
+    shapes = [d[f"de_W{k}"].shape for k in range(8) if f"de_W{k}" in d]
+    S = d["x"].shape[-1] + d["z"].shape[-1]
+    return d["x"].shape[-1] == 16 and d["z"].shape[-1] <= 8 and shapes == [(64, 3 * S), (64, 64), (64, 64), (16, 64)]
+
+
+@pytest.mark.parametrize("sweep", ["tape", "recompute"])
 @pytest.mark.parametrize("name", CASES)
-def test_backward_matches_reference(native_lib, name):
+def test_backward_matches_reference(native_lib, name, sweep, monkeypatch):
+    """sweep = tape: the forward records the activation tape and the tensor-core reverse sweep consumes it (where the
+    problem supports it); sweep = recompute: PSNODE_TAPE_MAX_GB=0 forces the generic recomputing sweep everywhere."""
+    from py_psnode_b200 import _native
     d = load_golden(name)
     if "gx" not in d:
         pytest.skip("fixture has no gradients")
+    if sweep == "recompute":
+        monkeypatch.setenv("PSNODE_TAPE_MAX_GB", "0")
+    else:
+        monkeypatch.delenv("PSNODE_TAPE_MAX_GB", raising=False)
     got = run_with_grads(d, name)
+    if sweep == "tape" and _tape_sweep_expected(d):
+        assert _native.last_kernel() == "psn_tc_grad_reduce_kernel", _native.last_kernel()
+    else:
+        assert _native.last_kernel() == "psn_grad_reduce_kernel", _native.last_kernel()
     rows = grad_errors(d, got)
     assert rows, "no gradient tensors compared"
     want_keys = {k[4:] for k in d if k.startswith("g64_") and d[k].size}
