@@ -119,7 +119,7 @@ int psnode_event_table(const float* t0, int64_t t_st, int32_t T, const float* ev
 int64_t psnode_tape_floats(const psnode_problem* p) {
     if (validate(p) != PSNODE_OK) return 0;
     if (p->impl != PSNODE_IMPL_AUTO && p->impl != PSNODE_IMPL_TC) return 0;
-    if (!psn_tc_supports(p)) return 0;
+    if (p->kind != PSNODE_ODE || !psn_tc_supports(p)) return 0;
     return psn_tc_tape_floats(p->B, p->T, p->method);
 }
 
@@ -152,7 +152,7 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
 int64_t psnode_backward_workspace(const psnode_problem* p, const psnode_adjoint* a) {
     if (validate(p) != PSNODE_OK || !a) return 0;
     const int64_t g = psn_generic_backward_workspace(p, a);
-    const int64_t t = psn_tc_supports(p) ? psn_tc_backward_workspace(p, a) : 0;
+    const int64_t t = (p->kind == PSNODE_ODE && psn_tc_supports(p)) ? psn_tc_backward_workspace(p, a) : 0;
     return g > t ? g : t;
 }
 

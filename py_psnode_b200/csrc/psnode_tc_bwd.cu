@@ -562,7 +562,7 @@ bool psn_tc_supports(const psnode_problem* p);
 
 // the tape-based reverse sweep covers what the scripts' ODE training step needs: parameter gradients, d_x0, d_a0
 bool psn_tc_bwd_supports(const psnode_problem* p, const psnode_adjoint* a) {
-    if (!psn_tc_supports(p) || !p->tape) return false;
+    if (p->kind != PSNODE_ODE || !psn_tc_supports(p) || !p->tape) return false;
     if (p->tape_floats < psn_tc_tape_floats(p->B, p->T, p->method)) return false;
     if (a->d_z.p || a->d_v.p || a->d_zjump || a->d_vjump || a->d_xteach.p || a->d_iteach.p) return false;
     return true;

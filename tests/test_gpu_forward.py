@@ -96,6 +96,64 @@ def test_ode_forward_tensor_core_matches_reference(native_lib, name):
     assert torch.allclose(got, want, rtol=RTOL, atol=ATOL), tol_report(got, want, want64)
 
 
+TC_DAE_CASES = ["dae01_euler_small", "dae01_midpoint_small", "dae01_rk4_small", "dae01_rk4_noevent", "dae01_rk4_inputgrads"]
+
+
+@pytest.mark.parametrize("name", TC_DAE_CASES)
+def test_dae_forward_tensor_core_matches_reference(native_lib, name):
+    """tcgen05 DAE kernel (DE net from TMEM, AE net from shared memory) against the reference's fp32 x_sol / i_sol."""
+    from py_psnode_b200 import _native
+    d = load_golden(name)
+    d["_name"] = name
+    with torch.no_grad():
+        gx, gi = run_dae_case(d, "tc")
+    assert _native.last_kernel().startswith("psn_tc_dae_kernel"), _native.last_kernel()
+    gx, gi = gx.cpu(), gi.cpu()
+    wx, wi = torch.from_numpy(d["x_sol"]), torch.from_numpy(d["i_sol"])
+    assert torch.equal(gx[0], torch.from_numpy(d["x_init"]))
+    assert torch.allclose(gx, wx, rtol=RTOL, atol=ATOL), "x: " + tol_report(gx, wx, torch.from_numpy(d["x_sol64"]))
+    assert torch.allclose(gi, wi, rtol=RTOL, atol=ATOL), "i: " + tol_report(gi, wi, torch.from_numpy(d["i_sol64"]))
+
+
+@pytest.mark.parametrize("teacher", [False, True])
+def test_dae_teacher_forcing_falls_back_to_generic(native_lib, teacher):
+    """impl="tc" with teacher forcing is refused (EUNSUPPORTED); "auto" silently takes the generic kernel."""
+    from py_psnode_b200 import _native
+    d = load_golden("dae01_rk4_tx" if teacher else "dae01_rk4_small")
+    d["_name"] = "dae01"
+    with torch.no_grad():
+        run_dae_case(d, "auto")
+    assert _native.last_kernel().startswith("psn_generic_fwd_kernel" if teacher else "psn_tc_dae_kernel")
+    if teacher:
+        with pytest.raises(RuntimeError):
+            run_dae_case(d, "tc")
+
+
+def test_dae_tensor_core_matches_generic_at_scale(native_lib):
+    """B = 5000 trajectories (ragged last group, two groups per CTA), 150 steps, one event: tensor-core DAE vs generic kernel."""
+    from py_psnode_b200 import AE_Func, DAE_Event, DE_Func, RK4
+    torch.manual_seed(5)
+    dev = "cuda:0"
+    B, N, X, Z, V, I, H = 5000, 150, 16, 1, 2, 4, 64
+    T = N + 1
+    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H, v_dim=V, i_dim=I).to(dev)
+    ae = AE_Func(x_dim=X, v_dim=V, i_dim=I, hidden_dim=H, z_dim=Z).to(dev)
+    t = (torch.arange(T, dtype=torch.float32, device=dev) * 0.01).view(T, 1, 1).repeat(1, B, 1)
+    mk = lambda w: torch.randn(T, B, w, device=dev) * 0.1
+    x, z, v, i = mk(X), mk(Z), mk(V), mk(I)
+    x_init = torch.randn(B, X, device=dev) * 0.1
+    ev = DAE_Event()
+    ev.set_event(t=t[N // 3].view(B, 1, 1).clone(), z=torch.randn(B, 1, Z, device=dev) * 0.1, v=torch.randn(B, 1, V, device=dev) * 0.1)
+    a0 = torch.cat((x_init, z[0], v[0], i[0]), dim=-1)
+    outs = {}
+    with torch.no_grad():
+        for impl in ("generic", "tc"):
+            outs[impl] = RK4(impl=impl).integrate_DAE(x_init=x_init, x_func=de, i_func=ae, t=t, x=x, z=z, v=v, i=i, all_initial=a0,
+                                                      event_fn=ev.event_fn, jump_change_fn=ev.jump_change_fn)
+    for k, nm in ((0, "x"), (1, "i")):
+        assert torch.allclose(outs["tc"][k], outs["generic"][k], rtol=RTOL, atol=ATOL), nm + ": " + tol_report(outs["tc"][k].cpu(), outs["generic"][k].cpu())
+
+
 def test_tensor_core_matches_fused_at_scale(native_lib):
     """B = 5000 trajectories (ragged last group, two groups per CTA), 200 steps: tensor-core vs CUDA-core fused kernel."""
     from py_psnode_b200 import DE_Func, ODE_Event, RK4
