@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused", "tc"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused", "tc", "tc8"])
     ap.add_argument("--cpu-sample-steps", type=int, default=200)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -322,7 +322,7 @@ def main():
         def train_step():
             return parallel.sharded_training_step(lambda: call_integrate(w, solver, de, ae, resident), plist, bucket, numden)
 
-        for _ in range(2):
+        for _ in range(max(args.warmup, 3)):
             train_step()
         bwd_kernel = _native.last_kernel()
         barrier()
@@ -361,16 +361,17 @@ def main():
         hbm = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                "traffic": traffic, "peak_source": peak_src,
                "note": "algorithmic (compulsory) bytes per traj-step x units / kernel time; the path is ~1300 FLOP/byte, i.e. compute/latency bound"}
-        if kernel_name.startswith("psn_tc_"):
+        if kernel_name.startswith("psn_tc"):
             tc_peak = peaks.get("bf16_tflops", 1590.0)
             tc_src = ("measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" if "bf16_tflops" in peaks
                       else "fallback 1590 TFLOP/s dense bf16 (B200_PROFILING.md)")
             roofline = {"bound": "tensor", "achieved": tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": tflops / tc_peak,
                         "traffic": traffic, "peak_source": tc_src,
-                        "note": "achieved = algorithmic FLOPs of the reference formulation (101376 per traj-step at cfg2) / kernel time. The kernel "
-                                "runs tcgen05 kind::tf32 (dense peak = half the bf16 figure) and needs 3 MMAs per product (3xTF32) to hold the "
-                                "reference's fp32 accuracy, with N = 16 trajectories per MMA (4096 trajectories / 148 SMs): it is bound by the "
-                                "serial layer chain (16000 dependent layers per trajectory), not by tensor throughput"}
+                        "note": f"achieved = algorithmic FLOPs of the reference formulation ({w['flop_per_unit']} per traj-step at "
+                                f"{args.workload}) / kernel time. The kernel runs tcgen05 kind::tf32 (dense peak = half the bf16 figure) and "
+                                "needs 3 MMAs per product (3xTF32) to hold the reference's fp32 accuracy, with N = 16 trajectories per MMA "
+                                "(4096 trajectories / 148 SMs): it is bound by the serial layer chain (>= 16000 dependent layers per "
+                                "trajectory), not by tensor throughput"}
         else:
             roofline = hbm
         line = {

@@ -118,7 +118,7 @@ int psnode_event_table(const float* t0, int64_t t_st, int32_t T, const float* ev
 
 int64_t psnode_tape_floats(const psnode_problem* p) {
     if (validate(p) != PSNODE_OK) return 0;
-    if (p->impl != PSNODE_IMPL_AUTO && p->impl != PSNODE_IMPL_TC) return 0;
+    if (p->impl != PSNODE_IMPL_AUTO && p->impl != PSNODE_IMPL_TC && p->impl != PSNODE_IMPL_TC8) return 0;
     if (p->kind != PSNODE_ODE || !psn_tc_supports(p)) return 0;
     return psn_tc_tape_floats(p->B, p->T, p->method);
 }
@@ -140,11 +140,15 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
         if (!psn_tc_supports(p)) return PSNODE_EUNSUPPORTED;
         return psn_tc_forward(p, workspace, workspace_bytes, s);
     }
+    if (p->impl == PSNODE_IMPL_TC8) {
+        if (!psn_tc_supports(p)) return PSNODE_EUNSUPPORTED;
+        return psn_tc8_forward(p, workspace, workspace_bytes, s);
+    }
     if (p->impl == PSNODE_IMPL_FUSED) {
         if (!psn_fused_supports(p)) return PSNODE_EUNSUPPORTED;
         return psn_fused_forward(p, workspace, workspace_bytes, s);
     }
-    if (p->impl == PSNODE_IMPL_AUTO && psn_tc_supports(p)) return psn_tc_forward(p, workspace, workspace_bytes, s);
+    if (p->impl == PSNODE_IMPL_AUTO && psn_tc_supports(p)) return psn_tc8_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_fused_supports(p)) return psn_fused_forward(p, workspace, workspace_bytes, s);
     return psn_generic_forward(p, workspace, workspace_bytes, s);
 }
@@ -161,7 +165,7 @@ int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* work
     const int st = validate(p);
     if (st != PSNODE_OK) return st;
     if (!a || !a->d_theta) return PSNODE_EINVAL;
-    if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC) && psn_tc_bwd_supports(p, a))
+    if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC || p->impl == PSNODE_IMPL_TC8) && psn_tc_bwd_supports(p, a))
         return psn_tc_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     return psn_generic_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }

@@ -186,6 +186,35 @@ def _tape_budget_bytes(device: torch.device) -> int:
     return int(0.6 * (free + reusable))
 
 
+_tape_pool = {}      # device index -> idle tape buffer (one per device; a second concurrent call allocates its own)
+
+
+def _take_tape(device: torch.device, n_floats: int) -> torch.Tensor:
+    """Lease a tape buffer: the idle pooled one if it is large enough, else a fresh allocation (13.6 GB at cfg2 -- not
+    something to hand back to the caching allocator and re-request every optimiser step)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    buf = _tape_pool.pop(key, None)
+    if buf is None or buf.numel() < n_floats:
+        buf = None                      # drop the smaller buffer before asking for the larger one
+        buf = torch.empty(n_floats, dtype=torch.float32, device=device)
+    return buf
+
+
+def _give_tape(buf: Optional[torch.Tensor]) -> None:
+    """Return a leased tape buffer after the reverse sweep consumed it (stream order keeps the next forward behind it)."""
+    if buf is None:
+        return
+    key = buf.device.index
+    old = _tape_pool.get(key)
+    if old is None or old.numel() < buf.numel():
+        _tape_pool[key] = buf
+
+
+def release_tape_pool() -> None:
+    """Free the pooled tape buffers (e.g. before an evaluation phase that needs the memory)."""
+    _tape_pool.clear()
+
+
 def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]], want_tape: bool = False):
     """Run the forward kernel; returns time-major contiguous (x_sol, i_sol) -- and, with `want_tape`, the activation tape
     the tensor-core reverse sweep consumes (None when the problem has no tape-based sweep or the tape would not fit)."""
@@ -201,9 +230,12 @@ def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]], want_tape: 
         tape = None
         if want_tape:
             n_tape = int(L.psnode_tape_floats(C.byref(p)))
-            if 0 < n_tape * 4 <= _tape_budget_bytes(t.device):
-                tape = torch.empty(n_tape, dtype=torch.float32, device=t.device)
-                p.tape, p.tape_floats = tape.data_ptr(), n_tape
+            key = t.device.index if t.device.index is not None else torch.cuda.current_device()
+            pooled = _tape_pool.get(key)
+            if n_tape > 0 and ((pooled is not None and pooled.numel() >= n_tape and os.environ.get("PSNODE_TAPE_MAX_GB") is None)
+                               or n_tape * 4 <= _tape_budget_bytes(t.device)):
+                tape = _take_tape(t.device, n_tape)
+                p.tape, p.tape_floats = tape.data_ptr(), tape.numel()
         ws = _workspace(t.device, L.psnode_forward_workspace(C.byref(p)))
         stream = torch.cuda.current_stream(t.device).cuda_stream
         N.check(L.psnode_forward(C.byref(p), ws.data_ptr(), ws.numel(), stream), "psnode_forward")
@@ -245,6 +277,7 @@ class _Integrate(torch.autograd.Function):
         i_sol = next(it) if cfg.kind == N.DAE else None
         tape, ctx.tape = ctx.tape, None
         grads = backward_raw(cfg, tens, x_sol, i_sol, gx, gi if cfg.kind == N.DAE else None, ctx.needs_input_grad[1:], tape)
+        _give_tape(tape)
         return (None, *grads)
 
 

@@ -81,15 +81,17 @@ TC_CASES = ["ode01_rk4_small", "ode01_midpoint_small", "ode01_rk4_noevent", "ode
             "ode01_rk4_long"]
 
 
+@pytest.mark.parametrize("impl", ["tc", "tc8"])
 @pytest.mark.parametrize("name", TC_CASES)
-def test_ode_forward_tensor_core_matches_reference(native_lib, name):
-    """tcgen05 3xTF32 kernel (impl="tc") against the reference's fp32 output at the same rtol=1e-5 / atol=1e-6."""
+def test_ode_forward_tensor_core_matches_reference(native_lib, name, impl):
+    """tcgen05 3xTF32 kernels (impl="tc": 4 warps per group, "tc8": 8 warps per group) against the reference's fp32 output
+    at the same rtol=1e-5 / atol=1e-6."""
     from py_psnode_b200 import _native
     d = load_golden(name)
     d["_name"] = name
     with torch.no_grad():
-        got = run_ode_case(d, "tc").cpu()
-    assert _native.last_kernel().startswith("psn_tc_ode_kernel")
+        got = run_ode_case(d, impl).cpu()
+    assert _native.last_kernel().startswith(f"psn_{impl}_ode_kernel")
     want = torch.from_numpy(d["x_sol"])
     want64 = torch.from_numpy(d["x_sol64"])
     assert torch.equal(got[0], want[0])
@@ -99,15 +101,16 @@ def test_ode_forward_tensor_core_matches_reference(native_lib, name):
 TC_DAE_CASES = ["dae01_euler_small", "dae01_midpoint_small", "dae01_rk4_small", "dae01_rk4_noevent", "dae01_rk4_inputgrads"]
 
 
+@pytest.mark.parametrize("impl", ["tc", "tc8"])
 @pytest.mark.parametrize("name", TC_DAE_CASES)
-def test_dae_forward_tensor_core_matches_reference(native_lib, name):
-    """tcgen05 DAE kernel (DE net from TMEM, AE net from shared memory) against the reference's fp32 x_sol / i_sol."""
+def test_dae_forward_tensor_core_matches_reference(native_lib, name, impl):
+    """tcgen05 DAE kernels (DE net from TMEM, AE net from shared memory) against the reference's fp32 x_sol / i_sol."""
     from py_psnode_b200 import _native
     d = load_golden(name)
     d["_name"] = name
     with torch.no_grad():
-        gx, gi = run_dae_case(d, "tc")
-    assert _native.last_kernel().startswith("psn_tc_dae_kernel"), _native.last_kernel()
+        gx, gi = run_dae_case(d, impl)
+    assert _native.last_kernel().startswith(f"psn_{impl}_dae_kernel"), _native.last_kernel()
     gx, gi = gx.cpu(), gi.cpu()
     wx, wi = torch.from_numpy(d["x_sol"]), torch.from_numpy(d["i_sol"])
     assert torch.equal(gx[0], torch.from_numpy(d["x_init"]))
@@ -123,7 +126,7 @@ def test_dae_teacher_forcing_falls_back_to_generic(native_lib, teacher):
     d["_name"] = "dae01"
     with torch.no_grad():
         run_dae_case(d, "auto")
-    assert _native.last_kernel().startswith("psn_generic_fwd_kernel" if teacher else "psn_tc_dae_kernel")
+    assert _native.last_kernel().startswith("psn_generic_fwd_kernel" if teacher else "psn_tc8_dae_kernel")
     if teacher:
         with pytest.raises(RuntimeError):
             run_dae_case(d, "tc")
@@ -147,11 +150,13 @@ def test_dae_tensor_core_matches_generic_at_scale(native_lib):
     a0 = torch.cat((x_init, z[0], v[0], i[0]), dim=-1)
     outs = {}
     with torch.no_grad():
-        for impl in ("generic", "tc"):
+        for impl in ("generic", "tc", "tc8"):
             outs[impl] = RK4(impl=impl).integrate_DAE(x_init=x_init, x_func=de, i_func=ae, t=t, x=x, z=z, v=v, i=i, all_initial=a0,
                                                       event_fn=ev.event_fn, jump_change_fn=ev.jump_change_fn)
-    for k, nm in ((0, "x"), (1, "i")):
-        assert torch.allclose(outs["tc"][k], outs["generic"][k], rtol=RTOL, atol=ATOL), nm + ": " + tol_report(outs["tc"][k].cpu(), outs["generic"][k].cpu())
+    for impl in ("tc", "tc8"):
+        for k, nm in ((0, "x"), (1, "i")):
+            assert torch.allclose(outs[impl][k], outs["generic"][k], rtol=RTOL, atol=ATOL), \
+                f"{impl} {nm}: " + tol_report(outs[impl][k].cpu(), outs["generic"][k].cpu())
 
 
 def test_tensor_core_matches_fused_at_scale(native_lib):
@@ -170,10 +175,12 @@ def test_tensor_core_matches_fused_at_scale(native_lib):
     a0 = torch.cat((x[0], z[0]), dim=-1)
     outs = {}
     with torch.no_grad():
-        for impl in ("fused", "tc"):
+        for impl in ("fused", "tc", "tc8"):
             outs[impl] = RK4(impl=impl).integrate_ODE(x_func=de, t=t, x=x, z=z, all_initial=a0, event_fn=ev.event_fn,
                                                       jump_change_fn=ev.jump_change_fn)
     assert torch.allclose(outs["tc"], outs["fused"], rtol=RTOL, atol=ATOL), tol_report(outs["tc"].cpu(), outs["fused"].cpu())
+    assert torch.allclose(outs["tc8"], outs["fused"], rtol=RTOL, atol=ATOL), tol_report(outs["tc8"].cpu(), outs["fused"].cpu())
+    assert torch.equal(outs["tc8"], outs["tc"]), "tc and tc8 run the same arithmetic in the same order"
 
 
 @pytest.mark.parametrize("pinned", [False, True])
