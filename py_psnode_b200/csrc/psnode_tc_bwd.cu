@@ -11,9 +11,14 @@
 //     g2 = W3^T d3            d2 = g2 * elu'(a2)        dW3   += d3 a2^T        db3 += d3
 //     g1 = W2^T d2            d1 = g1 * elu'(a1)        dW2   += d2 a1^T        db2 += d2
 //     gy = (Wb+Wc)_x^T d1                               dW1f  += d1 [y;u]^T     D1  += d1   (per trajectory)
-//   * data path (left column): the TRANSPOSED weights are the A operand (M = 64) in shared memory, the 16-row delta tile is the
-//     B operand; 24 MMAs per layer issued by the 4 warps of the group in parallel into 4 partial accumulators, exactly like
-//     the forward kernel.  (Wb+Wc)_x^T (16 rows) is replicated into every 16-row block so each warp receives the whole
+//   * data path (left column): the TRANSPOSED weights are the A operand (M = 64), resident in TMEM for the whole kernel like
+//     the forward kernel's (W3^T, W2^T, (Wb+Wc)_x^T, hi + lo: 384 columns; W4^T, K = 16, stays in shared memory), the 16-row
+//     delta tile is the B operand; 24 MMAs per layer issued by the 4 warps of the group in parallel into 4 partial
+//     accumulators.  With the weights in shared memory the kernel was bound by the operand fetch (2 KB of A per MMA:
+//     1300 of 2330 cycles per layer pair, profiles/r01_ncu_tc_bwd_cfg2.txt).
+//   * TMEM plan: an M = 64 operand or accumulator occupies only 16 of the 32 lanes of each sub-partition.  The data path
+//     (TS MMAs: A and D must sit at the same lanes) uses lanes 0..15: 128 accumulator + 384 weight columns = all 512.  The
+//     weight-gradient accumulators (SS MMAs) live in lanes 16..31 of the same columns: 2 x 176.  (Wb+Wc)_x^T (16 rows) is replicated into every 16-row block so each warp receives the whole
 //     dL/dy tile and handles two state elements per thread: the Runge-Kutta adjoint algebra stays in registers.
 //   * weight gradients (right column): one MMA chain per layer with K = the 16 trajectories (A = delta tile [m][n],
 //     B = activation tile [k][n], N = 64), accumulated in TMEM over ALL stages and steps of the launch: 176 columns per group
@@ -41,11 +46,14 @@ constexpr int LBO = 144;               // delta tile as B operand of the data MM
 constexpr int SBO_ACT = (TH / 4) * LBO;
 constexpr int ACT_TILE = (TN / 8) * SBO_ACT;
 constexpr int LBO_W = 128;             // every other tile: contiguous 8 x 16 B core matrices
-constexpr int SBO_W64 = (TH / 4) * LBO_W, W64_TILE = (TH / 8) * SBO_W64;     // 64 rows x K = 64   (16 KB)
+
 constexpr int SBO_K16 = (TN / 4) * LBO_W, K16_TILE = (TH / 8) * SBO_K16;     // 64 rows x K = 16   ( 4 KB)
 constexpr int DKB_TILE = (TX / 8) * SBO_K16;                                 // 16 rows x K = 16   ( 1 KB)
 // TMEM columns of one group
-constexpr int TM_ACC = 0, TM_DW2 = 64, TM_DW3 = 128, TM_DW4T = 192, TM_DW1F = 208, TM_GROUP = 240;
+constexpr int TM_ACC = 0;                                       // lanes 0..15: 2 groups x 4 partial accumulators x 16
+constexpr int TM_W3T = 128, TM_W2T = 256, TM_W1T = 384;         // lanes 0..15: resident transposed weights, hi at +0, lo at +64
+constexpr uint32_t TM_UPPER = 16u << 16;                        // lanes 16..31 of every sub-partition
+constexpr int TM_DW2 = 0, TM_DW3 = 64, TM_DW4T = 128, TM_DW1F = 144, TM_DWGROUP = 176;   // per group, upper half-lanes
 constexpr int TM_COLS = 512;
 constexpr int GROUP_THREADS = 128;
 constexpr int PSN_DW_FLUSH = 4;        // steps between two flushes of the TMEM weight-gradient accumulators
@@ -78,9 +86,6 @@ struct __align__(128) BwdGroupSmem {
 };
 
 struct __align__(128) BwdCtaSmem {
-    unsigned char w3t_hi[W64_TILE], w3t_lo[W64_TILE];     // A[k][m] = W3[m][k]
-    unsigned char w2t_hi[W64_TILE], w2t_lo[W64_TILE];
-    unsigned char w1t_hi[W64_TILE], w1t_lo[W64_TILE];     // A[r][m] = (Wb+Wc)[m][r & 15]  (x columns, replicated 4 times)
     unsigned char w4t_hi[K16_TILE], w4t_lo[K16_TILE];     // A[k][m] = W4[m][k], K = 16
     BwdGroupSmem g[2];
     uint32_t tmem_base;
@@ -110,18 +115,6 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     // ---- one-time setup -------------------------------------------------------------------------------
     if (tid == 0) { mbar_init(&sm.g[0].bar, 4); mbar_init(&sm.g[1].bar, 4); fence_mbar_init(); }
     if ((tid >> 5) == 0) tmem_alloc(&sm.tmem_base, TM_COLS);
-    for (int e = tid; e < TH * TH; e += 2 * GROUP_THREADS) {       // e = m * 64 + k (coalesced reads)
-        const int m = e >> 6, k = e & 63;
-        float hi, lo;
-        const int o = tile_byte(k, m, LBO_W, SBO_W64);
-        split_tf32(__ldg(q.W3 + e), hi, lo); st_f32(sm.w3t_hi, o, hi); st_f32(sm.w3t_lo, o, lo);
-        split_tf32(__ldg(q.W2 + e), hi, lo); st_f32(sm.w2t_hi, o, hi); st_f32(sm.w2t_lo, o, lo);
-        // replicated transposed folded layer 1: row r = e >> 6, K index m1 = e & 63
-        const int r = m, m1 = k, c = r & 15;
-        split_tf32(__ldg(q.W1 + m1 * K1 + S + c) + __ldg(q.W1 + m1 * K1 + 2 * S + c), hi, lo);
-        const int o1 = tile_byte(r, m1, LBO_W, SBO_W64);
-        st_f32(sm.w1t_hi, o1, hi); st_f32(sm.w1t_lo, o1, lo);
-    }
     for (int e = tid; e < TX * TH; e += 2 * GROUP_THREADS) {       // e = m * 64 + k, m < 16
         const int m = e >> 6, k = e & 63;
         float hi, lo;
@@ -136,7 +129,33 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
     const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
-    const uint32_t tm_g = tmem + (uint32_t)(g * TM_GROUP);
+    const uint32_t tm_dw = tmem + TM_UPPER + (uint32_t)(g * TM_DWGROUP);     // this group's weight-gradient accumulators
+    // resident transposed weights -> TMEM lanes 0..15 (group 0 writes; read through the tensor core only):
+    //   A[k][m] = W3[m][k], W2[m][k];  A[r][m] = (Wb+Wc)[m][r & 15]  (x columns of the folded layer 1, replicated 4 times)
+    if (g == 0) {
+        const int r0 = 16 * warp + (lane >> 2), cc0 = 2 * (lane & 3);
+        for (int half = 0; half < 2; half++) {
+            for (int cb = 0; cb < 4; cb++) {
+                float w3[8], w2[8], w1[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int row = r0 + ((i >> 1) & 1) * 8, col = 16 * cb + cc0 + (i & 1) + (i >> 2) * 8;   // A[row][col]
+                    float hi, lo;
+                    split_tf32(__ldg(q.W3 + col * TH + row), hi, lo); w3[i] = half ? lo : hi;
+                    split_tf32(__ldg(q.W2 + col * TH + row), hi, lo); w2[i] = half ? lo : hi;
+                    split_tf32(__ldg(q.W1 + col * K1 + S + (row & 15)) + __ldg(q.W1 + col * K1 + 2 * S + (row & 15)), hi, lo);
+                    w1[i] = half ? lo : hi;
+                }
+                tmem_st_16x256b_x2(tmem + lane_base + TM_W3T + 64 * half + 16 * cb, w3);
+                tmem_st_16x256b_x2(tmem + lane_base + TM_W2T + 64 * half + 16 * cb, w2);
+                tmem_st_16x256b_x2(tmem + lane_base + TM_W1T + 64 * half + 16 * cb, w1);
+            }
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     // fragment maps (as in the forward kernel): element i <-> (row m0 + 8*((i>>1)&1), trajectory c0 + (i&1) + 8*(i>>2))
     const int m0 = 16 * warp + (lane >> 2), c0 = 2 * (lane & 3);
     auto frag_row = [&](int i) { return m0 + ((i >> 1) & 1) * 8; };
@@ -155,32 +174,29 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     // descriptors
     const uint32_t idesc16 = make_idesc_tf32(TH, TN), idesc24 = make_idesc_tf32(TH, TK1), idesc64 = make_idesc_tf32(TH, TH);
     const uint64_t d_dT_hi = make_desc(smem_u32(gs.dT_hi), LBO, SBO_ACT), d_dT_lo = make_desc(smem_u32(gs.dT_lo), LBO, SBO_ACT);
-    const uint64_t d_w3t_hi = make_desc(smem_u32(sm.w3t_hi), LBO_W, SBO_W64), d_w3t_lo = make_desc(smem_u32(sm.w3t_lo), LBO_W, SBO_W64);
-    const uint64_t d_w2t_hi = make_desc(smem_u32(sm.w2t_hi), LBO_W, SBO_W64), d_w2t_lo = make_desc(smem_u32(sm.w2t_lo), LBO_W, SBO_W64);
-    const uint64_t d_w1t_hi = make_desc(smem_u32(sm.w1t_hi), LBO_W, SBO_W64), d_w1t_lo = make_desc(smem_u32(sm.w1t_lo), LBO_W, SBO_W64);
     const uint64_t d_w4t_hi = make_desc(smem_u32(sm.w4t_hi), LBO_W, SBO_K16), d_w4t_lo = make_desc(smem_u32(sm.w4t_lo), LBO_W, SBO_K16);
     const uint64_t d_dA_hi0 = make_desc(smem_u32(gs.dA_hi[0]), LBO_W, SBO_K16), d_dA_lo0 = make_desc(smem_u32(gs.dA_lo[0]), LBO_W, SBO_K16);
     const uint64_t d_dA_hi1 = make_desc(smem_u32(gs.dA_hi[1]), LBO_W, SBO_K16), d_dA_lo1 = make_desc(smem_u32(gs.dA_lo[1]), LBO_W, SBO_K16);
     const uint64_t d_aB_hi0 = make_desc(smem_u32(gs.aB_hi[0]), LBO_W, SBO_K16), d_aB_lo0 = make_desc(smem_u32(gs.aB_lo[0]), LBO_W, SBO_K16);
     const uint64_t d_aB_hi1 = make_desc(smem_u32(gs.aB_hi[1]), LBO_W, SBO_K16), d_aB_lo1 = make_desc(smem_u32(gs.aB_lo[1]), LBO_W, SBO_K16);
     const uint64_t d_dkB_hi = make_desc(smem_u32(gs.dkB_hi), LBO_W, SBO_K16), d_dkB_lo = make_desc(smem_u32(gs.dkB_lo), LBO_W, SBO_K16);
-    const uint32_t acc_base = tm_g + TM_ACC;
+    const uint32_t acc_base = tmem + TM_ACC + (uint32_t)(g * 4) * TN;
     const uint32_t my_acc = acc_base + (uint32_t)warp * TN;
     constexpr uint64_t KSTEP_B = (uint64_t)((2 * LBO) >> 4), KSTEP_W = (uint64_t)((2 * LBO_W) >> 4);
     uint32_t phase = 0;
 
     // ---- helpers ---------------------------------------------------------------------------------------
     // data MMA with K = 64: this warp's two K-steps for the three 3xTF32 terms (small terms first), then commit
-    auto issue_data = [&](uint64_t a_hi, uint64_t a_lo) {
+    auto issue_data = [&](uint32_t w_tm) {          // w_tm: TMEM column of the resident operand (hi; lo at +64)
         if (elect_one()) {
             tc_fence_after();
             uint32_t accumulate = 0;
             for (int term = 0; term < 3; term++) {
-                const uint64_t ad = term == 0 ? a_lo : a_hi;
+                const uint32_t wa = term == 0 ? w_tm + 64 : w_tm;
                 const uint64_t bd = term == 1 ? d_dT_lo : d_dT_hi;
                 for (int kk = 0; kk < 2; kk++) {
                     const int ks = 2 * warp + kk;
-                    mma_tf32(my_acc, ad + KSTEP_W * ks, bd + KSTEP_B * ks, idesc16, accumulate);
+                    mma_tf32_ts(my_acc, tmem + wa + 8 * ks, bd + KSTEP_B * ks, idesc16, accumulate);
                     accumulate = 1;
                 }
             }
@@ -315,21 +331,21 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
             *reinterpret_cast<float2*>(dst) = o;
         };
         for (int cb = 0; cb < 4; cb++) {
-            tmem_ld_16x256b_x2(tm_g + lane_base + TM_DW2 + 16 * cb, v);
+            tmem_ld_16x256b_x2(tm_dw + lane_base + TM_DW2 + 16 * cb, v);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 8; i += 2) add2(sl + oW2 + frag_row(i) * TH + 16 * cb + frag_col(i), v[i], v[i + 1]);
-            tmem_ld_16x256b_x2(tm_g + lane_base + TM_DW3 + 16 * cb, v);
+            tmem_ld_16x256b_x2(tm_dw + lane_base + TM_DW3 + 16 * cb, v);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 8; i += 2) add2(sl + oW3 + frag_row(i) * TH + 16 * cb + frag_col(i), v[i], v[i + 1]);
         }
-        tmem_ld_16x256b_x2(tm_g + lane_base + TM_DW4T, v);          // rows = hidden k, columns = output m
+        tmem_ld_16x256b_x2(tm_dw + lane_base + TM_DW4T, v);          // rows = hidden k, columns = output m
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; i++) sl[oW4 + frag_col(i) * TH + frag_row(i)] += v[i];
         for (int cb = 0; cb < 2; cb++) {
-            tmem_ld_16x256b_x2(tm_g + lane_base + TM_DW1F + 16 * cb, v);
+            tmem_ld_16x256b_x2(tm_dw + lane_base + TM_DW1F + 16 * cb, v);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
@@ -401,23 +417,23 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
                 store_pairs(gs.aB_hi[0], gs.aB_lo[0], a3);
                 publish();
                 issue_m1();
-                if (warp == 0) issue_dw(d_aB_hi0, d_aB_lo0, d_dkB_hi, d_dkB_lo, tm_g + TM_DW4T, idesc16, fresh);
+                if (warp == 0) issue_dw(d_aB_hi0, d_aB_lo0, d_dkB_hi, d_dkB_lo, tm_dw + TM_DW4T, idesc16, fresh);
                 // ---- P1: d3 ; a2 -> aB[1]; g2 = W3^T d3 ; dW3 += d3 a2^T ----
                 collect(gsum);
                 make_delta(gsum, a3, dB3, gs.dA_hi[1], gs.dA_lo[1]);
                 store_pairs(gs.aB_hi[1], gs.aB_lo[1], a2);
                 if (has_next) ld_frag(tpn + 2 * PSN_TAPE_FRAG, a3);
                 publish();
-                issue_data(d_w3t_hi, d_w3t_lo);
-                if (warp == 1) issue_dw(d_dA_hi1, d_dA_lo1, d_aB_hi1, d_aB_lo1, tm_g + TM_DW3, idesc64, fresh);
+                issue_data(TM_W3T);
+                if (warp == 1) issue_dw(d_dA_hi1, d_dA_lo1, d_aB_hi1, d_aB_lo1, tm_dw + TM_DW3, idesc64, fresh);
                 // ---- P2: d2 ; a1 -> aB[0]; g1 = W2^T d2 ; dW2 += d2 a1^T ----
                 collect(gsum);
                 make_delta(gsum, a2, dB2, gs.dA_hi[0], gs.dA_lo[0]);
                 store_pairs(gs.aB_hi[0], gs.aB_lo[0], a1);
                 if (has_next) ld_frag(tpn + PSN_TAPE_FRAG, a2);
                 publish();
-                issue_data(d_w2t_hi, d_w2t_lo);
-                if (warp == 2) issue_dw(d_dA_hi0, d_dA_lo0, d_aB_hi0, d_aB_lo0, tm_g + TM_DW2, idesc64, fresh);
+                issue_data(TM_W2T);
+                if (warp == 2) issue_dw(d_dA_hi0, d_dA_lo0, d_aB_hi0, d_aB_lo0, tm_dw + TM_DW2, idesc64, fresh);
                 // ---- P3: d1 ; [y; u] -> aB[1] rows 0..23; gy = (Wb+Wc)_x^T d1 ; dW1f += d1 [y;u]^T ----
                 collect(gsum);
                 make_delta(gsum, a1, D1, gs.dA_hi[1], gs.dA_lo[1]);
@@ -442,8 +458,8 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
                     yv[0] = y2.x; yv[1] = y2.y;
                 }
                 publish();
-                issue_data(d_w1t_hi, d_w1t_lo);
-                if (warp == 3) issue_dw(d_dA_hi1, d_dA_lo1, d_aB_hi1, d_aB_lo1, tm_g + TM_DW1F, idesc24, fresh);
+                issue_data(TM_W1T);
+                if (warp == 3) issue_dw(d_dA_hi1, d_dA_lo1, d_aB_hi1, d_aB_lo1, tm_dw + TM_DW1F, idesc24, fresh);
                 // ---- P4: dL/dy of this stage -> Runge-Kutta adjoint algebra (my_fixed_grid.py:15-59 reversed) ----
                 float gy[2];
                 collect_gy(gy);
