@@ -55,7 +55,7 @@ constexpr int TM_W3T = 128, TM_W2T = 256, TM_W1T = 384;         // lanes 0..15: 
 constexpr uint32_t TM_UPPER = 16u << 16;                        // lanes 16..31 of every sub-partition
 constexpr int TM_DW2 = 0, TM_DW3 = 64, TM_DW4T = 128, TM_DW1F = 144, TM_DWGROUP = 176;   // per group, upper half-lanes
 constexpr int TM_COLS = 512;
-constexpr int GROUP_THREADS = 128;
+constexpr int GROUP_THREADS = 256;     // 8 warps per 16-trajectory group: warps k and k + 4 share TMEM sub-partition k
 constexpr int PSN_DW_FLUSH = 4;        // steps between two flushes of the TMEM weight-gradient accumulators
 constexpr int G_AREA = TH * TK1;       // floats of the dW1f (folded layer 1) accumulator kept behind each group's slab
 
@@ -104,8 +104,10 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     extern __shared__ unsigned char smem_raw[];
     BwdCtaSmem& sm = *reinterpret_cast<BwdCtaSmem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x;
-    const int g = tid >> 7, gt = tid & 127;
-    const int warp = gt >> 5, lane = gt & 31;     // warp within the group == TMEM sub-partition
+    const int g = tid >> 8, gt = tid & 255;
+    const int wk = gt >> 5, lane = gt & 31;       // warp within the group
+    const int wq = wk & 3, h = wk >> 2;           // TMEM sub-partition (== CTA warp index % 4), trajectory-column half
+    const bool issuer = h == 0;                   // warps 0..3 issue the MMAs (4 partial accumulators)
     BwdGroupSmem& gs = sm.g[g];
     const int B = q.B, T = q.T, Z = q.Z, S = q.S, K1 = 3 * q.S;
     const int gid = blockIdx.x * q.groups + g;
@@ -128,12 +130,12 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
-    const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+    const uint32_t lane_base = (uint32_t)(32 * wq) << 16;
     const uint32_t tm_dw = tmem + TM_UPPER + (uint32_t)(g * TM_DWGROUP);     // this group's weight-gradient accumulators
-    // resident transposed weights -> TMEM lanes 0..15 (group 0 writes; read through the tensor core only):
+    // resident transposed weights -> TMEM lanes 0..15 (warps 0..3 of group 0 write; read through the tensor core only):
     //   A[k][m] = W3[m][k], W2[m][k];  A[r][m] = (Wb+Wc)[m][r & 15]  (x columns of the folded layer 1, replicated 4 times)
-    if (g == 0) {
-        const int r0 = 16 * warp + (lane >> 2), cc0 = 2 * (lane & 3);
+    if (g == 0 && issuer) {
+        const int r0 = 16 * wq + (lane >> 2), cc0 = 2 * (lane & 3);
         for (int half = 0; half < 2; half++) {
             for (int cb = 0; cb < 4; cb++) {
                 float w3[8], w2[8], w1[8];
@@ -156,20 +158,21 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // fragment maps (as in the forward kernel): element i <-> (row m0 + 8*((i>>1)&1), trajectory c0 + (i&1) + 8*(i>>2))
-    const int m0 = 16 * warp + (lane >> 2), c0 = 2 * (lane & 3);
-    auto frag_row = [&](int i) { return m0 + ((i >> 1) & 1) * 8; };
-    auto frag_col = [&](int i) { return c0 + (i & 1) + (i >> 2) * 8; };
-    int off_act[8];      // delta tile [n][m]
+    // fragment maps (as in the tc8 forward kernel): element i (0..3) <-> (row m0 + 8*(i>>1), trajectory 8h + c0 + (i&1))
+    const int m0 = 16 * wq + (lane >> 2), c0 = 2 * (lane & 3);
+    auto frag_row = [&](int i) { return m0 + (i >> 1) * 8; };
+    auto frag_col = [&](int i) { return 8 * h + c0 + (i & 1); };
+    int off_act[4];      // delta tile [n][m]
 #pragma unroll
-    for (int i = 0; i < 8; i++) off_act[i] = tile_byte(frag_col(i), frag_row(i), LBO, SBO_ACT);
-    int off2[4];         // [m][n] tiles: pair p = elements (ia, ia + 1), ia = 2*(p&1) + 4*(p>>1)
-#pragma unroll
-    for (int p = 0; p < 4; p++) off2[p] = tile_byte(m0 + 8 * (p & 1), c0 + 8 * (p >> 1), LBO_W, SBO_K16);
-    // the two state elements this thread owns in the stage algebra: states sm0, sm0 + 8 of trajectory column sn
-    const int sm0 = lane >> 2, sn = c0 + (warp & 1) + 8 * (warp >> 1);
-    const int off_dk[2] = {(int)tile_byte(sn, sm0, LBO, SBO_ACT), (int)tile_byte(sn, sm0 + 8, LBO, SBO_ACT)};
-    const int off_sq[2] = {(int)tile_byte(sm0, sn, LBO_W, SBO_K16), (int)tile_byte(sm0 + 8, sn, LBO_W, SBO_K16)};   // [state][n]
+    for (int i = 0; i < 4; i++) off_act[i] = tile_byte(frag_col(i), frag_row(i), LBO, SBO_ACT);
+    // [m][n] tiles: pair p = elements (2p, 2p + 1) = row m0 + 8p, trajectories 8h + c0, 8h + c0 + 1
+    const int off2[2] = {(int)tile_byte(m0, 8 * h + c0, LBO_W, SBO_K16), (int)tile_byte(m0 + 8, 8 * h + c0, LBO_W, SBO_K16)};
+    // the state element this thread owns in the stage algebra: state srow of trajectory column sn
+    const int srow = (lane >> 2) + 8 * h, sn = c0 + (wq & 1) + 8 * (wq >> 1);
+    const int off_dk = (int)tile_byte(sn, srow, LBO, SBO_ACT);
+    const int off_sq = (int)tile_byte(srow, sn, LBO_W, SBO_K16);   // [state][n]
+    const int ftape = (32 * wq + lane) * 8 + 4 * h;                // this thread's 4 floats of a tape fragment block
+    const int ytape = 3 * PSN_TAPE_FRAG + (32 * wq + lane) * 2 + h;
 
     // descriptors
     const uint32_t idesc16 = make_idesc_tf32(TH, TN), idesc24 = make_idesc_tf32(TH, TK1), idesc64 = make_idesc_tf32(TH, TH);
@@ -181,44 +184,48 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     const uint64_t d_aB_hi1 = make_desc(smem_u32(gs.aB_hi[1]), LBO_W, SBO_K16), d_aB_lo1 = make_desc(smem_u32(gs.aB_lo[1]), LBO_W, SBO_K16);
     const uint64_t d_dkB_hi = make_desc(smem_u32(gs.dkB_hi), LBO_W, SBO_K16), d_dkB_lo = make_desc(smem_u32(gs.dkB_lo), LBO_W, SBO_K16);
     const uint32_t acc_base = tmem + TM_ACC + (uint32_t)(g * 4) * TN;
-    const uint32_t my_acc = acc_base + (uint32_t)warp * TN;
+    const uint32_t my_acc = acc_base + (uint32_t)wq * TN;
     constexpr uint64_t KSTEP_B = (uint64_t)((2 * LBO) >> 4), KSTEP_W = (uint64_t)((2 * LBO_W) >> 4);
     uint32_t phase = 0;
 
     // ---- helpers ---------------------------------------------------------------------------------------
-    // data MMA with K = 64: this warp's two K-steps for the three 3xTF32 terms (small terms first), then commit
+    // data MMA with K = 64 (A resident in TMEM): issuing warp wq takes K-steps 2wq, 2wq+1 of the three 3xTF32 terms, then commits
     auto issue_data = [&](uint32_t w_tm) {          // w_tm: TMEM column of the resident operand (hi; lo at +64)
-        if (elect_one()) {
-            tc_fence_after();
-            uint32_t accumulate = 0;
-            for (int term = 0; term < 3; term++) {
-                const uint32_t wa = term == 0 ? w_tm + 64 : w_tm;
-                const uint64_t bd = term == 1 ? d_dT_lo : d_dT_hi;
-                for (int kk = 0; kk < 2; kk++) {
-                    const int ks = 2 * warp + kk;
-                    mma_tf32_ts(my_acc, tmem + wa + 8 * ks, bd + KSTEP_B * ks, idesc16, accumulate);
+        if (issuer) {
+            if (elect_one()) {
+                tc_fence_after();
+                uint32_t accumulate = 0;
+                for (int term = 0; term < 3; term++) {
+                    const uint32_t wa = term == 0 ? w_tm + 64 : w_tm;
+                    const uint64_t bd = term == 1 ? d_dT_lo : d_dT_hi;
+                    for (int kk = 0; kk < 2; kk++) {
+                        const int ks = 2 * wq + kk;
+                        mma_tf32_ts(my_acc, tmem + wa + 8 * ks, bd + KSTEP_B * ks, idesc16, accumulate);
+                        accumulate = 1;
+                    }
+                }
+                mma_commit(&gs.bar);
+            }
+            __syncwarp();
+        }
+    };
+    // g3 = W4^T dk (K = 16): six MMAs, entry e = 2*term + kstep, issuing warp wq takes e = wq and e = wq + 4
+    auto issue_m1 = [&]() {
+        if (issuer) {
+            if (elect_one()) {
+                tc_fence_after();
+                uint32_t accumulate = 0;
+                for (int e = wq; e < 6; e += 4) {
+                    const int term = e >> 1, ks = e & 1;
+                    const uint64_t ad = term == 0 ? d_w4t_lo : d_w4t_hi;
+                    const uint64_t bd = term == 1 ? d_dT_lo : d_dT_hi;
+                    mma_tf32(my_acc, ad + KSTEP_W * ks, bd + KSTEP_B * ks, idesc16, accumulate);
                     accumulate = 1;
                 }
+                mma_commit(&gs.bar);
             }
-            mma_commit(&gs.bar);
+            __syncwarp();
         }
-        __syncwarp();
-    };
-    // g3 = W4^T dk (K = 16): six MMAs, entry e = 2*term + kstep, warp w takes e = w and e = w + 4
-    auto issue_m1 = [&]() {
-        if (elect_one()) {
-            tc_fence_after();
-            uint32_t accumulate = 0;
-            for (int e = warp; e < 6; e += 4) {
-                const int term = e >> 1, ks = e & 1;
-                const uint64_t ad = term == 0 ? d_w4t_lo : d_w4t_hi;
-                const uint64_t bd = term == 1 ? d_dT_lo : d_dT_hi;
-                mma_tf32(my_acc, ad + KSTEP_W * ks, bd + KSTEP_B * ks, idesc16, accumulate);
-                accumulate = 1;
-            }
-            mma_commit(&gs.bar);
-        }
-        __syncwarp();
     };
     // weight-gradient chain (K = 16 trajectories), accumulated in TMEM; issued AFTER this warp's commit: off the critical path
     // (`fresh`: first chain after a flush overwrites the accumulator)
@@ -241,30 +248,33 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
         phase ^= 1;
         tc_fence_after();
     };
-    auto collect = [&](float (&d)[8]) {
-        wait_mma();
-        float t0[8], t1[8], t2[8], t3[8];
-        tmem_ld_16x256b_x2(acc_base + lane_base + 0 * TN, t0);
-        tmem_ld_16x256b_x2(acc_base + lane_base + 1 * TN, t1);
-        tmem_ld_16x256b_x2(acc_base + lane_base + 2 * TN, t2);
-        tmem_ld_16x256b_x2(acc_base + lane_base + 3 * TN, t3);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; i++) d[i] = (t0[i] + t1[i]) + (t2[i] + t3[i]);
-    };
-    // dL/dy elements (state sm0 / sm0 + 8, trajectory sn) of this thread; every 16-row block holds the same 16 x 16 tile
-    auto collect_gy = [&](float (&kv)[2]) {
+    auto collect = [&](float (&d)[4]) {
         wait_mma();
         float t0[4], t1[4], t2[4], t3[4];
-        const uint32_t a = acc_base + lane_base + 8 * (warp >> 1);
+        const uint32_t a = acc_base + lane_base + 8 * h;
         tmem_ld_16x256b_x1(a + 0 * TN, t0);
         tmem_ld_16x256b_x1(a + 1 * TN, t1);
         tmem_ld_16x256b_x1(a + 2 * TN, t2);
         tmem_ld_16x256b_x1(a + 3 * TN, t3);
         tmem_ld_wait();
-        const bool o = (warp & 1) != 0;
-        kv[0] = ((o ? t0[1] : t0[0]) + (o ? t1[1] : t1[0])) + ((o ? t2[1] : t2[0]) + (o ? t3[1] : t3[0]));
-        kv[1] = ((o ? t0[3] : t0[2]) + (o ? t1[3] : t1[2])) + ((o ? t2[3] : t2[2]) + (o ? t3[3] : t3[2]));
+#pragma unroll
+        for (int i = 0; i < 4; i++) d[i] = (t0[i] + t1[i]) + (t2[i] + t3[i]);
+    };
+    // dL/dy element (state srow, trajectory sn) of this thread; every 16-row block holds the same 16 x 16 tile
+    auto collect_gy = [&]() {
+        wait_mma();
+        float t0[4], t1[4], t2[4], t3[4];
+        const uint32_t a = acc_base + lane_base + 8 * (wq >> 1);
+        tmem_ld_16x256b_x1(a + 0 * TN, t0);
+        tmem_ld_16x256b_x1(a + 1 * TN, t1);
+        tmem_ld_16x256b_x1(a + 2 * TN, t2);
+        tmem_ld_16x256b_x1(a + 3 * TN, t3);
+        tmem_ld_wait();
+        const int sel = 2 * h + (wq & 1);
+        float sv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) sv[i] = (t0[i] + t1[i]) + (t2[i] + t3[i]);
+        return sel == 0 ? sv[0] : (sel == 1 ? sv[1] : (sel == 2 ? sv[2] : sv[3]));
     };
     auto publish = [&]() {
         fence_async_smem();
@@ -272,22 +282,21 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
         group_sync(g);
     };
     // fragment -> [row][n] tile (hi / lo), 8-byte stores of the two adjacent trajectories
-    auto store_pairs = [&](unsigned char* hi_t, unsigned char* lo_t, const float (&v)[8]) {
+    auto store_pairs = [&](unsigned char* hi_t, unsigned char* lo_t, const float (&v)[4]) {
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
-            const int ia = 2 * (p & 1) + 4 * (p >> 1);
+        for (int p = 0; p < 2; p++) {
             float h0, l0, h1, l1;
-            split_tf32_fast(v[ia], h0, l0);
-            split_tf32_fast(v[ia + 1], h1, l1);
+            split_tf32_fast(v[2 * p], h0, l0);
+            split_tf32_fast(v[2 * p + 1], h1, l1);
             st_f32x2(hi_t, off2[p], h0, h1);
             st_f32x2(lo_t, off2[p], l0, l1);
         }
     };
     // delta = g * elu'(a); delta -> dT tile [n][m] and dA tile [m][n]; running sums for the bias gradient
-    auto make_delta = [&](const float (&gsum)[8], const float (&act)[8], float (&bsum)[8], unsigned char* dA_hi, unsigned char* dA_lo) {
-        float d[8];
+    auto make_delta = [&](const float (&gsum)[4], const float (&act)[4], float (&bsum)[4], unsigned char* dA_hi, unsigned char* dA_lo) {
+        float d[4];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < 4; i++) {
             d[i] = gsum[i] * psn_elu_grad_from_out(act[i]);
             bsum[i] += d[i];
             float hi, lo;
@@ -297,12 +306,11 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
         }
         store_pairs(dA_hi, dA_lo, d);
     };
-    auto ld_frag = [&](const float* src, float (&v)[8]) {
-        const float4 a = __ldcs(reinterpret_cast<const float4*>(src + gt * 8));
-        const float4 b = __ldcs(reinterpret_cast<const float4*>(src + gt * 8) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    auto ld_frag = [&](const float* src, float (&v)[4]) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(src + ftape));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
     };
-    // held inputs of the step that ends at grid point j (warp 1, lane = trajectory), as in the forward kernel
+    // held inputs of the step that ends at grid point j (warp 4, lane = trajectory), as in the forward kernel
     auto load_held = [&](int j, float (&u)[TU]) {
         const int bb = min(b0 + (lane & 15), B - 1);
         const int k = q.event_idx ? __ldg(q.event_idx + (j - 1)) : -1;
@@ -319,38 +327,64 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
               ob4 = oW4 + TX * TH;
 
     // drain the tensor pipe and add the TMEM weight-gradient accumulators into the slab (round-to-nearest fp32 adds; every
-    // element is owned by one thread, the slab was zeroed by the launcher)
+    // element is owned by one thread, the slab was zeroed by the launcher).  Warp (wq, h) owns rows 16wq.. and the 8-column
+    // blocks of parity h.
     auto flush_dw = [&]() {
-        if (elect_one()) { tc_fence_after(); mma_commit(&gs.bar); }
-        __syncwarp();
-        wait_mma();
-        float v[8];
-        auto add2 = [&](float* dst, float x, float y) {
-            float2 o = *reinterpret_cast<float2*>(dst);
-            o.x += x; o.y += y;
-            *reinterpret_cast<float2*>(dst) = o;
-        };
-        for (int cb = 0; cb < 4; cb++) {
-            tmem_ld_16x256b_x2(tm_dw + lane_base + TM_DW2 + 16 * cb, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) add2(sl + oW2 + frag_row(i) * TH + 16 * cb + frag_col(i), v[i], v[i + 1]);
-            tmem_ld_16x256b_x2(tm_dw + lane_base + TM_DW3 + 16 * cb, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) add2(sl + oW3 + frag_row(i) * TH + 16 * cb + frag_col(i), v[i], v[i + 1]);
+        if (issuer) {
+            if (elect_one()) { tc_fence_after(); mma_commit(&gs.bar); }
+            __syncwarp();
         }
-        tmem_ld_16x256b_x2(tm_dw + lane_base + TM_DW4T, v);          // rows = hidden k, columns = output m
-        tmem_ld_wait();
+        wait_mma();
+        // the slab values are fetched first, all at once (independent L2 round trips), then combined with the accumulators
+        const int r0 = m0, cc = c0;
+        float2 o2[4][2], o3[4][2], og[2][2];
+        float o4[4];
 #pragma unroll
-        for (int i = 0; i < 8; i++) sl[oW4 + frag_col(i) * TH + frag_row(i)] += v[i];
-        for (int cb = 0; cb < 2; cb++) {
-            tmem_ld_16x256b_x2(tm_dw + lane_base + TM_DW1F + 16 * cb, v);
+        for (int q4 = 0; q4 < 4; q4++) {          // dW2 / dW3: 64 columns = 8 blocks of 8, this warp takes blocks h, h+2, h+4, h+6
+            const int cb = h + 2 * q4;
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                o2[q4][r] = *reinterpret_cast<const float2*>(sl + oW2 + (r0 + 8 * r) * TH + 8 * cb + cc);
+                o3[q4][r] = *reinterpret_cast<const float2*>(sl + oW3 + (r0 + 8 * r) * TH + 8 * cb + cc);
+            }
+        }
+        const int mc = 8 * h + cc;                // dW4^T: rows = hidden k, columns = output m (16): block h
+        o4[0] = sl[oW4 + mc * TH + r0]; o4[1] = sl[oW4 + (mc + 1) * TH + r0];
+        o4[2] = sl[oW4 + mc * TH + r0 + 8]; o4[3] = sl[oW4 + (mc + 1) * TH + r0 + 8];
+#pragma unroll
+        for (int q2 = 0; q2 < 2; q2++) {          // dW1f: 24 columns = 3 blocks of 8: blocks h and h + 2 (< 3)
+            const int cb = h + 2 * q2;
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+                og[q2][r] = cb < 3 ? *reinterpret_cast<const float2*>(garea + (r0 + 8 * r) * TK1 + 8 * cb + cc) : make_float2(0.f, 0.f);
+        }
+        float v[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; q4++) {
+            const int cb = h + 2 * q4;
+            tmem_ld_16x256b_x1(tm_dw + lane_base + TM_DW2 + 8 * cb, v);
             tmem_ld_wait();
+            *reinterpret_cast<float2*>(sl + oW2 + r0 * TH + 8 * cb + cc) = make_float2(o2[q4][0].x + v[0], o2[q4][0].y + v[1]);
+            *reinterpret_cast<float2*>(sl + oW2 + (r0 + 8) * TH + 8 * cb + cc) = make_float2(o2[q4][1].x + v[2], o2[q4][1].y + v[3]);
+            tmem_ld_16x256b_x1(tm_dw + lane_base + TM_DW3 + 8 * cb, v);
+            tmem_ld_wait();
+            *reinterpret_cast<float2*>(sl + oW3 + r0 * TH + 8 * cb + cc) = make_float2(o3[q4][0].x + v[0], o3[q4][0].y + v[1]);
+            *reinterpret_cast<float2*>(sl + oW3 + (r0 + 8) * TH + 8 * cb + cc) = make_float2(o3[q4][1].x + v[2], o3[q4][1].y + v[3]);
+        }
+        tmem_ld_16x256b_x1(tm_dw + lane_base + TM_DW4T + 8 * h, v);
+        tmem_ld_wait();
+        sl[oW4 + mc * TH + r0] = o4[0] + v[0];
+        sl[oW4 + (mc + 1) * TH + r0] = o4[1] + v[1];
+        sl[oW4 + mc * TH + r0 + 8] = o4[2] + v[2];
+        sl[oW4 + (mc + 1) * TH + r0 + 8] = o4[3] + v[3];
 #pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-                const int c = 16 * cb + frag_col(i);
-                if (c < TK1) add2(garea + frag_row(i) * TK1 + c, v[i], v[i + 1]);
+        for (int q2 = 0; q2 < 2; q2++) {
+            const int cb = h + 2 * q2;
+            if (cb < 3) {                          // warp-uniform
+                tmem_ld_16x256b_x1(tm_dw + lane_base + TM_DW1F + 8 * cb, v);
+                tmem_ld_wait();
+                *reinterpret_cast<float2*>(garea + r0 * TK1 + 8 * cb + cc) = make_float2(og[q2][0].x + v[0], og[q2][0].y + v[1]);
+                *reinterpret_cast<float2*>(garea + (r0 + 8) * TK1 + 8 * cb + cc) = make_float2(og[q2][1].x + v[2], og[q2][1].y + v[3]);
             }
         }
     };
@@ -359,65 +393,58 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
         bool fresh = true;
         const int bown = b0 + sn, bbown = min(bown, B - 1);
         const bool valid = bown < B;
-        float lam[2], D1[8], dB2[8], dB3[8], dB4[2] = {0.f, 0.f};
+        float lam, D1[4], dB2[4], dB3[4], dB4 = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 8; i++) { D1[i] = 0.f; dB2[i] = 0.f; dB3[i] = 0.f; }
-#pragma unroll
-        for (int r = 0; r < 2; r++) lam[r] = (valid && q.gx.p) ? ldser(q.gx, T - 1, bown, sm0 + 8 * r) : 0.0f;
+        for (int i = 0; i < 4; i++) { D1[i] = 0.f; dB2[i] = 0.f; dB3[i] = 0.f; }
+        lam = (valid && q.gx.p) ? ldser(q.gx, T - 1, bown, srow) : 0.0f;
 
         const float c13 = (float)(1.0 / 3.0);
         const float* tp = q.tape + ((int64_t)gid * (T - 1) * NST + (int64_t)(T - 1) * NST - 1) * PSN_TAPE_STAGE;   // last record
-        float a1[8], a2[8], a3[8], yv[2] = {0.f, 0.f};
-        float dtn = 0.0f, un[TU];
+        float a1[4], a2[4], a3[4], yv = 0.0f;
+        float tan = 0.0f, tbn = 0.0f, un[TU];       // grid times of the next step to process (subtracted when it starts)
 #pragma unroll
         for (int c = 0; c < TU; c++) un[c] = 0.0f;
         if (T > 1) {
             ld_frag(tp, a1); ld_frag(tp + PSN_TAPE_FRAG, a2); ld_frag(tp + 2 * PSN_TAPE_FRAG, a3);
-            const float2 y2 = __ldcs(reinterpret_cast<const float2*>(tp + 3 * PSN_TAPE_FRAG + gt * 2));
-            yv[0] = y2.x; yv[1] = y2.y;
-            dtn = __fsub_rn(ldser(q.t, T - 1, bbown, 0), ldser(q.t, T - 2, bbown, 0));
-            if (warp == 1) load_held(T - 1, un);
+            yv = __ldcs(tp + ytape);
+            tan = ldser(q.t, T - 1, bbown, 0); tbn = ldser(q.t, T - 2, bbown, 0);
+            if (wk == 4) load_held(T - 1, un);
         }
 
         for (int j = T - 1; j >= 1; j--) {
-            const float dt = dtn;
+            const float dt = __fsub_rn(tan, tbn);
             float u[TU];
 #pragma unroll
             for (int c = 0; c < TU; c++) u[c] = un[c];
-            float gxn[2];
-#pragma unroll
-            for (int r = 0; r < 2; r++) gxn[r] = (valid && q.gx.p) ? ldser(q.gx, j - 1, bown, sm0 + 8 * r) : 0.0f;
+            const float gxn = (valid && q.gx.p) ? ldser(q.gx, j - 1, bown, srow) : 0.0f;
             if (j > 1) {
-                dtn = __fsub_rn(ldser(q.t, j - 1, bbown, 0), ldser(q.t, j - 2, bbown, 0));
-                if (warp == 1) load_held(j - 1, un);
+                tan = tbn; tbn = ldser(q.t, j - 2, bbown, 0);
+                if (wk == 4) load_held(j - 1, un);
             }
             // x_j = x_{j-1} + dt * sum_s bw[s] k_s : dL/dk_s starts at lam * dt * bw[s]; dxs collects dL/dx_{j-1}
-            float dxs[2], d1[2] = {0.f, 0.f}, d2[2] = {0.f, 0.f}, d3[2] = {0.f, 0.f}, dcur[2];
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                const float ld = lam[r] * dt;
-                dxs[r] = lam[r];
-                if (METHOD == PSNODE_RK4) { d1[r] = ld * 0.125f; d2[r] = ld * 0.375f; d3[r] = ld * 0.375f; dcur[r] = ld * 0.125f; }
-                else dcur[r] = ld;
+            float dxs = lam, d1 = 0.f, d2 = 0.f, d3 = 0.f, dcur;
+            {
+                const float ld = lam * dt;
+                if (METHOD == PSNODE_RK4) { d1 = ld * 0.125f; d2 = ld * 0.375f; d3 = ld * 0.375f; dcur = ld * 0.125f; }
+                else dcur = ld;
             }
 #pragma unroll 1
             for (int e = NST - 1; e >= 0; e--) {
                 const bool has_next = !(j == 1 && e == 0);
                 const float* tpn = tp - PSN_TAPE_STAGE;
-                float gsum[8];
+                float gsum[4];
                 // ---- P0: dk tiles, a3 -> aB[0]; g3 = W4^T dk ; dW4^T += a3 dk^T ----
-#pragma unroll
-                for (int r = 0; r < 2; r++) {
+                {
                     float hi, lo;
-                    split_tf32_fast(dcur[r], hi, lo);
-                    st_f32(gs.dT_hi, off_dk[r], hi); st_f32(gs.dT_lo, off_dk[r], lo);
-                    st_f32(gs.dkB_hi, off_sq[r], hi); st_f32(gs.dkB_lo, off_sq[r], lo);
-                    dB4[r] += dcur[r];
+                    split_tf32_fast(dcur, hi, lo);
+                    st_f32(gs.dT_hi, off_dk, hi); st_f32(gs.dT_lo, off_dk, lo);
+                    st_f32(gs.dkB_hi, off_sq, hi); st_f32(gs.dkB_lo, off_sq, lo);
+                    dB4 += dcur;
                 }
                 store_pairs(gs.aB_hi[0], gs.aB_lo[0], a3);
                 publish();
                 issue_m1();
-                if (warp == 0) issue_dw(d_aB_hi0, d_aB_lo0, d_dkB_hi, d_dkB_lo, tm_dw + TM_DW4T, idesc16, fresh);
+                if (wk == 0) issue_dw(d_aB_hi0, d_aB_lo0, d_dkB_hi, d_dkB_lo, tm_dw + TM_DW4T, idesc16, fresh);
                 // ---- P1: d3 ; a2 -> aB[1]; g2 = W3^T d3 ; dW3 += d3 a2^T ----
                 collect(gsum);
                 make_delta(gsum, a3, dB3, gs.dA_hi[1], gs.dA_lo[1]);
@@ -425,7 +452,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
                 if (has_next) ld_frag(tpn + 2 * PSN_TAPE_FRAG, a3);
                 publish();
                 issue_data(TM_W3T);
-                if (warp == 1) issue_dw(d_dA_hi1, d_dA_lo1, d_aB_hi1, d_aB_lo1, tm_dw + TM_DW3, idesc64, fresh);
+                if (wk == 1) issue_dw(d_dA_hi1, d_dA_lo1, d_aB_hi1, d_aB_lo1, tm_dw + TM_DW3, idesc64, fresh);
                 // ---- P2: d2 ; a1 -> aB[0]; g1 = W2^T d2 ; dW2 += d2 a1^T ----
                 collect(gsum);
                 make_delta(gsum, a2, dB2, gs.dA_hi[0], gs.dA_lo[0]);
@@ -433,17 +460,16 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
                 if (has_next) ld_frag(tpn + PSN_TAPE_FRAG, a2);
                 publish();
                 issue_data(TM_W2T);
-                if (warp == 2) issue_dw(d_dA_hi0, d_dA_lo0, d_aB_hi0, d_aB_lo0, tm_dw + TM_DW2, idesc64, fresh);
+                if (wk == 2) issue_dw(d_dA_hi0, d_dA_lo0, d_aB_hi0, d_aB_lo0, tm_dw + TM_DW2, idesc64, fresh);
                 // ---- P3: d1 ; [y; u] -> aB[1] rows 0..23; gy = (Wb+Wc)_x^T d1 ; dW1f += d1 [y;u]^T ----
                 collect(gsum);
                 make_delta(gsum, a1, D1, gs.dA_hi[1], gs.dA_lo[1]);
-#pragma unroll
-                for (int r = 0; r < 2; r++) {
+                {
                     float hi, lo;
-                    split_tf32_fast(yv[r], hi, lo);
-                    st_f32(gs.aB_hi[1], off_sq[r], hi); st_f32(gs.aB_lo[1], off_sq[r], lo);
+                    split_tf32_fast(yv, hi, lo);
+                    st_f32(gs.aB_hi[1], off_sq, hi); st_f32(gs.aB_lo[1], off_sq, lo);
                 }
-                if (warp == 1 && lane < TN) {
+                if (wk == 4 && lane < TN) {
 #pragma unroll
                     for (int c = 0; c < TU; c++) {
                         float hi, lo;
@@ -454,80 +480,65 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
                 }
                 if (has_next) {
                     ld_frag(tpn, a1);
-                    const float2 y2 = __ldcs(reinterpret_cast<const float2*>(tpn + 3 * PSN_TAPE_FRAG + gt * 2));
-                    yv[0] = y2.x; yv[1] = y2.y;
+                    yv = __ldcs(tpn + ytape);
                 }
                 publish();
                 issue_data(TM_W1T);
-                if (warp == 3) issue_dw(d_dA_hi1, d_dA_lo1, d_aB_hi1, d_aB_lo1, tm_dw + TM_DW1F, idesc24, fresh);
+                if (wk == 3) issue_dw(d_dA_hi1, d_dA_lo1, d_aB_hi1, d_aB_lo1, tm_dw + TM_DW1F, idesc24, fresh);
                 // ---- P4: dL/dy of this stage -> Runge-Kutta adjoint algebra (my_fixed_grid.py:15-59 reversed) ----
-                float gy[2];
-                collect_gy(gy);
-#pragma unroll
-                for (int r = 0; r < 2; r++) {
-                    const float gq = gy[r];
-                    dxs[r] += gq;
-                    if (METHOD == PSNODE_RK4) {
-                        const float tg = dt * gq;
-                        if (e == 3) { d3[r] += tg; d2[r] -= tg; d1[r] += tg; dcur[r] = d3[r]; }
-                        else if (e == 2) { d2[r] += tg; d1[r] -= tg * c13; dcur[r] = d2[r]; }
-                        else if (e == 1) { d1[r] += tg * c13; dcur[r] = d1[r]; }
-                    } else if (METHOD == PSNODE_MIDPOINT) {
-                        if (e == 1) dcur[r] = (0.5f * dt) * gq;
-                    }
+                const float gq = collect_gy();
+                dxs += gq;
+                if (METHOD == PSNODE_RK4) {
+                    const float tg = dt * gq;
+                    if (e == 3) { d3 += tg; d2 -= tg; d1 += tg; dcur = d3; }
+                    else if (e == 2) { d2 += tg; d1 -= tg * c13; dcur = d2; }
+                    else if (e == 1) { d1 += tg * c13; dcur = d1; }
+                } else if (METHOD == PSNODE_MIDPOINT) {
+                    if (e == 1) dcur = (0.5f * dt) * gq;
                 }
                 tp = tpn;
                 fresh = false;
             }
-#pragma unroll
-            for (int r = 0; r < 2; r++) lam[r] = dxs[r] + gxn[r];
+            lam = dxs + gxn;
             if (((T - j) % PSN_DW_FLUSH) == 0 || j == 1) { flush_dw(); fresh = true; }
         }
-        if (q.d_x0 && valid) {
-#pragma unroll
-            for (int r = 0; r < 2; r++) q.d_x0[(int64_t)bown * q.d_x0_sb + sm0 + 8 * r] = lam[r];
-        }
+        if (q.d_x0 && valid) q.d_x0[(int64_t)bown * q.d_x0_sb + srow] = lam;
 
         // ---- the weight gradients are in the slab already (last flush); bias gradients and layer-1 unfolding follow ----
         group_sync(g);
         float* scr = reinterpret_cast<float*>(gs.dA_hi[0]);          // 32 KB of dead tiles: scratch
         float* D1s = scr;                 // [64][17]
-        float* Gs = D1s + TH * 17;        // [64][25]
+        float* B2s = D1s + TH * 17;       // [64][17]
+        float* B3s = B2s + TH * 17;       // [64][17]
+        float* Gs = B3s + TH * 17;        // [64][25]
         float* a0s = Gs + TH * 25;        // [16][25]
-        float* red = a0s + TN * 25;       // [4][16]
-        for (int e = gt; e < TH * TK1; e += GROUP_THREADS) Gs[(e / TK1) * 25 + (e % TK1)] = 0.0f;
-        group_sync(g);
+        float* dks = a0s + TN * 25;       // [16][17]   dB4 per (state, trajectory)
 #pragma unroll
-        for (int cb = 0; cb < 2; cb++)                               // read back this thread's own flushed elements
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int c = 16 * cb + frag_col(i);
-                if (c < TK1) Gs[frag_row(i) * 25 + c] = garea[frag_row(i) * TK1 + c];
-            }
-        // bias gradients: sum over the 4 trajectory columns of the fragment, then over the 4 lanes that share a row
-        auto row_sums = [&](const float (&v)[8], int off) {
-            float s0 = (v[0] + v[1]) + (v[4] + v[5]), s1 = (v[2] + v[3]) + (v[6] + v[7]);
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-            if ((lane & 3) == 0) { sl[off + m0] = s0; sl[off + m0 + 8] = s1; }
-        };
-        row_sums(D1, ob1);
-        row_sums(dB2, ob2);
-        row_sums(dB3, ob3);
-        {
-            float s0 = dB4[0], s1 = dB4[1];
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 2); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-            if ((lane & 3) == 0) { red[warp * 16 + sm0] = s0; red[warp * 16 + sm0 + 8] = s1; }
+        for (int i = 0; i < 4; i++) {
+            const int o = frag_row(i) * 17 + frag_col(i);
+            D1s[o] = D1[i]; B2s[o] = dB2[i]; B3s[o] = dB3[i];
         }
-#pragma unroll
-        for (int i = 0; i < 8; i++) D1s[frag_row(i) * 17 + frag_col(i)] = D1[i];
+        dks[srow * 17 + sn] = dB4;
+        for (int e = gt; e < TH * TK1; e += GROUP_THREADS) Gs[(e / TK1) * 25 + (e % TK1)] = garea[e];   // flushed before the group_sync above
         for (int e = gt; e < TN * S; e += GROUP_THREADS) {
             const int n = e / S, c = e - n * S;
             a0s[n * 25 + c] = __ldg(q.a0 + (int64_t)min(b0 + n, B - 1) * q.a0_sb + c);
         }
         group_sync(g);
-        if (gt < TX) sl[ob4 + gt] = (red[gt] + red[16 + gt]) + (red[32 + gt] + red[48 + gt]);
+        if (gt < 3 * TH) {                 // bias gradients of layers 1..3: row sums over the 16 trajectories
+            const int which = gt >> 6, m = gt & 63;
+            const float* src = (which == 0 ? D1s : (which == 1 ? B2s : B3s)) + m * 17;
+            float acc = 0.0f;
+#pragma unroll
+            for (int n = 0; n < TN; n++) acc += src[n];
+            sl[(which == 0 ? ob1 : (which == 1 ? ob2 : ob3)) + m] = acc;
+        } else if (gt < 3 * TH + TX) {
+            const int c = gt - 3 * TH;
+            float acc = 0.0f;
+#pragma unroll
+            for (int n = 0; n < TN; n++) acc += dks[c * 17 + n];
+            sl[ob4 + c] = acc;
+        }
         // unfold layer 1: W1 = [Wa | Wb | Wc] acting on [a0; s - a0; s]
         for (int e = gt; e < TH * S; e += GROUP_THREADS) {
             const int m = e / S, c = e - m * S;
