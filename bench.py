@@ -390,7 +390,7 @@ def main():
             line["e2e"] = e2e
         if train is not None:
             line["train"] = train
-        if not args.no_cpu and world >= 1:
+        if not args.no_cpu and world == 1:      # the CPU baseline is a 1-GPU-run item (other ranks would compete for the host cores)
             v, threads, secs = cpu_baseline(w, args.cpu_sample_steps)
             line["cpu_baseline"] = {"value": v, "unit": "traj-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"B={w['B']} x {args.cpu_sample_steps} of {w['N']} RK4 steps (per-step cost is constant), "
