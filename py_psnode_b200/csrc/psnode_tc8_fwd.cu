@@ -97,9 +97,12 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
     CtaSmemDae& smd = *reinterpret_cast<CtaSmemDae*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));   // AE part only if DAE
     CtaSmem& sm = smd.base;
     const int tid = threadIdx.x;
-    const int g = tid >> 8;                    // group
+    // warp-level indices come from a shuffle so that ptxas knows they are warp-uniform: descriptors, TMEM addresses and
+    // role branches then live in uniform registers instead of being moved there (R2UR) in front of every MMA
+    const int cta_warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int g = cta_warp >> 3;               // group
     const int gt = tid & 255;                  // thread within the group
-    const int wk = gt >> 5, lane = gt & 31;    // warp within the group
+    const int wk = cta_warp & 7, lane = tid & 31;   // warp within the group
     const int wq = wk & 3, h = wk >> 2;        // TMEM sub-partition (== CTA warp index % 4), column half
     const bool issuer = h == 0;
     GroupSmem& gs = sm.g[g];

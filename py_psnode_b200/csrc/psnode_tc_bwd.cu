@@ -104,8 +104,10 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     extern __shared__ unsigned char smem_raw[];
     BwdCtaSmem& sm = *reinterpret_cast<BwdCtaSmem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x;
-    const int g = tid >> 8, gt = tid & 255;
-    const int wk = gt >> 5, lane = gt & 31;       // warp within the group
+    // warp-level indices come from a shuffle so that ptxas knows they are warp-uniform (descriptors stay in uniform registers)
+    const int cta_warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int g = cta_warp >> 3, gt = tid & 255;
+    const int wk = cta_warp & 7, lane = tid & 31; // warp within the group
     const int wq = wk & 3, h = wk >> 2;           // TMEM sub-partition (== CTA warp index % 4), trajectory-column half
     const bool issuer = h == 0;                   // warps 0..3 issue the MMAs (4 partial accumulators)
     BwdGroupSmem& gs = sm.g[g];
