@@ -58,3 +58,57 @@ PSN_HD float psn_elu(float v) {
 }
 // derivative of ELU expressed through its OUTPUT y: 1 for y > 0, y + 1 (= exp(v)) otherwise.
 PSN_HD float psn_elu_grad_from_out(float y) { return y > 0.0f ? 1.0f : y + 1.0f; }
+
+#if defined(__CUDACC__)
+// ---- packed pairs (Blackwell fma/add/mul.rn.f32x2: two IEEE fp32 operations per issue slot) -------------------------------
+// psn_elu2 evaluates psn_elu on two values with exactly the operation sequence of the scalar routine above (every packed
+// instruction is two independent round-to-nearest fp32 operations), so its results are bit-identical to psn_elu.
+typedef unsigned long long psn_u64;
+__device__ __forceinline__ psn_u64 psn_pack2(float x, float y) {
+    psn_u64 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ void psn_unpack2(psn_u64 v, float& x, float& y) { asm("mov.b64 {%0,%1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ psn_u64 psn_fma2(psn_u64 a, psn_u64 b, psn_u64 c) {
+    psn_u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ psn_u64 psn_add2(psn_u64 a, psn_u64 b) {
+    psn_u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ psn_u64 psn_mul2(psn_u64 a, psn_u64 b) {
+    psn_u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ psn_u64 psn_dup2(float c) { return psn_pack2(c, c); }
+
+__device__ __forceinline__ void psn_elu2(float v0, float v1, float& o0, float& o1) {
+    const float x0 = fmaxf(fminf(v0, 0.0f), -17.5f), x1 = fmaxf(fminf(v1, 0.0f), -17.5f);
+    const psn_u64 x = psn_pack2(x0, x1);
+    psn_u64 kf = psn_fma2(x, psn_dup2(1.4426950408889634f), psn_dup2(12582912.0f));
+    float kf0, kf1;
+    psn_unpack2(kf, kf0, kf1);
+    const int ki0 = __float_as_int(kf0), ki1 = __float_as_int(kf1);
+    kf = psn_add2(kf, psn_dup2(-12582912.0f));
+    psn_u64 r = psn_fma2(kf, psn_dup2(-0.693145751953125f), x);
+    r = psn_fma2(kf, psn_dup2(-1.42860682030941723212e-6f), r);
+    psn_u64 q = psn_fma2(r, psn_dup2(1.9841270e-4f), psn_dup2(1.3888889e-3f));
+    q = psn_fma2(q, r, psn_dup2(8.3333333e-3f));
+    q = psn_fma2(q, r, psn_dup2(4.1666668e-2f));
+    q = psn_fma2(q, r, psn_dup2(1.6666667e-1f));
+    q = psn_fma2(q, r, psn_dup2(0.5f));
+    const psn_u64 p = psn_fma2(psn_mul2(r, r), q, r);
+    const float t0 = __int_as_float((int)((unsigned)ki0 << 23) + 0x3f800000), t1 = __int_as_float((int)((unsigned)ki1 << 23) + 0x3f800000);
+    const psn_u64 t = psn_pack2(t0, t1);
+    const psn_u64 e = psn_fma2(t, p, psn_add2(t, psn_dup2(-1.0f)));
+    float e0, e1;
+    psn_unpack2(e, e0, e1);
+    o0 = v0 > 0.0f ? v0 : e0;
+    o1 = v1 > 0.0f ? v1 : e1;
+}
+#endif

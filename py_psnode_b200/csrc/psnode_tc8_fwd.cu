@@ -319,7 +319,12 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
         if (nacc == 4) tmem_ld_16x256b_x1(a + 3 * TN, t3);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 4; i++) d[i] = nacc == 4 ? (t0[i] + t1[i]) + (t2[i] + t3[i]) : (t0[i] + t1[i]) + t2[i];
+        for (int pr = 0; pr < 2; pr++) {
+            const psn_u64 s01 = psn_add2(psn_pack2(t0[2 * pr], t0[2 * pr + 1]), psn_pack2(t1[2 * pr], t1[2 * pr + 1]));
+            const psn_u64 s23 = nacc == 4 ? psn_add2(psn_pack2(t2[2 * pr], t2[2 * pr + 1]), psn_pack2(t3[2 * pr], t3[2 * pr + 1]))
+                                          : psn_pack2(t2[2 * pr], t2[2 * pr + 1]);
+            psn_unpack2(psn_add2(s01, s23), d[2 * pr], d[2 * pr + 1]);
+        }
     };
     // layer 4: the slope element (state srow, trajectory sn) of this thread; every 16-row block holds the same 16 x 16 tile
     auto collect_slope = [&]() {
@@ -346,10 +351,15 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
     auto store_hidden = [&](const float (&d)[4], const float (&bias)[2], const float* cadd, float* trec) {
         float a[4];
 #pragma unroll
+        for (int pr = 0; pr < 2; pr++) {       // the two trajectory columns of one row share the bias: packed f32x2 arithmetic
+            const psn_u64 dd = psn_pack2(d[2 * pr], d[2 * pr + 1]);
+            const psn_u64 vv = psn_add2(dd, cadd ? psn_pack2(cadd[2 * pr], cadd[2 * pr + 1]) : psn_dup2(bias[pr]));
+            float v0, v1;
+            psn_unpack2(vv, v0, v1);
+            psn_elu2(v0, v1, a[2 * pr], a[2 * pr + 1]);
+        }
+#pragma unroll
         for (int i = 0; i < 4; i++) {
-            float v = d[i] + bias[i >> 1];
-            if (cadd) v = d[i] + cadd[i];
-            a[i] = psn_elu(v);
             float hi, lo;
             split_tf32_fast(a[i], hi, lo);
             st_f32(gs.act_hi, off_act[i], hi);
