@@ -144,13 +144,14 @@ def test_backward_matches_reference(native_lib, name, sweep, monkeypatch):
     assert not bad, "\n".join(bad)
 
 
+@pytest.mark.parametrize("impl", ["tc", "tc8"])
 @pytest.mark.parametrize("name", ["ode01_rk4_small", "ode01_midpoint_small", "ode01_rk4_noevent"])
-def test_backward_tape_written_by_tc8_forward(native_lib, name, monkeypatch):
-    """The 8-warp forward kernel records the same tape layout: tensor-core reverse sweep on a tape written by impl="tc8"."""
+def test_backward_tape_written_by_every_forward_kernel(native_lib, name, impl, monkeypatch):
+    """Both tensor-core forward kernels record the same tape layout: tensor-core reverse sweep on a tape written by each."""
     from py_psnode_b200 import _native
     monkeypatch.delenv("PSNODE_TAPE_MAX_GB", raising=False)
     d = load_golden(name)
-    got = run_with_grads(d, name, impl="tc8")
+    got = run_with_grads(d, name, impl=impl)
     assert _native.last_kernel() == "psn_tc_grad_reduce_kernel", _native.last_kernel()
     for key, scale, err, ref_err, mine, g64 in grad_errors(d, got):
         assert err <= max(8.0 * ref_err, 1e-5 * scale + 1e-7), f"{key}: {err:.3e} vs ref {ref_err:.3e} scale {scale:.3e}"
