@@ -32,11 +32,14 @@ constexpr int ACT_TILE = (TN / 8) * SBO_ACT;
 constexpr int B1_TILE = (TN / 8) * SBO_B1;
 constexpr int LBO_W = 128, SBO_W = (TK1 / 4) * LBO_W;    // folded layer-1 weight tiles in shared memory (64 rows x K = 24)
 constexpr int W1_TILE = (TH / 8) * SBO_W;
-constexpr int SBO_W64 = (TH / 4) * LBO_W, W64_TILE = (TH / 8) * SBO_W64;   // 64 x 64 weight tiles in shared memory (DAE: AE layers 2..4)
+
 // TMEM columns: accumulators first (2 groups x 4 issuing warps x 16), then the resident weights
 constexpr int TM_ACC = 0;
 constexpr int TM_W2 = 128, TM_W3 = 256, TM_W4 = 384;     // hi at +0, lo at +64
 constexpr int TM_COLS = 512;
+// An M = 64 operand / accumulator occupies lanes 0..15 of each TMEM sub-partition.  DAE: the AE net's layers 2..4 and their
+// accumulators use lanes 16..31 of the SAME columns (a TS MMA needs A and D at the same lanes).
+constexpr uint32_t TM_UPPER = 16u << 16;
 constexpr int GROUP_THREADS = 256;
 
 struct Tc8Params {
@@ -76,12 +79,9 @@ struct __align__(128) CtaSmem {
     GroupSmem g[2];
     uint32_t tmem_base;
 };
-struct __align__(128) CtaSmemDae {            // DAE: the AE net's weights follow (A operands read from shared memory)
+struct __align__(128) CtaSmemDae {            // DAE: the AE net's folded layer 1 follows (A operand read from shared memory)
     CtaSmem base;
     float wa1_hi[W1_TILE / 4], wa1_lo[W1_TILE / 4];
-    unsigned char wa2_hi[W64_TILE], wa2_lo[W64_TILE];
-    unsigned char wa3_hi[W64_TILE], wa3_lo[W64_TILE];
-    unsigned char wa4_hi[W64_TILE], wa4_lo[W64_TILE];
 };
 
 __device__ __forceinline__ float ldser(const psnode_series& s, int j, int b, int c) {
@@ -136,18 +136,6 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
             smd.wa1_hi[tile_byte(m, c, LBO_W, SBO_W) >> 2] = hi;
             smd.wa1_lo[tile_byte(m, c, LBO_W, SBO_W) >> 2] = lo;
         }
-        for (int e = tid; e < TH * TH; e += 2 * GROUP_THREADS) {
-            const int m = e >> 6, k = e & 63;
-            const int o = tile_byte(m, k, LBO_W, SBO_W64);
-            float hi, lo;
-            split_tf32(__ldg(q.A2 + e), hi, lo);
-            st_f32(smd.wa2_hi, o, hi); st_f32(smd.wa2_lo, o, lo);
-            split_tf32(__ldg(q.A3 + e), hi, lo);
-            st_f32(smd.wa3_hi, o, hi); st_f32(smd.wa3_lo, o, lo);
-            hi = 0.0f; lo = 0.0f;                              // layer 4 (I rows) replicated into every 16-row block
-            if ((m & 15) < q.I) split_tf32(__ldg(q.A4 + (m & 15) * TH + k), hi, lo);
-            st_f32(smd.wa4_hi, o, hi); st_f32(smd.wa4_lo, o, lo);
-        }
     }
     for (int e = gt; e < (int)(offsetof(GroupSmem, bar) / 4); e += GROUP_THREADS) reinterpret_cast<float*>(&gs)[e] = 0.0f;
     fence_async_smem();
@@ -178,6 +166,26 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                 tmem_st_16x256b_x2(tmem + lane_base + TM_W2 + 64 * half + 16 * cb, w2);
                 tmem_st_16x256b_x2(tmem + lane_base + TM_W3 + 64 * half + 16 * cb, w3);
                 tmem_st_16x256b_x2(tmem + lane_base + TM_W4 + 64 * half + 16 * cb, w4);
+            }
+        }
+        if constexpr (DAE) {       // AE layers 2..4 -> lanes 16..31 (layer 4: I rows replicated into every 16-row block, rest zero)
+            for (int half = 0; half < 2; half++) {
+                for (int cb = 0; cb < 4; cb++) {
+                    float w2[8], w3[8], w4[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int row = m0 + ((i >> 1) & 1) * 8, col = 16 * cb + c0 + (i & 1) + (i >> 2) * 8;
+                        float hi, lo;
+                        split_tf32(__ldg(q.A2 + row * TH + col), hi, lo); w2[i] = half ? lo : hi;
+                        split_tf32(__ldg(q.A3 + row * TH + col), hi, lo); w3[i] = half ? lo : hi;
+                        hi = 0.0f; lo = 0.0f;
+                        if ((row & 15) < q.I) split_tf32(__ldg(q.A4 + (row & 15) * TH + col), hi, lo);
+                        w4[i] = half ? lo : hi;
+                    }
+                    tmem_st_16x256b_x2(tmem + TM_UPPER + lane_base + TM_W2 + 64 * half + 16 * cb, w2);
+                    tmem_st_16x256b_x2(tmem + TM_UPPER + lane_base + TM_W3 + 64 * half + 16 * cb, w3);
+                    tmem_st_16x256b_x2(tmem + TM_UPPER + lane_base + TM_W4 + 64 * half + 16 * cb, w4);
+                }
             }
         }
         tmem_st_wait();
@@ -244,7 +252,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
 
     // ---- helpers ---------------------------------------------------------------------------------------
     // TS layers (weights in TMEM): issuing warp wq takes K-steps 2wq, 2wq+1 of the three 3xTF32 terms, small terms first
-    auto issue_ts = [&](uint32_t w_hi, uint32_t w_lo) {
+    auto issue_ts = [&](uint32_t w_hi, uint32_t w_lo, uint32_t up = 0u) {      // up = TM_UPPER: the AE net's lanes
         if (issuer) {
             if (elect_one()) {
                 tc_fence_after();
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                     const uint64_t bd = term == 1 ? d_act_lo : d_act_hi;
                     for (int kk = 0; kk < 2; kk++) {
                         const int ks = 2 * wq + kk;
-                        mma_tf32_ts(my_acc, tmem + wa + 8 * ks, bd + KSTEP_B * ks, idesc, accumulate);
+                        mma_tf32_ts(my_acc + up, tmem + up + wa + 8 * ks, bd + KSTEP_B * ks, idesc, accumulate);
                         accumulate = 1;
                     }
                 }
@@ -282,26 +290,6 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
             __syncwarp();
         }
     };
-    // A operand from shared memory, K = 64 (AE layers 2..4)
-    auto issue_ss64 = [&](uint64_t a_hi, uint64_t a_lo) {
-        if (issuer) {
-            if (elect_one()) {
-                tc_fence_after();
-                uint32_t accumulate = 0;
-                for (int term = 0; term < 3; term++) {
-                    const uint64_t ad = term == 0 ? a_lo : a_hi;
-                    const uint64_t bd = term == 1 ? d_act_lo : d_act_hi;
-                    for (int kk = 0; kk < 2; kk++) {
-                        const int ks = 2 * wq + kk;
-                        mma_tf32(my_acc, ad + KSTEP_W * ks, bd + KSTEP_B * ks, idesc, accumulate);
-                        accumulate = 1;
-                    }
-                }
-                mma_commit(&gs.bar);
-            }
-            __syncwarp();
-        }
-    };
     // wait for the group's 4 commits
     auto wait_mma = [&]() {
         if (!mbar_wait(&gs.bar, phase)) { atomicExch(q.err, 1); __trap(); }
@@ -309,10 +297,10 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
         tc_fence_after();
     };
     // sum the first `nacc` partial accumulators into d[4] (this thread's 2 rows x 2 trajectory columns)
-    auto collect = [&](float (&d)[4], int nacc) {
+    auto collect = [&](float (&d)[4], int nacc, uint32_t up = 0u) {
         wait_mma();
         float t0[4], t1[4], t2[4], t3[4];
-        const uint32_t a = acc_base + lane_base + 8 * h;
+        const uint32_t a = acc_base + up + lane_base + 8 * h;
         tmem_ld_16x256b_x1(a + 0 * TN, t0);
         tmem_ld_16x256b_x1(a + 1 * TN, t1);
         tmem_ld_16x256b_x1(a + 2 * TN, t2);
@@ -327,10 +315,10 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
         }
     };
     // layer 4: the slope element (state srow, trajectory sn) of this thread; every 16-row block holds the same 16 x 16 tile
-    auto collect_slope = [&]() {
+    auto collect_slope = [&](uint32_t up = 0u) {
         wait_mma();
         float t0[4], t1[4], t2[4], t3[4];
-        const uint32_t a = acc_base + lane_base + 8 * (wq >> 1);
+        const uint32_t a = acc_base + up + lane_base + 8 * (wq >> 1);
         tmem_ld_16x256b_x1(a + 0 * TN, t0);
         tmem_ld_16x256b_x1(a + 1 * TN, t1);
         tmem_ld_16x256b_x1(a + 2 * TN, t2);
@@ -404,24 +392,21 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
     auto ae_eval = [&](bool stage_out) {
         if constexpr (DAE) {
             const uint64_t d_wa1_hi = make_desc(smem_u32(smd.wa1_hi), LBO_W, SBO_W), d_wa1_lo = make_desc(smem_u32(smd.wa1_lo), LBO_W, SBO_W);
-            const uint64_t d_wa2_hi = make_desc(smem_u32(smd.wa2_hi), LBO_W, SBO_W64), d_wa2_lo = make_desc(smem_u32(smd.wa2_lo), LBO_W, SBO_W64);
-            const uint64_t d_wa3_hi = make_desc(smem_u32(smd.wa3_hi), LBO_W, SBO_W64), d_wa3_lo = make_desc(smem_u32(smd.wa3_lo), LBO_W, SBO_W64);
-            const uint64_t d_wa4_hi = make_desc(smem_u32(smd.wa4_hi), LBO_W, SBO_W64), d_wa4_lo = make_desc(smem_u32(smd.wa4_lo), LBO_W, SBO_W64);
             float d[4];
             issue_l1(d_wa1_hi, d_wa1_lo);
             collect(d, 3);
             store_hidden(d, biasA2, c1a, nullptr);
             publish();
-            issue_ss64(d_wa2_hi, d_wa2_lo);
-            collect(d, 4);
+            issue_ts(TM_W2, TM_W2 + 64, TM_UPPER);
+            collect(d, 4, TM_UPPER);
             store_hidden(d, biasA2, nullptr, nullptr);
             publish();
-            issue_ss64(d_wa3_hi, d_wa3_lo);
-            collect(d, 4);
+            issue_ts(TM_W3, TM_W3 + 64, TM_UPPER);
+            collect(d, 4, TM_UPPER);
             store_hidden(d, biasA3, nullptr, nullptr);
             publish();
-            issue_ss64(d_wa4_hi, d_wa4_lo);
-            const float kv = collect_slope();
+            issue_ts(TM_W4, TM_W4 + 64, TM_UPPER);
+            const float kv = collect_slope(TM_UPPER);
             if (srow < q.I) {
                 const float iv = kv + biasA4;
                 float hi, lo;
