@@ -40,6 +40,8 @@ constexpr int TM_COLS = 512;
 // An M = 64 operand / accumulator occupies lanes 0..15 of each TMEM sub-partition.  DAE: the AE net's layers 2..4 and their
 // accumulators use lanes 16..31 of the SAME columns (a TS MMA needs A and D at the same lanes).
 constexpr uint32_t TM_UPPER = 16u << 16;
+// ODE: lanes 16..31 are free, so the folded layer 1 (K = 24: hi at column 128, lo at 160) and its accumulators live there too.
+constexpr int TM_W1 = 128;
 constexpr int GROUP_THREADS = 256;
 
 struct Tc8Params {
@@ -168,6 +170,22 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                 tmem_st_16x256b_x2(tmem + lane_base + TM_W4 + 64 * half + 16 * cb, w4);
             }
         }
+        if constexpr (!DAE) {      // folded layer 1 -> lanes 16..31: A[m][c] = (Wb + Wc)[m][c] for c < 16 + U, zero up to column 32
+            const int K1 = 3 * S;
+            for (int half = 0; half < 2; half++) {
+                for (int cb = 0; cb < 2; cb++) {
+                    float w1[8];
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int row = m0 + ((i >> 1) & 1) * 8, col = 16 * cb + c0 + (i & 1) + (i >> 2) * 8;
+                        float hi = 0.0f, lo = 0.0f;
+                        if (col < TX + U) split_tf32(__ldg(q.W1 + row * K1 + S + col) + __ldg(q.W1 + row * K1 + 2 * S + col), hi, lo);
+                        w1[i] = half ? lo : hi;
+                    }
+                    tmem_st_16x256b_x2(tmem + TM_UPPER + lane_base + TM_W1 + 32 * half + 16 * cb, w1);
+                }
+            }
+        }
         if constexpr (DAE) {       // AE layers 2..4 -> lanes 16..31 (layer 4: I rows replicated into every 16-row block, rest zero)
             for (int half = 0; half < 2; half++) {
                 for (int cb = 0; cb < 4; cb++) {
@@ -272,16 +290,21 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
         }
     };
     // layer 1 (A from shared memory, K = 24): issuing warps 0..2 take one K-step each, warp 3 only commits
-    auto issue_l1 = [&](uint64_t a_hi, uint64_t a_lo) {
+    auto issue_l1 = [&](uint64_t a_hi, uint64_t a_lo, bool l1_tmem = false) {
         if (issuer) {
             if (elect_one()) {
                 tc_fence_after();
                 if (wq < 3) {
                     uint32_t accumulate = 0;
                     for (int term = 0; term < 3; term++) {
-                        const uint64_t ad = term == 0 ? a_lo : a_hi;
                         const uint64_t bd = term == 1 ? d_b1_lo : d_b1_hi;
-                        mma_tf32(my_acc, ad + KSTEP_W * wq, bd + KSTEP_B * wq, idesc, accumulate);
+                        if (l1_tmem) {          // ODE: folded layer 1 resident in TMEM lanes 16..31
+                            const uint32_t wa = TM_W1 + (term == 0 ? 32 : 0);
+                            mma_tf32_ts(my_acc + TM_UPPER, tmem + TM_UPPER + wa + 8 * wq, bd + KSTEP_B * wq, idesc, accumulate);
+                        } else {
+                            const uint64_t ad = term == 0 ? a_lo : a_hi;
+                            mma_tf32(my_acc, ad + KSTEP_W * wq, bd + KSTEP_B * wq, idesc, accumulate);
+                        }
                         accumulate = 1;
                     }
                 }
@@ -485,7 +508,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                 float d[4];
                 if (TAPE && trec) __stcs(trec + 3 * PSN_TAPE_FRAG + (32 * wq + lane) * 2 + h, ycur);
                 // ---- layer 1 (shared-memory weights) ----
-                issue_l1(d_w1_hi, d_w1_lo);
+                issue_l1(d_w1_hi, d_w1_lo, !DAE);
                 if (e == 0 && wk == 4) {
                     // next step's held inputs; DAE: the un-jumped z[j], v[j] (they feed i_j first), ODE: jumped if step j+1 fires
                     if (DAE) load_zv(j, -1, un);
@@ -493,7 +516,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                     if (have_next) dtn = load_dt(j + 1);
                 }
                 if (e == 0 && j > 1) { store_x_row(j - 1); flush_i(j - 1); }    // rows staged by the previous step
-                collect(d, 3);
+                collect(d, 3, DAE ? 0u : TM_UPPER);
                 store_hidden(d, bias2, c1, trec);
                 publish();
                 // ---- layer 2 ----
