@@ -54,6 +54,8 @@ constexpr int TM_ACC = 0;                                       // lanes 0..15: 
 constexpr int TM_W3T = 128, TM_W2T = 256, TM_W1T = 384;         // lanes 0..15: resident transposed weights, hi at +0, lo at +64
 constexpr uint32_t TM_UPPER = 16u << 16;                        // lanes 16..31 of every sub-partition
 constexpr int TM_DW2 = 0, TM_DW3 = 64, TM_DW4T = 128, TM_DW1F = 144, TM_DWGROUP = 176;   // per group, upper half-lanes
+constexpr int TM_W4T = 352;       // lanes 16..31: W4^T (K = 16), hi at +0, lo at +16 -- with its own accumulators (TS: same lanes)
+constexpr int TM_ACC_M1 = 384;    // lanes 16..31: 2 groups x 4 partial accumulators x 16 for g3 = W4^T dk
 constexpr int TM_COLS = 512;
 constexpr int GROUP_THREADS = 256;     // 8 warps per 16-trajectory group: warps k and k + 4 share TMEM sub-partition k
 constexpr int PSN_DW_FLUSH = 4;        // steps between two flushes of the TMEM weight-gradient accumulators
@@ -86,7 +88,6 @@ struct __align__(128) BwdGroupSmem {
 };
 
 struct __align__(128) BwdCtaSmem {
-    unsigned char w4t_hi[K16_TILE], w4t_lo[K16_TILE];     // A[k][m] = W4[m][k], K = 16
     BwdGroupSmem g[2];
     uint32_t tmem_base;
 };
@@ -119,13 +120,6 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     // ---- one-time setup -------------------------------------------------------------------------------
     if (tid == 0) { mbar_init(&sm.g[0].bar, 4); mbar_init(&sm.g[1].bar, 4); fence_mbar_init(); }
     if ((tid >> 5) == 0) tmem_alloc(&sm.tmem_base, TM_COLS);
-    for (int e = tid; e < TX * TH; e += 2 * GROUP_THREADS) {       // e = m * 64 + k, m < 16
-        const int m = e >> 6, k = e & 63;
-        float hi, lo;
-        split_tf32(__ldg(q.W4 + e), hi, lo);
-        const int o = tile_byte(k, m, LBO_W, SBO_K16);
-        st_f32(sm.w4t_hi, o, hi); st_f32(sm.w4t_lo, o, lo);
-    }
     for (int e = gt; e < (int)(offsetof(BwdGroupSmem, bar) / 4); e += GROUP_THREADS) reinterpret_cast<float*>(&gs)[e] = 0.0f;
     fence_async_smem();
     tc_fence_before();
@@ -155,6 +149,17 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
                 tmem_st_16x256b_x2(tmem + lane_base + TM_W1T + 64 * half + 16 * cb, w1);
             }
         }
+        for (int half = 0; half < 2; half++) {      // W4^T -> lanes 16..31: A[k][m] = W4[m][k], m < 16
+            float w4[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int row = r0 + ((i >> 1) & 1) * 8, col = cc0 + (i & 1) + (i >> 2) * 8;
+                float hi, lo;
+                split_tf32(__ldg(q.W4 + col * TH + row), hi, lo);
+                w4[i] = half ? lo : hi;
+            }
+            tmem_st_16x256b_x2(tmem + TM_UPPER + lane_base + TM_W4T + 16 * half, w4);
+        }
         tmem_st_wait();
     }
     tc_fence_before();
@@ -179,7 +184,6 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     // descriptors
     const uint32_t idesc16 = make_idesc_tf32(TH, TN), idesc24 = make_idesc_tf32(TH, TK1), idesc64 = make_idesc_tf32(TH, TH);
     const uint64_t d_dT_hi = make_desc(smem_u32(gs.dT_hi), LBO, SBO_ACT), d_dT_lo = make_desc(smem_u32(gs.dT_lo), LBO, SBO_ACT);
-    const uint64_t d_w4t_hi = make_desc(smem_u32(sm.w4t_hi), LBO_W, SBO_K16), d_w4t_lo = make_desc(smem_u32(sm.w4t_lo), LBO_W, SBO_K16);
     const uint64_t d_dA_hi0 = make_desc(smem_u32(gs.dA_hi[0]), LBO_W, SBO_K16), d_dA_lo0 = make_desc(smem_u32(gs.dA_lo[0]), LBO_W, SBO_K16);
     const uint64_t d_dA_hi1 = make_desc(smem_u32(gs.dA_hi[1]), LBO_W, SBO_K16), d_dA_lo1 = make_desc(smem_u32(gs.dA_lo[1]), LBO_W, SBO_K16);
     const uint64_t d_aB_hi0 = make_desc(smem_u32(gs.aB_hi[0]), LBO_W, SBO_K16), d_aB_lo0 = make_desc(smem_u32(gs.aB_lo[0]), LBO_W, SBO_K16);
@@ -187,6 +191,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     const uint64_t d_dkB_hi = make_desc(smem_u32(gs.dkB_hi), LBO_W, SBO_K16), d_dkB_lo = make_desc(smem_u32(gs.dkB_lo), LBO_W, SBO_K16);
     const uint32_t acc_base = tmem + TM_ACC + (uint32_t)(g * 4) * TN;
     const uint32_t my_acc = acc_base + (uint32_t)wq * TN;
+    const uint32_t acc_m1 = tmem + TM_UPPER + TM_ACC_M1 + (uint32_t)(g * 4) * TN;      // accumulators of g3 = W4^T dk (lanes 16..31)
     constexpr uint64_t KSTEP_B = (uint64_t)((2 * LBO) >> 4), KSTEP_W = (uint64_t)((2 * LBO_W) >> 4);
     uint32_t phase = 0;
 
@@ -219,9 +224,9 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
                 uint32_t accumulate = 0;
                 for (int e = wq; e < 6; e += 4) {
                     const int term = e >> 1, ks = e & 1;
-                    const uint64_t ad = term == 0 ? d_w4t_lo : d_w4t_hi;
+                    const uint32_t wa = TM_W4T + (term == 0 ? 16 : 0);
                     const uint64_t bd = term == 1 ? d_dT_lo : d_dT_hi;
-                    mma_tf32(my_acc, ad + KSTEP_W * ks, bd + KSTEP_B * ks, idesc16, accumulate);
+                    mma_tf32_ts(acc_m1 + (uint32_t)wq * TN, tmem + TM_UPPER + wa + 8 * ks, bd + KSTEP_B * ks, idesc16, accumulate);
                     accumulate = 1;
                 }
                 mma_commit(&gs.bar);
@@ -250,10 +255,10 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
         phase ^= 1;
         tc_fence_after();
     };
-    auto collect = [&](float (&d)[4]) {
+    auto collect = [&](float (&d)[4], bool m1 = false) {
         wait_mma();
         float t0[4], t1[4], t2[4], t3[4];
-        const uint32_t a = acc_base + lane_base + 8 * h;
+        const uint32_t a = (m1 ? acc_m1 : acc_base) + lane_base + 8 * h;
         tmem_ld_16x256b_x1(a + 0 * TN, t0);
         tmem_ld_16x256b_x1(a + 1 * TN, t1);
         tmem_ld_16x256b_x1(a + 2 * TN, t2);
@@ -448,7 +453,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
                 issue_m1();
                 if (wk == 0) issue_dw(d_aB_hi0, d_aB_lo0, d_dkB_hi, d_dkB_lo, tm_dw + TM_DW4T, idesc16, fresh);
                 // ---- P1: d3 ; a2 -> aB[1]; g2 = W3^T d3 ; dW3 += d3 a2^T ----
-                collect(gsum);
+                collect(gsum, true);
                 make_delta(gsum, a3, dB3, gs.dA_hi[1], gs.dA_lo[1]);
                 store_pairs(gs.aB_hi[1], gs.aB_lo[1], a2);
                 if (has_next) ld_frag(tpn + 2 * PSN_TAPE_FRAG, a3);
