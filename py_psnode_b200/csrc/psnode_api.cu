@@ -126,6 +126,7 @@ int64_t psnode_tape_floats(const psnode_problem* p) {
 int64_t psnode_forward_workspace(const psnode_problem* p) {
     if (validate(p) != PSNODE_OK) return 0;
     int64_t g = psn_generic_forward_workspace(p);
+    { const int64_t g2 = psn_generic_forward_workspace_tb2(p); if (g2 > g) g = g2; }
     int64_t f = psn_fused_supports(p) ? psn_fused_forward_workspace(p) : 0;
     int64_t t = psn_tc_supports(p) ? psn_tc_forward_workspace(p) : 0;
     if (f > g) g = f;
@@ -150,12 +151,15 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
     }
     if (p->impl == PSNODE_IMPL_AUTO && psn_tc_supports(p)) return psn_tc8_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_fused_supports(p)) return psn_fused_forward(p, workspace, workspace_bytes, s);
-    return psn_generic_forward(p, workspace, workspace_bytes, s);
+    const int gst = psn_generic_forward(p, workspace, workspace_bytes, s);
+    if (gst != PSNODE_EUNSUPPORTED) return gst;
+    return psn_generic_forward_tb2(p, workspace, workspace_bytes, s);      // per-trajectory vectors too wide for 8 trajectories per CTA
 }
 
 int64_t psnode_backward_workspace(const psnode_problem* p, const psnode_adjoint* a) {
     if (validate(p) != PSNODE_OK || !a) return 0;
-    const int64_t g = psn_generic_backward_workspace(p, a);
+    int64_t g = psn_generic_backward_workspace(p, a);
+    { const int64_t g2 = psn_generic_backward_workspace_tb2(p, a); if (g2 > g) g = g2; }
     const int64_t t = (p->kind == PSNODE_ODE && psn_tc_supports(p)) ? psn_tc_backward_workspace(p, a) : 0;
     return g > t ? g : t;
 }
@@ -167,7 +171,9 @@ int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* work
     if (!a || !a->d_theta) return PSNODE_EINVAL;
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC || p->impl == PSNODE_IMPL_TC8) && psn_tc_bwd_supports(p, a))
         return psn_tc_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
-    return psn_generic_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    const int gst = psn_generic_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    if (gst != PSNODE_EUNSUPPORTED) return gst;
+    return psn_generic_backward_tb2(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -7,8 +7,17 @@
 namespace {
 
 
-constexpr int G_TB = 8;     // trajectories per CTA
-constexpr int G_TM = 4;     // trajectories per work item (register tile height)
+// Trajectories per CTA.  The default build uses 8; psnode_generic_tb2.cu compiles the same kernels with 2 for the latent
+// widths of the `*_02_direct_encode` models at H = 256 (BASELINE configs[4]: S = 1024, layer-1 input 3072 floats per
+// trajectory -- 8 trajectories of per-trajectory vectors alone would exceed the 227 KB of shared memory).
+#ifndef PSN_G_TB
+#define PSN_G_TB 8
+#endif
+#ifndef PSN_G_NAME
+#define PSN_G_NAME(x) x
+#endif
+constexpr int G_TB = PSN_G_TB;                 // trajectories per CTA
+constexpr int G_TM = G_TB < 4 ? G_TB : 4;      // trajectories per work item (register tile height)
 constexpr int G_NT = 128;   // threads per CTA
 constexpr int G_MAXNETLAYERS = 2 * PSNODE_MAX_LAYERS;
 

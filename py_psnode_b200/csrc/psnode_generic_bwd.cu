@@ -555,7 +555,7 @@ int build_bwd_params(const psnode_problem* p, const psnode_adjoint* a, BwdParams
 
 }  // namespace
 
-int64_t psn_generic_backward_workspace(const psnode_problem* p, const psnode_adjoint*) {
+int64_t PSN_G_NAME(psn_generic_backward_workspace)(const psnode_problem* p, const psnode_adjoint*) {
     int cursor = 0;
     PsnPackedNet de, ae;
     pack_layout(p->de, de, cursor);
@@ -563,7 +563,7 @@ int64_t psn_generic_backward_workspace(const psnode_problem* p, const psnode_adj
     return (int64_t)cursor * 4 * (1 + bwd_grid(p));
 }
 
-int psn_generic_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+int PSN_G_NAME(psn_generic_backward)(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream) {
     static BwdParams q;   // large POD; single-caller library (no re-entrancy)
     int dev = 0, max_smem = 0;
     PSN_CUDA(cudaGetDevice(&dev));

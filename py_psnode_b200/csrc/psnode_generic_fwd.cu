@@ -198,14 +198,14 @@ __global__ void __launch_bounds__(G_NT) psn_generic_fwd_kernel(const __grid_cons
 
 }  // namespace
 
-int64_t psn_generic_forward_workspace(const psnode_problem* p) {
+int64_t PSN_G_NAME(psn_generic_forward_workspace)(const psnode_problem* p) {
     GenericParams q;
     int packed_floats = 0;
     build_params(p, q, packed_floats, 227 * 1024);
     return (int64_t)packed_floats * 4;
 }
 
-int psn_generic_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+int PSN_G_NAME(psn_generic_forward)(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream) {
     static GenericParams q;   // large POD; the library is documented as single-caller (no re-entrancy)
     int packed_floats = 0;
     int dev = 0, max_smem = 0;

@@ -44,6 +44,11 @@ int psn_generic_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cud
 int64_t psn_generic_forward_workspace(const psnode_problem* p);
 int psn_generic_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
 int64_t psn_generic_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);
+// same kernels with 2 trajectories per CTA: taken when the 8-trajectory layout does not fit shared memory (EUNSUPPORTED)
+int psn_generic_forward_tb2(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream);
+int64_t psn_generic_forward_workspace_tb2(const psnode_problem* p);
+int psn_generic_backward_tb2(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
+int64_t psn_generic_backward_workspace_tb2(const psnode_problem* p, const psnode_adjoint* a);
 
 bool psn_fused_supports(const psnode_problem* p);
 int psn_fused_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream);
