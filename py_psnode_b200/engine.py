@@ -215,6 +215,13 @@ def release_tape_pool() -> None:
     _tape_pool.clear()
 
 
+class TapeChunks:
+    """Marker returned instead of a tape when the activation tape of the whole batch would not fit in HBM."""
+
+    def __init__(self, rows: int):
+        self.rows = rows
+
+
 def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]], want_tape: bool = False):
     """Run the forward kernel; returns time-major contiguous (x_sol, i_sol) -- and, with `want_tape`, the activation tape
     the tensor-core reverse sweep consumes (None when the problem has no tape-based sweep or the tape would not fit)."""
@@ -236,6 +243,13 @@ def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]], want_tape: 
                                or n_tape * 4 <= _tape_budget_bytes(t.device)):
                 tape = _take_tape(t.device, n_tape)
                 p.tape, p.tape_floats = tape.data_ptr(), tape.numel()
+            elif n_tape > 0:
+                # the whole batch's tape does not fit: the reverse sweep will re-integrate and differentiate the batch in
+                # chunks of `TapeChunks.rows` trajectories (each with its own tape) instead of falling back to the generic sweep
+                per_group = n_tape // ((B + 15) // 16)
+                rows = 16 * int(_tape_budget_bytes(t.device) // (4 * per_group))
+                if rows >= 32:
+                    tape = TapeChunks(rows)
         ws = _workspace(t.device, L.psnode_forward_workspace(C.byref(p)))
         stream = torch.cuda.current_stream(t.device).cuda_stream
         N.check(L.psnode_forward(C.byref(p), ws.data_ptr(), ws.numel(), stream), "psnode_forward")
@@ -276,9 +290,56 @@ class _Integrate(torch.autograd.Function):
         x_sol = next(it)
         i_sol = next(it) if cfg.kind == N.DAE else None
         tape, ctx.tape = ctx.tape, None
-        grads = backward_raw(cfg, tens, x_sol, i_sol, gx, gi if cfg.kind == N.DAE else None, ctx.needs_input_grad[1:], tape)
-        _give_tape(tape)
+        needs = ctx.needs_input_grad[1:]
+        if isinstance(tape, TapeChunks):
+            grads = _backward_chunked(cfg, tens, gx, needs, tape.rows)
+        else:
+            grads = backward_raw(cfg, tens, x_sol, i_sol, gx, gi if cfg.kind == N.DAE else None, needs, tape)
+            _give_tape(tape)
         return (None, *grads)
+
+
+def _backward_chunked(cfg: Config, tens, gx, needs, rows: int) -> List[Optional[torch.Tensor]]:
+    """Tape-based reverse sweep for a batch whose tape does not fit: trajectories are independent, so the batch is
+    re-integrated chunk by chunk (forward with tape, then the tensor-core sweep), parameter gradients are summed and the
+    per-trajectory gradients concatenated.  ODE only (the only problems that have a tape)."""
+    import dataclasses
+    t = tens[_T]
+    T, B = t.shape[0], t.shape[1]
+    if cfg.has_event and cfg.event_ref is None:      # every chunk must test the events of the GLOBAL sample 0
+        E = tens[_EVT].shape[1]
+        cfg = dataclasses.replace(cfg, event_ref=(t[:, 0, 0], tens[_EVT][0].reshape(E)))
+    series = (_T, _X, _Zs, _Vs, _Is)
+    rows_major = (_XINIT, _A0, _EVT, _ZJ, _VJ)
+    total: List[Optional[torch.Tensor]] = [None] * len(tens)
+    parts: List[list] = [[] for _ in tens]
+    if gx is None:
+        gx = torch.zeros((T, B, cfg.X), dtype=torch.float32, device=t.device)
+    for b0 in range(0, B, rows):
+        b1 = min(B, b0 + rows)
+        sub = list(tens)
+        for k in series:
+            if sub[k] is not None:
+                sub[k] = sub[k][:, b0:b1]
+        for k in rows_major:
+            if sub[k] is not None:
+                sub[k] = sub[k][b0:b1]
+        xs, _is, tape = forward_raw(cfg, sub, want_tape=True)
+        if tape is None or isinstance(tape, TapeChunks):
+            raise RuntimeError("activation tape chunk could not be allocated")
+        g = backward_raw(cfg, sub, xs, None, gx[:, b0:b1], None, needs, tape)
+        _give_tape(tape)
+        for k, gk in enumerate(g):
+            if gk is None:
+                continue
+            if k >= _NFIXED:
+                total[k] = gk.clone() if total[k] is None else total[k].add_(gk)
+            else:
+                parts[k].append(gk)
+    for k in range(_NFIXED):
+        if parts[k]:
+            total[k] = torch.cat(parts[k], dim=1 if k in series else 0)
+    return total
 
 
 def backward_raw(cfg: Config, tens, x_sol, i_sol, gx, gi, needs, tape=None) -> List[Optional[torch.Tensor]]:

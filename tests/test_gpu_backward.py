@@ -197,3 +197,41 @@ if __name__ == "__main__":      # error table for tolerance tuning: python tests
         for key, scale, err, ref_err, _, _ in grad_errors(d, got):
             flag = "" if err <= max(8 * ref_err, 1e-5 * scale + 1e-7) else "  <<<<"
             print(f"{name:28s} {key:12s} scale {scale:9.3e} err {err:9.3e} ref32 {ref_err:9.3e}{flag}")
+
+
+def test_tape_sweep_in_batch_chunks_when_the_tape_does_not_fit(native_lib, monkeypatch):
+    """B = 200 trajectories with room for a 32-trajectory tape only: the reverse sweep re-integrates the batch in 7 chunks on
+    the tensor-core kernels (not the generic sweep) and must reproduce the gradients of the single-tape run."""
+    from py_psnode_b200 import DE_Func, ODE_Event, RK4, _native
+    torch.manual_seed(61)
+    dev = "cuda:0"
+    B, N, X, Z, H = 200, 50, 16, 2, 64
+    T = N + 1
+    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H).to(dev)
+    t = (torch.arange(T, dtype=torch.float32, device=dev) * 0.01).view(T, 1, 1).repeat(1, B, 1)
+    x = torch.randn(T, B, X, device=dev) * 0.1
+    z = torch.randn(T, B, Z, device=dev) * 0.1
+    w = torch.randn(T, B, X, device=dev) * 0.1
+    ev = ODE_Event()
+    ev.set_event(t=t[N // 2].view(B, 1, 1).clone(), z=torch.randn(B, 1, Z, device=dev) * 0.1)
+    per_group_bytes = N * 4 * 3328 * 4                      # (T-1) steps x 4 stages x 3328 floats
+    grads = {}
+    for mode in ("single", "chunked"):
+        if mode == "chunked":
+            monkeypatch.setenv("PSNODE_TAPE_MAX_GB", str(2.5 * per_group_bytes / 2 ** 30))      # room for two 16-trajectory groups
+        else:
+            monkeypatch.delenv("PSNODE_TAPE_MAX_GB", raising=False)
+        for p in de.parameters():
+            p.grad = None
+        xd = x.clone().requires_grad_(True)
+        a0 = torch.cat((x[0], z[0]), dim=-1).requires_grad_(True)
+        n0 = _native.launch_count()
+        sol = RK4().integrate_ODE(x_func=de, t=t, x=xd, z=z, all_initial=a0, event_fn=ev.event_fn, jump_change_fn=ev.jump_change_fn)
+        (sol * w).sum().backward()
+        assert _native.last_kernel() == "psn_tc_grad_reduce_kernel", _native.last_kernel()
+        launches = _native.launch_count() - n0
+        assert launches > 20 if mode == "chunked" else launches < 10, launches
+        grads[mode] = [p.grad.clone() for p in de.parameters()] + [xd.grad.clone(), a0.grad.clone()]
+    for k, (a, b) in enumerate(zip(grads["chunked"], grads["single"])):
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 2e-6 * scale + 1e-9, f"tensor {k}"
