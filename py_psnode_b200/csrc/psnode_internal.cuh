@@ -63,3 +63,7 @@ bool psn_tc_bwd_supports(const psnode_problem* p, const psnode_adjoint* a);
 int psn_tc_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
 int64_t psn_tc_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);
 int psn_tc8_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream);   // psnode_tc8_fwd.cu
+// tape-based tensor-core reverse sweep for the H = 64 DAE nets (psnode_tc_bwd_dae.cu)
+bool psn_tc_dae_bwd_supports(const psnode_problem* p, const psnode_adjoint* a);
+int psn_tc_dae_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
+int64_t psn_tc_dae_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);

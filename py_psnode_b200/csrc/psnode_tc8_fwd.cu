@@ -46,7 +46,7 @@ constexpr int GROUP_THREADS = 256;
 
 struct Tc8Params {
     int B, T, Z, S, groups;
-    int V, I;                                  // DAE only (0 for an ODE); U = Z + V + I <= 8 held-input columns
+    int V, I, E;                               // DAE only (0 for an ODE); U = Z + V + I <= 8 held-input columns; E events
     psnode_series t, x, z, v;
     const float* x_init; int64_t x_init_sb;
     const float* v_jump; int64_t vj_sb, vj_se;
@@ -412,21 +412,21 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
     auto event_of_step = [&](int j) { return q.event_idx ? __ldg(q.event_idx + (j - 1)) : -1; };   // step that ENDS at j
     // DAE: i = ae(x, z, v) on the current layer-1 B tile (AE_Func.forward, neural_01_DAE_01_no_encode.py:74-83); the result goes
     // into the tile's i columns (held input of the next DE evaluations) and, with `stage_out`, into istage (-> i_sol row).
-    auto ae_eval = [&](bool stage_out) {
+    auto ae_eval = [&](bool stage_out, float* rec = nullptr, bool rec_i0 = false) {     // rec: tape record of this evaluation
         if constexpr (DAE) {
             const uint64_t d_wa1_hi = make_desc(smem_u32(smd.wa1_hi), LBO_W, SBO_W), d_wa1_lo = make_desc(smem_u32(smd.wa1_lo), LBO_W, SBO_W);
             float d[4];
             issue_l1(d_wa1_hi, d_wa1_lo);
             collect(d, 3);
-            store_hidden(d, biasA2, c1a, nullptr);
+            store_hidden(d, biasA2, c1a, rec);
             publish();
             issue_ts(TM_W2, TM_W2 + 64, TM_UPPER);
             collect(d, 4, TM_UPPER);
-            store_hidden(d, biasA2, nullptr, nullptr);
+            store_hidden(d, biasA2, nullptr, rec ? rec + PSN_TAPE_FRAG : nullptr);
             publish();
             issue_ts(TM_W3, TM_W3 + 64, TM_UPPER);
             collect(d, 4, TM_UPPER);
-            store_hidden(d, biasA3, nullptr, nullptr);
+            store_hidden(d, biasA3, nullptr, rec ? rec + 2 * PSN_TAPE_FRAG : nullptr);
             publish();
             issue_ts(TM_W4, TM_W4 + 64, TM_UPPER);
             const float kv = collect_slope(TM_UPPER);
@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                 st_f32(gs.b1_hi, off_i, hi);
                 st_f32(gs.b1_lo, off_i, lo);
                 if (stage_out) gs.istage[sn][srow] = iv;
+                if (TAPE && rec && rec_i0) __stcs(rec + 3 * PSN_TAPE_FRAG + (32 * wq + lane) * 2 + h, iv);    // re-evaluated i_0
             }
             publish();
         }
@@ -483,13 +484,15 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
             if (T > 1 && lane < TN) gs.dts[1][lane] = load_dt(1);
         }
         publish();
+        // DAE tape: records of this group (psnode_tc_tape.cuh)
+        float* dbase = (DAE && TAPE && q.tape) ? q.tape + (int64_t)gid * psn_dae_group_recs(T, NST, q.E) * PSN_TAPE_STAGE : nullptr;
         if constexpr (DAE) {
-            ae_eval(true);
+            ae_eval(true, dbase ? dbase + psn_dae_rec_point(0, T, NST) * PSN_TAPE_STAGE : nullptr);
             flush_i(0);
         }
 
         const float c13 = (float)(1.0 / 3.0);
-        float* trec = (TAPE && q.tape) ? q.tape + (int64_t)gid * (T - 1) * NST * PSN_TAPE_STAGE : nullptr;
+        float* trec = (TAPE && q.tape) ? (DAE ? dbase : q.tape + (int64_t)gid * (T - 1) * NST * PSN_TAPE_STAGE) : nullptr;
         float ycur = x0;                                    // input of the current stage (recorded on the tape)
         for (int j = 1; j < T; j++) {
             float un[TU] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dtn = 0.0f;   // next step's inputs, prefetched by warp 4 during stage 0
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                 if (k >= 0) {                                  // event: jumped z / v replace the held inputs and i_0 is re-evaluated
                     if (wk == 4) { float uj[TU]; load_zv(j - 1, k, uj); store_zv(uj); }
                     publish();
-                    ae_eval(false);
+                    ae_eval(false, dbase ? dbase + psn_dae_rec_event(k, T, NST) * PSN_TAPE_STAGE : nullptr, true);
                 }
             }
 #pragma unroll 1
@@ -563,7 +566,10 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                 }
                 publish();
             }
-            if constexpr (DAE) ae_eval(true);                   // i_j = ae(x_j, z[j], v[j])  (my_solvers.py:121)
+            if constexpr (DAE) {                                // i_j = ae(x_j, z[j], v[j])  (my_solvers.py:121)
+                ae_eval(true, (TAPE && trec) ? trec : nullptr);         // its record follows the step's stage records
+                if (TAPE && trec) trec += PSN_TAPE_STAGE;
+            }
         }
         if (T > 1) { store_x_row(T - 1); flush_i(T - 1); }
     }
@@ -582,7 +588,7 @@ int psn_tc8_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStr
     const bool dae = p->kind == PSNODE_DAE;
     Tc8Params q;
     q.B = p->B; q.T = p->T; q.Z = p->Z; q.S = p->X + p->Z + p->V + p->I;
-    q.V = p->V; q.I = p->I;
+    q.V = p->V; q.I = p->I; q.E = p->event_idx ? p->E : 0;
     q.t = p->t; q.x = p->x; q.z = p->z; q.v = p->v;
     q.x_init = p->x_init; q.x_init_sb = p->x_init_sb;
     q.a0 = p->a0; q.a0_sb = p->a0_sb;
@@ -596,7 +602,8 @@ int psn_tc8_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStr
     q.A1 = p->ae.W[0]; q.ab1 = p->ae.b[0]; q.A2 = p->ae.W[1]; q.ab2 = p->ae.b[1];
     q.A3 = p->ae.W[2]; q.ab3 = p->ae.b[2]; q.A4 = p->ae.W[3]; q.ab4 = p->ae.b[3];
     q.vec_out = ((reinterpret_cast<uintptr_t>(p->x_sol.p) & 15) == 0 && (p->x_sol.st & 3) == 0 && (p->x_sol.sb & 3) == 0) ? 1 : 0;
-    q.tape = (!dae && p->tape && p->tape_floats >= psn_tc_tape_floats(p->B, p->T, p->method)) ? p->tape : nullptr;
+    const int64_t tape_need = dae ? psn_tc_dae_tape_floats(p->B, p->T, p->method, q.E) : psn_tc_tape_floats(p->B, p->T, p->method);
+    q.tape = (p->tape && p->tape_floats >= tape_need) ? p->tape : nullptr;
     q.err = static_cast<int*>(ws);
     PSN_CUDA(cudaMemsetAsync(q.err, 0, 4, stream));
     const int ngroups = psn_tc_ngroups(p->B);
@@ -610,6 +617,13 @@ int psn_tc8_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStr
         PSN_CUDA(cudaGetLastError());
         return PSNODE_OK;
     };
+    if (dae && q.tape) {
+        switch (p->method) {
+            case PSNODE_EULER: return launch(psn_tc8_kernel<PSNODE_EULER, true, true>, "psn_tc8_dae_kernel<euler,tape>");
+            case PSNODE_MIDPOINT: return launch(psn_tc8_kernel<PSNODE_MIDPOINT, true, true>, "psn_tc8_dae_kernel<midpoint,tape>");
+            default: return launch(psn_tc8_kernel<PSNODE_RK4, true, true>, "psn_tc8_dae_kernel<rk4,tape>");
+        }
+    }
     if (dae) {
         switch (p->method) {
             case PSNODE_EULER: return launch(psn_tc8_kernel<PSNODE_EULER, true, false>, "psn_tc8_dae_kernel<euler>");

@@ -30,3 +30,22 @@ static inline int psn_tc_nstages(int method) { return method == 0 ? 1 : (method 
 static inline int64_t psn_tc_tape_floats(int B, int T, int method) {
     return (int64_t)psn_tc_ngroups(B) * (T > 1 ? T - 1 : 0) * psn_tc_nstages(method) * PSN_TAPE_STAGE;
 }
+
+// ---- DAE tape (integrate_DAE, my_solvers.py:82-131): the same PSN_TAPE_STAGE-sized records, per 16-trajectory group ----
+//   step j (1..T-1): NST stage records, then the record of the algebraic evaluation i_j = ae(x_j, z[j], v[j])   (:121)
+//   then one record for i_0 = ae(x_0, z[0], v[0]) (:95) and one per event k for the re-evaluated i_0 (:108-110), whose
+//   "stage input" slot holds that i_0 (thread (w, h, lane) owns row lane/4 + 8h of trajectory c0 + (w&1) + 8(w>>1)).
+__host__ __device__ static inline int psn_dae_recs_per_step(int nst) { return nst + 1; }
+__host__ __device__ static inline int64_t psn_dae_group_recs(int T, int nst, int E) {
+    return (int64_t)(T > 1 ? T - 1 : 0) * (nst + 1) + 1 + (E > 0 ? E : 0);
+}
+__host__ __device__ static inline int64_t psn_dae_rec_stage(int j, int e, int nst) { return (int64_t)(j - 1) * (nst + 1) + e; }
+__host__ __device__ static inline int64_t psn_dae_rec_point(int j, int T, int nst) {       // j = 0..T-1
+    return j == 0 ? (int64_t)(T > 1 ? T - 1 : 0) * (nst + 1) : (int64_t)(j - 1) * (nst + 1) + nst;
+}
+__host__ __device__ static inline int64_t psn_dae_rec_event(int k, int T, int nst) {
+    return (int64_t)(T > 1 ? T - 1 : 0) * (nst + 1) + 1 + k;
+}
+static inline int64_t psn_tc_dae_tape_floats(int B, int T, int method, int E) {
+    return (int64_t)psn_tc_ngroups(B) * psn_dae_group_recs(T, psn_tc_nstages(method), E) * PSN_TAPE_STAGE;
+}

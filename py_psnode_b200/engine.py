@@ -243,7 +243,7 @@ def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]], want_tape: 
                                or n_tape * 4 <= _tape_budget_bytes(t.device)):
                 tape = _take_tape(t.device, n_tape)
                 p.tape, p.tape_floats = tape.data_ptr(), tape.numel()
-            elif n_tape > 0:
+            elif n_tape > 0 and cfg.kind == N.ODE:
                 # the whole batch's tape does not fit: the reverse sweep will re-integrate and differentiate the batch in
                 # chunks of `TapeChunks.rows` trajectories (each with its own tape) instead of falling back to the generic sweep
                 per_group = n_tape // ((B + 15) // 16)

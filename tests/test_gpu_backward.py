@@ -105,13 +105,22 @@ CASES = [n for n in golden_names() if "model" not in n and "long" not in n]
 
 
 def _tape_sweep_expected(d):
-    """True when the tensor-core reverse sweep (activation tape) must be the kernel that runs: H = 64 4-layer ODE net,
-    X = 16, no teacher forcing, no input-series gradients."""
-    if str(d["kind"]) != "ode" or bool(d["teacher_x"]) or ("g_z" in d) or ("g_x" in d):
-        return False
-    shapes = [d[f"de_W{k}"].shape for k in range(8) if f"de_W{k}" in d]
-    S = d["x"].shape[-1] + d["z"].shape[-1]
-    return d["x"].shape[-1] == 16 and d["z"].shape[-1] <= 8 and shapes == [(64, 3 * S), (64, 64), (64, 64), (16, 64)]
+    """Name of the reduce kernel of the tensor-core reverse sweep (activation tape) when it must be the one that runs --
+    H = 64 4-layer nets, X = 16, no teacher forcing, no input-series gradients -- else None."""
+    if ("g_z" in d) or ("g_x" in d) or bool(d["teacher_x"]) or ("teacher_i" in d and bool(d["teacher_i"])):
+        return None
+    de = [d[f"de_W{k}"].shape for k in range(8) if f"de_W{k}" in d]
+    X = 16
+    if str(d["kind"]) == "ode":
+        S = d["x"].shape[-1] + d["z"].shape[-1]
+        ok = d["x"].shape[-1] == X and d["z"].shape[-1] <= 8 and de == [(64, 3 * S), (64, 64), (64, 64), (16, 64)]
+        return "psn_tc_grad_reduce_kernel" if ok else None
+    Z, V, I = d["z"].shape[-1], d["v"].shape[-1], d["i"].shape[-1]
+    S = X + Z + V + I
+    ae = [d[f"ae_W{k}"].shape for k in range(8) if f"ae_W{k}" in d]
+    ok = (d["x_init"].shape[-1] == X and Z + V + I <= 8 and de == [(64, 3 * S), (64, 64), (64, 64), (16, 64)]
+          and ae == [(64, S + X + Z + V), (64, 64), (64, 64), (I, 64)])
+    return "psn_tc_dae_grad_reduce_kernel" if ok else None
 
 
 @pytest.mark.parametrize("sweep", ["tape", "recompute"])
@@ -129,7 +138,7 @@ def test_backward_matches_reference(native_lib, name, sweep, monkeypatch):
         monkeypatch.delenv("PSNODE_TAPE_MAX_GB", raising=False)
     got = run_with_grads(d, name)
     if sweep == "tape" and _tape_sweep_expected(d):
-        assert _native.last_kernel() == "psn_tc_grad_reduce_kernel", _native.last_kernel()
+        assert _native.last_kernel() == _tape_sweep_expected(d), _native.last_kernel()
     else:
         assert _native.last_kernel() == "psn_grad_reduce_kernel", _native.last_kernel()
     rows = grad_errors(d, got)
