@@ -130,3 +130,36 @@ def test_cfg2_gradients_full_size_tape_vs_recompute(native_lib, monkeypatch):
         scale = float(b.abs().max())
         err = float((a - b).abs().max())
         assert err <= 2e-5 * scale + 1e-9, f"tensor {k}: max|tape - recompute| = {err:.3e}, scale {scale:.3e}"
+
+
+def test_cfg3_gradients_full_size_tape_vs_recompute(native_lib, monkeypatch):
+    """cfg3 (DAE) at full size: tensor-core reverse sweep (DAE tape) against the generic recomputing sweep."""
+    from py_psnode_b200 import AE_Func, DE_Func, RK4, _native
+    dev = "cuda:0"
+    torch.manual_seed(33)
+    Z, V, I = 1, 2, 4
+    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H, v_dim=V, i_dim=I).to(dev)
+    ae = AE_Func(x_dim=X, v_dim=V, i_dim=I, hidden_dim=H, z_dim=Z).to(dev)
+    _, d = _inputs(34, {"z": Z, "v": V, "i": I}, dev)
+    wx = torch.randn(T, B, X, device=dev) * 1e-3
+    wi = torch.randn(T, B, I, device=dev) * 1e-3
+    plist = list(de.parameters()) + list(ae.parameters())
+    grads = {}
+    for sweep in ("tape", "recompute"):
+        if sweep == "recompute":
+            monkeypatch.setenv("PSNODE_TAPE_MAX_GB", "0")
+        else:
+            monkeypatch.delenv("PSNODE_TAPE_MAX_GB", raising=False)
+        for p in plist:
+            p.grad = None
+        x0 = d["x0"].clone().requires_grad_(True)
+        a0 = torch.cat((x0.detach(), d["z"][0], d["v"][0], d["i"][0]), dim=-1).requires_grad_(True)
+        x_view = d["x0"].unsqueeze(0).expand(T, B, X)
+        gx, gi = RK4().integrate_DAE(x_init=x0, x_func=de, i_func=ae, t=d["t"], x=x_view, z=d["z"], v=d["v"], i=d["i"], all_initial=a0)
+        ((gx * wx).sum() + (gi * wi).sum()).backward()
+        assert _native.last_kernel() == ("psn_tc_dae_grad_reduce_kernel" if sweep == "tape" else "psn_grad_reduce_kernel")
+        grads[sweep] = [p.grad.clone() for p in plist] + [x0.grad.clone(), a0.grad.clone()]
+    for k, (a, b) in enumerate(zip(grads["tape"], grads["recompute"])):
+        scale = float(b.abs().max())
+        err = float((a - b).abs().max())
+        assert err <= 2e-5 * scale + 1e-9, f"tensor {k}: max|tape - recompute| = {err:.3e}, scale {scale:.3e}"

@@ -87,3 +87,52 @@ def test_dae_tc_forward_all_methods(native_lib, method):
     assert _native.last_kernel().startswith("psn_tc8_dae_kernel")
     assert torch.allclose(gx.cpu(), wx, rtol=RTOL, atol=ATOL), "x: " + tol_report(gx.cpu(), wx)
     assert torch.allclose(gi.cpu(), wi, rtol=RTOL, atol=ATOL), "i: " + tol_report(gi.cpu(), wi)
+
+
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
+def test_dae_tc_tape_gradients_all_methods(native_lib, method, monkeypatch):
+    """DAE reverse sweep on tensor cores (ragged batch, an event on the very first step and one mid-way) against float64
+    autograd through the oracle: both nets' parameters, x_init and all_initial."""
+    from oracle import psnode_oracle as O
+    from py_psnode_b200 import AE_Func, DAE_Event, DE_Func, Euler, Midpoint, RK4, _native
+    monkeypatch.delenv("PSNODE_TAPE_MAX_GB", raising=False)
+    torch.manual_seed(53)
+    dev = "cuda:0"
+    B, N, X, Z, V, I, H = 40, 24, 16, 1, 2, 4, 64
+    T = N + 1
+    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H, v_dim=V, i_dim=I)
+    ae = AE_Func(x_dim=X, v_dim=V, i_dim=I, hidden_dim=H, z_dim=Z)
+    t = (torch.arange(T, dtype=torch.float32) * 0.02).view(T, 1, 1).repeat(1, B, 1)
+    mk = lambda wd: torch.randn(T, B, wd) * 0.2
+    x, z, v, i = mk(X), mk(Z), mk(V), mk(I)
+    x_init = torch.randn(B, X) * 0.2
+    a0 = torch.cat((x_init, z[0], v[0], i[0]), dim=-1)
+    event_t = torch.cat((t[0].view(B, 1, 1), t[N // 2].view(B, 1, 1)), dim=1).clone()     # events on step 1 and mid-way
+    z_jump, v_jump = torch.randn(B, 2, Z) * 0.2, torch.randn(B, 2, V) * 0.2
+    wx, wi = torch.randn(T, B, X) * 0.1, torch.randn(T, B, I) * 0.1
+    pd = [(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in _params(de.x_dot)]
+    pa = [(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in _params(ae.i_calculator)]
+    xi64, a064 = x_init.double().requires_grad_(True), a0.double().requires_grad_(True)
+    sx, si = O.integrate_dae(method, pd, pa, xi64, t.double(), x.double(), z.double(), v.double(), i.double(), a064,
+                             event_t.double(), z_jump.double(), v_jump.double())
+    ((sx * wx.double()).sum() + (si * wi.double()).sum()).backward()
+    S = {"euler": Euler, "midpoint": Midpoint, "rk4": RK4}[method]
+    de_d, ae_d = de.to(dev), ae.to(dev)
+    ev = DAE_Event()
+    ev.set_event(t=event_t.to(dev), z=z_jump.to(dev), v=v_jump.to(dev))
+    xid, a0d = x_init.to(dev).requires_grad_(True), a0.to(dev).requires_grad_(True)
+    gx, gi = S().integrate_DAE(x_init=xid, x_func=de_d, i_func=ae_d, t=t.to(dev), x=x.to(dev), z=z.to(dev), v=v.to(dev), i=i.to(dev),
+                               all_initial=a0d, event_fn=ev.event_fn, jump_change_fn=ev.jump_change_fn)
+    assert _native.last_kernel().startswith("psn_tc8_dae_kernel") and "tape" in _native.last_kernel()
+    assert torch.allclose(gx.detach().cpu(), sx.detach().float(), rtol=RTOL, atol=ATOL)
+    ((gx * wx.to(dev)).sum() + (gi * wi.to(dev)).sum()).backward()
+    assert _native.last_kernel() == "psn_tc_dae_grad_reduce_kernel"
+    lin_d = [m for m in de_d.x_dot if isinstance(m, torch.nn.Linear)]
+    lin_a = [m for m in ae_d.i_calculator if isinstance(m, torch.nn.Linear)]
+    pairs = [(lin_d[k].weight.grad, pd[k][0].grad) for k in range(4)] + [(lin_d[k].bias.grad, pd[k][1].grad) for k in range(4)]
+    pairs += [(lin_a[k].weight.grad, pa[k][0].grad) for k in range(4)] + [(lin_a[k].bias.grad, pa[k][1].grad) for k in range(4)]
+    pairs += [(xid.grad, xi64.grad), (a0d.grad, a064.grad)]
+    for k, (g, g64) in enumerate(pairs):
+        scale = float(g64.abs().max())
+        err = float((g.cpu().double() - g64).abs().max())
+        assert err <= 1e-5 * scale + 1e-7, f"{method} tensor {k}: err {err:.3e} scale {scale:.3e}"
