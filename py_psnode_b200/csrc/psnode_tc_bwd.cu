@@ -28,7 +28,7 @@
 //     group at the end: dWc = G, dWb = G - D1 a0^T, dWa = D1 a0^T, db1 = sum_n D1, d_a0 = (Wa-Wb)^T D1  (G = dW1f accumulator).
 //   * the tensor core's fp32 accumulate TRUNCATES (measured: a chain of N accumulations into one TMEM accumulator is biased
 //     towards zero by ~N * 2^-24), so the TMEM gradient accumulators are flushed into the group's slab with round-to-nearest
-//     adds every PSN_DW_FLUSH steps (<= 16 accumulations per chain) instead of once at the end.
+//     adds every 16 / NST steps (<= 16 accumulations per chain) instead of once at the end.
 //   * every group writes its gradient to a private slab; psn_tc_grad_reduce_kernel sums the slabs in a fixed order
 //     (deterministic, no floating-point atomics).
 #include <cstddef>
@@ -58,7 +58,7 @@ constexpr int TM_W4T = 352;       // lanes 16..31: W4^T (K = 16), hi at +0, lo a
 constexpr int TM_ACC_M1 = 384;    // lanes 16..31: 2 groups x 4 partial accumulators x 16 for g3 = W4^T dk
 constexpr int TM_COLS = 512;
 constexpr int GROUP_THREADS = 256;     // 8 warps per 16-trajectory group: warps k and k + 4 share TMEM sub-partition k
-constexpr int PSN_DW_FLUSH = 4;        // steps between two flushes of the TMEM weight-gradient accumulators
+constexpr int PSN_DW_CHAIN = 16;       // accumulations into a TMEM weight-gradient accumulator between two flushes (16 / NST steps)
 constexpr int G_AREA = TH * TK1;       // floats of the dW1f (folded layer 1) accumulator kept behind each group's slab
 
 struct TcBwdParams {
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
                 fresh = false;
             }
             lam = dxs + gxn;
-            if (((T - j) % PSN_DW_FLUSH) == 0 || j == 1) { flush_dw(); fresh = true; }
+            if (((T - j) % (PSN_DW_CHAIN / NST)) == 0 || j == 1) { flush_dw(); fresh = true; }
         }
         if (q.d_x0 && valid) q.d_x0[(int64_t)bown * q.d_x0_sb + srow] = lam;
 

@@ -45,7 +45,7 @@ constexpr int TM_DW2 = 0, TM_DW3 = 64, TM_DW4T = 128, TM_DW1F = 144, TM_DWNET = 
 constexpr int TM_ACC_M5 = 352;
 constexpr int TM_COLS = 512;
 constexpr int GROUP_THREADS = 256;
-constexpr int PSN_DW_FLUSH = 4;
+constexpr int PSN_DW_CHAIN = 16;       // accumulations into a TMEM weight-gradient accumulator between two flushes (16 / NST steps)
 constexpr int G_AREA = TH * TK1;
 
 struct DaeBwdParams {
@@ -340,35 +340,56 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
 
     // drain the tensor pipe and add one net's TMEM weight-gradient accumulators into the slab (round-to-nearest adds)
     auto flush_net = [&](uint32_t tm_dw, int o2, int o3, int o4, int n4, float* garea) {
+        // the slab values are fetched first, all at once (independent L2 round trips), then combined with the accumulators
         const int r0 = m0, cc = c0;
+        float2 p2[4][2], p3[4][2], pg[2][2];
+        float p4[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; q4++) {          // dW2 / dW3: 64 columns = 8 blocks of 8, this warp takes blocks h, h+2, h+4, h+6
+            const int cb = h + 2 * q4;
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                p2[q4][r] = *reinterpret_cast<const float2*>(sl + o2 + (r0 + 8 * r) * TH + 8 * cb + cc);
+                p3[q4][r] = *reinterpret_cast<const float2*>(sl + o3 + (r0 + 8 * r) * TH + 8 * cb + cc);
+            }
+        }
+        const int mc = 8 * h + cc;                // layer 4, transposed: rows = hidden k, columns = output m (n4 real)
+        const bool ok0 = mc < n4, ok1 = mc + 1 < n4;
+        p4[0] = ok0 ? sl[o4 + mc * TH + r0] : 0.0f; p4[1] = ok1 ? sl[o4 + (mc + 1) * TH + r0] : 0.0f;
+        p4[2] = ok0 ? sl[o4 + mc * TH + r0 + 8] : 0.0f; p4[3] = ok1 ? sl[o4 + (mc + 1) * TH + r0 + 8] : 0.0f;
+#pragma unroll
+        for (int q2 = 0; q2 < 2; q2++) {          // folded layer 1: 24 columns = 3 blocks of 8: blocks h and h + 2 (< 3)
+            const int cb = h + 2 * q2;
+#pragma unroll
+            for (int r = 0; r < 2; r++)
+                pg[q2][r] = cb < 3 ? *reinterpret_cast<const float2*>(garea + (r0 + 8 * r) * TK1 + 8 * cb + cc) : make_float2(0.f, 0.f);
+        }
         float v[4];
-        auto add2 = [&](float* dst, float x, float y) {
-            float2 o = *reinterpret_cast<float2*>(dst);
-            o.x += x; o.y += y;
-            *reinterpret_cast<float2*>(dst) = o;
-        };
-        for (int cb = h; cb < 8; cb += 2) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; q4++) {
+            const int cb = h + 2 * q4;
             tmem_ld_16x256b_x1(tm_dw + lane_base + TM_DW2 + 8 * cb, v);
             tmem_ld_wait();
-            add2(sl + o2 + r0 * TH + 8 * cb + cc, v[0], v[1]);
-            add2(sl + o2 + (r0 + 8) * TH + 8 * cb + cc, v[2], v[3]);
+            *reinterpret_cast<float2*>(sl + o2 + r0 * TH + 8 * cb + cc) = make_float2(p2[q4][0].x + v[0], p2[q4][0].y + v[1]);
+            *reinterpret_cast<float2*>(sl + o2 + (r0 + 8) * TH + 8 * cb + cc) = make_float2(p2[q4][1].x + v[2], p2[q4][1].y + v[3]);
             tmem_ld_16x256b_x1(tm_dw + lane_base + TM_DW3 + 8 * cb, v);
             tmem_ld_wait();
-            add2(sl + o3 + r0 * TH + 8 * cb + cc, v[0], v[1]);
-            add2(sl + o3 + (r0 + 8) * TH + 8 * cb + cc, v[2], v[3]);
+            *reinterpret_cast<float2*>(sl + o3 + r0 * TH + 8 * cb + cc) = make_float2(p3[q4][0].x + v[0], p3[q4][0].y + v[1]);
+            *reinterpret_cast<float2*>(sl + o3 + (r0 + 8) * TH + 8 * cb + cc) = make_float2(p3[q4][1].x + v[2], p3[q4][1].y + v[3]);
         }
-        {   // layer 4, transposed: rows = hidden k, columns = output m (n4 real rows of the net's last layer)
-            tmem_ld_16x256b_x1(tm_dw + lane_base + TM_DW4T + 8 * h, v);
-            tmem_ld_wait();
-            const int mc = 8 * h + cc;
-            if (mc < n4) { sl[o4 + mc * TH + r0] += v[0]; sl[o4 + mc * TH + r0 + 8] += v[2]; }
-            if (mc + 1 < n4) { sl[o4 + (mc + 1) * TH + r0] += v[1]; sl[o4 + (mc + 1) * TH + r0 + 8] += v[3]; }
-        }
-        for (int cb = h; cb < 3; cb += 2) {
-            tmem_ld_16x256b_x1(tm_dw + lane_base + TM_DW1F + 8 * cb, v);
-            tmem_ld_wait();
-            add2(garea + r0 * TK1 + 8 * cb + cc, v[0], v[1]);
-            add2(garea + (r0 + 8) * TK1 + 8 * cb + cc, v[2], v[3]);
+        tmem_ld_16x256b_x1(tm_dw + lane_base + TM_DW4T + 8 * h, v);
+        tmem_ld_wait();
+        if (ok0) { sl[o4 + mc * TH + r0] = p4[0] + v[0]; sl[o4 + mc * TH + r0 + 8] = p4[2] + v[2]; }
+        if (ok1) { sl[o4 + (mc + 1) * TH + r0] = p4[1] + v[1]; sl[o4 + (mc + 1) * TH + r0 + 8] = p4[3] + v[3]; }
+#pragma unroll
+        for (int q2 = 0; q2 < 2; q2++) {
+            const int cb = h + 2 * q2;
+            if (cb < 3) {                          // warp-uniform
+                tmem_ld_16x256b_x1(tm_dw + lane_base + TM_DW1F + 8 * cb, v);
+                tmem_ld_wait();
+                *reinterpret_cast<float2*>(garea + r0 * TK1 + 8 * cb + cc) = make_float2(pg[q2][0].x + v[0], pg[q2][0].y + v[1]);
+                *reinterpret_cast<float2*>(garea + (r0 + 8) * TK1 + 8 * cb + cc) = make_float2(pg[q2][1].x + v[2], pg[q2][1].y + v[3]);
+            }
         }
     };
     auto flush_dw = [&](bool de_dirty, bool ae_dirty) {      // a net's accumulators hold data only after one of its chains ran
@@ -489,35 +510,51 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
         auto own_gi = [&](int j) { return (valid && own_i && q.gi.p) ? ldser(q.gi, j, bown, srow) : 0.0f; };
         float lam = own_gx(T - 1), mu = own_gi(T - 1);
         const float c13 = (float)(1.0 / 3.0);
-        float u[TU], dui_dummy = 0.0f;
+        float dui_dummy = 0.0f;
+        // held inputs [z0 v0 i0] of step j (warp 4, trajectory = lane): jumped z / v and the re-evaluated i_0 on an event step
+        auto load_held = [&](int j, int k, float (&uh)[TU]) {
+            load_zv(j - 1, k, uh);
+            const int n = lane & 15, bb = min(b0 + n, B - 1);
 #pragma unroll
-        for (int c = 0; c < TU; c++) u[c] = 0.0f;
-        load_rec(rec_ptr(psn_dae_rec_point(T - 1, T, NST)));
-        for (int j = T - 1; j >= 1; j--) {
-            // ---- point j: i_j = ae(x_j, z[j], v[j]) ----
-            if (wk == 4) load_zv(j, -1, u);
-            lam += chain(AE_NET{}, own_i ? mu : 0.0f, own_x(j), u, rec_ptr(psn_dae_rec_stage(j, NST - 1, NST)), fresh_ae,
-                         D1a, dB2a, dB3a, dB4a, dui_dummy);
-            fresh_ae = false;
-            // ---- step j ----
-            const int k = event_of_step(j);
-            const float dt = __fsub_rn(ldser(q.t, j, bbown, 0), ldser(q.t, j - 1, bbown, 0));
-            if (wk == 4) {          // held inputs [z0 v0 i0] of the step (trajectory = lane)
-                load_zv(j - 1, k, u);
-                const int n = lane & 15, bb = min(b0 + n, B - 1);
-#pragma unroll
-                for (int c = 0; c < TU; c++) {
-                    if (c >= ZV && c < ZV + I) {
-                        const int ci = c - ZV;
-                        if (k >= 0) {   // re-evaluated i_0, recorded by forward thread (w, h, lane') that owns (row ci, trajectory n)
-                            const int wf = (n & 1) + 2 * (n >> 3), lf = 4 * (ci & 7) + ((n & 7) >> 1), hf = ci >> 3;
-                            u[c] = __ldcs(rec_ptr(psn_dae_rec_event(k, T, NST)) + 3 * PSN_TAPE_FRAG + (32 * wf + lf) * 2 + hf);
-                        } else {
-                            u[c] = __ldg(q.i_sol + (int64_t)(j - 1) * q.is_st + (int64_t)bb * q.is_sb + ci);
-                        }
+            for (int c = 0; c < TU; c++) {
+                if (c >= ZV && c < ZV + I) {
+                    const int ci = c - ZV;
+                    if (k >= 0) {   // recorded by forward thread (w, h, lane') that owns (row ci, trajectory n)
+                        const int wf = (n & 1) + 2 * (n >> 3), lf = 4 * (ci & 7) + ((n & 7) >> 1), hf = ci >> 3;
+                        uh[c] = __ldcs(rec_ptr(psn_dae_rec_event(k, T, NST)) + 3 * PSN_TAPE_FRAG + (32 * wf + lf) * 2 + hf);
+                    } else {
+                        uh[c] = __ldg(q.i_sol + (int64_t)(j - 1) * q.is_st + (int64_t)bb * q.is_sb + ci);
                     }
                 }
             }
+        };
+        // everything a step needs from global memory is fetched one step ahead (registers *_n)
+        float un_ae[TU], un_de[TU], tan = 0.0f, tbn = 0.0f;
+#pragma unroll
+        for (int c = 0; c < TU; c++) { un_ae[c] = 0.0f; un_de[c] = 0.0f; }
+        if (wk == 4) load_zv(T - 1, -1, un_ae);
+        if (T > 1) {
+            tan = ldser(q.t, T - 1, bbown, 0); tbn = ldser(q.t, T - 2, bbown, 0);
+            if (wk == 4) load_held(T - 1, event_of_step(T - 1), un_de);
+        }
+        load_rec(rec_ptr(psn_dae_rec_point(T - 1, T, NST)));
+        for (int j = T - 1; j >= 1; j--) {
+            const int k = event_of_step(j);
+            const float dt = __fsub_rn(tan, tbn);
+            float u_ae[TU], u_de[TU];
+#pragma unroll
+            for (int c = 0; c < TU; c++) { u_ae[c] = un_ae[c]; u_de[c] = un_de[c]; }
+            const float gxn = own_gx(j - 1), gin = own_gi(j - 1);
+            if (wk == 4) load_zv(j - 1, -1, un_ae);                       // point j-1
+            if (j > 1) {
+                tan = tbn; tbn = ldser(q.t, j - 2, bbown, 0);
+                if (wk == 4) load_held(j - 1, event_of_step(j - 1), un_de);
+            }
+            // ---- point j: i_j = ae(x_j, z[j], v[j]) ----
+            lam += chain(AE_NET{}, own_i ? mu : 0.0f, own_x(j), u_ae, rec_ptr(psn_dae_rec_stage(j, NST - 1, NST)), fresh_ae,
+                         D1a, dB2a, dB3a, dB4a, dui_dummy);
+            fresh_ae = false;
+            // ---- step j ----
             float dxs = lam, d1 = 0.f, d2 = 0.f, d3 = 0.f, dcur, dui = 0.0f;
             {
                 const float ld = lam * dt;
@@ -531,7 +568,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
                 const float* rnext = e > 0 ? rec - PSN_TAPE_STAGE : rec_ptr(after_step);
                 const float yv = __ldcs(rec + ytape);
                 float du_e = 0.0f;
-                const float gq = chain(DE_NET{}, dcur, yv, u, rnext, fresh_de, D1, dB2, dB3, dB4, du_e);
+                const float gq = chain(DE_NET{}, dcur, yv, u_de, rnext, fresh_de, D1, dB2, dB3, dB4, du_e);
                 fresh_de = false;
                 dui += du_e;
                 dxs += gq;
@@ -544,20 +581,19 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
                     if (e == 1) dcur = (0.5f * dt) * gq;
                 }
             }
-            lam = dxs + own_gx(j - 1);
-            if (k >= 0) {           // back through i_0 = ae(x_{j-1}, z_jump[k], v_jump[k])  (my_solvers.py:108-110)
-                if (wk == 4) load_zv(j - 1, k, u);
-                lam += chain(AE_NET{}, own_i ? dui : 0.0f, own_x(j - 1), u, rec_ptr(psn_dae_rec_point(j - 1, T, NST)), fresh_ae,
+            lam = dxs + gxn;
+            if (k >= 0) {           // back through i_0 = ae(x_{j-1}, z_jump[k], v_jump[k])  (my_solvers.py:108-110); the z / v part of
+                                    // u_de is exactly that input (its i columns only reach unused columns of the AE's G area)
+                lam += chain(AE_NET{}, own_i ? dui : 0.0f, own_x(j - 1), u_de, rec_ptr(psn_dae_rec_point(j - 1, T, NST)), fresh_ae,
                              D1a, dB2a, dB3a, dB4a, dui_dummy);
-                mu = own_gi(j - 1);
+                mu = gin;
             } else {
-                mu = dui + own_gi(j - 1);
+                mu = dui + gin;
             }
-            if (((T - j) % PSN_DW_FLUSH) == 0) { flush_dw(!fresh_de, !fresh_ae); fresh_de = true; fresh_ae = true; }
+            if (((T - j) % (PSN_DW_CHAIN / NST)) == 0) { flush_dw(!fresh_de, !fresh_ae); fresh_de = true; fresh_ae = true; }
         }
         // ---- point 0: i_0 = ae(x_0, z[0], v[0])  (my_solvers.py:95) ----
-        if (wk == 4) load_zv(0, -1, u);
-        lam += chain(AE_NET{}, own_i ? mu : 0.0f, own_x(0), u, nullptr, fresh_ae, D1a, dB2a, dB3a, dB4a, dui_dummy);
+        lam += chain(AE_NET{}, own_i ? mu : 0.0f, own_x(0), un_ae, nullptr, fresh_ae, D1a, dB2a, dB3a, dB4a, dui_dummy);
         flush_dw(!fresh_de, true);
         if (q.d_x0 && valid) q.d_x0[(int64_t)bown * q.d_x0_sb + srow] = lam;
 
