@@ -243,7 +243,7 @@ def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]], want_tape: 
                                or n_tape * 4 <= _tape_budget_bytes(t.device)):
                 tape = _take_tape(t.device, n_tape)
                 p.tape, p.tape_floats = tape.data_ptr(), tape.numel()
-            elif n_tape > 0 and cfg.kind == N.ODE:
+            elif n_tape > 0:
                 # the whole batch's tape does not fit: the reverse sweep will re-integrate and differentiate the batch in
                 # chunks of `TapeChunks.rows` trajectories (each with its own tape) instead of falling back to the generic sweep
                 per_group = n_tape // ((B + 15) // 16)
@@ -292,17 +292,17 @@ class _Integrate(torch.autograd.Function):
         tape, ctx.tape = ctx.tape, None
         needs = ctx.needs_input_grad[1:]
         if isinstance(tape, TapeChunks):
-            grads = _backward_chunked(cfg, tens, gx, needs, tape.rows)
+            grads = _backward_chunked(cfg, tens, gx, gi if cfg.kind == N.DAE else None, needs, tape.rows)
         else:
             grads = backward_raw(cfg, tens, x_sol, i_sol, gx, gi if cfg.kind == N.DAE else None, needs, tape)
             _give_tape(tape)
         return (None, *grads)
 
 
-def _backward_chunked(cfg: Config, tens, gx, needs, rows: int) -> List[Optional[torch.Tensor]]:
+def _backward_chunked(cfg: Config, tens, gx, gi, needs, rows: int) -> List[Optional[torch.Tensor]]:
     """Tape-based reverse sweep for a batch whose tape does not fit: trajectories are independent, so the batch is
     re-integrated chunk by chunk (forward with tape, then the tensor-core sweep), parameter gradients are summed and the
-    per-trajectory gradients concatenated.  ODE only (the only problems that have a tape)."""
+    per-trajectory gradients concatenated."""
     import dataclasses
     t = tens[_T]
     T, B = t.shape[0], t.shape[1]
@@ -315,6 +315,8 @@ def _backward_chunked(cfg: Config, tens, gx, needs, rows: int) -> List[Optional[
     parts: List[list] = [[] for _ in tens]
     if gx is None:
         gx = torch.zeros((T, B, cfg.X), dtype=torch.float32, device=t.device)
+    if cfg.kind == N.DAE and gi is None:
+        gi = torch.zeros((T, B, cfg.I), dtype=torch.float32, device=t.device)
     for b0 in range(0, B, rows):
         b1 = min(B, b0 + rows)
         sub = list(tens)
@@ -327,7 +329,7 @@ def _backward_chunked(cfg: Config, tens, gx, needs, rows: int) -> List[Optional[
         xs, _is, tape = forward_raw(cfg, sub, want_tape=True)
         if tape is None or isinstance(tape, TapeChunks):
             raise RuntimeError("activation tape chunk could not be allocated")
-        g = backward_raw(cfg, sub, xs, None, gx[:, b0:b1], None, needs, tape)
+        g = backward_raw(cfg, sub, xs, _is, gx[:, b0:b1], gi[:, b0:b1] if gi is not None else None, needs, tape)
         _give_tape(tape)
         for k, gk in enumerate(g):
             if gk is None:

@@ -244,3 +244,44 @@ def test_tape_sweep_in_batch_chunks_when_the_tape_does_not_fit(native_lib, monke
     for k, (a, b) in enumerate(zip(grads["chunked"], grads["single"])):
         scale = float(b.abs().max())
         assert float((a - b).abs().max()) <= 2e-6 * scale + 1e-9, f"tensor {k}"
+
+
+def test_dae_tape_sweep_in_batch_chunks(native_lib, monkeypatch):
+    """Same as above for the DAE sweep (B = 72 trajectories, tape room for 32): chunked == single-tape gradients."""
+    from py_psnode_b200 import AE_Func, DAE_Event, DE_Func, RK4, _native
+    torch.manual_seed(62)
+    dev = "cuda:0"
+    B, N, X, Z, V, I, H = 72, 20, 16, 1, 2, 4, 64
+    T = N + 1
+    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H, v_dim=V, i_dim=I).to(dev)
+    ae = AE_Func(x_dim=X, v_dim=V, i_dim=I, hidden_dim=H, z_dim=Z).to(dev)
+    t = (torch.arange(T, dtype=torch.float32, device=dev) * 0.01).view(T, 1, 1).repeat(1, B, 1)
+    mk = lambda wd: torch.randn(T, B, wd, device=dev) * 0.1
+    x, z, v, i = mk(X), mk(Z), mk(V), mk(I)
+    x_init = torch.randn(B, X, device=dev) * 0.1
+    wx, wi = mk(X), mk(I)
+    ev = DAE_Event()
+    ev.set_event(t=t[N // 2].view(B, 1, 1).clone(), z=torch.randn(B, 1, Z, device=dev) * 0.1, v=torch.randn(B, 1, V, device=dev) * 0.1)
+    per_group_bytes = (N * 5 + 2) * 3328 * 4
+    plist = list(de.parameters()) + list(ae.parameters())
+    grads = {}
+    for mode in ("single", "chunked"):
+        if mode == "chunked":
+            monkeypatch.setenv("PSNODE_TAPE_MAX_GB", str(2.5 * per_group_bytes / 2 ** 30))
+        else:
+            monkeypatch.delenv("PSNODE_TAPE_MAX_GB", raising=False)
+        for p in plist:
+            p.grad = None
+        xi = x_init.clone().requires_grad_(True)
+        a0 = torch.cat((x_init, z[0], v[0], i[0]), dim=-1).requires_grad_(True)
+        n0 = _native.launch_count()
+        gx, gi = RK4().integrate_DAE(x_init=xi, x_func=de, i_func=ae, t=t, x=x, z=z, v=v, i=i, all_initial=a0, event_fn=ev.event_fn,
+                                     jump_change_fn=ev.jump_change_fn)
+        ((gx * wx).sum() + (gi * wi).sum()).backward()
+        assert _native.last_kernel() == "psn_tc_dae_grad_reduce_kernel", _native.last_kernel()
+        launches = _native.launch_count() - n0
+        assert launches > 10 if mode == "chunked" else launches < 10, launches
+        grads[mode] = [p.grad.clone() for p in plist] + [xi.grad.clone(), a0.grad.clone()]
+    for k, (a, b) in enumerate(zip(grads["chunked"], grads["single"])):
+        scale = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 2e-6 * scale + 1e-9, f"tensor {k}"
