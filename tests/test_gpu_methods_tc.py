@@ -136,3 +136,61 @@ def test_dae_tc_tape_gradients_all_methods(native_lib, method, monkeypatch):
         scale = float(g64.abs().max())
         err = float((g.cpu().double() - g64).abs().max())
         assert err <= 1e-5 * scale + 1e-7, f"{method} tensor {k}: err {err:.3e} scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("T", [1, 2, 3])
+@pytest.mark.parametrize("kind", ["ode", "dae"])
+def test_tc_degenerate_grids(native_lib, kind, T, monkeypatch):
+    """Grids with 0, 1 and 2 steps (the reference's loop simply does not iterate for T = 1): tensor-core forward + tape sweeps
+    against float64 autograd through the oracle."""
+    from oracle import psnode_oracle as O
+    from py_psnode_b200 import AE_Func, DE_Func, RK4
+    monkeypatch.delenv("PSNODE_TAPE_MAX_GB", raising=False)
+    torch.manual_seed(70 + T)
+    dev = "cuda:0"
+    B, X, Z, V, I, H = 20, 16, 1, 2, 4, 64
+    dae = kind == "dae"
+    t = (torch.arange(T, dtype=torch.float32) * 0.05).view(T, 1, 1).repeat(1, B, 1)
+    mk = lambda wd: torch.randn(T, B, wd) * 0.2
+    x, z, v, i = mk(X), mk(Z), mk(V), mk(I)
+    wx, wi = torch.randn(T, B, X) * 0.1, torch.randn(T, B, I) * 0.1
+    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H, v_dim=V if dae else 0, i_dim=I if dae else 0)
+    pd = [(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in _params(de.x_dot)]
+    if dae:
+        ae = AE_Func(x_dim=X, v_dim=V, i_dim=I, hidden_dim=H, z_dim=Z)
+        pa = [(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in _params(ae.i_calculator)]
+        x_init = torch.randn(B, X) * 0.2
+        a0 = torch.cat((x_init, z[0], v[0], i[0]), dim=-1)
+        xi64, a064 = x_init.double().requires_grad_(True), a0.double().requires_grad_(True)
+        sx, si = O.integrate_dae("rk4", pd, pa, xi64, t.double(), x.double(), z.double(), v.double(), i.double(), a064)
+        ((sx * wx.double()).sum() + (si * wi.double()).sum()).backward()
+        de_d, ae_d = de.to(dev), ae.to(dev)
+        xid, a0d = x_init.to(dev).requires_grad_(True), a0.to(dev).requires_grad_(True)
+        gx, gi = RK4().integrate_DAE(x_init=xid, x_func=de_d, i_func=ae_d, t=t.to(dev), x=x.to(dev), z=z.to(dev), v=v.to(dev),
+                                     i=i.to(dev), all_initial=a0d)
+        assert torch.allclose(gx.detach().cpu(), sx.detach().float(), rtol=RTOL, atol=ATOL)
+        assert torch.allclose(gi.detach().cpu(), si.detach().float(), rtol=RTOL, atol=ATOL)
+        ((gx * wx.to(dev)).sum() + (gi * wi.to(dev)).sum()).backward()
+        lin_a = [m for m in ae_d.i_calculator if isinstance(m, torch.nn.Linear)]
+        pairs = [(lin_a[k].weight.grad, pa[k][0].grad) for k in range(4)] + [(lin_a[k].bias.grad, pa[k][1].grad) for k in range(4)]
+        pairs += [(xid.grad, xi64.grad), (a0d.grad, a064.grad)]
+    else:
+        a0 = torch.cat((x[0], z[0]), dim=-1)
+        x64, a064 = x.double().requires_grad_(True), a0.double().requires_grad_(True)
+        sx = O.integrate_ode("rk4", pd, t.double(), x64, z.double(), a064)
+        (sx * wx.double()).sum().backward()
+        de_d = de.to(dev)
+        xd, a0d = x.to(dev).requires_grad_(True), a0.to(dev).requires_grad_(True)
+        gx = RK4().integrate_ODE(x_func=de_d, t=t.to(dev), x=xd, z=z.to(dev), all_initial=a0d)
+        assert torch.allclose(gx.detach().cpu(), sx.detach().float(), rtol=RTOL, atol=ATOL)
+        (gx * wx.to(dev)).sum().backward()
+        pairs = [(xd.grad, x64.grad), (a0d.grad if a0d.grad is not None else torch.zeros_like(a0d), a064.grad if a064.grad is not None else torch.zeros_like(a064))]
+    lin_d = [m for m in de_d.x_dot if isinstance(m, torch.nn.Linear)]
+    for k in range(4):
+        gW = lin_d[k].weight.grad if lin_d[k].weight.grad is not None else torch.zeros_like(lin_d[k].weight)
+        gW64 = pd[k][0].grad if pd[k][0].grad is not None else torch.zeros_like(pd[k][0])
+        pairs.append((gW, gW64))
+    for k, (g, g64) in enumerate(pairs):
+        scale = float(g64.abs().max())
+        err = float((g.cpu().double() - g64).abs().max())
+        assert err <= 1e-5 * scale + 1e-7, f"{kind} T={T} tensor {k}: err {err:.3e} scale {scale:.3e}"
