@@ -340,7 +340,9 @@ def main():
         train = {"value": units * world / (tr_ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": tr_ms,
                  "what": "forward + reverse sweep (discrete adjoint, all parameter grads) + masked-MSE + one flat gradient all-reduce",
                  "allreduce_bytes": bucket.nbytes, "kernel": bwd_kernel, "gpu_launches": int(_native.launch_count() - l0),
-                 "loss": loss_val}
+                 "loss": loss_val,
+                 # forward + exact reverse mode = 3x the forward's algorithmic FLOPs (the tape-based sweep does not recompute)
+                 "achieved_tflops_reference_formulation": 3 * w["flop_per_unit"] * units / (tr_ms * 1e-3) / 1e12}
 
     if rank == 0:
         peaks = {}
