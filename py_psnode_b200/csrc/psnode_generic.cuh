@@ -18,7 +18,8 @@ namespace {
 #endif
 constexpr int G_TB = PSN_G_TB;                 // trajectories per CTA
 constexpr int G_TM = G_TB < 4 ? G_TB : 4;      // trajectories per work item (register tile height)
-constexpr int G_NT = 128;   // threads per CTA
+constexpr int G_NT = 128;   // threads per CTA (nets resident in shared memory)
+constexpr int G_NT_MAX = 512;  // threads per CTA when layers stream from L2 (wide latent nets)
 constexpr int G_MAXNETLAYERS = 2 * PSNODE_MAX_LAYERS;
 
 struct PackDesc {

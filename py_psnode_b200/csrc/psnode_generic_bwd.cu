@@ -23,7 +23,8 @@
 
 namespace {
 
-constexpr int R_NT = 256;   // threads per CTA
+constexpr int R_NT_MAX = 1024;   // threads per CTA: 256 for nets that live in shared memory, 1024 when weights / gradients
+                                // stream through L2 (wide latent nets: the sweep is then bound by L2 latency, not by issue slots)
 constexpr int R_MAXST = 4;  // stages
 
 struct BwdParams {
@@ -74,7 +75,7 @@ __device__ float* mlp_backward(const PsnPackedNet& net, const float* __restrict_
         const int K = net.in_dim[l], N = net.out_dim[l], kp = net.kpad[l], kq = kp >> 2;
         // ---- dW[n][k] += sum_i delta[i][n] * in[i][k]  (4 columns per work item; pad columns of `in` are zero) ----
         float* gW = gw_off[l] >= 0 ? sm + gw_off[l] : slab + net.w_off[l];
-        for (int e = tid; e < N * kq; e += R_NT) {
+        for (int e = tid; e < N * kq; e += (int)blockDim.x) {
             const int n = e / kq, k4 = (e - n * kq) << 2;
             float4 g = *reinterpret_cast<const float4*>(gW + (size_t)n * kp + k4);
 #pragma unroll
@@ -86,7 +87,7 @@ __device__ float* mlp_backward(const PsnPackedNet& net, const float* __restrict_
             *reinterpret_cast<float4*>(gW + (size_t)n * kp + k4) = g;
         }
         float* gB = sm + gb_off[l];
-        for (int n = tid; n < N; n += R_NT) {
+        for (int n = tid; n < N; n += (int)blockDim.x) {
             float g = gB[n];
 #pragma unroll
             for (int i = 0; i < G_TB; i++) g += dcur[i * DM + n];
@@ -95,7 +96,7 @@ __device__ float* mlp_backward(const PsnPackedNet& net, const float* __restrict_
         // ---- delta_in[i][k] = (sum_n W[n][k] delta[i][n]) * elu'(in[i][k]) ----
         const bool wsmem = net.smem_off[l] >= 0;
         const float* W = wsmem ? wsm + net.smem_off[l] : packed + net.w_off[l];
-        for (int e = tid; e < G_TB * K; e += R_NT) {
+        for (int e = tid; e < G_TB * K; e += (int)blockDim.x) {
             const int i = e / K, k = e - i * K;
             const float* dr = dcur + i * DM;
             float acc = 0.0f;
@@ -114,7 +115,7 @@ __device__ float* mlp_backward(const PsnPackedNet& net, const float* __restrict_
 }
 
 template <bool DAE>
-__global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_constant__ BwdParams q) {
+__global__ void __launch_bounds__(R_NT_MAX) psn_generic_bwd_kernel(const __grid_constant__ BwdParams q) {
     extern __shared__ float4 smem4[];
     float* sm = reinterpret_cast<float*>(smem4);
     const psnode_problem& p = q.p;
@@ -168,10 +169,10 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
             const int n4 = pn.out_dim[l] * pn.kpad[l] / 4;
             const float4* g = reinterpret_cast<const float4*>(q.packed + pn.w_off[l]);
             float4* s = reinterpret_cast<float4*>(wsm + pn.smem_off[l]);
-            for (int e = tid; e < n4; e += R_NT) s[e] = __ldg(g + e);
+            for (int e = tid; e < n4; e += (int)blockDim.x) s[e] = __ldg(g + e);
         }
     }
-    for (int e = q.g_begin + tid; e < q.g_end; e += R_NT) sm[e] = 0.0f;
+    for (int e = q.g_begin + tid; e < q.g_end; e += (int)blockDim.x) sm[e] = 0.0f;
 
     auto set_state = [&](int i, int c, float xv) {
         u3[i * K0 + S + c] = __fsub_rn(xv, a0s[i * S4 + c]);
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
     // AE input vector: x part from smem rows (stride X4) or the teacher series at grid point jx; z/v of grid point jz or event k
     auto ae_forward = [&](int b0, const float* xsrc, int jx_teacher, int jz, int k, float* out) {
         const int W3 = X + Z + V;
-        for (int e = tid; e < G_TB * W3; e += R_NT) {
+        for (int e = tid; e < G_TB * W3; e += (int)blockDim.x) {
             const int i = e / W3, c = e - i * W3;
             const int bb = min(b0 + i, B - 1);
             float val;
@@ -201,9 +202,9 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
     for (int tile = blockIdx.x; tile < q.n_tiles; tile += gridDim.x) {
         const int b0 = tile * G_TB;
         __syncthreads();
-        for (int e = q.zero_begin + tid; e < q.zero_end; e += R_NT) sm[e] = 0.0f;
+        for (int e = q.zero_begin + tid; e < q.zero_end; e += (int)blockDim.x) sm[e] = 0.0f;
         __syncthreads();
-        for (int e = tid; e < G_TB * S; e += R_NT) {
+        for (int e = tid; e < G_TB * S; e += (int)blockDim.x) {
             const int i = e / S, c = e - i * S;
             const int bb = min(b0 + i, B - 1);
             const float av = __ldg(p.a0 + (int64_t)bb * p.a0_sb + c);
@@ -214,12 +215,12 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
         // jump gradients are accumulated (+=) over the steps that fire the same event: clear this tile's rows first
         if (p.event_idx) {
             if (a.d_zjump && Z > 0)
-                for (int e = tid; e < G_TB * p.E * Z; e += R_NT) {
+                for (int e = tid; e < G_TB * p.E * Z; e += (int)blockDim.x) {
                     const int i = e / (p.E * Z), r = e - i * (p.E * Z), b = b0 + i;
                     if (b < B) a.d_zjump[(int64_t)b * a.d_zj_sb + (int64_t)(r / Z) * a.d_zj_se + (r % Z)] = 0.0f;
                 }
             if (DAE && a.d_vjump && V > 0)
-                for (int e = tid; e < G_TB * p.E * V; e += R_NT) {
+                for (int e = tid; e < G_TB * p.E * V; e += (int)blockDim.x) {
                     const int i = e / (p.E * V), r = e - i * (p.E * V), b = b0 + i;
                     if (b < B) a.d_vjump[(int64_t)b * a.d_vj_sb + (int64_t)(r / V) * a.d_vj_se + (r % V)] = 0.0f;
                 }
@@ -228,27 +229,27 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
 
         for (int j = T - 1; j >= 0; j--) {
             // ================= point j =================
-            for (int e = tid; e < G_TB * X; e += R_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, b = b0 + i;
                 if (b < B && a.gx.p) lam[i * X4 + c] += ld_series(a.gx, j, b, c);
             }
             if (DAE) {
-                for (int e = tid; e < G_TB * I; e += R_NT) {
+                for (int e = tid; e < G_TB * I; e += (int)blockDim.x) {
                     const int i = e / I, c = e - i * I, b = b0 + i;
                     if (b < B && a.gi.p) mu[i * I4 + c] += ld_series(a.gi, j, b, c);
                 }
                 // x_j rows for the AE input (x_sol[j]; for j = 0 this is x_init, written by the forward kernel)
                 if (!p.teacher_x)
-                    for (int e = tid; e < G_TB * X; e += R_NT) {
+                    for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                         const int i = e / X, c = e - i * X, bb = min(b0 + i, B - 1);
                         start[i * X4 + c] = __ldg(p.x_sol.p + (int64_t)j * p.x_sol.st + (int64_t)bb * p.x_sol.sb + c);
                     }
                 __syncthreads();
                 ae_forward(b0, start, p.teacher_x ? j : -1, j, -1, itmp);
-                for (int e = tid; e < G_TB * I; e += R_NT) { const int i = e / I, c = e - i * I; dA[i * DM + c] = mu[i * I4 + c]; }
+                for (int e = tid; e < G_TB * I; e += (int)blockDim.x) { const int i = e / I, c = e - i * I; dA[i * DM + c] = mu[i * I4 + c]; }
                 __syncthreads();
                 const float* du = mlp_backward(q.ae, q.packed, wsm, sm, q.gw_ae, q.gb_ae, slab, uae, KA0, aeacts, HM, dA, dB, DM);
-                for (int e = tid; e < G_TB * KA0; e += R_NT) {
+                for (int e = tid; e < G_TB * KA0; e += (int)blockDim.x) {
                     const int i = e / KA0, c = e - i * KA0;
                     if (c >= S + X + Z + V) continue;
                     const float g = du[i * DM + c];
@@ -261,22 +262,22 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
             __syncthreads();
             // gradients of the input series at grid point j are complete
             if (a.d_z.p)
-                for (int e = tid; e < G_TB * Z; e += R_NT) {
+                for (int e = tid; e < G_TB * Z; e += (int)blockDim.x) {
                     const int i = e / Z, c = e - i * Z, b = b0 + i;
                     if (b < B) a.d_z.p[(int64_t)j * a.d_z.st + (int64_t)b * a.d_z.sb + c] = pz[i * Z4 + c];
                 }
             if (DAE && a.d_v.p)
-                for (int e = tid; e < G_TB * V; e += R_NT) {
+                for (int e = tid; e < G_TB * V; e += (int)blockDim.x) {
                     const int i = e / V, c = e - i * V, b = b0 + i;
                     if (b < B) a.d_v.p[(int64_t)j * a.d_v.st + (int64_t)b * a.d_v.sb + c] = pv[i * V4 + c];
                 }
             if (a.d_xteach.p)
-                for (int e = tid; e < G_TB * X; e += R_NT) {
+                for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                     const int i = e / X, c = e - i * X, b = b0 + i;
                     if (b < B) a.d_xteach.p[(int64_t)j * a.d_xteach.st + (int64_t)b * a.d_xteach.sb + c] = pxt[i * X4 + c];
                 }
             if (DAE && a.d_iteach.p)
-                for (int e = tid; e < G_TB * I; e += R_NT) {
+                for (int e = tid; e < G_TB * I; e += (int)blockDim.x) {
                     const int i = e / I, c = e - i * I, b = b0 + i;
                     if (b < B) a.d_iteach.p[(int64_t)j * a.d_iteach.st + (int64_t)b * a.d_iteach.sb + c] = pit[i * I4 + c];
                 }
@@ -285,26 +286,26 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
 
             // ================= step j: recompute =================
             const int k = p.event_idx ? __ldg(p.event_idx + (j - 1)) : -1;
-            for (int i = tid; i < G_TB; i += R_NT) {
+            for (int i = tid; i < G_TB; i += (int)blockDim.x) {
                 const int bb = min(b0 + i, B - 1);
                 dts[i] = __fsub_rn(ld_series(p.t, j, bb, 0), ld_series(p.t, j - 1, bb, 0));
             }
             // predicted previous state (needed for the event AE even under teacher forcing)
-            for (int e = tid; e < G_TB * X; e += R_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, bb = min(b0 + i, B - 1);
                 dy[i * X4 + c] = __ldg(p.x_sol.p + (int64_t)(j - 1) * p.x_sol.st + (int64_t)bb * p.x_sol.sb + c);
             }
             __syncthreads();
             const bool event_ae = DAE && k >= 0 && !p.teacher_i;
             if (event_ae) ae_forward(b0, dy, -1, j - 1, k, ihold);   // i_0 from the jumped inputs (my_solvers.py:109-110)
-            for (int e = tid; e < G_TB * X; e += R_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, bb = min(b0 + i, B - 1);
                 const float xv = p.teacher_x ? ld_series(p.x, j - 1, bb, c) : dy[i * X4 + c];
                 start[i * X4 + c] = xv;
                 ys[i * X4 + c] = xv;
                 set_state(i, c, xv);
             }
-            for (int e = tid; e < G_TB * U; e += R_NT) {
+            for (int e = tid; e < G_TB * U; e += (int)blockDim.x) {
                 const int i = e / U, c = e - i * U, bb = min(b0 + i, B - 1);
                 float hv;
                 if (c < Z) hv = (k >= 0) ? __ldg(p.z_jump + (int64_t)bb * p.zj_sb + (int64_t)k * p.zj_se + c) : ld_series(p.z, j - 1, bb, c);
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
             __syncthreads();
             for (int s = 0; s < nst; s++) {
                 if (s > 0) {   // y_s, same operation order as the forward kernels
-                    for (int e = tid; e < G_TB * X; e += R_NT) {
+                    for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                         const int i = e / X, c = e - i * X, o = i * X4 + c;
                         const float dt = dts[i];
                         const float* k1 = kst; const float* k2 = kst + G_TB * X4; const float* k3 = kst + 2 * G_TB * X4;
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
                 run_mlp_keep(q.de, q.packed, wsm, u3, K0, kst + s * G_TB * X4, X4, X, acts + s * acts_stage, HM);
             }
             // ================= step j: reverse =================
-            for (int e = tid; e < G_TB * X; e += R_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, o = i * X4 + c;
                 const float l = lam[o], dt = dts[i];
                 dxs[o] = l;
@@ -349,14 +350,14 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
             }
             __syncthreads();
             for (int s = nst - 1; s >= 0; s--) {
-                for (int e = tid; e < G_TB * X; e += R_NT) {
+                for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                     const int i = e / X, c = e - i * X, o = i * X4 + c;
                     set_state(i, c, ys[s * G_TB * X4 + o]);
                     dA[i * DM + c] = dk[s * G_TB * X4 + o];
                 }
                 __syncthreads();
                 const float* du = mlp_backward(q.de, q.packed, wsm, sm, q.gw_de, q.gb_de, slab, u3, K0, acts + s * acts_stage, HM, dA, dB, DM);
-                for (int e = tid; e < G_TB * S; e += R_NT) {
+                for (int e = tid; e < G_TB * S; e += (int)blockDim.x) {
                     const int i = e / S, c = e - i * S;
                     const float ga = du[i * DM + c], gb = du[i * DM + S + c], gc = du[i * DM + 2 * S + c];
                     da0[i * S4 + c] += ga - gb;
@@ -371,11 +372,11 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
                 __syncthreads();
             }
             // ================= route the step's input gradients =================
-            for (int e = tid; e < G_TB * X; e += R_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, o = i * X4 + c;
                 if (p.teacher_x) { pxt[o] = dxs[o]; lam[o] = 0.0f; } else { lam[o] = dxs[o]; pxt[o] = 0.0f; }
             }
-            for (int e = tid; e < G_TB * U; e += R_NT) {
+            for (int e = tid; e < G_TB * U; e += (int)blockDim.x) {
                 const int i = e / U, c = e - i * U, b = b0 + i;
                 const float g = dheld[i * U4 + c];
                 if (c < Z) {
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
             __syncthreads();
             if (event_ae) {   // back through i_0 = ae(x_{j-1}, z_jump[k], v_jump[k]); uae / aeacts still hold that evaluation
                 const float* du = mlp_backward(q.ae, q.packed, wsm, sm, q.gw_ae, q.gb_ae, slab, uae, KA0, aeacts, HM, dA, dB, DM);
-                for (int e = tid; e < G_TB * KA0; e += R_NT) {
+                for (int e = tid; e < G_TB * KA0; e += (int)blockDim.x) {
                     const int i = e / KA0, c = e - i * KA0, b = b0 + i;
                     if (c >= S + X + Z + V) continue;
                     const float g = du[i * DM + c];
@@ -410,12 +411,12 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
         // ---- tile epilogue: gradients of the initial state and of all_initial ----
         __syncthreads();
         if (a.d_x0)
-            for (int e = tid; e < G_TB * X; e += R_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, b = b0 + i;
                 if (b < B) a.d_x0[(int64_t)b * a.d_x0_sb + c] = lam[i * X4 + c];
             }
         if (a.d_a0)
-            for (int e = tid; e < G_TB * S; e += R_NT) {
+            for (int e = tid; e < G_TB * S; e += (int)blockDim.x) {
                 const int i = e / S, c = e - i * S, b = b0 + i;
                 if (b < B) a.d_a0[(int64_t)b * a.d_a0_sb + c] = da0[i * S4 + c];
             }
@@ -428,8 +429,8 @@ __global__ void __launch_bounds__(R_NT) psn_generic_bwd_kernel(const __grid_cons
         const int* gb = net ? q.gb_ae : q.gb_de;
         for (int l = 0; l < pn.n_layers; l++) {
             if (gw[l] >= 0)
-                for (int e = tid; e < pn.out_dim[l] * pn.kpad[l]; e += R_NT) slab[pn.w_off[l] + e] = sm[gw[l] + e];
-            for (int e = tid; e < pn.out_dim[l]; e += R_NT) slab[pn.b_off[l] + e] = sm[gb[l] + e];
+                for (int e = tid; e < pn.out_dim[l] * pn.kpad[l]; e += (int)blockDim.x) slab[pn.w_off[l] + e] = sm[gw[l] + e];
+            for (int e = tid; e < pn.out_dim[l]; e += (int)blockDim.x) slab[pn.b_off[l] + e] = sm[gb[l] + e];
         }
     }
 }
@@ -604,13 +605,18 @@ int PSN_G_NAME(psn_generic_backward)(const psnode_problem* p, const psnode_adjoi
     psn_count_launch("psn_pack_kernel");
     PSN_CUDA(cudaGetLastError());
     PSN_CUDA(cudaMemsetAsync(q.slab, 0, (size_t)q.packed_floats * 4 * grid, stream));
+    // nets whose weights or gradient accumulators do not fit shared memory stream them through L2: hide that latency with 4x the warps
+    bool streamed = false;
+    for (int l = 0; l < q.de.n_layers; l++) streamed |= q.de.smem_off[l] < 0 || q.gw_de[l] < 0;
+    for (int l = 0; l < q.ae.n_layers; l++) streamed |= q.ae.smem_off[l] < 0 || q.gw_ae[l] < 0;
+    const int nthreads = streamed ? R_NT_MAX : 256;
     if (dae) {
         PSN_CUDA(cudaFuncSetAttribute(psn_generic_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        psn_generic_bwd_kernel<true><<<grid, R_NT, smem_bytes, stream>>>(q);
+        psn_generic_bwd_kernel<true><<<grid, nthreads, smem_bytes, stream>>>(q);
         psn_count_launch("psn_generic_bwd_kernel<dae>");
     } else {
         PSN_CUDA(cudaFuncSetAttribute(psn_generic_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        psn_generic_bwd_kernel<false><<<grid, R_NT, smem_bytes, stream>>>(q);
+        psn_generic_bwd_kernel<false><<<grid, nthreads, smem_bytes, stream>>>(q);
         psn_count_launch("psn_generic_bwd_kernel<ode>");
     }
     PSN_CUDA(cudaGetLastError());

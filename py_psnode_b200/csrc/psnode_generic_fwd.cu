@@ -15,7 +15,7 @@
 namespace {
 
 template <bool DAE>
-__global__ void __launch_bounds__(G_NT) psn_generic_fwd_kernel(const __grid_constant__ GenericParams q) {
+__global__ void __launch_bounds__(G_NT_MAX) psn_generic_fwd_kernel(const __grid_constant__ GenericParams q) {
     extern __shared__ float4 smem4[];
     float* sm = reinterpret_cast<float*>(smem4);
     const psnode_problem& p = q.p;
@@ -46,12 +46,12 @@ __global__ void __launch_bounds__(G_NT) psn_generic_fwd_kernel(const __grid_cons
             const int n4 = pn.out_dim[l] * pn.kpad[l] / 4;
             const float4* g = reinterpret_cast<const float4*>(q.packed + pn.w_off[l]);
             float4* s = reinterpret_cast<float4*>(wsm + pn.smem_off[l]);
-            for (int e = tid; e < n4; e += G_NT) s[e] = __ldg(g + e);
+            for (int e = tid; e < n4; e += (int)blockDim.x) s[e] = __ldg(g + e);
         }
     }
-    for (int e = q.buf_begin + tid; e < q.total_floats; e += G_NT) sm[e] = 0.0f;
+    for (int e = q.buf_begin + tid; e < q.total_floats; e += (int)blockDim.x) sm[e] = 0.0f;
     __syncthreads();
-    for (int e = tid; e < G_TB * S; e += G_NT) {
+    for (int e = tid; e < G_TB * S; e += (int)blockDim.x) {
         const int i = e / S, c = e - i * S;
         const int bb = min(b0 + i, B - 1);
         const float a = __ldg(p.a0 + (int64_t)bb * p.a0_sb + c);
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(G_NT) psn_generic_fwd_kernel(const __grid_cons
         u3[i * K0 + c] = a;
         if (DAE) uae[i * KA0 + c] = a;
     }
-    for (int e = tid; e < G_TB * X; e += G_NT) {
+    for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
         const int i = e / X, c = e - i * X;
         const int b = b0 + i, bb = min(b, B - 1);
         const float xv = DAE ? __ldg(p.x_init + (int64_t)bb * p.x_init_sb + c) : ld_series(p.x, 0, bb, c);
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(G_NT) psn_generic_fwd_kernel(const __grid_cons
 
     // AE evaluation helper: x source (smem, stride X4) or teacher series at grid point jx; z/v from grid point jz or event k
     auto ae_eval = [&](const float* xsrc, int jx_teacher, int jz, int k) {
-        for (int e = tid; e < G_TB * (X + Z + V); e += G_NT) {
+        for (int e = tid; e < G_TB * (X + Z + V); e += (int)blockDim.x) {
             const int i = e / (X + Z + V), c = e - i * (X + Z + V);
             const int bb = min(b0 + i, B - 1);
             float val;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(G_NT) psn_generic_fwd_kernel(const __grid_cons
         run_mlp(q.ae, q.packed, wsm, uae, KA0, iprev, I4, I, actA, actB, HM);
     };
     auto store_i = [&](int j) {
-        for (int e = tid; e < G_TB * I; e += G_NT) {
+        for (int e = tid; e < G_TB * I; e += (int)blockDim.x) {
             const int i = e / I, c = e - i * I;
             const int b = b0 + i;
             if (b < B) p.i_sol.p[(int64_t)j * p.i_sol.st + (int64_t)b * p.i_sol.sb + c] = iprev[i * I4 + c];
@@ -116,11 +116,11 @@ __global__ void __launch_bounds__(G_NT) psn_generic_fwd_kernel(const __grid_cons
         const int k = p.event_idx ? __ldg(p.event_idx + (j - 1)) : -1;
         if (DAE && k >= 0) ae_eval(xprev, -1, j - 1, k);   // i_0 recomputed from the jumped inputs (my_solvers.py:109-110)
         // per-step inputs: dt, start state, held inputs
-        for (int i = tid; i < G_TB; i += G_NT) {
+        for (int i = tid; i < G_TB; i += (int)blockDim.x) {
             const int bb = min(b0 + i, B - 1);
             dts[i] = __fsub_rn(ld_series(p.t, j, bb, 0), ld_series(p.t, j - 1, bb, 0));
         }
-        for (int e = tid; e < G_TB * X; e += G_NT) {
+        for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
             const int i = e / X, c = e - i * X;
             const int bb = min(b0 + i, B - 1);
             const float xv = p.teacher_x ? ld_series(p.x, j - 1, bb, c) : xprev[i * X4 + c];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(G_NT) psn_generic_fwd_kernel(const __grid_cons
             set_state(i, c, xv);
         }
         const int U = S - X;
-        for (int e = tid; e < G_TB * U; e += G_NT) {
+        for (int e = tid; e < G_TB * U; e += (int)blockDim.x) {
             const int i = e / U, c = e - i * U;
             const int bb = min(b0 + i, B - 1);
             float hv;
@@ -145,45 +145,45 @@ __global__ void __launch_bounds__(G_NT) psn_generic_fwd_kernel(const __grid_cons
         }
         rhs(k1);
         if (p.method == PSNODE_EULER) {
-            for (int e = tid; e < G_TB * X; e += G_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, o = i * X4 + c;
                 xprev[o] = __fadd_rn(start[o], __fmul_rn(dts[i], k1[o]));
             }
         } else if (p.method == PSNODE_MIDPOINT) {
-            for (int e = tid; e < G_TB * X; e += G_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, o = i * X4 + c;
                 const float half_dt = __fmul_rn(0.5f, dts[i]);
                 set_state(i, c, __fadd_rn(start[o], __fmul_rn(k1[o], half_dt)));
             }
             rhs(k2);
-            for (int e = tid; e < G_TB * X; e += G_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, o = i * X4 + c;
                 xprev[o] = __fadd_rn(start[o], __fmul_rn(dts[i], k2[o]));
             }
         } else {   // RK4, 3/8 rule; operation order of rk4_alt_step_func (my_fixed_grid.py:38-51)
-            for (int e = tid; e < G_TB * X; e += G_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, o = i * X4 + c;
                 set_state(i, c, __fadd_rn(start[o], __fmul_rn(__fmul_rn(dts[i], k1[o]), c13)));
             }
             rhs(k2);
-            for (int e = tid; e < G_TB * X; e += G_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, o = i * X4 + c;
                 set_state(i, c, __fadd_rn(start[o], __fmul_rn(dts[i], __fsub_rn(k2[o], __fmul_rn(k1[o], c13)))));
             }
             rhs(k3);
-            for (int e = tid; e < G_TB * X; e += G_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, o = i * X4 + c;
                 set_state(i, c, __fadd_rn(start[o], __fmul_rn(dts[i], __fadd_rn(__fsub_rn(k1[o], k2[o]), k3[o]))));
             }
             rhs(k4);
-            for (int e = tid; e < G_TB * X; e += G_NT) {
+            for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
                 const int i = e / X, c = e - i * X, o = i * X4 + c;
                 const float ks = __fadd_rn(__fadd_rn(k1[o], __fmul_rn(3.0f, __fadd_rn(k2[o], k3[o]))), k4[o]);
                 xprev[o] = __fadd_rn(start[o], __fmul_rn(__fmul_rn(ks, dts[i]), 0.125f));
             }
         }
         // every thread re-reads only the xprev entries it wrote itself (same e -> (i,c) mapping)
-        for (int e = tid; e < G_TB * X; e += G_NT) {
+        for (int e = tid; e < G_TB * X; e += (int)blockDim.x) {
             const int i = e / X, c = e - i * X;
             const int b = b0 + i;
             if (b < B) p.x_sol.p[(int64_t)j * p.x_sol.st + (int64_t)b * p.x_sol.sb + c] = xprev[i * X4 + c];
@@ -234,13 +234,18 @@ int PSN_G_NAME(psn_generic_forward)(const psnode_problem* p, void* ws, int64_t w
     PSN_CUDA(cudaGetLastError());
 
     const int grid = (p->B + G_TB - 1) / G_TB;
+    // layers that do not fit shared memory stream from L2: hide that latency with 4x the warps
+    bool streamed = false;
+    for (int l = 0; l < q.de.n_layers; l++) streamed |= q.de.smem_off[l] < 0;
+    for (int l = 0; l < q.ae.n_layers; l++) streamed |= q.ae.smem_off[l] < 0;
+    const int nthreads = streamed ? G_NT_MAX : G_NT;
     if (p->kind == PSNODE_DAE) {
         PSN_CUDA(cudaFuncSetAttribute(psn_generic_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        psn_generic_fwd_kernel<true><<<grid, G_NT, smem_bytes, stream>>>(q);
+        psn_generic_fwd_kernel<true><<<grid, nthreads, smem_bytes, stream>>>(q);
         psn_count_launch("psn_generic_fwd_kernel<dae>");
     } else {
         PSN_CUDA(cudaFuncSetAttribute(psn_generic_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        psn_generic_fwd_kernel<false><<<grid, G_NT, smem_bytes, stream>>>(q);
+        psn_generic_fwd_kernel<false><<<grid, nthreads, smem_bytes, stream>>>(q);
         psn_count_launch("psn_generic_fwd_kernel<ode>");
     }
     PSN_CUDA(cudaGetLastError());
