@@ -140,7 +140,7 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
     if (st != PSNODE_OK) return st;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (p->impl == PSNODE_IMPL_TC) {
-        if (!psn_tc_supports(p)) return PSNODE_EUNSUPPORTED;
+        if (!psn_tc_supports(p) || p->X != 16) return PSNODE_EUNSUPPORTED;      // the 4-warp kernel keeps X = 16
         return psn_tc_forward(p, workspace, workspace_bytes, s);
     }
     if (p->impl == PSNODE_IMPL_TC8) {

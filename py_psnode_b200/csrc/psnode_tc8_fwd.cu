@@ -45,7 +45,7 @@ constexpr int TM_W1 = 128;
 constexpr int GROUP_THREADS = 256;
 
 struct Tc8Params {
-    int B, T, Z, S, groups;
+    int B, T, X, Z, S, groups;                 // X <= 16 state variables (rows / columns X..15 of the tiles are zero padding)
     int V, I, E;                               // DAE only (0 for an ODE); U = Z + V + I <= 8 held-input columns; E events
     psnode_series t, x, z, v;
     const float* x_init; int64_t x_init_sb;
@@ -108,9 +108,11 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
     const int wq = wk & 3, h = wk >> 2;        // TMEM sub-partition (== CTA warp index % 4), column half
     const bool issuer = h == 0;
     GroupSmem& gs = sm.g[g];
-    const int B = q.B, T = q.T, Z = q.Z, S = q.S;
+    const int B = q.B, T = q.T, X = q.X, Z = q.Z, S = q.S;
     const int ZV = Z + (DAE ? q.V : 0);                // columns of the B tile fed from the z / v series
     const int U = ZV + (DAE ? q.I : 0);                // held-input columns (i columns are written by the AE epilogue)
+    // tile column c of the layer-1 B tile [x (16, X used) | held inputs (8, U used)] -> index into s = cat(x, z, v, i), or -1
+    auto scol = [&](int c) { return c < TX ? (c < X ? c : -1) : (c - TX < U ? X + (c - TX) : -1); };
     const int gid = blockIdx.x * q.groups + g;
     const int b0 = gid * TN;
     const bool live = g < q.groups && b0 < B;
@@ -123,18 +125,20 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
         for (int e = tid; e < TH * TK1; e += 2 * GROUP_THREADS) {
             const int m = e / TK1, c = e - m * TK1;
             float hi = 0.0f, lo = 0.0f;
-            if (c < TX + U) split_tf32(__ldg(q.W1 + m * K1 + S + c) + __ldg(q.W1 + m * K1 + 2 * S + c), hi, lo);
+            const int sc = scol(c);
+            if (sc >= 0) split_tf32(__ldg(q.W1 + m * K1 + S + sc) + __ldg(q.W1 + m * K1 + 2 * S + sc), hi, lo);
             sm.w1_hi[tile_byte(m, c, LBO_W, SBO_W) >> 2] = hi;
             sm.w1_lo[tile_byte(m, c, LBO_W, SBO_W) >> 2] = lo;
         }
     }
     if constexpr (DAE) {
         // AE layer 1 folded onto the same B tile: columns [x | z v] carry W[:, S + c], the i columns (and the padding) zero
-        const int KA = S + TX + ZV;
+        const int KA = S + X + ZV;
         for (int e = tid; e < TH * TK1; e += 2 * GROUP_THREADS) {
             const int m = e / TK1, c = e - m * TK1;
             float hi = 0.0f, lo = 0.0f;
-            if (c < TX + ZV) split_tf32(__ldg(q.A1 + m * KA + S + c), hi, lo);
+            const int sc = scol(c);
+            if (sc >= 0 && sc < X + ZV) split_tf32(__ldg(q.A1 + m * KA + S + sc), hi, lo);
             smd.wa1_hi[tile_byte(m, c, LBO_W, SBO_W) >> 2] = hi;
             smd.wa1_lo[tile_byte(m, c, LBO_W, SBO_W) >> 2] = lo;
         }
@@ -163,7 +167,9 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                     float hi, lo;
                     split_tf32(__ldg(q.W2 + row * TH + col), hi, lo); w2[i] = half ? lo : hi;
                     split_tf32(__ldg(q.W3 + row * TH + col), hi, lo); w3[i] = half ? lo : hi;
-                    split_tf32(__ldg(q.W4 + (row & 15) * TH + col), hi, lo); w4[i] = half ? lo : hi;
+                    hi = 0.0f; lo = 0.0f;
+                    if ((row & 15) < X) split_tf32(__ldg(q.W4 + (row & 15) * TH + col), hi, lo);
+                    w4[i] = half ? lo : hi;
                 }
                 tmem_st_16x256b_x2(tmem + lane_base + TM_W2 + 64 * half + 16 * cb, w2);
                 tmem_st_16x256b_x2(tmem + lane_base + TM_W3 + 64 * half + 16 * cb, w3);
@@ -179,7 +185,8 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                     for (int i = 0; i < 8; i++) {
                         const int row = m0 + ((i >> 1) & 1) * 8, col = 16 * cb + c0 + (i & 1) + (i >> 2) * 8;
                         float hi = 0.0f, lo = 0.0f;
-                        if (col < TX + U) split_tf32(__ldg(q.W1 + row * K1 + S + col) + __ldg(q.W1 + row * K1 + 2 * S + col), hi, lo);
+                        const int sc = scol(col);
+                        if (col < TK1 && sc >= 0) split_tf32(__ldg(q.W1 + row * K1 + S + sc) + __ldg(q.W1 + row * K1 + 2 * S + sc), hi, lo);
                         w1[i] = half ? lo : hi;
                     }
                     tmem_st_16x256b_x2(tmem + TM_UPPER + lane_base + TM_W1 + 32 * half + 16 * cb, w1);
@@ -232,10 +239,10 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
     }
     // the state element this thread owns in the layer-4 epilogue: state srow of trajectory column sn
     const int srow = (lane >> 2) + 8 * h, sn = c0 + (wq & 1) + 8 * (wq >> 1);
-    const float bias4 = __ldg(q.b4 + srow);
+    const float bias4 = srow < X ? __ldg(q.b4 + srow) : 0.0f;
     float biasA2[2] = {0.f, 0.f}, biasA3[2] = {0.f, 0.f}, biasA4 = 0.0f, c1a[4] = {0.f, 0.f, 0.f, 0.f};   // AE net (DAE)
     if constexpr (DAE) {
-        const int KA = S + TX + ZV;
+        const int KA = S + X + ZV;
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             biasA2[r] = __ldg(q.ab2 + m0 + 8 * r);
@@ -451,15 +458,17 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
             }
         }
     };
-    auto store_x_row = [&](int jrow) {      // trajectory row jrow of the group: 16 x 64 B, 128-bit stores
-        if (gt < 64) {
-            const int n = gt >> 2, c4 = gt & 3, b = b0 + n;
-            if (b < B) {
-                float* dst = q.x_sol.p + (int64_t)jrow * q.x_sol.st + (int64_t)b * q.x_sol.sb + 4 * c4;
-                const float4 v = *reinterpret_cast<const float4*>(&gs.ostage[n][4 * c4]);
-                if (q.vec_out) *reinterpret_cast<float4*>(dst) = v;
-                else { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w; }
+    auto store_x_row = [&](int jrow) {      // trajectory row jrow of the group: 16 x 64 B as 128-bit stores (X = 16), else X floats per trajectory
+        if (q.vec_out) {
+            if (gt < 64) {
+                const int n = gt >> 2, c4 = gt & 3, b = b0 + n;
+                if (b < B)
+                    *reinterpret_cast<float4*>(q.x_sol.p + (int64_t)jrow * q.x_sol.st + (int64_t)b * q.x_sol.sb + 4 * c4) =
+                        *reinterpret_cast<const float4*>(&gs.ostage[n][4 * c4]);
             }
+        } else if (gt < TN * X) {
+            const int n = gt / X, c = gt - n * X, b = b0 + n;
+            if (b < B) q.x_sol.p[(int64_t)jrow * q.x_sol.st + (int64_t)b * q.x_sol.sb + c] = gs.ostage[n][c];
         }
     };
 
@@ -468,9 +477,9 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
         float x0, k1 = 0.f, k2 = 0.f, k3 = 0.f;
         {
             const int b = b0 + sn, bb = min(b, B - 1);
-            const float xv = DAE ? __ldg(q.x_init + (int64_t)bb * q.x_init_sb + srow) : ldser(q.x, 0, bb, srow);
+            const float xv = srow < X ? (DAE ? __ldg(q.x_init + (int64_t)bb * q.x_init_sb + srow) : ldser(q.x, 0, bb, srow)) : 0.0f;
             x0 = xv;
-            if (b < B) q.x_sol.p[(int64_t)b * q.x_sol.sb + srow] = xv;
+            if (b < B && srow < X) q.x_sol.p[(int64_t)b * q.x_sol.sb + srow] = xv;
             float hi, lo;
             split_tf32_fast(xv, hi, lo);
             st_f32(gs.b1_hi, off_x, hi);
@@ -587,7 +596,7 @@ int psn_tc8_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStr
     if (ws == nullptr || ws_bytes < 4) return PSNODE_EWORKSPACE;
     const bool dae = p->kind == PSNODE_DAE;
     Tc8Params q;
-    q.B = p->B; q.T = p->T; q.Z = p->Z; q.S = p->X + p->Z + p->V + p->I;
+    q.B = p->B; q.T = p->T; q.X = p->X; q.Z = p->Z; q.S = p->X + p->Z + p->V + p->I;
     q.V = p->V; q.I = p->I; q.E = p->event_idx ? p->E : 0;
     q.t = p->t; q.x = p->x; q.z = p->z; q.v = p->v;
     q.x_init = p->x_init; q.x_init_sb = p->x_init_sb;
@@ -601,7 +610,7 @@ int psn_tc8_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStr
     q.W3 = p->de.W[2]; q.b3 = p->de.b[2]; q.W4 = p->de.W[3]; q.b4 = p->de.b[3];
     q.A1 = p->ae.W[0]; q.ab1 = p->ae.b[0]; q.A2 = p->ae.W[1]; q.ab2 = p->ae.b[1];
     q.A3 = p->ae.W[2]; q.ab3 = p->ae.b[2]; q.A4 = p->ae.W[3]; q.ab4 = p->ae.b[3];
-    q.vec_out = ((reinterpret_cast<uintptr_t>(p->x_sol.p) & 15) == 0 && (p->x_sol.st & 3) == 0 && (p->x_sol.sb & 3) == 0) ? 1 : 0;
+    q.vec_out = (p->X == TX && (reinterpret_cast<uintptr_t>(p->x_sol.p) & 15) == 0 && (p->x_sol.st & 3) == 0 && (p->x_sol.sb & 3) == 0) ? 1 : 0;
     const int64_t tape_need = dae ? psn_tc_dae_tape_floats(p->B, p->T, p->method, q.E) : psn_tc_tape_floats(p->B, p->T, p->method);
     q.tape = (p->tape && p->tape_floats >= tape_need) ? p->tape : nullptr;
     q.err = static_cast<int*>(ws);

@@ -59,10 +59,11 @@ constexpr int TM_ACC_M1 = 384;    // lanes 16..31: 2 groups x 4 partial accumula
 constexpr int TM_COLS = 512;
 constexpr int GROUP_THREADS = 256;     // 8 warps per 16-trajectory group: warps k and k + 4 share TMEM sub-partition k
 constexpr int PSN_DW_CHAIN = 16;       // accumulations into a TMEM weight-gradient accumulator between two flushes (16 / NST steps)
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }   // slabs stay 16-byte aligned when X is odd
 constexpr int G_AREA = TH * TK1;       // floats of the dW1f (folded layer 1) accumulator kept behind each group's slab
 
 struct TcBwdParams {
-    int B, T, Z, S, groups, n_theta;
+    int B, T, X, Z, S, groups, n_theta;        // X <= 16 state variables (rows / columns X..15 of the tiles are zero padding)
     psnode_series t, z, gx;
     const float* a0; int64_t a0_sb;
     const int32_t* event_idx;
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     const int wq = wk & 3, h = wk >> 2;           // TMEM sub-partition (== CTA warp index % 4), trajectory-column half
     const bool issuer = h == 0;                   // warps 0..3 issue the MMAs (4 partial accumulators)
     BwdGroupSmem& gs = sm.g[g];
-    const int B = q.B, T = q.T, Z = q.Z, S = q.S, K1 = 3 * q.S;
+    const int B = q.B, T = q.T, X = q.X, Z = q.Z, S = q.S, K1 = 3 * q.S;
     const int gid = blockIdx.x * q.groups + g;
     const int b0 = gid * TN;
     const bool live = g < q.groups && b0 < B;
@@ -141,7 +142,8 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
                     float hi, lo;
                     split_tf32(__ldg(q.W3 + col * TH + row), hi, lo); w3[i] = half ? lo : hi;
                     split_tf32(__ldg(q.W2 + col * TH + row), hi, lo); w2[i] = half ? lo : hi;
-                    split_tf32(__ldg(q.W1 + col * K1 + S + (row & 15)) + __ldg(q.W1 + col * K1 + 2 * S + (row & 15)), hi, lo);
+                    hi = 0.0f; lo = 0.0f;
+                    if ((row & 15) < X) split_tf32(__ldg(q.W1 + col * K1 + S + (row & 15)) + __ldg(q.W1 + col * K1 + 2 * S + (row & 15)), hi, lo);
                     w1[i] = half ? lo : hi;
                 }
                 tmem_st_16x256b_x2(tmem + lane_base + TM_W3T + 64 * half + 16 * cb, w3);
@@ -155,7 +157,8 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
             for (int i = 0; i < 8; i++) {
                 const int row = r0 + ((i >> 1) & 1) * 8, col = cc0 + (i & 1) + (i >> 2) * 8;
                 float hi, lo;
-                split_tf32(__ldg(q.W4 + col * TH + row), hi, lo);
+                hi = 0.0f; lo = 0.0f;
+                if (col < X) split_tf32(__ldg(q.W4 + col * TH + row), hi, lo);
                 w4[i] = half ? lo : hi;
             }
             tmem_st_16x256b_x2(tmem + TM_UPPER + lane_base + TM_W4T + 16 * half, w4);
@@ -328,10 +331,10 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
         }
     };
 
-    float* sl = q.slab + (int64_t)gid * (q.n_theta + G_AREA);
-    float* garea = sl + q.n_theta;        // [64][24] running dW1f
+    float* sl = q.slab + (int64_t)gid * (pad4(q.n_theta) + G_AREA);
+    float* garea = sl + pad4(q.n_theta);        // [64][24] running dW1f
     const int oW1 = 0, ob1 = TH * K1, oW2 = ob1 + TH, ob2 = oW2 + TH * TH, oW3 = ob2 + TH, ob3 = oW3 + TH * TH, oW4 = ob3 + TH,
-              ob4 = oW4 + TX * TH;
+              ob4 = oW4 + X * TH;
 
     // drain the tensor pipe and add the TMEM weight-gradient accumulators into the slab (round-to-nearest fp32 adds; every
     // element is owned by one thread, the slab was zeroed by the launcher).  Warp (wq, h) owns rows 16wq.. and the 8-column
@@ -356,8 +359,8 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
             }
         }
         const int mc = 8 * h + cc;                // dW4^T: rows = hidden k, columns = output m (16): block h
-        o4[0] = sl[oW4 + mc * TH + r0]; o4[1] = sl[oW4 + (mc + 1) * TH + r0];
-        o4[2] = sl[oW4 + mc * TH + r0 + 8]; o4[3] = sl[oW4 + (mc + 1) * TH + r0 + 8];
+        o4[0] = mc < X ? sl[oW4 + mc * TH + r0] : 0.0f; o4[1] = mc + 1 < X ? sl[oW4 + (mc + 1) * TH + r0] : 0.0f;
+        o4[2] = mc < X ? sl[oW4 + mc * TH + r0 + 8] : 0.0f; o4[3] = mc + 1 < X ? sl[oW4 + (mc + 1) * TH + r0 + 8] : 0.0f;
 #pragma unroll
         for (int q2 = 0; q2 < 2; q2++) {          // dW1f: 24 columns = 3 blocks of 8: blocks h and h + 2 (< 3)
             const int cb = h + 2 * q2;
@@ -380,10 +383,8 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
         }
         tmem_ld_16x256b_x1(tm_dw + lane_base + TM_DW4T + 8 * h, v);
         tmem_ld_wait();
-        sl[oW4 + mc * TH + r0] = o4[0] + v[0];
-        sl[oW4 + (mc + 1) * TH + r0] = o4[1] + v[1];
-        sl[oW4 + mc * TH + r0 + 8] = o4[2] + v[2];
-        sl[oW4 + (mc + 1) * TH + r0 + 8] = o4[3] + v[3];
+        if (mc < X) { sl[oW4 + mc * TH + r0] = o4[0] + v[0]; sl[oW4 + mc * TH + r0 + 8] = o4[2] + v[2]; }
+        if (mc + 1 < X) { sl[oW4 + (mc + 1) * TH + r0] = o4[1] + v[1]; sl[oW4 + (mc + 1) * TH + r0 + 8] = o4[3] + v[3]; }
 #pragma unroll
         for (int q2 = 0; q2 < 2; q2++) {
             const int cb = h + 2 * q2;
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
     if (live) {
         bool fresh = true;
         const int bown = b0 + sn, bbown = min(bown, B - 1);
-        const bool valid = bown < B;
+        const bool valid = bown < B && srow < X;
         float lam, D1[4], dB2[4], dB3[4], dB4 = 0.0f;
 #pragma unroll
         for (int i = 0; i < 4; i++) { D1[i] = 0.f; dB2[i] = 0.f; dB3[i] = 0.f; }
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
 #pragma unroll
             for (int n = 0; n < TN; n++) acc += src[n];
             sl[(which == 0 ? ob1 : (which == 1 ? ob2 : ob3)) + m] = acc;
-        } else if (gt < 3 * TH + TX) {
+        } else if (gt < 3 * TH + X) {
             const int c = gt - 3 * TH;
             float acc = 0.0f;
 #pragma unroll
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
             float P = 0.0f;
 #pragma unroll
             for (int n = 0; n < TN; n++) P = fmaf(D1s[m * 17 + n], a0s[n * 25 + c], P);
-            const float G = Gs[m * 25 + c];
+            const float G = Gs[m * 25 + (c < X ? c : TX + (c - X))];      // tile column of s[c]: x in 0..15, held inputs from 16
             sl[oW1 + m * K1 + c] = P;
             sl[oW1 + m * K1 + S + c] = G - P;
             sl[oW1 + m * K1 + 2 * S + c] = G;
@@ -604,7 +605,7 @@ bool psn_tc_bwd_supports(const psnode_problem* p, const psnode_adjoint* a) {
 
 int64_t psn_tc_backward_workspace(const psnode_problem* p, const psnode_adjoint*) {
     const int64_t n_theta = psnode_mlp_param_count(&p->de);
-    return 256 + (int64_t)psn_tc_ngroups(p->B) * (n_theta + G_AREA) * 4;
+    return 256 + (int64_t)psn_tc_ngroups(p->B) * (pad4((int)n_theta) + G_AREA) * 4;
 }
 
 int psn_tc_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream) {
@@ -612,7 +613,7 @@ int psn_tc_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
     const int64_t n_theta = psnode_mlp_param_count(&p->de);
     if (a->n_theta != n_theta) return PSNODE_EINVAL;
     TcBwdParams q;
-    q.B = p->B; q.T = p->T; q.Z = p->Z; q.S = p->X + p->Z;
+    q.B = p->B; q.T = p->T; q.X = p->X; q.Z = p->Z; q.S = p->X + p->Z;
     q.n_theta = (int)n_theta;
     q.t = p->t; q.z = p->z; q.gx = a->gx;
     q.a0 = p->a0; q.a0_sb = p->a0_sb;
@@ -627,7 +628,7 @@ int psn_tc_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
     const int ngroups = psn_tc_ngroups(p->B);
     q.groups = psn_tc_groups_per_cta(p->B);
     const int grid = (ngroups + q.groups - 1) / q.groups;
-    PSN_CUDA(cudaMemsetAsync(ws, 0, 256 + (size_t)ngroups * (n_theta + G_AREA) * 4, stream));
+    PSN_CUDA(cudaMemsetAsync(ws, 0, 256 + (size_t)ngroups * (pad4((int)n_theta) + G_AREA) * 4, stream));
     const int smem = (int)sizeof(BwdCtaSmem) + 128;
     auto launch = [&](auto kern, const char* name) -> int {
         PSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -643,7 +644,7 @@ int psn_tc_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
         default: st = launch(psn_tc_bwd_kernel<PSNODE_RK4>, "psn_tc_bwd_kernel<rk4>"); break;
     }
     if (st != PSNODE_OK) return st;
-    psn_tc_grad_reduce_kernel<<<32, 256, 0, stream>>>(q.slab, ngroups, (int)n_theta, (int)n_theta + G_AREA, a->d_theta);
+    psn_tc_grad_reduce_kernel<<<32, 256, 0, stream>>>(q.slab, ngroups, (int)n_theta, pad4((int)n_theta) + G_AREA, a->d_theta);
     psn_count_launch("psn_tc_grad_reduce_kernel");
     PSN_CUDA(cudaGetLastError());
     return PSNODE_OK;

@@ -47,9 +47,12 @@ constexpr int TM_COLS = 512;
 constexpr int GROUP_THREADS = 256;
 constexpr int PSN_DW_CHAIN = 16;       // accumulations into a TMEM weight-gradient accumulator between two flushes (16 / NST steps)
 constexpr int G_AREA = TH * TK1;
+// slab = [DE parameters | pad to 4 | AE parameters | pad to 4 | two folded-layer-1 areas]: 16-byte aligned for odd X / I
+__host__ __device__ constexpr int pad4(int n) { return (n + 3) & ~3; }
+__host__ __device__ constexpr int slab_floats(int n_de, int n_ae) { return pad4(n_de) + pad4(n_ae) + 2 * G_AREA; }
 
 struct DaeBwdParams {
-    int B, T, Z, V, I, S, E, n_theta, n_theta_de;
+    int B, T, X, Z, V, I, S, E, n_theta, n_theta_de;       // X <= 16 state variables (tile rows / columns X..15 are zero padding)
     psnode_series t, z, v, gx, gi;
     const float* x_sol; int64_t xs_st, xs_sb;
     const float* i_sol; int64_t is_st, is_sb;
@@ -99,8 +102,8 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
     const int gt = tid;
     const int wq = wk & 3, h = wk >> 2;
     const bool issuer = h == 0;
-    const int B = q.B, T = q.T, Z = q.Z, V = q.V, I = q.I, S = q.S, K1 = 3 * q.S;
-    const int ZV = Z + V, KA = S + TX + ZV;
+    const int B = q.B, T = q.T, X = q.X, Z = q.Z, V = q.V, I = q.I, S = q.S, K1 = 3 * q.S;
+    const int ZV = Z + V, KA = S + X + ZV;
     const int gid = blockIdx.x;
     const int b0 = gid * TN;
 
@@ -113,10 +116,12 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
         const int o = tile_byte(r, m, LBO_W, SBO_W64);
         split_tf32(__ldg(q.A3 + m * TH + r), hi, lo); st_f32(gs.a3t_hi, o, hi); st_f32(gs.a3t_lo, o, lo);
         split_tf32(__ldg(q.A2 + m * TH + r), hi, lo); st_f32(gs.a2t_hi, o, hi); st_f32(gs.a2t_lo, o, lo);
-        split_tf32(__ldg(q.A1 + m * KA + S + (r & 15)), hi, lo); st_f32(gs.a1t_hi, o, hi); st_f32(gs.a1t_lo, o, lo);
+        hi = 0.0f; lo = 0.0f;
+        if ((r & 15) < X) split_tf32(__ldg(q.A1 + m * KA + S + (r & 15)), hi, lo);
+        st_f32(gs.a1t_hi, o, hi); st_f32(gs.a1t_lo, o, lo);
         hi = 0.0f; lo = 0.0f;
         if ((r & 15) < I) {
-            const int c = TX + ZV + (r & 15);
+            const int c = X + ZV + (r & 15);            // index of i[r & 15] in s = cat(x, z, v, i)
             split_tf32(__ldg(q.W1 + m * K1 + S + c) + __ldg(q.W1 + m * K1 + 2 * S + c), hi, lo);
         }
         st_f32(gs.wit_hi, o, hi); st_f32(gs.wit_lo, o, lo);
@@ -142,7 +147,8 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
                     float hi, lo;
                     split_tf32(__ldg(q.W3 + col * TH + row), hi, lo); w3[i] = half ? lo : hi;
                     split_tf32(__ldg(q.W2 + col * TH + row), hi, lo); w2[i] = half ? lo : hi;
-                    split_tf32(__ldg(q.W1 + col * K1 + S + (row & 15)) + __ldg(q.W1 + col * K1 + 2 * S + (row & 15)), hi, lo);
+                    hi = 0.0f; lo = 0.0f;
+                    if ((row & 15) < X) split_tf32(__ldg(q.W1 + col * K1 + S + (row & 15)) + __ldg(q.W1 + col * K1 + 2 * S + (row & 15)), hi, lo);
                     w1[i] = half ? lo : hi;
                 }
                 tmem_st_16x256b_x2(tmem + lane_base + TM_W3T + 64 * half + 16 * cb, w3);
@@ -154,7 +160,8 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
             for (int i = 0; i < 8; i++) {
                 const int row = r0 + ((i >> 1) & 1) * 8, col = cc0 + (i & 1) + (i >> 2) * 8;
                 float hi, lo;
-                split_tf32(__ldg(q.W4 + col * TH + row), hi, lo);
+                hi = 0.0f; lo = 0.0f;
+                if (col < X) split_tf32(__ldg(q.W4 + col * TH + row), hi, lo);
                 w4[i] = half ? lo : hi;
                 hi = 0.0f; lo = 0.0f;
                 if (col < I) split_tf32(__ldg(q.A4 + col * TH + row), hi, lo);
@@ -330,12 +337,12 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
     };
 
     // ---- slab layout: the reference's parameter order (DE net, then AE net), then the two folded-layer-1 areas ------------
-    float* sl = q.slab + (int64_t)gid * (q.n_theta + 2 * G_AREA);
-    float* garea_de = sl + q.n_theta;
+    float* sl = q.slab + (int64_t)gid * slab_floats(q.n_theta_de, q.n_theta - q.n_theta_de);
+    float* garea_de = sl + pad4(q.n_theta_de) + pad4(q.n_theta - q.n_theta_de);
     float* garea_ae = garea_de + G_AREA;
     const int oW1 = 0, ob1 = TH * K1, oW2 = ob1 + TH, ob2 = oW2 + TH * TH, oW3 = ob2 + TH, ob3 = oW3 + TH * TH, oW4 = ob3 + TH,
-              ob4 = oW4 + TX * TH;
-    const int oA1 = q.n_theta_de, oab1 = oA1 + TH * KA, oA2 = oab1 + TH, oab2 = oA2 + TH * TH, oA3 = oab2 + TH, oab3 = oA3 + TH * TH,
+              ob4 = oW4 + X * TH;
+    const int oA1 = pad4(q.n_theta_de), oab1 = oA1 + TH * KA, oA2 = oab1 + TH, oab2 = oA2 + TH * TH, oA3 = oab2 + TH, oab3 = oA3 + TH * TH,
               oA4 = oab3 + TH, oab4 = oA4 + I * TH;
 
     // drain the tensor pipe and add one net's TMEM weight-gradient accumulators into the slab (round-to-nearest adds)
@@ -398,13 +405,14 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
             __syncwarp();
         }
         wait_mma();
-        if (de_dirty) flush_net(tmem + TM_UPPER, oW2, oW3, oW4, TX, garea_de);
+        if (de_dirty) flush_net(tmem + TM_UPPER, oW2, oW3, oW4, X, garea_de);
         if (ae_dirty) flush_net(tmem + TM_UPPER + TM_DWNET, oA2, oA3, oA4, I, garea_ae);
     };
 
     if (b0 < B) {
         const int bown = b0 + sn, bbown = min(bown, B - 1);
         const bool valid = bown < B;
+        const bool own_x_ok = srow < X;
         // register accumulators: sums of delta_1 per (neuron, trajectory) and bias gradients of layers 2..4, per net
         float D1[4], dB2[4], dB3[4], dB4 = 0.0f, D1a[4], dB2a[4], dB3a[4], dB4a = 0.0f;
 #pragma unroll
@@ -505,8 +513,8 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
         };
 
         // ---- reverse sweep ---------------------------------------------------------------------------------
-        auto own_x = [&](int j) { return __ldg(q.x_sol + (int64_t)j * q.xs_st + (int64_t)bbown * q.xs_sb + srow); };
-        auto own_gx = [&](int j) { return (valid && q.gx.p) ? ldser(q.gx, j, bown, srow) : 0.0f; };
+        auto own_x = [&](int j) { return own_x_ok ? __ldg(q.x_sol + (int64_t)j * q.xs_st + (int64_t)bbown * q.xs_sb + srow) : 0.0f; };
+        auto own_gx = [&](int j) { return (valid && own_x_ok && q.gx.p) ? ldser(q.gx, j, bown, srow) : 0.0f; };
         auto own_gi = [&](int j) { return (valid && own_i && q.gi.p) ? ldser(q.gi, j, bown, srow) : 0.0f; };
         float lam = own_gx(T - 1), mu = own_gi(T - 1);
         const float c13 = (float)(1.0 / 3.0);
@@ -595,7 +603,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
         // ---- point 0: i_0 = ae(x_0, z[0], v[0])  (my_solvers.py:95) ----
         lam += chain(AE_NET{}, own_i ? mu : 0.0f, own_x(0), un_ae, nullptr, fresh_ae, D1a, dB2a, dB3a, dB4a, dui_dummy);
         flush_dw(!fresh_de, true);
-        if (q.d_x0 && valid) q.d_x0[(int64_t)bown * q.d_x0_sb + srow] = lam;
+        if (q.d_x0 && valid && own_x_ok) q.d_x0[(int64_t)bown * q.d_x0_sb + srow] = lam;
 
         // ---- bias gradients and layer-1 unfolding, one net after the other through the same scratch ----------------
         float* scr = reinterpret_cast<float*>(gs.dA_hi[0]);          // 32 KB of dead tiles
@@ -622,7 +630,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
                 }
             group_sync();
             const int ob_1 = net ? oab1 : ob1, ob_2 = net ? oab2 : ob2, ob_3 = net ? oab3 : ob3, ob_4 = net ? oab4 : ob4;
-            const int n4 = net ? I : TX;
+            const int n4 = net ? I : X;
             if (gt < 3 * TH) {
                 const int which = gt >> 6, m = gt & 63;
                 const float* src = (which == 0 ? D1s : (which == 1 ? B2s : B3s)) + m * 17;
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
                     float P = 0.0f;
 #pragma unroll
                     for (int n = 0; n < TN; n++) P = fmaf(D1s[m * 17 + n], a0s[n * 25 + c], P);
-                    const float G = Gs[m * 25 + c];
+                    const float G = Gs[m * 25 + (c < X ? c : TX + (c - X))];      // tile column of s[c]
                     sl[oW1 + m * K1 + c] = P;
                     sl[oW1 + m * K1 + S + c] = G - P;
                     sl[oW1 + m * K1 + 2 * S + c] = G;
@@ -657,7 +665,8 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
 #pragma unroll
                         for (int n = 0; n < TN; n++) val = fmaf(D1s[m * 17 + n], a0s[n * 25 + c], val);
                     } else {
-                        val = Gs[m * 25 + (c - S)];
+                        const int sc = c - S;                                     // index into cat(x, z, v)
+                        val = Gs[m * 25 + (sc < X ? sc : TX + (sc - X))];
                     }
                     sl[oA1 + m * KA + c] = val;
                 }
@@ -685,8 +694,9 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
     if (wk == 0) tmem_dealloc(tmem, TM_COLS);
 }
 
-__global__ void psn_tc_dae_grad_reduce_kernel(const float* __restrict__ slab, int n_slabs, int n_theta, int stride, float* __restrict__ d_theta) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_theta; i += gridDim.x * blockDim.x) {
+__global__ void psn_tc_dae_grad_reduce_kernel(const float* __restrict__ slab, int n_slabs, int n_theta, int n_de, int stride, float* __restrict__ d_theta) {
+    for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < n_theta; o += gridDim.x * blockDim.x) {
+        const int i = o < n_de ? o : o - n_de + pad4(n_de);      // slab position of parameter o
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         int s = 0;
         for (; s + 3 < n_slabs; s += 4) {
@@ -696,7 +706,7 @@ __global__ void psn_tc_dae_grad_reduce_kernel(const float* __restrict__ slab, in
             a3 += slab[(size_t)(s + 3) * stride + i];
         }
         for (; s < n_slabs; s++) a0 += slab[(size_t)s * stride + i];
-        d_theta[i] = (a0 + a1) + (a2 + a3);
+        d_theta[o] = (a0 + a1) + (a2 + a3);
     }
 }
 
@@ -713,8 +723,7 @@ bool psn_tc_dae_bwd_supports(const psnode_problem* p, const psnode_adjoint* a) {
 }
 
 int64_t psn_tc_dae_backward_workspace(const psnode_problem* p, const psnode_adjoint*) {
-    const int64_t n_theta = psnode_mlp_param_count(&p->de) + psnode_mlp_param_count(&p->ae);
-    return 256 + (int64_t)psn_tc_ngroups(p->B) * (n_theta + 2 * G_AREA) * 4;
+    return 256 + (int64_t)psn_tc_ngroups(p->B) * slab_floats((int)psnode_mlp_param_count(&p->de), (int)psnode_mlp_param_count(&p->ae)) * 4;
 }
 
 int psn_tc_dae_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream) {
@@ -722,7 +731,7 @@ int psn_tc_dae_backward(const psnode_problem* p, const psnode_adjoint* a, void* 
     const int64_t n_de = psnode_mlp_param_count(&p->de), n_theta = n_de + psnode_mlp_param_count(&p->ae);
     if (a->n_theta != n_theta) return PSNODE_EINVAL;
     DaeBwdParams q;
-    q.B = p->B; q.T = p->T; q.Z = p->Z; q.V = p->V; q.I = p->I; q.S = p->X + p->Z + p->V + p->I;
+    q.B = p->B; q.T = p->T; q.X = p->X; q.Z = p->Z; q.V = p->V; q.I = p->I; q.S = p->X + p->Z + p->V + p->I;
     q.E = p->event_idx ? p->E : 0;
     q.n_theta = (int)n_theta; q.n_theta_de = (int)n_de;
     q.t = p->t; q.z = p->z; q.v = p->v; q.gx = a->gx; q.gi = a->gi;
@@ -740,7 +749,7 @@ int psn_tc_dae_backward(const psnode_problem* p, const psnode_adjoint* a, void* 
     q.d_x0 = a->d_x0; q.d_x0_sb = a->d_x0_sb;
     q.d_a0 = a->d_a0; q.d_a0_sb = a->d_a0_sb;
     const int ngroups = psn_tc_ngroups(p->B);
-    PSN_CUDA(cudaMemsetAsync(ws, 0, 256 + (size_t)ngroups * (n_theta + 2 * G_AREA) * 4, stream));
+    PSN_CUDA(cudaMemsetAsync(ws, 0, 256 + (size_t)ngroups * slab_floats((int)n_de, (int)(n_theta - n_de)) * 4, stream));
     const int smem = (int)sizeof(DaeBwdSmem) + 128;
     auto launch = [&](auto kern, const char* name) -> int {
         PSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -756,7 +765,7 @@ int psn_tc_dae_backward(const psnode_problem* p, const psnode_adjoint* a, void* 
         default: st = launch(psn_tc_bwd_dae_kernel<PSNODE_RK4>, "psn_tc_bwd_dae_kernel<rk4>"); break;
     }
     if (st != PSNODE_OK) return st;
-    psn_tc_dae_grad_reduce_kernel<<<32, 256, 0, stream>>>(q.slab, ngroups, (int)n_theta, (int)n_theta + 2 * G_AREA, a->d_theta);
+    psn_tc_dae_grad_reduce_kernel<<<32, 256, 0, stream>>>(q.slab, ngroups, (int)n_theta, (int)n_de, slab_floats((int)n_de, (int)(n_theta - n_de)), a->d_theta);
     psn_count_launch("psn_tc_dae_grad_reduce_kernel");
     PSN_CUDA(cudaGetLastError());
     return PSNODE_OK;

@@ -588,11 +588,12 @@ static bool h64_net(const psnode_mlp& m, int in0, int out_last) {
            m.out_dim[3] == out_last;
 }
 
+// shapes of the tensor-core kernels: 4-layer H = 64 nets, up to 16 state variables, up to 8 held-input columns
 bool psn_tc_supports(const psnode_problem* p) {
-    if (p->teacher_x || p->teacher_i || p->X != TX) return false;
+    if (p->teacher_x || p->teacher_i || p->X < 1 || p->X > TX) return false;
     const int S = p->X + p->Z + p->V + p->I;
     if (S - p->X > TU) return false;
-    if (!h64_net(p->de, 3 * S, TX)) return false;
+    if (!h64_net(p->de, 3 * S, p->X)) return false;
     if (p->kind == PSNODE_DAE) return p->I >= 1 && h64_net(p->ae, S + p->X + p->Z + p->V, p->I);
     return p->kind == PSNODE_ODE;
 }

@@ -13,14 +13,15 @@ def _params(mod):
     return [(m.weight.detach().cpu(), m.bias.detach().cpu()) for m in mod if isinstance(m, torch.nn.Linear)]
 
 
+@pytest.mark.parametrize("X", [16, 6, 11])
 @pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
-def test_ode_tc_forward_and_tape_gradients(native_lib, method, monkeypatch):
+def test_ode_tc_forward_and_tape_gradients(native_lib, method, X, monkeypatch):
     from oracle import psnode_oracle as O
     from py_psnode_b200 import DE_Func, Euler, Midpoint, ODE_Event, RK4, _native
     monkeypatch.delenv("PSNODE_TAPE_MAX_GB", raising=False)
     torch.manual_seed(51)
     dev = "cuda:0"
-    B, N, X, Z, H = 40, 30, 16, 2, 64
+    B, N, Z, H = 40, 30, 2, 64
     T = N + 1
     de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H)
     t = (torch.arange(T, dtype=torch.float32) * 0.02).view(T, 1, 1).repeat(1, B, 1)
@@ -60,13 +61,14 @@ def test_ode_tc_forward_and_tape_gradients(native_lib, method, monkeypatch):
     assert float(xd.grad[1:].abs().max()) == 0.0, "only x[0] (the initial state) receives a gradient without teacher forcing"
 
 
+@pytest.mark.parametrize("X", [16, 5])
 @pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
-def test_dae_tc_forward_all_methods(native_lib, method):
+def test_dae_tc_forward_all_methods(native_lib, method, X):
     from oracle import psnode_oracle as O
     from py_psnode_b200 import AE_Func, DAE_Event, DE_Func, Euler, Midpoint, RK4, _native
     torch.manual_seed(52)
     dev = "cuda:0"
-    B, N, X, Z, V, I, H = 40, 30, 16, 1, 2, 4, 64
+    B, N, Z, V, I, H = 40, 30, 1, 2, 4, 64
     T = N + 1
     de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H, v_dim=V, i_dim=I)
     ae = AE_Func(x_dim=X, v_dim=V, i_dim=I, hidden_dim=H, z_dim=Z)
@@ -89,8 +91,9 @@ def test_dae_tc_forward_all_methods(native_lib, method):
     assert torch.allclose(gi.cpu(), wi, rtol=RTOL, atol=ATOL), "i: " + tol_report(gi.cpu(), wi)
 
 
+@pytest.mark.parametrize("X", [16, 7])
 @pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
-def test_dae_tc_tape_gradients_all_methods(native_lib, method, monkeypatch):
+def test_dae_tc_tape_gradients_all_methods(native_lib, method, X, monkeypatch):
     """DAE reverse sweep on tensor cores (ragged batch, an event on the very first step and one mid-way) against float64
     autograd through the oracle: both nets' parameters, x_init and all_initial."""
     from oracle import psnode_oracle as O
@@ -98,7 +101,7 @@ def test_dae_tc_tape_gradients_all_methods(native_lib, method, monkeypatch):
     monkeypatch.delenv("PSNODE_TAPE_MAX_GB", raising=False)
     torch.manual_seed(53)
     dev = "cuda:0"
-    B, N, X, Z, V, I, H = 40, 24, 16, 1, 2, 4, 64
+    B, N, Z, V, I, H = 40, 24, 1, 2, 4, 64
     T = N + 1
     de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H, v_dim=V, i_dim=I)
     ae = AE_Func(x_dim=X, v_dim=V, i_dim=I, hidden_dim=H, z_dim=Z)
@@ -194,3 +197,21 @@ def test_tc_degenerate_grids(native_lib, kind, T, monkeypatch):
         scale = float(g64.abs().max())
         err = float((g.cpu().double() - g64).abs().max())
         assert err <= 1e-5 * scale + 1e-7, f"{kind} T={T} tensor {k}: err {err:.3e} scale {scale:.3e}"
+
+
+def test_four_warp_ab_kernel_refuses_narrow_state(native_lib):
+    """Only the 8-warp kernel carries the X < 16 zero-padding; the 4-warp A/B build (impl="tc") must refuse, not mis-integrate."""
+    from py_psnode_b200 import DE_Func, RK4, _native
+    torch.manual_seed(3)
+    dev = "cuda:0"
+    B, T, X, Z = 16, 5, 6, 2
+    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=64).to(dev)
+    t = (torch.arange(T, dtype=torch.float32, device=dev) * 0.02).view(T, 1, 1).repeat(1, B, 1)
+    x = torch.randn(T, B, X, device=dev) * 0.2
+    z = torch.randn(T, B, Z, device=dev) * 0.2
+    a0 = torch.cat((x[0], z[0]), dim=-1)
+    with torch.no_grad():
+        RK4(impl="tc8").integrate_ODE(x_func=de, t=t, x=x, z=z, all_initial=a0)
+        assert _native.last_kernel().startswith("psn_tc8_ode_kernel")
+        with pytest.raises(RuntimeError):
+            RK4(impl="tc").integrate_ODE(x_func=de, t=t, x=x, z=z, all_initial=a0)
