@@ -307,7 +307,7 @@ def main():
         T = w["N"] + 1
         gen = torch.Generator(device=dev).manual_seed(1234 + rank)
         x_target = torch.randn((T, w["B"], w["X"]), device=dev, generator=gen) * 0.1
-        mask = torch.ones((T, w["B"], w["X"]), device=dev)
+        mask = torch.ones((T, w["B"], 1), device=dev)       # one value per (trajectory, grid point), as in the scripts
         i_target = torch.randn((T, w["B"], w["I"]), device=dev, generator=gen) * 0.1 if w["kind"] == "dae" else None
         plist = list(de.parameters()) + (list(ae.parameters()) if ae is not None else [])
         bucket = parallel.GradBucket(plist, n_extras=2)
@@ -316,7 +316,7 @@ def main():
             xs, is_ = out
             num, den = parallel.masked_mse_sum(xs, x_target, mask)
             if is_ is not None:
-                num = num + parallel.masked_mse_sum(is_, i_target, mask[..., :1].expand_as(is_))[0]
+                num = num + parallel.masked_mse_sum(is_, i_target, mask)[0]
             return num, den
 
         def train_step():

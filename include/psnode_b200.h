@@ -206,6 +206,25 @@ int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* work
  */
 int psnode_forward_host(const psnode_problem* p, void* stream, int64_t* h2d_bytes, int64_t* d2h_bytes);
 
+/*
+ * Masked squared-error loss numerator of the training scripts and its gradient, one pass over the trajectory each
+ * (SURVEY 8f next-2).  Replaces `torch.sum(Loss_func(x_pred, x, reduction='none') * mask)` and its autograd backward
+ * (neural_00_ODE_01_no_encode.py:353-355; neural_01_DAE_01_no_encode.py:414-418 with per-feature weights):
+ *     loss[0] = sum_{o,i,c} w_c * mask[o,i] * (pred[o,i,c] - target[o,i,c])^2          (w = NULL: all ones)
+ *     grad[o,i,c] = upstream[0] * 2 * w_c * mask[o,i] * (pred[o,i,c] - target[o,i,c])
+ * The three inputs are strided (n_outer, n_inner, X) views with unit feature stride (`st` = outer stride, `sb` = inner
+ * stride; mask has width 1); pass the dimension with the smaller stride as the inner one -- (T,B,X) solver output or the
+ * scripts' batch-major (B,T,X) both work.  `loss`, `upstream` are device scalars (no host synchronisation); the caller
+ * divides by sum(mask).  Deterministic summation order.
+ */
+int64_t psnode_masked_sse_workspace(void);
+int psnode_masked_sse(const psnode_series* pred, const psnode_series* target, const psnode_series* mask,
+                      const float* feat_weight, int32_t n_outer, int32_t n_inner, int32_t X, float* loss,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+int psnode_masked_sse_grad(const psnode_series* pred, const psnode_series* target, const psnode_series* mask,
+                           const float* feat_weight, int32_t n_outer, int32_t n_inner, int32_t X,
+                           const float* upstream, const psnode_series_out* grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,6 +74,11 @@ SYMBOLS = [
     ("psnode_forward", C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_int64, C.c_void_p]),
     ("psnode_backward", C.c_int, [C.POINTER(Problem), C.POINTER(Adjoint), C.c_void_p, C.c_int64, C.c_void_p]),
     ("psnode_forward_host", C.c_int, [C.POINTER(Problem), C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("psnode_masked_sse_workspace", C.c_int64, []),
+    ("psnode_masked_sse", C.c_int, [C.POINTER(Series), C.POINTER(Series), C.POINTER(Series), C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("psnode_masked_sse_grad", C.c_int, [C.POINTER(Series), C.POINTER(Series), C.POINTER(Series), C.c_void_p, C.c_int32,
+                                         C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Series), C.c_void_p]),
 ]
 
 # PSNODE_B200_LIB selects an alternative build of the SAME library (A/B kernel experiments); never a different backend.

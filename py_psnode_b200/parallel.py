@@ -115,6 +115,10 @@ class GradBucket:
 def masked_mse_sum(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """(sum(mse * mask), sum(mask)) of a shard: numerator and denominator of the reference's masked loss
     (neural_00_ODE_01_no_encode.py:353-355) kept apart so the division can use the all-reduced denominator."""
+    if pred.is_cuda and (mask.shape[-1] == 1 or mask.stride(-1) == 0):      # one fused pass (csrc/psnode_loss.cu)
+        from .losses import masked_sse
+        return masked_sse(pred, target, mask), mask.sum()
+    # host tensors (the gloo tests of the sharding logic) and per-feature masks: plain torch
     se = torch.nn.functional.mse_loss(pred, target, reduction="none") * mask
     return se.sum(), mask.sum()
 
