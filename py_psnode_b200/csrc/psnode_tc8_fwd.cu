@@ -485,13 +485,21 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
             st_f32(gs.b1_hi, off_x, hi);
             st_f32(gs.b1_lo, off_x, lo);
         }
+        float t_prev = 0.0f;        // warp 4: time of the grid point the staged step size ends at
         if (wk == 4) {
             float u[TU];
             if (DAE) load_zv(0, -1, u);                        // i_0 = ae(x_0, z[0], v[0])  (my_solvers.py:95)
             else if (T > 1) load_zv(0, event_of_step(1), u);
             if (DAE || T > 1) store_zv(u);
-            if (T > 1 && lane < TN) gs.dts[1][lane] = load_dt(1);
+            if (T > 1) {
+                const int bb = min(b0 + (lane & 15), B - 1);
+                t_prev = ldser(q.t, 1, bb, 0);
+                if (lane < TN) gs.dts[1][lane] = __fsub_rn(t_prev, ldser(q.t, 0, bb, 0));
+            }
         }
+        // event index of the NEXT step, fetched one step ahead so that no thread ever waits on it
+        int k_next = T > 2 ? event_of_step(2) : -1;
+        int k_cur = (DAE && T > 1) ? event_of_step(1) : -1;
         publish();
         // DAE tape: records of this group (psnode_tc_tape.cuh)
         float* dbase = (DAE && TAPE && q.tape) ? q.tape + (int64_t)gid * psn_dae_group_recs(T, NST, q.E) * PSN_TAPE_STAGE : nullptr;
@@ -504,11 +512,14 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
         float* trec = (TAPE && q.tape) ? (DAE ? dbase : q.tape + (int64_t)gid * (T - 1) * NST * PSN_TAPE_STAGE) : nullptr;
         float ycur = x0;                                    // input of the current stage (recorded on the tape)
         for (int j = 1; j < T; j++) {
-            float un[TU] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dtn = 0.0f;   // next step's inputs, prefetched by warp 4 during stage 0
+            float un[TU] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, tn = 0.0f;   // next step's inputs: raw loads issued by warp 4 during stage 0, first used in the last stage
             const bool have_next = j + 1 < T;
             const float dt = gs.dts[j & 1][sn];
+            const int k_after = k_next;                         // event of step j + 1
+            k_next = j + 2 < T ? event_of_step(j + 2) : -1;     // in flight until the next iteration reads it
             if constexpr (DAE) {
-                const int k = event_of_step(j);
+                const int k = k_cur;
+                k_cur = k_after;
                 if (k >= 0) {                                  // event: jumped z / v replace the held inputs and i_0 is re-evaluated
                     if (wk == 4) { float uj[TU]; load_zv(j - 1, k, uj); store_zv(uj); }
                     publish();
@@ -524,8 +535,8 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                 if (e == 0 && wk == 4) {
                     // next step's held inputs; DAE: the un-jumped z[j], v[j] (they feed i_j first), ODE: jumped if step j+1 fires
                     if (DAE) load_zv(j, -1, un);
-                    else if (have_next) load_zv(j, event_of_step(j + 1), un);
-                    if (have_next) dtn = load_dt(j + 1);
+                    else if (have_next) load_zv(j, k_after, un);
+                    if (have_next) tn = ldser(q.t, j + 1, min(b0 + (lane & 15), B - 1), 0);
                 }
                 if (e == 0 && j > 1) { store_x_row(j - 1); flush_i(j - 1); }    // rows staged by the previous step
                 collect(d, 3, DAE ? 0u : TM_UPPER);
@@ -571,7 +582,10 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                 if (TAPE && trec) trec += PSN_TAPE_STAGE;
                 if (wk == 4 && last && (DAE || have_next)) {        // all layer-1 MMAs of this step are done
                     store_zv(un);
-                    if (have_next && lane < TN) gs.dts[(j + 1) & 1][lane] = dtn;
+                    if (have_next) {
+                        if (lane < TN) gs.dts[(j + 1) & 1][lane] = __fsub_rn(tn, t_prev);
+                        t_prev = tn;
+                    }
                 }
                 publish();
             }
