@@ -21,4 +21,8 @@ ncu --set full --clock-control none --import-source on -k regex:psn_tc_bwd -s 1 
     python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/${TAG}_ncu_full_bwd.log 2>&1; echo "ncu bwd rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:psn_tc8 -s 2 -c 1 -f -o gpurun_out/${TAG}_ncu_tc8_dae_cfg3 \
     python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-train --workload cfg3 > gpurun_out/${TAG}_ncu_full_dae.log 2>&1; echo "ncu dae rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:psn_tc_bwd_dae -s 1 -c 1 -f -o gpurun_out/${TAG}_ncu_tc_bwd_dae_cfg3 \
+    python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --workload cfg3 > gpurun_out/${TAG}_ncu_full_bwd_dae.log 2>&1; echo "ncu dae bwd rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:psn_masked_sse -s 6 -c 3 -f -o gpurun_out/${TAG}_ncu_masked_sse_cfg2 \
+    python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > gpurun_out/${TAG}_ncu_full_loss.log 2>&1; echo "ncu loss rc=$?"
 tail -3 gpurun_out/${TAG}_pytest_gpu.log; tail -3 gpurun_out/${TAG}_smoke.log; cat gpurun_out/${TAG}_bench_cfg2.json
