@@ -267,9 +267,15 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
     const int off_i = (int)tile_byte(sn, min(TX + ZV + srow, TK1 - 1), LBO, SBO_B1);
     // descriptors
     const uint32_t idesc = make_idesc_tf32(TH, TN);
-    const uint64_t d_act_hi = make_desc(smem_u32(gs.act_hi), LBO, SBO_ACT), d_act_lo = make_desc(smem_u32(gs.act_lo), LBO, SBO_ACT);
-    const uint64_t d_b1_hi = make_desc(smem_u32(gs.b1_hi), LBO, SBO_B1), d_b1_lo = make_desc(smem_u32(gs.b1_lo), LBO, SBO_B1);
-    const uint64_t d_w1_hi = make_desc(smem_u32(sm.w1_hi), LBO_W, SBO_W), d_w1_lo = make_desc(smem_u32(sm.w1_lo), LBO_W, SBO_W);
+    // every lo tile directly follows its hi tile: the lo descriptor is the hi one plus a constant in the start-address field,
+    // which halves the descriptors ptxas has to keep in uniform registers (it spilled them to vector registers + R2UR chains
+    // in front of the MMAs of some instantiations)
+    static_assert(offsetof(GroupSmem, act_lo) - offsetof(GroupSmem, act_hi) == ACT_TILE, "act_lo must follow act_hi");
+    static_assert(offsetof(GroupSmem, b1_lo) - offsetof(GroupSmem, b1_hi) == B1_TILE + 64, "b1_lo must follow b1_hi");
+    static_assert(offsetof(CtaSmem, w1_lo) - offsetof(CtaSmem, w1_hi) == W1_TILE, "w1_lo must follow w1_hi");
+    const uint64_t d_act_hi = make_desc(smem_u32(gs.act_hi), LBO, SBO_ACT), d_act_lo = d_act_hi + (uint64_t)(ACT_TILE >> 4);
+    const uint64_t d_b1_hi = make_desc(smem_u32(gs.b1_hi), LBO, SBO_B1), d_b1_lo = d_b1_hi + (uint64_t)((B1_TILE + 64) >> 4);
+    const uint64_t d_w1_hi = make_desc(smem_u32(sm.w1_hi), LBO_W, SBO_W), d_w1_lo = d_w1_hi + (uint64_t)(W1_TILE >> 4);
     const uint32_t acc_base = tmem + TM_ACC + (uint32_t)(g * 4) * TN;      // 4 partial accumulators of this group
     const uint32_t my_acc = acc_base + (uint32_t)wq * TN;                  // the one this (issuing) warp's MMAs write
     constexpr uint64_t KSTEP_B = (uint64_t)((2 * LBO) >> 4), KSTEP_W = (uint64_t)((2 * LBO_W) >> 4);
@@ -421,7 +427,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
     // into the tile's i columns (held input of the next DE evaluations) and, with `stage_out`, into istage (-> i_sol row).
     auto ae_eval = [&](bool stage_out, float* rec = nullptr, bool rec_i0 = false) {     // rec: tape record of this evaluation
         if constexpr (DAE) {
-            const uint64_t d_wa1_hi = make_desc(smem_u32(smd.wa1_hi), LBO_W, SBO_W), d_wa1_lo = make_desc(smem_u32(smd.wa1_lo), LBO_W, SBO_W);
+            const uint64_t d_wa1_hi = make_desc(smem_u32(smd.wa1_hi), LBO_W, SBO_W), d_wa1_lo = d_wa1_hi + (uint64_t)(W1_TILE >> 4);
             float d[4];
             issue_l1(d_wa1_hi, d_wa1_lo);
             collect(d, 3);
