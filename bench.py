@@ -16,6 +16,7 @@ FMA-bound, not HBM-bound: `fp32` gives the fraction of the fp32-FMA peak); `cpu_
 ops as the reference) timed on this box's host cores on a bounded sample.
 """
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -73,20 +74,28 @@ def call_integrate(w, solver, de, ae, d):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled every 25 ms.  Started BEFORE the warm-up (NVML initialisation inside a
+    50 ms timed region perturbed it); only the samples stamped inside [mark_begin, mark_end] are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = datetime.datetime.now()
+
+    def mark_end(self):
+        self.t1 = datetime.datetime.now()
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25",
                                           "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -100,24 +109,31 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 f = [q.strip() for q in line.split(",")]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    stamp = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                    rows.append((stamp, float(f[1]), float(f[2]), f[5:9]))
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        window = "timed region"
+        if not inside:          # region shorter than one sampling period: the samples closest to it (warm-up just before)
+            inside, window = rows[-4:], "nearest samples (region shorter than the sampling period)"
+        sm, mx, reasons = [r[1] for r in inside], [r[2] for r in inside], set()
+        for r in inside:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 def cpu_baseline(w, sample_steps, repeats=3, threads=None):
@@ -224,15 +240,16 @@ def main():
     units = w["B"] * w["N"]
 
     # ---- kernel-resident timing ------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             out = call_integrate(w, solver, de, ae, resident)
         kernel_name = _native.last_kernel()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        sampler = ClockSampler(local_rank)
         barrier()
-        if rank == 0:
-            sampler.start()
+        sampler.mark_begin()
         launches0 = _native.launch_count()
         e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_all0.record()
@@ -242,6 +259,7 @@ def main():
             b.record()
         e_all1.record()
         barrier()
+        sampler.mark_end()
         launches = _native.launch_count() - launches0
         clocks = sampler.stop() if rank == 0 else None
         total_ms = e_all0.elapsed_time(e_all1)
