@@ -93,6 +93,18 @@ def test_cpu_tensors_fail_loudly():
         RK4(step_size=0.1, grid_constructor=lambda *a: None)
 
 
+def test_fused_loss_has_no_cpu_path():
+    """losses.masked_sse is CUDA-only like the integrators; parallel.masked_mse_sum keeps plain torch for host tensors
+    (the gloo tests of the sharding logic)."""
+    from py_psnode_b200 import parallel
+    from py_psnode_b200.losses import masked_sse
+    pred, target, mask = torch.randn(3, 4, 2), torch.randn(3, 4, 2), torch.ones(3, 4, 1)
+    with pytest.raises(TypeError, match="no CPU path"):
+        masked_sse(pred, target, mask)
+    num, den = parallel.masked_mse_sum(pred, target, mask)
+    assert torch.allclose(num, ((pred - target) ** 2 * mask).sum()) and float(den) == 12.0
+
+
 def test_missing_library_is_an_error(monkeypatch, tmp_path):
     from py_psnode_b200 import _native
     monkeypatch.setattr(_native, "_lib", None)
