@@ -404,10 +404,6 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                 u[c] = k >= 0 ? __ldg(q.v_jump + (int64_t)bb * q.vj_sb + (int64_t)k * q.vj_se + (c - Z)) : ldser(q.v, jp, bb, c - Z);
         }
     };
-    auto load_dt = [&](int j) {      // step that ENDS at grid point j
-        const int bb = min(b0 + (lane & 15), B - 1);
-        return __fsub_rn(ldser(q.t, j, bb, 0), ldser(q.t, j - 1, bb, 0));
-    };
     auto store_zv = [&](const float (&u)[TU]) {
         if (lane < TN) {
 #pragma unroll

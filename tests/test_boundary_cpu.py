@@ -124,3 +124,28 @@ def test_step_integrate_contract_on_cpu():
         assert torch.allclose(x1, torch.full_like(x0, want), atol=1e-6)
         assert torch.equal(f0, -x0)
     assert (Euler.order, Midpoint.order, RK4.order) == (1, 2, 4)
+
+
+def test_mma_descriptors_stay_in_uniform_registers(native_lib):
+    """SASS check of the built objects: no R2UR (vector -> uniform register move) chain directly in front of the UTCHMMA
+    of the product tensor-core kernels.  ptxas spilling the tile descriptors to vector registers cost 3.5 % at cfg3
+    (DESIGN.md section 9); tools/sass_r2ur_check.py prints the same count per kernel."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    lib_dir = os.path.join(ROOT, "py_psnode_b200", "_lib")
+    for unit, allowed in (("psnode_tc8_fwd.o", 0), ("psnode_tc_bwd.o", 2), ("psnode_tc_bwd_dae.o", 4)):
+        obj = os.path.join(lib_dir, unit)
+        if not os.path.exists(obj):
+            pytest.skip(f"{unit} not built")
+        txt = subprocess.run(["cuobjdump", "-sass", obj], stdout=subprocess.PIPE, text=True, check=True).stdout
+        kernels = re.split(r"\n\s*Function : ", txt)[1:]
+        assert kernels, f"no kernels found in {unit}"
+        for f in kernels:
+            ops = [m.group(1) for m in (re.search(r"/\*[0-9a-f]{4,5}\*/\s+(.*?);", l) for l in f.split("\n")) if m]
+            mma = [i for i, o in enumerate(ops) if "UTCHMMA" in o]
+            if not mma:
+                continue
+            near = sum(1 for i, o in enumerate(ops) if "R2UR" in o and any(0 < j - i <= 14 for j in mma))
+            assert near <= allowed, f"{unit}: {near} R2UR in front of UTCHMMA in {f.splitlines()[0][:80]}"
