@@ -186,12 +186,19 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
 
     // descriptors
     const uint32_t idesc16 = make_idesc_tf32(TH, TN), idesc24 = make_idesc_tf32(TH, TK1), idesc64 = make_idesc_tf32(TH, TH);
-    const uint64_t d_dT_hi = make_desc(smem_u32(gs.dT_hi), LBO, SBO_ACT), d_dT_lo = make_desc(smem_u32(gs.dT_lo), LBO, SBO_ACT);
-    const uint64_t d_dA_hi0 = make_desc(smem_u32(gs.dA_hi[0]), LBO_W, SBO_K16), d_dA_lo0 = make_desc(smem_u32(gs.dA_lo[0]), LBO_W, SBO_K16);
-    const uint64_t d_dA_hi1 = make_desc(smem_u32(gs.dA_hi[1]), LBO_W, SBO_K16), d_dA_lo1 = make_desc(smem_u32(gs.dA_lo[1]), LBO_W, SBO_K16);
-    const uint64_t d_aB_hi0 = make_desc(smem_u32(gs.aB_hi[0]), LBO_W, SBO_K16), d_aB_lo0 = make_desc(smem_u32(gs.aB_lo[0]), LBO_W, SBO_K16);
-    const uint64_t d_aB_hi1 = make_desc(smem_u32(gs.aB_hi[1]), LBO_W, SBO_K16), d_aB_lo1 = make_desc(smem_u32(gs.aB_lo[1]), LBO_W, SBO_K16);
-    const uint64_t d_dkB_hi = make_desc(smem_u32(gs.dkB_hi), LBO_W, SBO_K16), d_dkB_lo = make_desc(smem_u32(gs.dkB_lo), LBO_W, SBO_K16);
+    // two base descriptors; every other tile shares one of the two (LBO, SBO) pairs and sits at a constant byte offset, so its
+    // descriptor is base + (offset >> 4) in the start-address field: ptxas keeps 2 descriptors in uniform registers instead of
+    // rebuilding 14 of them (shift / mask / or chains) in front of every MMA batch
+    const uint64_t d_dT_hi = make_desc(smem_u32(gs.dT_hi), LBO, SBO_ACT);
+    const uint64_t d_k16 = make_desc(smem_u32(gs.dA_hi[0]), LBO_W, SBO_K16);
+    auto at = [](uint64_t base, size_t from, size_t to) { return base + (uint64_t)((to - from) >> 4); };
+    constexpr size_t o_dA = offsetof(BwdGroupSmem, dA_hi);
+    const uint64_t d_dT_lo = at(d_dT_hi, offsetof(BwdGroupSmem, dT_hi), offsetof(BwdGroupSmem, dT_lo));
+    const uint64_t d_dA_hi0 = d_k16, d_dA_hi1 = at(d_k16, 0, K16_TILE);
+    const uint64_t d_dA_lo0 = at(d_k16, o_dA, offsetof(BwdGroupSmem, dA_lo)), d_dA_lo1 = at(d_k16, o_dA, offsetof(BwdGroupSmem, dA_lo) + K16_TILE);
+    const uint64_t d_aB_hi0 = at(d_k16, o_dA, offsetof(BwdGroupSmem, aB_hi)), d_aB_hi1 = at(d_k16, o_dA, offsetof(BwdGroupSmem, aB_hi) + K16_TILE);
+    const uint64_t d_aB_lo0 = at(d_k16, o_dA, offsetof(BwdGroupSmem, aB_lo)), d_aB_lo1 = at(d_k16, o_dA, offsetof(BwdGroupSmem, aB_lo) + K16_TILE);
+    const uint64_t d_dkB_hi = at(d_k16, o_dA, offsetof(BwdGroupSmem, dkB_hi)), d_dkB_lo = at(d_k16, o_dA, offsetof(BwdGroupSmem, dkB_lo));
     const uint32_t acc_base = tmem + TM_ACC + (uint32_t)(g * 4) * TN;
     const uint32_t my_acc = acc_base + (uint32_t)wq * TN;
     const uint32_t acc_m1 = tmem + TM_UPPER + TM_ACC_M1 + (uint32_t)(g * 4) * TN;      // accumulators of g3 = W4^T dk (lanes 16..31)

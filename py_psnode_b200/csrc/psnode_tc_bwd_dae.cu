@@ -192,16 +192,23 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
     const bool own_i = srow < I;
 
     const uint32_t idesc16 = make_idesc_tf32(TH, TN), idesc24 = make_idesc_tf32(TH, TK1), idesc64 = make_idesc_tf32(TH, TH);
-    const uint64_t d_dT_hi = make_desc(smem_u32(gs.dT_hi), LBO, SBO_ACT), d_dT_lo = make_desc(smem_u32(gs.dT_lo), LBO, SBO_ACT);
-    const uint64_t d_a3t_hi = make_desc(smem_u32(gs.a3t_hi), LBO_W, SBO_W64), d_a3t_lo = make_desc(smem_u32(gs.a3t_lo), LBO_W, SBO_W64);
-    const uint64_t d_a2t_hi = make_desc(smem_u32(gs.a2t_hi), LBO_W, SBO_W64), d_a2t_lo = make_desc(smem_u32(gs.a2t_lo), LBO_W, SBO_W64);
-    const uint64_t d_a1t_hi = make_desc(smem_u32(gs.a1t_hi), LBO_W, SBO_W64), d_a1t_lo = make_desc(smem_u32(gs.a1t_lo), LBO_W, SBO_W64);
-    const uint64_t d_wit_hi = make_desc(smem_u32(gs.wit_hi), LBO_W, SBO_W64), d_wit_lo = make_desc(smem_u32(gs.wit_lo), LBO_W, SBO_W64);
-    const uint64_t d_dA_hi0 = make_desc(smem_u32(gs.dA_hi[0]), LBO_W, SBO_K16), d_dA_lo0 = make_desc(smem_u32(gs.dA_lo[0]), LBO_W, SBO_K16);
-    const uint64_t d_dA_hi1 = make_desc(smem_u32(gs.dA_hi[1]), LBO_W, SBO_K16), d_dA_lo1 = make_desc(smem_u32(gs.dA_lo[1]), LBO_W, SBO_K16);
-    const uint64_t d_aB_hi0 = make_desc(smem_u32(gs.aB_hi[0]), LBO_W, SBO_K16), d_aB_lo0 = make_desc(smem_u32(gs.aB_lo[0]), LBO_W, SBO_K16);
-    const uint64_t d_aB_hi1 = make_desc(smem_u32(gs.aB_hi[1]), LBO_W, SBO_K16), d_aB_lo1 = make_desc(smem_u32(gs.aB_lo[1]), LBO_W, SBO_K16);
-    const uint64_t d_dkB_hi = make_desc(smem_u32(gs.dkB_hi), LBO_W, SBO_K16), d_dkB_lo = make_desc(smem_u32(gs.dkB_lo), LBO_W, SBO_K16);
+    // three base descriptors, one per (LBO, SBO) pair; every other tile sits at a constant byte offset from its base, so its
+    // descriptor is base + (offset >> 4): ptxas keeps 3 descriptors in uniform registers instead of rebuilding 20
+    const uint64_t d_dT_hi = make_desc(smem_u32(gs.dT_hi), LBO, SBO_ACT);
+    const uint64_t d_w64 = make_desc(smem_u32(gs.a3t_hi), LBO_W, SBO_W64);
+    const uint64_t d_k16 = make_desc(smem_u32(gs.dA_hi[0]), LBO_W, SBO_K16);
+    auto at = [](uint64_t base, size_t from, size_t to) { return base + (uint64_t)((to - from) >> 4); };
+    constexpr size_t o_w = offsetof(DaeBwdSmem, a3t_hi), o_dA = offsetof(DaeBwdSmem, dA_hi);
+    const uint64_t d_dT_lo = at(d_dT_hi, offsetof(DaeBwdSmem, dT_hi), offsetof(DaeBwdSmem, dT_lo));
+    const uint64_t d_a3t_hi = d_w64, d_a3t_lo = at(d_w64, o_w, offsetof(DaeBwdSmem, a3t_lo));
+    const uint64_t d_a2t_hi = at(d_w64, o_w, offsetof(DaeBwdSmem, a2t_hi)), d_a2t_lo = at(d_w64, o_w, offsetof(DaeBwdSmem, a2t_lo));
+    const uint64_t d_a1t_hi = at(d_w64, o_w, offsetof(DaeBwdSmem, a1t_hi)), d_a1t_lo = at(d_w64, o_w, offsetof(DaeBwdSmem, a1t_lo));
+    const uint64_t d_wit_hi = at(d_w64, o_w, offsetof(DaeBwdSmem, wit_hi)), d_wit_lo = at(d_w64, o_w, offsetof(DaeBwdSmem, wit_lo));
+    const uint64_t d_dA_hi0 = d_k16, d_dA_hi1 = at(d_k16, 0, K16_TILE);
+    const uint64_t d_dA_lo0 = at(d_k16, o_dA, offsetof(DaeBwdSmem, dA_lo)), d_dA_lo1 = at(d_k16, o_dA, offsetof(DaeBwdSmem, dA_lo) + K16_TILE);
+    const uint64_t d_aB_hi0 = at(d_k16, o_dA, offsetof(DaeBwdSmem, aB_hi)), d_aB_hi1 = at(d_k16, o_dA, offsetof(DaeBwdSmem, aB_hi) + K16_TILE);
+    const uint64_t d_aB_lo0 = at(d_k16, o_dA, offsetof(DaeBwdSmem, aB_lo)), d_aB_lo1 = at(d_k16, o_dA, offsetof(DaeBwdSmem, aB_lo) + K16_TILE);
+    const uint64_t d_dkB_hi = at(d_k16, o_dA, offsetof(DaeBwdSmem, dkB_hi)), d_dkB_lo = at(d_k16, o_dA, offsetof(DaeBwdSmem, dkB_lo));
     const uint32_t acc_base = tmem + TM_ACC;
     const uint32_t my_acc = acc_base + (uint32_t)wq * TN;
     const uint32_t acc_m5 = tmem + TM_UPPER + TM_ACC_M5;
