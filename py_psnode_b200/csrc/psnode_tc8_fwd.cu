@@ -528,8 +528,21 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                     ae_eval(false, dbase ? dbase + psn_dae_rec_event(k, T, NST) * PSN_TAPE_STAGE : nullptr, true);
                 }
             }
+            int e = 0;
+            // Next step's held inputs and step size go into the tile / dts once the step's last layer-1 MMA has completed, in
+            // DAE: in the shadow of the layer-2 MMAs of the last stage (warp 4 issues none; cfg3 9.00 -> 8.76 ms).  The ODE kernel and
+            // Euler (whose only stage also issued the loads) keep them at the end of the stage (moving them cost the ODE 1.7 %).
+            auto stage_next = [&]() {
+                if (wk == 4 && e == NST - 1 && (DAE || have_next)) {
+                    store_zv(un);
+                    if (have_next) {
+                        if (lane < TN) gs.dts[(j + 1) & 1][lane] = __fsub_rn(tn, t_prev);
+                        t_prev = tn;
+                    }
+                }
+            };
 #pragma unroll 1
-            for (int e = 0; e < NST; e++) {
+            for (e = 0; e < NST; e++) {
                 float d[4];
                 if (TAPE && trec) __stcs(trec + 3 * PSN_TAPE_FRAG + (32 * wq + lane) * 2 + h, ycur);
                 // ---- layer 1 (shared-memory weights) ----
@@ -546,6 +559,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                 publish();
                 // ---- layer 2 ----
                 issue_ts(TM_W2, TM_W2 + 64);
+                if (DAE && NST > 1) stage_next();
                 collect(d, 4);
                 store_hidden(d, bias2, nullptr, trec ? trec + PSN_TAPE_FRAG : nullptr);
                 publish();
@@ -582,13 +596,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc8_kernel(const __g
                 ycur = xn;
                 if (last) { x0 = xn; gs.ostage[sn][srow] = xn; }
                 if (TAPE && trec) trec += PSN_TAPE_STAGE;
-                if (wk == 4 && last && (DAE || have_next)) {        // all layer-1 MMAs of this step are done
-                    store_zv(un);
-                    if (have_next) {
-                        if (lane < TN) gs.dts[(j + 1) & 1][lane] = __fsub_rn(tn, t_prev);
-                        t_prev = tn;
-                    }
-                }
+                if (!DAE || NST == 1) stage_next();
                 publish();
             }
             if constexpr (DAE) {                                // i_j = ae(x_j, z[j], v[j])  (my_solvers.py:121)
