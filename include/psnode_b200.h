@@ -49,11 +49,13 @@ extern "C" {
 #define PSNODE_DAE 1
 
 /* kernel selection for psnode_forward / psnode_backward (`impl` field) */
-#define PSNODE_IMPL_AUTO 0     /* fastest kernel that supports the problem: TC8, else FUSED, else GENERIC */
+#define PSNODE_IMPL_AUTO 0     /* fastest kernel that supports the problem: TC8 / WIDE, else FUSED, else GENERIC */
 #define PSNODE_IMPL_GENERIC 1  /* shared-memory-weight kernel, reference formulation of layer 1  */
 #define PSNODE_IMPL_FUSED 2    /* register-resident-weight kernel, folded layer 1 (H = 64 nets)  */
 #define PSNODE_IMPL_TC 3       /* tcgen05 tensor-core kernel: 3xTF32, weights resident in TMEM (H = 64 ODE / DAE nets) */
 #define PSNODE_IMPL_TC8 4      /* same, 8 warps per 16-trajectory group (4 accumulator elements per thread) */
+#define PSNODE_IMPL_WIDE 5     /* tcgen05 kernels for the latent `*_02_direct_encode` nets (X = Z = H = 128, 2 layers): TMA-staged
+                                  input series, hoisted input GEMM, both weight matrices resident in TMEM */
 
 /* A small ELU MLP: Linear -> ELU -> ... -> Linear, weights in nn.Linear layout W[out][in] (row major,
  * contiguous), as built by the script-local DE_Func / AE_Func classes

@@ -6,6 +6,7 @@
 #include <mutex>
 #include "psnode_internal.cuh"
 #include "psnode_tc_tape.cuh"
+#include "psnode_wide.cuh"
 
 namespace {
 std::atomic<int64_t> g_launches{0};
@@ -132,6 +133,7 @@ int64_t psnode_forward_workspace(const psnode_problem* p) {
     int64_t f = psn_fused_supports(p) ? psn_fused_forward_workspace(p) : 0;
     int64_t t = psn_tc_supports(p) ? psn_tc_forward_workspace(p) : 0;
     if (f > g) g = f;
+    if (psn_wide_supports(p)) { const int64_t w = psn_wide_forward_workspace(p); if (w > g) g = w; }
     return g > t ? g : t;
 }
 
@@ -151,7 +153,12 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
         if (!psn_fused_supports(p)) return PSNODE_EUNSUPPORTED;
         return psn_fused_forward(p, workspace, workspace_bytes, s);
     }
+    if (p->impl == PSNODE_IMPL_WIDE) {
+        if (!psn_wide_supports(p)) return PSNODE_EUNSUPPORTED;
+        return psn_wide_forward(p, workspace, workspace_bytes, s);
+    }
     if (p->impl == PSNODE_IMPL_AUTO && psn_tc_supports(p)) return psn_tc8_forward(p, workspace, workspace_bytes, s);
+    if (p->impl == PSNODE_IMPL_AUTO && psn_wide_supports(p)) return psn_wide_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_fused_supports(p)) return psn_fused_forward(p, workspace, workspace_bytes, s);
     const int gst = psn_generic_forward(p, workspace, workspace_bytes, s);
     if (gst != PSNODE_EUNSUPPORTED) return gst;

@@ -32,7 +32,7 @@ def test_cfg4_shape_latent_ode_h128(native_lib, solver):
     S = {"euler": Euler, "rk4": RK4}[solver]
     with torch.no_grad():
         got = S().integrate_ODE(x_func=de.to(dev), t=t.to(dev), x=x.to(dev), z=z.to(dev), all_initial=a0.to(dev)).cpu()
-    assert _native.last_kernel().startswith("psn_generic_fwd_kernel")
+    assert _native.last_kernel().startswith("psn_wide_fwd_kernel")      # round 2: tcgen05 kernels for the latent widths
     assert torch.allclose(got, want, rtol=RTOL, atol=ATOL), tol_report(got, want)
 
 
