@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PSNODE_ABI_VERSION 2
+#define PSNODE_ABI_VERSION 3
 #define PSNODE_MAX_LAYERS 8
 
 /* status codes */
@@ -186,6 +186,11 @@ int psnode_event_table(const float* t0, int64_t t_st, int32_t T, const float* ev
 /* floats of activation tape psnode_forward can record for this problem (0: this problem has no tape-based reverse
  * sweep, psnode_backward recomputes from x_sol) */
 int64_t psnode_tape_floats(const psnode_problem* p);
+
+/* 1 if the tape-based reverse sweep of this problem also produces the input-series / jump gradients (d_z, d_zjump) --
+ * the latent `*_02_direct_encode` nets, whose encoders always need them (neural_00_ODE_02_direct_encode.py:75-86);
+ * 0: requesting those gradients sends psnode_backward to the recomputing sweep and a tape would be wasted. */
+int psnode_tape_covers_input_grads(const psnode_problem* p);
 
 /* workspace sizes in bytes (0 is possible) */
 int64_t psnode_forward_workspace(const psnode_problem* p);

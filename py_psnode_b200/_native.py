@@ -8,7 +8,7 @@ import os
 import threading
 
 PSNODE_MAX_LAYERS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, EINVAL, EUNSUPPORTED, EWORKSPACE, ECUDA, ENODEVICE = 0, -1, -2, -3, -4, -5
 EULER, MIDPOINT, RK4 = 0, 1, 2
@@ -69,6 +69,7 @@ SYMBOLS = [
     ("psnode_event_table", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     ("psnode_tape_floats", C.c_int64, [C.POINTER(Problem)]),
+    ("psnode_tape_covers_input_grads", C.c_int, [C.POINTER(Problem)]),
     ("psnode_forward_workspace", C.c_int64, [C.POINTER(Problem)]),
     ("psnode_backward_workspace", C.c_int64, [C.POINTER(Problem), C.POINTER(Adjoint)]),
     ("psnode_forward", C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_int64, C.c_void_p]),

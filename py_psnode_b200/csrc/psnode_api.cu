@@ -117,8 +117,15 @@ int psnode_event_table(const float* t0, int64_t t_st, int32_t T, const float* ev
     return PSNODE_OK;
 }
 
+int psnode_tape_covers_input_grads(const psnode_problem* p) {
+    if (validate(p) != PSNODE_OK) return 0;
+    return ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_WIDE) && psn_wide_supports(p)) ? 1 : 0;
+}
+
 int64_t psnode_tape_floats(const psnode_problem* p) {
     if (validate(p) != PSNODE_OK) return 0;
+    if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_WIDE) && psn_wide_supports(p) && !psn_tc_supports(p))
+        return psw_tape_floats(p->B, p->T, p->method);
     if (p->impl != PSNODE_IMPL_AUTO && p->impl != PSNODE_IMPL_TC && p->impl != PSNODE_IMPL_TC8) return 0;
     if (!psn_tc_supports(p)) return 0;
     if (p->kind == PSNODE_DAE)      // only the 8-warp forward kernel records the DAE tape
@@ -170,6 +177,7 @@ int64_t psnode_backward_workspace(const psnode_problem* p, const psnode_adjoint*
     int64_t g = psn_generic_backward_workspace(p, a);
     { const int64_t g2 = psn_generic_backward_workspace_tb2(p, a); if (g2 > g) g = g2; }
     const int64_t t = !psn_tc_supports(p) ? 0 : (p->kind == PSNODE_ODE ? psn_tc_backward_workspace(p, a) : psn_tc_dae_backward_workspace(p, a));
+    if (psn_wide_bwd_supports(p, a)) { const int64_t w = psn_wide_backward_workspace(p, a); if (w > g) g = w; }
     return g > t ? g : t;
 }
 
@@ -178,6 +186,8 @@ int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* work
     const int st = validate(p);
     if (st != PSNODE_OK) return st;
     if (!a || !a->d_theta) return PSNODE_EINVAL;
+    if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_WIDE) && psn_wide_bwd_supports(p, a))
+        return psn_wide_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC || p->impl == PSNODE_IMPL_TC8) && psn_tc_bwd_supports(p, a))
         return psn_tc_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC8) && psn_tc_dae_bwd_supports(p, a))

@@ -51,10 +51,12 @@ PSN_HD float psn_expm1_neg(float x) {
     return fmaf(t, p, t - 1.0f);
 }
 
-// ELU(v), alpha = 1, branch free.
+// ELU(v), alpha = 1, branch free.  The select is written `v <= 0 ? e : v` so that a NaN input comes out as NaN, as in
+// torch's nn.ELU (fminf(NaN, 0) = 0 would otherwise turn it into 0 and hide a diverged trajectory from the scripts'
+// `loss != loss` guards, utils.py:33-42).
 PSN_HD float psn_elu(float v) {
     const float e = psn_expm1_neg(fminf(v, 0.0f));
-    return v > 0.0f ? v : e;
+    return v <= 0.0f ? e : v;
 }
 // derivative of ELU expressed through its OUTPUT y: 1 for y > 0, y + 1 (= exp(v)) otherwise.
 PSN_HD float psn_elu_grad_from_out(float y) { return y > 0.0f ? 1.0f : y + 1.0f; }
@@ -108,7 +110,7 @@ __device__ __forceinline__ void psn_elu2(float v0, float v1, float& o0, float& o
     const psn_u64 e = psn_fma2(t, p, psn_add2(t, psn_dup2(-1.0f)));
     float e0, e1;
     psn_unpack2(e, e0, e1);
-    o0 = v0 > 0.0f ? v0 : e0;
-    o1 = v1 > 0.0f ? v1 : e1;
+    o0 = v0 <= 0.0f ? e0 : v0;      // NaN propagates (see psn_elu)
+    o1 = v1 <= 0.0f ? e1 : v1;
 }
 #endif

@@ -93,7 +93,7 @@ class Config:
     n_de: int                       # number of Linear layers of the DE net
     n_ae: int
     has_event: bool
-    check_events: bool = False
+    check_events: bool = True
     event_ref: Optional[tuple] = None   # (t_row (T,), ev_row (E,)) of the GLOBAL sample 0 in batch-sharded runs
 
 
@@ -142,7 +142,7 @@ def _build_problem(cfg: Config, tens: Sequence[Optional[torch.Tensor]], x_sol, i
             if t00.numel() != T or ev0.numel() != E:
                 raise ValueError("pinned event reference rows do not match (T,) / (E,)")
         idx = torch.empty(max(T - 1, 1), dtype=torch.int32, device=t.device)
-        err = torch.empty(1, dtype=torch.int32, device=t.device)
+        err = torch.zeros(1, dtype=torch.int32, device=t.device)
         keep.extend((ev0, t00, idx, err))
         N.check(N.lib().psnode_event_table(t00.data_ptr(), t00.stride(0), T, ev0.data_ptr(), ev0.stride(0), E,
                                            idx.data_ptr(), err.data_ptr(), torch.cuda.current_stream(t.device).cuda_stream),
@@ -222,9 +222,13 @@ class TapeChunks:
         self.rows = rows
 
 
-def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]], want_tape: bool = False):
+def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]], want_tape: bool = False, input_grads: bool = False,
+                force_tape: bool = False):
     """Run the forward kernel; returns time-major contiguous (x_sol, i_sol) -- and, with `want_tape`, the activation tape
-    the tensor-core reverse sweep consumes (None when the problem has no tape-based sweep or the tape would not fit)."""
+    the tensor-core reverse sweep consumes (None when the problem has no tape-based sweep or the tape would not fit).
+    `input_grads`: the caller will ask for input-series / jump gradients, so a tape is only worth recording if the tape-based
+    sweep of this problem produces them (psnode_tape_covers_input_grads).  `force_tape`: skip the HBM budget check (the
+    chunked reverse sweep sized its chunks against the budget already)."""
     t = tens[_T]
     _require_cuda_f32("t", t)
     L = N.lib()
@@ -235,11 +239,14 @@ def forward_raw(cfg: Config, tens: Sequence[Optional[torch.Tensor]], want_tape: 
         keep: list = []
         p = _build_problem(cfg, tens, x_sol, i_sol, keep)
         tape = None
+        if want_tape and input_grads and not L.psnode_tape_covers_input_grads(C.byref(p)):
+            want_tape = False
         if want_tape:
             n_tape = int(L.psnode_tape_floats(C.byref(p)))
             key = t.device.index if t.device.index is not None else torch.cuda.current_device()
             pooled = _tape_pool.get(key)
-            if n_tape > 0 and ((pooled is not None and pooled.numel() >= n_tape and os.environ.get("PSNODE_TAPE_MAX_GB") is None)
+            if n_tape > 0 and (force_tape
+                               or (pooled is not None and pooled.numel() >= n_tape and os.environ.get("PSNODE_TAPE_MAX_GB") is None)
                                or n_tape * 4 <= _tape_budget_bytes(t.device)):
                 tape = _take_tape(t.device, n_tape)
                 p.tape, p.tape_floats = tape.data_ptr(), tape.numel()
@@ -266,9 +273,10 @@ class _Integrate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg: Config, *tens):
         needs = ctx.needs_input_grad[1:]
-        # the tape-based reverse sweep produces parameter, x0 and all_initial gradients; anything else is recomputed
-        want_tape = not (cfg.teacher_x or cfg.teacher_i or any(needs[k] for k in (_Zs, _Vs, _Is, _ZJ, _VJ)))
-        x_sol, i_sol, tape = forward_raw(cfg, tens, want_tape=want_tape)
+        # the tape-based reverse sweeps produce parameter, x0 and all_initial gradients -- and, for the latent `*_02` nets, the
+        # input-series / jump gradients too; anything else is recomputed from the stored trajectory
+        input_grads = any(needs[k] for k in (_Zs, _Vs, _Is, _ZJ, _VJ))
+        x_sol, i_sol, tape = forward_raw(cfg, tens, want_tape=not (cfg.teacher_x or cfg.teacher_i), input_grads=input_grads)
         ctx.tape = tape
         ctx.cfg = cfg
         ctx.n_in = len(tens)
@@ -326,9 +334,18 @@ def _backward_chunked(cfg: Config, tens, gx, gi, needs, rows: int) -> List[Optio
         for k in rows_major:
             if sub[k] is not None:
                 sub[k] = sub[k][b0:b1]
-        xs, _is, tape = forward_raw(cfg, sub, want_tape=True)
-        if tape is None or isinstance(tape, TapeChunks):
-            raise RuntimeError("activation tape chunk could not be allocated")
+        # the chunk size was derived from the budget at forward time; by now x_sol, the upstream gradient and the loss
+        # temporaries are allocated, so the budget is NOT re-checked here: take the tape, and if the allocator cannot
+        # provide it fall back to the recomputing sweep for this chunk instead of failing the training step
+        input_grads = any(needs[k] for k in (_Zs, _Vs, _Is, _ZJ, _VJ))
+        try:
+            xs, _is, tape = forward_raw(cfg, sub, want_tape=True, input_grads=input_grads, force_tape=True)
+        except torch.cuda.OutOfMemoryError:
+            release_tape_pool()
+            torch.cuda.empty_cache()
+            xs, _is, tape = forward_raw(cfg, sub, want_tape=False)
+        if isinstance(tape, TapeChunks):
+            tape = None
         g = backward_raw(cfg, sub, xs, _is, gx[:, b0:b1], gi[:, b0:b1] if gi is not None else None, needs, tape)
         _give_tape(tape)
         for k, gk in enumerate(g):

@@ -145,6 +145,8 @@ def match_event(event_fn, jump_change_fn, dae: bool) -> Optional[Tuple[torch.Ten
         raise UnsupportedModuleError("jump_change_fn must be the bound `jump_change_fn` of the same event object as event_fn")
     if owner.event_t is None:
         return None            # set_event() never called: event_fn() is constantly False (neural_base.py:53)
+    if owner.event_t.dim() >= 2 and owner.event_t.shape[1] == 0:
+        return None            # a dataset without events: `t0[0] in event_t[0]` is False for an empty table (neural_base.py:54)
     if dae:
         if not hasattr(owner, "v_jump"):
             raise UnsupportedModuleError("DAE integration needs a DAE_Event (z_jump and v_jump)")

@@ -39,7 +39,7 @@ class FixedGridODESolver(metaclass=abc.ABCMeta):
     _method: int
 
     def __init__(self, step_size=None, grid_constructor=None, interp="linear", impl: str = "auto",
-                 check_events: bool = False):
+                 check_events: bool = True):
         if step_size is not None and grid_constructor is not None:
             raise ValueError("step_size and grid_constructor are mutually exclusive arguments.")
         self.step_size = step_size
