@@ -1,19 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- RK4 trajectory-steps/s of the fused integrator on BASELINE.json's configs[1].
+"""bench.py -- RK4 trajectory-steps/s of the fused integrator on BASELINE.json's configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5] [--no-others]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-One "step" = one `RK4().integrate_ODE(...)` call (the reference's hot path, neural_dae/my_solvers.py:52-80) over a
-synthetic batch of B = 4096 trajectories x 1000 grid steps per GPU (ODE_01 `DE_Func`, X=16, Z=2,
-H=64; t = 0.01*j; series ~ N(0, 0.1^2); seed 0; default nn.Linear init).  Batch sharding is the only parallelism
-(independent trajectories, no data-path collective), so N GPUs integrate N x 4096 trajectories: "scaling": "weak".
+The JSON line's top level is BASELINE.json's headline: configs[1] ("cfg2": RK4, ODE_01 DE_Func X=16 Z=2 H=64, B = 4096 x 1000
+steps per GPU, weak scaling -- independent trajectories, no data-path collective).  One "step" = one `RK4().integrate_ODE(...)`
+call (the reference's hot path, neural_dae/my_solvers.py:52-80) over the synthetic batch of SURVEY.md 8d (t = 0.01 j, series
+~ N(0, 0.1^2), seeded, default nn.Linear init).  `value` = traj-steps/s with inputs resident in HBM; `e2e` = the same metric
+through the host-buffer C ABI with pinned-host inputs and outputs (every byte crosses PCIe inside the timed region);
+`train` = forward + reverse sweep + masked MSE + the ONE flat gradient all-reduce; `roofline` / `cpu_baseline` per the contract.
 
-Printed JSON (one line, rank 0): see the task contract.  `value` = traj-steps/s with inputs resident in HBM;
-`e2e` = same metric through the public Python call with pinned-host inputs copied in and the trajectory copied back
-inside the timed region; `roofline` = algorithmic HBM bytes / kernel time vs the measured copy bandwidth (the path is
-FMA-bound, not HBM-bound: `fp32` gives the fraction of the fp32-FMA peak); `cpu_baseline` = the oracle port (same ATen
-ops as the reference) timed on this box's host cores on a bounded sample.
+`others` carries the same measurements for the remaining BASELINE configs in the same run, so the driver's default
+invocation records them:
+  cfg3  RK4 DAE_01 (DE_Func + AE_Func, H = 64), B = 4096 x 1000 per GPU (weak)
+  cfg4  RK4 ODE_02 latent net X = Z = H = 128, GLOBAL batch 16384 x 500 steps sharded over the N ranks (strong; BASELINE quotes
+        it on 4 GPUs), training leg = adjoint with latent-input gradients + 0.67 MB gradient all-reduce
+  cfg5  RK4 DAE_02 latent net H = 256, GLOBAL batch 65536 x 2000 steps sharded over 8 ranks (BASELINE quotes it on 8 GPUs); with
+        fewer than 8 ranks each rank integrates one 1/8 shard (B = 8192).  The H = 256 nets still run on the CUDA-core
+        generic kernel, so the timed call covers a bounded number of grid steps (stated in `sample`).
+CPU legs: the UNMODIFIED reference from oracle/_ref (vendored by oracle/make_ref.py, executed by oracle/ref_runner.py in a
+subprocess; `kind: "reference"`), or the oracle port when oracle/_ref is absent (`kind: "port"`).
 """
 import argparse
 import datetime
@@ -30,32 +37,55 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (kind, X, Z, V, I, H, B per GPU, N steps, bytes/traj-step, FLOP/traj-step reference formulation)
-    "cfg2": dict(kind="ode", X=16, Z=2, V=0, I=0, H=64, B=4096, N=1000, bytes_per_unit=76, flop_per_unit=101376,
+    # bytes_per_unit / flop_per_unit: SURVEY.md 8d (compulsory HBM bytes and reference-formulation FLOPs per trajectory-step)
+    "cfg2": dict(kind="ode", net="01", X=16, Z=2, V=0, I=0, H=64, B=4096, N=1000, scaling="weak", bytes_per_unit=76, flop_per_unit=101376,
                  desc="RK4 fixed-step, ODE_01 DE_Func 54-64-64-64-16 + external input z(t), batch 4096 x 1000 steps"),
-    "cfg3": dict(kind="dae", X=16, Z=1, V=2, I=4, H=64, B=4096, N=1000, bytes_per_unit=96, flop_per_unit=131328,
+    "cfg3": dict(kind="dae", net="01", X=16, Z=1, V=2, I=4, H=64, B=4096, N=1000, scaling="weak", bytes_per_unit=96, flop_per_unit=131328,
                  desc="RK4 fixed-step, DAE_01 DE_Func 69-64-64-64-16 + AE_Func 42-64-64-64-4 (one explicit AE eval/step), "
                       "batch 4096 x 1000 steps"),
+    "cfg4": dict(kind="ode", net="02", X=128, Z=128, V=0, I=0, H=128, B=16384, N=500, scaling="strong", quoted_gpus=4,
+                 bytes_per_unit=1028, flop_per_unit=917504,
+                 desc="RK4 fixed-step, ODE_02 latent DE_Func 768-128-128 (x_dim=z_dim=hidden=128), global batch 16384 x 500 steps, "
+                      "adjoint training with latent-input gradients"),
+    "cfg5": dict(kind="dae", net="02", X=256, Z=256, V=256, I=256, H=256, B=65536, N=2000, scaling="strong", quoted_gpus=8,
+                 bytes_per_unit=4100, flop_per_unit=7864320, sample_steps=40,
+                 desc="RK4 fixed-step, DAE_02 latent DE_Func 3072-256-256 + AE_Func 1792-256-256, global batch 65536 x 2000 steps"),
 }
 FP32_PEAK_TFLOPS = 74.4     # nominal: 148 SM x 128 lanes x 2 x 1.965 GHz; measured 72.1 by bench_micro/micro.cu
 
 
-def make_problem(w, seed=0):
-    """Synthetic inputs on the CPU (pinned by the caller when needed) + freshly initialised modules."""
+def rank_batch(w, world):
+    """Trajectories one rank integrates: weak workloads keep B per GPU, strong ones shard the global batch (cfg5 never
+    fewer than 8 ways: one 1/8 shard per rank is what fits and what BASELINE quotes)."""
+    if w["scaling"] == "weak":
+        return w["B"]
+    ways = max(world, 8) if w.get("quoted_gpus") == 8 else world
+    return w["B"] // ways
+
+
+def make_modules(w, seed=0):
     import torch
     from py_psnode_b200 import DE_Func, AE_Func
     torch.manual_seed(seed)
-    B, T = w["B"], w["N"] + 1
+    depth = 4 if w["net"] == "01" else 2
     X, Z, V, I, H = w["X"], w["Z"], w["V"], w["I"], w["H"]
-    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H, v_dim=V, i_dim=I)
-    ae = AE_Func(x_dim=X, v_dim=V, i_dim=I, hidden_dim=H, z_dim=Z) if w["kind"] == "dae" else None
-    t = (torch.arange(T, dtype=torch.float32) * 0.01).view(T, 1, 1).repeat(1, B, 1).contiguous()
-    g = torch.Generator().manual_seed(seed + 1)
-    mk = lambda width: (torch.randn(T, B, width, generator=g) * 0.1)
-    data = dict(t=t, z=mk(Z), x0=torch.randn(B, X, generator=g) * 0.1)
+    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H, v_dim=V, i_dim=I, depth=depth)
+    ae = AE_Func(x_dim=X, v_dim=V, i_dim=I, hidden_dim=H, z_dim=Z, depth=depth) if w["kind"] == "dae" else None
+    return de, ae
+
+
+def make_data(w, B, steps, seed=0, device="cpu"):
+    """Synthetic inputs of SURVEY.md 8d.  On the CPU the draw order matches oracle/ref_runner.py (same tensors on both arms)."""
+    import torch
+    T = steps + 1
+    X, Z, V, I = w["X"], w["Z"], w["V"], w["I"]
+    g = torch.Generator(device=device).manual_seed(seed + 1)
+    t = (torch.arange(T, dtype=torch.float32, device=device) * 0.01).view(T, 1, 1).repeat(1, B, 1).contiguous()
+    mk = lambda width: (torch.randn(T, B, width, generator=g, device=device) * 0.1)
+    data = dict(t=t, z=mk(Z), x0=torch.randn(B, X, generator=g, device=device) * 0.1)
     if w["kind"] == "dae":
-        data.update(v=mk(V), i0=torch.randn(B, I, generator=g) * 0.1)
-    return de, ae, data
+        data.update(v=mk(V), i0=torch.randn(B, I, generator=g, device=device) * 0.1)
+    return data
 
 
 def call_integrate(w, solver, de, ae, d):
@@ -136,19 +166,38 @@ class ClockSampler:
                 "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
-def cpu_baseline(w, sample_steps, repeats=3, threads=None):
-    """The oracle port (same ATen ops as the reference's loop) on the host cores; returns traj-steps/s (best of `repeats`)."""
+# ------------------------------------------------------------------------------------------------------------- CPU legs
+def ref_available():
+    return os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "src", "neural_dae", "my_solvers.py"))
+
+
+def cpu_reference(w, B, sample_steps, repeats, threads=None, timeout=900):
+    """The UNMODIFIED reference (oracle/_ref) in a subprocess on the host cores.  Returns (traj-steps/s of the best repeat,
+    threads, [seconds of every repeat])."""
+    threads = threads or os.cpu_count()
+    job = dict(kind=w["kind"], net=w["net"], X=w["X"], Z=w["Z"], V=w["V"], I=w["I"], H=w["H"], B=B, steps=sample_steps, seed=0,
+               repeats=repeats, threads=threads, method="rk4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "time", json.dumps(job)],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout, cwd=os.path.join(ROOT, "oracle"))
+    if out.returncode != 0:
+        raise RuntimeError("oracle/ref_runner.py failed: " + out.stderr[-400:])
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    return B * sample_steps / res["seconds"], res["threads"], res["all_seconds"]
+
+
+def cpu_port(w, B, sample_steps, repeats=2, threads=None):
+    """The oracle port (same ATen ops as the reference's loop) on the host cores; same return convention as cpu_reference."""
     import torch
     from oracle import psnode_oracle as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    de, ae, d = make_problem(w)
+    de, ae = make_modules(w)
+    d = make_data(w, B, sample_steps)
     T = sample_steps + 1
-    t, z, x0 = d["t"][:T], d["z"][:T], d["x0"]
-    B = t.shape[1]
+    t, z, x0 = d["t"], d["z"], d["x0"]
     pd = [(m.weight.detach(), m.bias.detach()) for m in de.x_dot if hasattr(m, "weight")]
     x = x0.unsqueeze(0).expand(T, B, w["X"])
-    best = float("inf")
+    secs = []
     with torch.no_grad():
         for r in range(repeats + 1):          # first pass is the warm-up
             t0 = time.perf_counter()
@@ -157,97 +206,193 @@ def cpu_baseline(w, sample_steps, repeats=3, threads=None):
                 O.integrate_ode("rk4", pd, t, x, z, a0)
             else:
                 pa = [(m.weight.detach(), m.bias.detach()) for m in ae.i_calculator if hasattr(m, "weight")]
-                v, i0 = d["v"][:T], d["i0"]
+                v, i0 = d["v"], d["i0"]
                 a0 = torch.cat((x0, z[0], v[0], i0), dim=-1)
                 O.integrate_dae("rk4", pd, pa, x0, t, x, z, v, i0.unsqueeze(0).expand(T, B, w["I"]), a0)
-            dt = time.perf_counter() - t0
             if r > 0:
-                best = min(best, dt)
-    return B * sample_steps / best, threads, best
+                secs.append(time.perf_counter() - t0)
+    return B * sample_steps / min(secs), threads, secs
 
 
-def run_reference_arm(args, w, rank):
-    """`--impl reference`: the reference's CPU implementation of the path (oracle port; /root/reference cannot travel to the
-    GPU box and the reference has no installable package) on all host threads.  Each step = a bounded sample."""
+def cpu_leg(w, B, sample_steps, repeats):
+    """(value, cores, kind, seconds list)"""
+    if ref_available():
+        try:
+            v, th, secs = cpu_reference(w, B, sample_steps, repeats)
+            return v, th, "reference", secs
+        except Exception as exc:           # fall back to the port, and say so
+            sys.stderr.write(f"bench.py: reference runner failed ({exc}); timing the oracle port instead\n")
+    v, th, secs = cpu_port(w, B, sample_steps, repeats)
+    return v, th, "port", secs
+
+
+def cpu_sample_plan(name, w):
+    """(B, steps, note) of the CPU sample per workload: the full job where it costs seconds, >= the stated number of steps at
+    full batch otherwise (the loop has no step-dependent state: per-step cost is constant)."""
+    if name in ("cfg2", "cfg3"):
+        return w["B"], w["N"], f"the whole job: B={w['B']} x {w['N']} RK4 steps"
+    if name == "cfg4":
+        return w["B"], 50, f"B={w['B']} (full batch) x 50 of {w['N']} RK4 steps, scaled linearly"
+    return w["B"], 10, f"B={w['B']} (full batch) x 10 of {w['N']} RK4 steps, scaled linearly (one step = 257 GMAC on the CPU)"
+
+
+def run_reference_arm(args, name, w, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path on all host threads.  Rank 0 only."""
     if rank != 0:
         return
     import torch
-    sample_steps = 50
-    threads = os.cpu_count()
-    vals = []
-    for k in range(args.warmup + args.steps):
-        v, threads, secs = cpu_baseline(w, sample_steps, repeats=1, threads=threads)
-        if k >= args.warmup:
-            vals.append((v, secs))
-    value = sum(v for v, _ in vals) / len(vals)
-    ms = 1e3 * sum(s for _, s in vals) / len(vals)
-    sample = f"B={w['B']} x {sample_steps} RK4 steps per step (of {w['N']}), torch {torch.__version__} CPU, {threads} threads, no_grad"
+    B, steps_full, note = cpu_sample_plan(name, w)
+    # bound the whole K + W run to a few minutes: probe 20 steps, then size the per-step sample
+    _, threads, kind, probe = cpu_leg(w, B, min(20, steps_full), 1)
+    per_step = min(probe) / min(20, steps_full)
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    sample_steps = max(min(steps_full, int(budget / per_step)), min(20, steps_full))
+    v, threads, kind, secs = cpu_leg(w, B, sample_steps, args.steps + args.warmup - 1 if args.steps + args.warmup > 1 else 1)
+    secs = secs[-args.steps:]
+    value = B * sample_steps / statistics.mean(secs)
+    ms = 1e3 * statistics.mean(secs)
+    sample = (f"B={B} x {sample_steps} RK4 steps per step (of {w['N']}), torch {torch.__version__} CPU, {threads} threads, no_grad, "
+              + ("unmodified reference from oracle/_ref with its event callbacks" if kind == "reference" else "oracle port"))
     line = {"impl": "reference", "metric": "rk4_traj_steps_per_sec", "value": value, "unit": "traj-steps/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + w["desc"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "traj-steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": name + ": " + w["desc"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "traj-steps/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "traj-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused", "tc", "tc8"])
-    ap.add_argument("--cpu-sample-steps", type=int, default=200)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-train", action="store_true", help="skip the forward+reverse-sweep(+grad all-reduce) leg")
-    args = ap.parse_args()
-    w = WORKLOADS[args.workload]
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+# ------------------------------------------------------------------------------------------------------------- GPU legs
+def _e2e_leg(w, legs, host, resident, solver, de, ae, B, n_steps, units, active, steps, barrier, reduce_max):
+    import torch
+    e2e = None
+    if "e2e" in legs and host is not None:
+        import copy
+        T = n_steps + 1
+        pinned = {k: v.pin_memory() for k, v in host.items()}
+        de_cpu = copy.deepcopy(de).cpu()
+        ae_cpu = copy.deepcopy(ae).cpu() if ae is not None else None
+        out_host = torch.empty((T, B, w["X"]), dtype=torch.float32).pin_memory()
+        iout_host = torch.empty((T, B, w["I"]), dtype=torch.float32).pin_memory() if w["kind"] == "dae" else None
+        moved = [0, 0]
 
-    if args.impl == "reference":
-        run_reference_arm(args, w, rank)
-        return
+        def e2e_step():
+            d = pinned
+            x_view = d["x0"].unsqueeze(0).expand(T, B, w["X"])
+            if w["kind"] == "ode":
+                a0 = torch.cat((d["x0"], d["z"][0]), dim=-1)
+                solver.integrate_ODE_host(x_func=de_cpu, t=d["t"], x=x_view, z=d["z"], all_initial=a0, out=out_host)
+            else:
+                i_view = d["i0"].unsqueeze(0).expand(T, B, w["I"])
+                a0 = torch.cat((d["x0"], d["z"][0], d["v"][0], d["i0"]), dim=-1)
+                solver.integrate_DAE_host(x_init=d["x0"], x_func=de_cpu, i_func=ae_cpu, t=d["t"], x=x_view, z=d["z"], v=d["v"],
+                                          i=i_view, all_initial=a0, out=(out_host, iout_host))
+            moved[0], moved[1] = solver.last_host_bytes
 
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.perf_counter()
+        a.record()
+        for _ in range(steps):
+            e2e_step()                                    # returns after the stream drained (results are in host memory)
+        b.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t_wall0) * 1e3
+        e2e_ms = reduce_max(max(a.elapsed_time(b), wall_ms)) / steps      # the call blocks the host: the larger of the two clocks
+        e2e = {"value": units * active / (e2e_ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": moved[0], "d2h_bytes_per_step": moved[1],
+               "path": "psnode_forward_host (C ABI, HOST pointers): pinned buffers read/written in place over PCIe by the kernel"}
+        del pinned, out_host, iout_host
+    elif "e2e" in legs:
+        # GB-sized series: staged end-to-end = pinned host -> device copy of the inputs, integrate, device -> pinned host copy
+        T = n_steps + 1
+        keys = [k for k in resident]
+        pinned = {k: torch.empty(resident[k].shape, dtype=torch.float32).pin_memory() for k in keys}
+        for k in keys:
+            pinned[k].copy_(resident[k])
+        out_host = torch.empty((T, B, w["X"]), dtype=torch.float32).pin_memory()
+        iout_host = torch.empty((T, B, w["I"]), dtype=torch.float32).pin_memory() if w["kind"] == "dae" else None
+        h2d = sum(v.numel() * 4 for v in pinned.values())
+        d2h = out_host.numel() * 4 + (iout_host.numel() * 4 if iout_host is not None else 0)
+
+        def e2e_step():
+            with torch.no_grad():
+                d = {k: resident[k].copy_(pinned[k], non_blocking=True) for k in keys}
+                xs, is_ = call_integrate(w, solver, de, ae, d)
+                out_host.copy_(xs, non_blocking=True)
+                if is_ is not None:
+                    iout_host.copy_(is_, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_step()
+        barrier()
+        t_wall0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        barrier()
+        e2e_ms = reduce_max((time.perf_counter() - t_wall0) * 1e3) / steps
+        e2e = {"value": units * active / (e2e_ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "path": "pinned host -> cudaMemcpyAsync -> solver.integrate_* (device) -> cudaMemcpyAsync -> pinned host"}
+        del pinned, out_host, iout_host
+    return e2e
+
+
+def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
+    """Measure one workload on this rank's GPU; returns the result dict (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from py_psnode_b200 import RK4, _native
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the integration path has no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+    rank, world, dev, local_rank = ctx["rank"], ctx["world"], ctx["dev"], ctx["local_rank"]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # each rank integrates its own shard of the global batch (seeded by rank): independent trajectories, no exchange
-    de, ae, host = make_problem(w, seed=rank)
+    def reduce_max(ms):
+        tt = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    B = rank_batch(w, world)
+    n_steps = w.get("sample_steps", w["N"])              # grid steps per timed call (cfg5: a bounded sample, stated)
+    units = B * n_steps
+    ways = w["B"] // B if w["scaling"] == "strong" else world
+    active = min(world, ways)
+    de, ae = make_modules(w, seed=0 if w["scaling"] == "strong" else rank)
     de = de.to(dev)
     ae = ae.to(dev) if ae is not None else None
-    pinned = {k: v.pin_memory() for k, v in host.items()}
-    resident = {k: v.to(dev) for k, v in host.items()}
-    solver = RK4(impl=args.kernel)
-    units = w["B"] * w["N"]
+    big = B * (n_steps + 1) * max(w["Z"], 1) * 4 > (1 << 30)
+    host = None
+    if big:                                               # GB-sized series are drawn on the device
+        resident = make_data(w, B, n_steps, seed=rank, device=dev)
+    else:
+        host = make_data(w, B, n_steps, seed=rank)
+        resident = {k: v.to(dev) for k, v in host.items()}
+    solver = RK4(impl=args.kernel if main_line else "auto")
+    res = {"workload": name + ": " + w["desc"], "batch_per_gpu": B, "grid_steps": n_steps, "scaling": w["scaling"]}
+    if n_steps != w["N"]:
+        res["sample"] = f"each timed call integrates {n_steps} of the {w['N']} grid steps (per-step cost is constant); throughput is per traj-step"
+    if w["scaling"] == "strong":
+        res["global_batch"] = w["B"]
+        res["shards"] = ways
+        if world < ways:
+            res["note"] = f"{world} rank(s) each integrate one 1/{ways} shard of the global batch (BASELINE quotes this config on {w.get('quoted_gpus')} GPUs)"
 
     # ---- kernel-resident timing ------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and main_line:
         sampler.start()
     with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(warmup, 3)):
             out = call_integrate(w, solver, de, ae, resident)
         kernel_name = _native.last_kernel()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         sampler.mark_begin()
         launches0 = _native.launch_count()
@@ -261,74 +406,40 @@ def main():
         barrier()
         sampler.mark_end()
         launches = _native.launch_count() - launches0
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop() if (rank == 0 and main_line) else None
         total_ms = e_all0.elapsed_time(e_all1)
         per_call_ms = [a.elapsed_time(b) for a, b in evs]
-    tt = torch.tensor([total_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tt.item())
-    ms_per_step = total_ms_max / args.steps
-    value = units * world / (ms_per_step * 1e-3)
-    kern_ms = statistics.mean(per_call_ms)      # dominant kernel ~ whole call (pack kernel is microseconds)
+    del out
+    ms_per_step = reduce_max(total_ms) / steps
+    value = units * active / (ms_per_step * 1e-3)
+    kern_ms = statistics.mean(per_call_ms)
+    res.update(value=value, unit="traj-steps/s", ms_per_step=ms_per_step, kernel=kernel_name, kernel_ms=kern_ms,
+               gpu_launches=int(launches))
 
-    # ---- end-to-end timing through the host-buffer C ABI (psnode_forward_host): inputs in pinned HOST memory, trajectory
-    #      delivered to pinned HOST memory; every byte crosses PCIe inside the timed region (read / written in place by the
-    #      kernel for pinned buffers, i.e. the copy is fused with the integration) -------------------------------------
+    # ---- end-to-end through the host-buffer C ABI (psnode_forward_host): pinned HOST inputs and outputs ------------------
     e2e = None
-    if not args.no_e2e:
-        import copy
-        T = w["N"] + 1
-        de_cpu = copy.deepcopy(de).cpu()
-        ae_cpu = copy.deepcopy(ae).cpu() if ae is not None else None
-        out_host = torch.empty((T, w["B"], w["X"]), dtype=torch.float32).pin_memory()
-        iout_host = torch.empty((T, w["B"], w["I"]), dtype=torch.float32).pin_memory() if w["kind"] == "dae" else None
-        moved = [0, 0]
-
-        def e2e_step():
-            d = pinned
-            x_view = d["x0"].unsqueeze(0).expand(T, w["B"], w["X"])
-            if w["kind"] == "ode":
-                a0 = torch.cat((d["x0"], d["z"][0]), dim=-1)
-                solver.integrate_ODE_host(x_func=de_cpu, t=d["t"], x=x_view, z=d["z"], all_initial=a0, out=out_host)
-            else:
-                i_view = d["i0"].unsqueeze(0).expand(T, w["B"], w["I"])
-                a0 = torch.cat((d["x0"], d["z"][0], d["v"][0], d["i0"]), dim=-1)
-                solver.integrate_DAE_host(x_init=d["x0"], x_func=de_cpu, i_func=ae_cpu, t=d["t"], x=x_view, z=d["z"], v=d["v"],
-                                          i=i_view, all_initial=a0, out=(out_host, iout_host))
-            moved[0], moved[1] = solver.last_host_bytes
-
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_wall0 = time.perf_counter()
-        a.record()
-        for _ in range(args.steps):
-            e2e_step()                                    # returns after the stream drained (results are in host memory)
-        b.record()
-        barrier()
-        wall_ms = (time.perf_counter() - t_wall0) * 1e3
-        ms = max(a.elapsed_time(b), wall_ms)              # the call blocks the host: take the larger of the two clocks
-        tt = torch.tensor([ms], device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item()) / args.steps
-        e2e = {"value": units * world / (e2e_ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": moved[0], "d2h_bytes_per_step": moved[1],
-               "path": "psnode_forward_host (C ABI, HOST pointers): pinned buffers read/written in place over PCIe by the kernel"}
+    try:
+        e2e = _e2e_leg(w, legs, host, resident, solver, de, ae, B, n_steps, units, active, steps, barrier, reduce_max)
+    except Exception as exc:
+        e2e = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+        torch.cuda.synchronize()
 
     # ---- training step: forward + reverse sweep (discrete adjoint) + ONE gradient all-reduce ---------------------
     train = None
-    if not args.no_train:
+    if "train" in legs:
         from py_psnode_b200 import parallel
-        T = w["N"] + 1
+        T = n_steps + 1
         gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-        x_target = torch.randn((T, w["B"], w["X"]), device=dev, generator=gen) * 0.1
-        mask = torch.ones((T, w["B"], 1), device=dev)       # one value per (trajectory, grid point), as in the scripts
-        i_target = torch.randn((T, w["B"], w["I"]), device=dev, generator=gen) * 0.1 if w["kind"] == "dae" else None
+        x_target = torch.randn((T, B, w["X"]), device=dev, generator=gen) * 0.1
+        mask = torch.ones((T, B, 1), device=dev)       # one value per (trajectory, grid point), as in the scripts
+        i_target = torch.randn((T, B, w["I"]), device=dev, generator=gen) * 0.1 if w["kind"] == "dae" else None
         plist = list(de.parameters()) + (list(ae.parameters()) if ae is not None else [])
         bucket = parallel.GradBucket(plist, n_extras=2)
+        tr_data = dict(resident)
+        if w["net"] == "02":        # the latent input series are functions of the encoder weights: they carry gradients
+            for k in ("z", "v"):
+                if k in tr_data:
+                    tr_data[k] = tr_data[k].detach().requires_grad_(True)
 
         def numden(out):
             xs, is_ = out
@@ -338,83 +449,154 @@ def main():
             return num, den
 
         def train_step():
-            return parallel.sharded_training_step(lambda: call_integrate(w, solver, de, ae, resident), plist, bucket, numden)
+            for k in ("z", "v"):
+                if k in tr_data and tr_data[k].requires_grad:
+                    tr_data[k].grad = None
+            return parallel.sharded_training_step(lambda: call_integrate(w, solver, de, ae, tr_data), plist, bucket, numden)
 
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(min(warmup, 3), 2)):
             train_step()
         bwd_kernel = _native.last_kernel()
         barrier()
         l0 = _native.launch_count()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             loss_val = train_step()
         b.record()
         barrier()
-        tt = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tr_ms = float(tt.item()) / args.steps
-        train = {"value": units * world / (tr_ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": tr_ms,
-                 "what": "forward + reverse sweep (discrete adjoint, all parameter grads) + masked-MSE + one flat gradient all-reduce",
+        tr_ms = reduce_max(a.elapsed_time(b)) / steps
+        train = {"value": units * active / (tr_ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": tr_ms,
+                 "what": "forward + reverse sweep (discrete adjoint: all parameter grads" + (", latent-input grads" if w["net"] == "02" else "")
+                         + ") + masked-MSE + one flat gradient all-reduce",
                  "allreduce_bytes": bucket.nbytes, "kernel": bwd_kernel, "gpu_launches": int(_native.launch_count() - l0),
                  "loss": loss_val,
-                 # forward + exact reverse mode = 3x the forward's algorithmic FLOPs (the tape-based sweep does not recompute)
+                 # forward + exact reverse mode = 3x the forward's algorithmic FLOPs (the tape-based sweeps do not recompute)
                  "achieved_tflops_reference_formulation": 3 * w["flop_per_unit"] * units / (tr_ms * 1e-3) / 1e12}
+        del x_target, mask, i_target, tr_data
+        from py_psnode_b200 import engine
+        engine.release_tape_pool()
+
+    if rank != 0:
+        return None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    alg_bytes = w["bytes_per_unit"] * units
+    achieved_gbs = alg_bytes / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name, {}).get(kernel_name)
+    except Exception:
+        pass
+    tflops = w["flop_per_unit"] * units / (kern_ms * 1e-3) / 1e12
+    hbm = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+           "traffic": traffic, "peak_source": peak_src,
+           "note": "algorithmic (compulsory) bytes per traj-step x units / call time; the path is ~900-1900 FLOP/byte, i.e. compute/latency bound"}
+    if kernel_name.startswith("psn_tc") or kernel_name.startswith("psn_wide"):
+        tc_peak = peaks.get("bf16_tflops", 1590.0)
+        tc_src = ("measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" if "bf16_tflops" in peaks
+                  else "fallback 1590 TFLOP/s dense bf16 (B200_PROFILING.md)")
+        roofline = {"bound": "tensor", "achieved": tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": tflops / tc_peak,
+                    "traffic": traffic, "peak_source": tc_src,
+                    "note": f"achieved = algorithmic FLOPs of the reference formulation ({w['flop_per_unit']} per traj-step at {name}) / call "
+                            "time. The kernels run tcgen05 kind::tf32 (dense peak = half the bf16 figure) with 3 MMAs per product (3xTF32) to "
+                            "hold the reference's fp32 accuracy and N = 16 trajectories per MMA: bound by the serial layer chain, not by "
+                            "tensor throughput"}
+    else:
+        roofline = hbm
+    res.update(roofline=roofline, roofline_hbm=hbm,
+               fp32={"achieved_tflops_reference_formulation": tflops, "peak_tflops_nominal": FP32_PEAK_TFLOPS,
+                     "frac": tflops / FP32_PEAK_TFLOPS, "note": "CUDA-core fp32 FMA peak, for scale"},
+               clocks=clocks)
+    if e2e is not None:
+        res["e2e"] = e2e
+    if train is not None:
+        res["train"] = train
+    if "cpu" in legs and world == 1:      # the CPU baseline is a 1-GPU-run item (other ranks would compete for the host cores)
+        cb, csteps, note = cpu_sample_plan(name, w)
+        try:
+            v, threads, kind, secs = cpu_leg(w, cb, csteps, 2 if name in ("cfg2", "cfg3") else 1)
+            res["cpu_baseline"] = {"value": v, "unit": "traj-steps/s", "cores": threads, "kind": kind,
+                                   "sample": f"{note}; best of {len(secs)} after 1 warm-up ({min(secs):.2f} s), torch CPU no_grad"}
+        except Exception as exc:
+            res["cpu_baseline"] = {"error": str(exc)[:300]}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--kernel", default="auto", choices=["auto", "generic", "fused", "tc", "tc8", "wide"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the forward+reverse-sweep(+grad all-reduce) legs")
+    ap.add_argument("--no-others", action="store_true", help="only the --workload line, no `others`")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, args.workload, w, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the integration path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}"
+    ctx = dict(rank=rank, world=world, dev=dev, local_rank=local_rank)
+    legs = {"e2e", "train", "cpu"} - ({"e2e"} if args.no_e2e else set()) - ({"train"} if args.no_train else set()) \
+        - ({"cpu"} if args.no_cpu else set())
+
+    res = run_workload(args.workload, w, args, ctx, args.steps, args.warmup, legs, main_line=True)
+    others = {}
+    if not args.no_others:
+        for name in WORKLOADS:
+            if name == args.workload:
+                continue
+            try:
+                torch.cuda.empty_cache()
+                o = run_workload(name, WORKLOADS[name], args, ctx, steps=3, warmup=2, legs=legs, main_line=False)
+            except Exception as exc:          # a failing extra workload must not take the headline line down
+                o = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+                torch.cuda.synchronize()
+            if rank == 0:
+                others[name] = o
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        alg_bytes = w["bytes_per_unit"] * units
-        achieved_gbs = alg_bytes / (kern_ms * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(kernel_name)
-        except Exception:
-            pass
-        tflops = w["flop_per_unit"] * units / (kern_ms * 1e-3) / 1e12
-        hbm = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-               "traffic": traffic, "peak_source": peak_src,
-               "note": "algorithmic (compulsory) bytes per traj-step x units / kernel time; the path is ~1300 FLOP/byte, i.e. compute/latency bound"}
-        if kernel_name.startswith("psn_tc"):
-            tc_peak = peaks.get("bf16_tflops", 1590.0)
-            tc_src = ("measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" if "bf16_tflops" in peaks
-                      else "fallback 1590 TFLOP/s dense bf16 (B200_PROFILING.md)")
-            roofline = {"bound": "tensor", "achieved": tflops, "peak": tc_peak, "unit": "TFLOP/s", "frac": tflops / tc_peak,
-                        "traffic": traffic, "peak_source": tc_src,
-                        "note": f"achieved = algorithmic FLOPs of the reference formulation ({w['flop_per_unit']} per traj-step at "
-                                f"{args.workload}) / kernel time. The kernel runs tcgen05 kind::tf32 (dense peak = half the bf16 figure) and "
-                                "needs 3 MMAs per product (3xTF32) to hold the reference's fp32 accuracy, with N = 16 trajectories per MMA "
-                                "(4096 trajectories / 148 SMs): it is bound by the serial layer chain (>= 16000 dependent layers per "
-                                "trajectory), not by tensor throughput"}
-        else:
-            roofline = hbm
+        B = res["batch_per_gpu"]
         line = {
-            "metric": "rk4_traj_steps_per_sec", "value": value, "unit": "traj-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": "rk4_traj_steps_per_sec", "value": res["value"], "unit": "traj-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + w["desc"], "batch_per_gpu": w["B"], "global_batch": w["B"] * world,
-                       "grid_steps": w["N"], "state_dim": w["X"], "hidden": w["H"], "parallelism": f"batch-shard x{world}",
-                       "kernel": kernel_name, "l2": "working set per call (inputs 49 MB + trajectory 262 MB) exceeds the 126 MB L2"},
-            "roofline": roofline, "roofline_hbm": hbm,
-            "fp32": {"achieved_tflops_reference_formulation": tflops, "peak_tflops_nominal": FP32_PEAK_TFLOPS,
-                     "frac": tflops / FP32_PEAK_TFLOPS, "note": "CUDA-core fp32 FMA peak, for scale"},
-            "kernel_ms": kern_ms, "gpu_launches": int(launches), "clocks": clocks,
+            "config": {"workload": res["workload"], "batch_per_gpu": B,
+                       "global_batch": B * world if w["scaling"] == "weak" else w["B"],
+                       "grid_steps": res["grid_steps"], "state_dim": w["X"], "hidden": w["H"], "parallelism": f"batch-shard x{world}",
+                       "kernel": res["kernel"],
+                       "l2": "working set per call (cfg2: inputs 49 MB + trajectory 262 MB) exceeds the 126 MB L2"},
+            "roofline": res["roofline"], "roofline_hbm": res["roofline_hbm"], "fp32": res["fp32"],
+            "kernel_ms": res["kernel_ms"], "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
         }
-        if e2e is not None:
-            line["e2e"] = e2e
-        if train is not None:
-            line["train"] = train
-        if not args.no_cpu and world == 1:      # the CPU baseline is a 1-GPU-run item (other ranks would compete for the host cores)
-            v, threads, secs = cpu_baseline(w, args.cpu_sample_steps)
-            line["cpu_baseline"] = {"value": v, "unit": "traj-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"B={w['B']} x {args.cpu_sample_steps} of {w['N']} RK4 steps (per-step cost is constant), "
-                                              f"best of 3 after 1 warm-up, {secs:.2f} s, torch CPU no_grad"}
+        for k in ("e2e", "train", "cpu_baseline", "sample", "note"):
+            if k in res:
+                line[k] = res[k]
+        if others:
+            line["others"] = others
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
