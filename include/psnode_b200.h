@@ -57,6 +57,9 @@ extern "C" {
 #define PSNODE_IMPL_WIDE 5     /* tcgen05 kernels for the latent `*_02_direct_encode` nets (X = Z = H = 128, 2 layers): TMA-staged
                                   input series, hoisted input GEMM, both weight matrices resident in TMEM */
 
+#define PSNODE_IMPL_LAYER 6    /* latent nets too wide for one SM (DAE_02 / ODE_02, X = Z (= V = I) = H = 128 or 256): one tcgen05 GEMM
+                                  launch per layer over the whole batch shard, TMA-streamed operands, fused epilogues */
+
 /* A small ELU MLP: Linear -> ELU -> ... -> Linear, weights in nn.Linear layout W[out][in] (row major,
  * contiguous), as built by the script-local DE_Func / AE_Func classes
  * (neural_00_ODE_01_no_encode.py:61-64, neural_00_ODE_02_direct_encode.py:52-53,

@@ -13,8 +13,8 @@ ABI_VERSION = 3
 OK, EINVAL, EUNSUPPORTED, EWORKSPACE, ECUDA, ENODEVICE = 0, -1, -2, -3, -4, -5
 EULER, MIDPOINT, RK4 = 0, 1, 2
 ODE, DAE = 0, 1
-IMPL_AUTO, IMPL_GENERIC, IMPL_FUSED, IMPL_TC, IMPL_TC8, IMPL_WIDE = 0, 1, 2, 3, 4, 5
-IMPL_BY_NAME = {"auto": IMPL_AUTO, "generic": IMPL_GENERIC, "fused": IMPL_FUSED, "tc": IMPL_TC, "tc8": IMPL_TC8, "wide": IMPL_WIDE}
+IMPL_AUTO, IMPL_GENERIC, IMPL_FUSED, IMPL_TC, IMPL_TC8, IMPL_WIDE, IMPL_LAYER = 0, 1, 2, 3, 4, 5, 6
+IMPL_BY_NAME = {"auto": IMPL_AUTO, "generic": IMPL_GENERIC, "fused": IMPL_FUSED, "tc": IMPL_TC, "tc8": IMPL_TC8, "wide": IMPL_WIDE, "layer": IMPL_LAYER}
 
 _fp = C.POINTER(C.c_float)
 

@@ -141,6 +141,7 @@ int64_t psnode_forward_workspace(const psnode_problem* p) {
     int64_t t = psn_tc_supports(p) ? psn_tc_forward_workspace(p) : 0;
     if (f > g) g = f;
     if (psn_wide_supports(p)) { const int64_t w = psn_wide_forward_workspace(p); if (w > g) g = w; }
+    if (psn_lg_supports(p)) { const int64_t w = psn_lg_forward_workspace(p); if (w > g) g = w; }
     return g > t ? g : t;
 }
 
@@ -164,8 +165,13 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
         if (!psn_wide_supports(p)) return PSNODE_EUNSUPPORTED;
         return psn_wide_forward(p, workspace, workspace_bytes, s);
     }
+    if (p->impl == PSNODE_IMPL_LAYER) {
+        if (!psn_lg_supports(p)) return PSNODE_EUNSUPPORTED;
+        return psn_lg_forward(p, workspace, workspace_bytes, s);
+    }
     if (p->impl == PSNODE_IMPL_AUTO && psn_tc_supports(p)) return psn_tc8_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_wide_supports(p)) return psn_wide_forward(p, workspace, workspace_bytes, s);
+    if (p->impl == PSNODE_IMPL_AUTO && psn_lg_supports(p)) return psn_lg_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_fused_supports(p)) return psn_fused_forward(p, workspace, workspace_bytes, s);
     const int gst = psn_generic_forward(p, workspace, workspace_bytes, s);
     if (gst != PSNODE_EUNSUPPORTED) return gst;

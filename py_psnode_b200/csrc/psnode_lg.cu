@@ -1,0 +1,561 @@
+// psnode_lg.cu -- "layer GEMM" path (impl = layer) for the latent `*_02_direct_encode` nets whose weights do not fit on one SM:
+// DAE_02 / ODE_02 with X = Z (= V = I) = hidden = 128 or 256 (BASELINE configs[4]: DAE_Model, H = 256, 8192 trajectories per GPU;
+// neural_01_DAE_02_direct_encode.py:70-100, :122, :137-147; integrate_DAE, neural_dae/my_solvers.py:82-131).
+//
+// At these shapes ONE layer of the stage MLP over the whole batch shard is a 1 GFLOP dense GEMM (8192 x 256 x 256), large
+// enough to fill the chip by itself, while the five in-loop weight matrices (2.5 MB as tf32 hi + lo) exceed any SM's shared
+// memory + TMEM.  So the time loop is a stream of per-layer tcgen05 GEMM launches with fused epilogues instead of one
+// persistent kernel; activations (8 MB per tensor) stay L2-resident between launches.  Per step of the DAE:
+//     [event: h = ELU(A1x x + preAE_jump[k]);  i0 = A2 h + ab2]                       (my_solvers.py:108-110)
+//     G  = F_i i0                                                                     (held across the stages)
+//     per stage:  a1 = ELU(F_x y + preDE[row] + G);   k = W2 a1 + b2 -> Runge-Kutta algebra -> next y / x_j
+//     h  = ELU(A1x x_j + preAE[j]);   i_j = A2 h + ab2                                (:121, one explicit evaluation)
+// with the folded layer 1 of SURVEY 8d: F = W_b + W_c, and the state-independent halves hoisted over the whole series by the
+// same kernel:  preDE[r] = [F_z | F_v] [z[r]; v[r]] + c_de,  preAE[r] = [A1z | A1v] [z[r]; v[r]] + c_ae.
+//
+// GEMM kernel: D[feature m][trajectory n] = A . B^T, CTA tile 128 x 128, K in chunks of 32 (one SWIZZLE_128B slab).
+//   A = prepared weights, tf32 hi and lo planes written once per call (lg_prep_kernel), streamed by TMA (UTMALDG);
+//   B = fp32 activations / series rows, streamed by TMA through 3-D tensor maps over the strided views, split into hi / lo
+//       in shared memory by the threads (3xTF32: A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, fp32 accumulation in TMEM, 2 K-partials);
+//   3-stage mbarrier pipeline, single-thread MMA issue, epilogue from TMEM with one output feature per lane so that every
+//   global access of a warp is a full 128-byte line of the (trajectory, feature) row-major tensors.
+// Bound per launch: L2 -> SM operand traffic (384 KB per CTA) against 96 M128.N128.K8 MMAs.
+#include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "psnode_wide.cuh"
+
+namespace {
+using namespace psn_tc;
+
+constexpr int TM = 128, TN = 128;
+constexpr int NST = 3;
+constexpr int SLAB = TN * 128;          // 16 KB: 128 rows x 32 fp32
+constexpr int LG_THREADS = 256;
+constexpr int NPART = 2;                // K-partials (truncating fp32 accumulate: short chains)
+
+enum { LG_PLAIN = 0, LG_HIDDEN = 1, LG_RK = 2 };
+// epilogue kinds (template parameter of the GEMM kernel)
+enum { EPI_PLAIN = 0, EPI_HIDDEN, EPI_EULER, EPI_MID0, EPI_MID1, EPI_RK0, EPI_RK1, EPI_RK2, EPI_RK3 };
+
+struct __align__(1024) LgSmem {
+    unsigned char a_hi[NST][SLAB], a_lo[NST][SLAB], b_hi[NST][SLAB], b_lo[NST][SLAB];
+    uint64_t full[NST], done[NST];
+    uint32_t tmem_base;
+};
+
+__device__ long long g_lg_dbg[64];        // clock64 stamps of one CTA (PSNODE_LG_DBG=<cta index + 1>): phase breakdown on the device
+
+struct LgParams {
+    int dbg, rotate;
+    int N, R, nbt;                      // trajectories per row, rows (1 for a layer launch), n-tiles per row
+    int nsrc, kchunks;                  // B sources (K segments) and 32-wide chunks per source
+    int mode;
+    // event handling (neural_base.py:52-65, 180-196): ev[ev_j] = index of the event that fires when leaving grid point ev_j, or -1
+    const int32_t* ev; int ev_j; int skip_unless_event;
+    const float* add1; int64_t add1_sr, add1_ld;             // [r][n][m]  (hoisted layer-1 half / per-trajectory constant)
+    const float* add1_jump; int64_t add1_jump_sr;            // event rows of add1 (selected when ev[ev_j] >= 0)
+    const float* add2; int64_t add2_ld;                      // [n][m]
+    const float* bias;                                       // [m]
+    float* out; int64_t out_sr, out_ld;                      // [r][n][m]
+    float* out2; int64_t out2_ld;                            // second copy (trajectory row / i_sol row)
+    // Runge-Kutta epilogue
+    int method, stage;
+    float* x0; float* k1; float* k2; float* k3; int64_t st_ld;
+    const float* t_cur; const float* t_prev; int64_t t_sb;   // t[j], t[j-1] rows (element n at n * t_sb)
+    int* err;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                                                                   const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
+                                                                   const __grid_constant__ LgParams q) {
+    int evk = -1;
+    if (q.ev) evk = __ldg(q.ev + q.ev_j);
+    if (q.skip_unless_event && evk < 0) return;
+    extern __shared__ unsigned char smem_raw[];
+    LgSmem& sm = *reinterpret_cast<LgSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cw = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int wq = cw & 3, hh = cw >> 2;
+    const int r = blockIdx.x / q.nbt, b0 = (blockIdx.x - r * q.nbt) * TN;
+    const int mblk = blockIdx.y;
+    const int nchunk = q.nsrc * q.kchunks;
+
+    const bool dbg = q.dbg != 0 && blockIdx.x == q.dbg - 1 && blockIdx.y == 0 && tid == 0;
+    int dbg_n = 0;
+    auto stamp = [&]() { if (dbg && dbg_n < 32) g_lg_dbg[dbg_n++] = clock64(); };
+    stamp();
+    // K chunks are visited in an order rotated by the CTA index: at any moment the 64 CTAs that share a weight block read
+    // different chunks of it instead of all hitting the same L2 lines (fixed, deterministic order per trajectory tile)
+    const int rot = q.rotate ? (int)(blockIdx.x % (unsigned)nchunk) : 0;
+    auto load_chunk = [&](int c) {          // thread 0; c = position in this CTA's order
+        const int s = c % NST;
+        int ck = c + rot; if (ck >= nchunk) ck -= nchunk;
+        const int src = ck / q.kchunks, kc = ck - src * q.kchunks;
+        mbar_expect_tx(&sm.full[s], 3 * SLAB);
+        tma_load_3d(sm.a_hi[s], &map_a_hi, ck * 32, mblk * TM, 0, &sm.full[s]);
+        tma_load_3d(sm.a_lo[s], &map_a_lo, ck * 32, mblk * TM, 0, &sm.full[s]);
+        tma_load_3d(sm.b_hi[s], src == 0 ? &map_b0 : &map_b1, kc * 32, b0, r, &sm.full[s]);
+    };
+    if (tid == 0) {                         // the first operand chunks are in flight before TMEM is even allocated
+        for (int s = 0; s < NST; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.done[s], 1); }
+        fence_mbar_init();
+        for (int c = 0; c < NST && c < nchunk; c++) load_chunk(c);
+    }
+    __syncwarp();
+    if (cw == 0) tmem_alloc(&sm.tmem_base, NPART * TN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    const uint32_t lane_base = (uint32_t)(32 * wq) << 16;
+    stamp();
+
+    const uint32_t idesc = make_idesc_tf32(TM, TN);
+    for (int c = 0; c < nchunk; c++) {
+        const int s = c % NST;
+        if (!mbar_wait(&sm.full[s], (uint32_t)((c / NST) & 1))) { atomicExch(q.err, 11); __trap(); }
+        stamp();
+        {   // B: raw fp32 -> tf32 hi (in place) + lo (elementwise: the swizzled layout is preserved)
+            float4* h4 = reinterpret_cast<float4*>(sm.b_hi[s]);
+            float4* l4 = reinterpret_cast<float4*>(sm.b_lo[s]);
+#pragma unroll
+            for (int e = 0; e < SLAB / 16 / LG_THREADS; e++) {
+                const int idx = tid + e * LG_THREADS;
+                float4 lo;
+                const float4 hi = split4_hi(h4[idx], lo);
+                h4[idx] = hi;
+                l4[idx] = lo;
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (cw == 0) {
+            if (elect_one()) {
+                tc_fence_after();
+                const uint64_t da_hi = make_desc_sw128(smem_u32(sm.a_hi[s])), da_lo = make_desc_sw128(smem_u32(sm.a_lo[s]));
+                const uint64_t db_hi = make_desc_sw128(smem_u32(sm.b_hi[s])), db_lo = make_desc_sw128(smem_u32(sm.b_lo[s]));
+                const int part = (c * NPART) / nchunk;
+                const bool first = c == (part * nchunk + NPART - 1) / NPART;       // first chunk of this partial
+                uint32_t accumulate = first ? 0u : 1u;
+#pragma unroll
+                for (int term = 0; term < 3; term++) {
+                    const uint64_t ad = term == 0 ? da_lo : da_hi;
+                    const uint64_t bd = term == 1 ? db_lo : db_hi;
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        mma_tf32(tmem + (uint32_t)(part * TN), ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc, accumulate);
+                        accumulate = 1;
+                    }
+                }
+                mma_commit(&sm.done[s]);
+            }
+            __syncwarp();
+        }
+        if (tid == 0 && c >= 1 && c - 1 + NST < nchunk) {       // refill the slot of chunk c - 1 once its MMAs have completed
+            const int sp = (c - 1) % NST;
+            if (!mbar_wait(&sm.done[sp], (uint32_t)(((c - 1) / NST) & 1))) { atomicExch(q.err, 12); __trap(); }
+            fence_async_smem();
+            load_chunk(c - 1 + NST);
+        }
+    }
+    stamp();
+    if (!mbar_wait(&sm.done[(nchunk - 1) % NST], (uint32_t)(((nchunk - 1) / NST) & 1))) { atomicExch(q.err, 13); __trap(); }
+    tc_fence_after();
+    stamp();
+
+    // ---- epilogue: lane = output feature, columns = trajectories ---------------------------------------------------------
+    // Operands of the fused epilogue (hoisted layer-1 half, G, or the Runge-Kutta state) are fetched 16 columns ahead of the
+    // arithmetic, so their L2 latency is paid once per tile.  The epilogue kind is a template parameter and the batch loop is
+    // rolled: the first version (run-time mode switch inside fully unrolled loops) was 16 000 instructions of straight-line
+    // code executed once per CTA and spent 38 000 of its 54 000 cycles waiting for instruction fetches (`no_inst` stalls).
+    {
+        constexpr bool rk = EPI >= EPI_EULER;
+        const int m = mblk * TM + 32 * wq + lane;
+        const float* add1 = q.add1;
+        int64_t add1_row = (int64_t)r * q.add1_sr;
+        if (evk >= 0 && q.add1_jump) { add1 = q.add1_jump; add1_row = (int64_t)evk * q.add1_jump_sr; }
+        const float bias = q.bias ? __ldg(q.bias + m) : 0.0f;
+        const float c13 = (float)(1.0 / 3.0);
+        struct Buf { float p0[16], p1[16], p2[16], p3[16], dt[16]; };
+        auto fetch = [&](int bt, Buf& e) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int nn = min(b0 + 64 * hh + 16 * bt + i, q.N - 1);
+                if constexpr (rk) {
+                    const int64_t so = (int64_t)nn * q.st_ld + m;
+                    e.p0[i] = q.x0[so];
+                    if constexpr (EPI >= EPI_RK1) e.p1[i] = q.k1[so];
+                    if constexpr (EPI >= EPI_RK2) e.p2[i] = q.k2[so];
+                    if constexpr (EPI >= EPI_RK3) e.p3[i] = q.k3[so];
+                    e.dt[i] = __fsub_rn(__ldg(q.t_cur + (int64_t)nn * q.t_sb), __ldg(q.t_prev + (int64_t)nn * q.t_sb));
+                } else {
+                    e.p0[i] = add1 ? __ldg(add1 + add1_row + (int64_t)nn * q.add1_ld + m) : 0.0f;
+                    e.p1[i] = q.add2 ? __ldg(q.add2 + (int64_t)nn * q.add2_ld + m) : 0.0f;
+                }
+            }
+        };
+        auto finish = [&](int bt, const Buf& e) {
+            const int n0 = 64 * hh + 16 * bt;
+            float t0[16], t1[16];
+            tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)n0, t0);
+            tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)(TN + n0), t1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int n = b0 + n0 + i;
+                if (n >= q.N) continue;
+                float v = (t0[i] + t1[i]) + bias;
+                if constexpr (!rk) {
+                    v = (v + e.p0[i]) + e.p1[i];
+                    if constexpr (EPI == EPI_HIDDEN) v = psn_elu(v);
+                    q.out[(int64_t)r * q.out_sr + (int64_t)n * q.out_ld + m] = v;
+                    if (q.out2) q.out2[(int64_t)n * q.out2_ld + m] = v;
+                } else {
+                    // reference operation order (neural_dae/my_fixed_grid.py:15-59)
+                    const int64_t so = (int64_t)n * q.st_ld + m;
+                    const float dt = e.dt[i], x0 = e.p0[i], kk = v;
+                    float xn;
+                    constexpr bool last = EPI == EPI_EULER || EPI == EPI_MID1 || EPI == EPI_RK3;
+                    if constexpr (EPI == EPI_EULER || EPI == EPI_MID1) xn = __fadd_rn(x0, __fmul_rn(dt, kk));
+                    else if constexpr (EPI == EPI_MID0) xn = __fadd_rn(x0, __fmul_rn(kk, __fmul_rn(0.5f, dt)));
+                    else if constexpr (EPI == EPI_RK0) { q.k1[so] = kk; xn = __fadd_rn(x0, __fmul_rn(__fmul_rn(dt, kk), c13)); }
+                    else if constexpr (EPI == EPI_RK1) { q.k2[so] = kk; xn = __fadd_rn(x0, __fmul_rn(dt, __fsub_rn(kk, __fmul_rn(e.p1[i], c13)))); }
+                    else if constexpr (EPI == EPI_RK2) { q.k3[so] = kk; xn = __fadd_rn(x0, __fmul_rn(dt, __fadd_rn(__fsub_rn(e.p1[i], e.p2[i]), kk))); }
+                    else {
+                        const float ksum = __fadd_rn(__fadd_rn(e.p1[i], __fmul_rn(3.0f, __fadd_rn(e.p2[i], e.p3[i]))), kk);
+                        xn = __fadd_rn(x0, __fmul_rn(__fmul_rn(ksum, dt), 0.125f));
+                    }
+                    q.out[(int64_t)n * q.out_ld + m] = xn;                       // next stage input / x_j
+                    if constexpr (last) {
+                        q.x0[so] = xn;
+                        if (q.out2) q.out2[(int64_t)n * q.out2_ld + m] = xn;     // trajectory row j
+                    }
+                }
+            }
+        };
+        Buf cur, nxt;
+        fetch(0, cur);
+#pragma unroll 1
+        for (int bt = 0; bt < 4; bt++) {
+            if (bt + 1 < 4) fetch(bt + 1, nxt);
+            finish(bt, cur);
+            cur = nxt;
+        }
+    }
+    stamp();
+    tc_fence_before();
+    __syncthreads();
+    if (cw == 0) tmem_dealloc(tmem, NPART * TN);
+    stamp();
+    if (dbg) g_lg_dbg[63] = dbg_n;
+}
+
+// ---- one-time preparation per call ------------------------------------------------------------------------------------------
+// dst_hi / dst_lo [m][k] (k < K) = split_tf32(W[m * ldw + col0 + k] (+ W[m * ldw + col1 + k] if col1 >= 0))
+__global__ void psn_lg_prep_kernel(const float* __restrict__ W, int ldw, int col0, int col1, int M, int K, float* __restrict__ hi, float* __restrict__ lo) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * K) return;
+    const int m = idx / K, k = idx - m * K;
+    float w = __ldg(W + (int64_t)m * ldw + col0 + k);
+    if (col1 >= 0) w += __ldg(W + (int64_t)m * ldw + col1 + k);
+    float h, l;
+    split_tf32(w, h, l);
+    hi[idx] = h;
+    lo[idx] = l;
+}
+// c[b][m] = bias[m] + sum_{k < S} (W[m][k] - (sub >= 0 ? W[m][sub + k] : 0)) a0[b][k]; block = 8 trajectories, thread = m (blockDim = H)
+__global__ void psn_lg_const_kernel(const float* __restrict__ W, int ldw, int sub, const float* __restrict__ bias, const float* __restrict__ a0,
+                                    int64_t a0_sb, int S, int B, int H, float* __restrict__ c) {
+    extern __shared__ float a[];            // [8][S]
+    const int m = threadIdx.x, b0 = blockIdx.x * 8;
+    for (int e = m; e < 8 * S; e += blockDim.x) {
+        const int n = e / S, k = e - n * S;
+        a[e] = __ldg(a0 + (int64_t)min(b0 + n, B - 1) * a0_sb + k);
+    }
+    __syncthreads();
+    float acc[8];
+    const float bv = __ldg(bias + m);
+#pragma unroll
+    for (int n = 0; n < 8; n++) acc[n] = bv;
+    for (int k = 0; k < S; k++) {
+        float w = __ldg(W + (int64_t)m * ldw + k);
+        if (sub >= 0) w -= __ldg(W + (int64_t)m * ldw + sub + k);
+#pragma unroll
+        for (int n = 0; n < 8; n++) acc[n] = fmaf(w, a[n * S + k], acc[n]);
+    }
+    for (int n = 0; n < 8; n++)
+        if (b0 + n < B) c[(int64_t)(b0 + n) * H + m] = acc[n];
+}
+// initial state: x0 = ycur = x_sol[0] = x_init (DAE) / x[0] (ODE)
+__global__ void psn_lg_init_kernel(const float* __restrict__ src, int64_t src_sb, int B, int H, float* __restrict__ x0, float* __restrict__ ycur,
+                                   float* __restrict__ xsol0, int64_t xsol_sb) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * H) return;
+    const int b = idx / H, m = idx - b * H;
+    const float v = __ldg(src + (int64_t)b * src_sb + m);
+    x0[idx] = v;
+    ycur[idx] = v;
+    xsol0[(int64_t)b * xsol_sb + m] = v;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn lg_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// 3-D map (feature, row-in-batch, outer row) over p[outer * s_outer + row * s_row + feature], box {32, 128, 1}, SWIZZLE_128B
+bool lg_make_map(CUtensorMap* map, const float* p, int width, int64_t rows, int64_t s_row, int64_t outer, int64_t s_outer) {
+    if (!lg_encode_fn() || (reinterpret_cast<uintptr_t>(p) & 15) || (s_row & 3) || (outer > 1 && (s_outer & 3))) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)width, (cuuint64_t)rows, (cuuint64_t)(outer > 0 ? outer : 1)};
+    const cuuint64_t gstr[2] = {(cuuint64_t)s_row * 4, (cuuint64_t)(outer > 1 ? s_outer : s_row * rows) * 4};
+    const cuuint32_t box[3] = {32, 128, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return lg_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int64_t al(int64_t floats) { return (floats + 63) & ~(int64_t)63; }
+
+struct LgLayout {
+    int H, KZV, nmat;
+    int64_t err, wts_hi[7], wts_lo[7], c_de, c_ae, pre_de, pre_ae, x0, k1, k2, k3, ycur, a1, hbuf, icur, G, total;
+    int64_t rows_de, rows_ae;
+};
+enum { M_DE1X = 0, M_DE1ZV, M_DE1I, M_DE2, M_AE1X, M_AE1ZV, M_AE2 };
+
+LgLayout lg_layout(const psnode_problem* p) {
+    LgLayout L;
+    const bool dae = p->kind == PSNODE_DAE;
+    const int H = p->X, E = p->event_idx ? p->E : 0;
+    L.H = H;
+    L.KZV = p->Z + p->V;
+    L.nmat = dae ? 7 : 4;
+    int64_t o = 64;
+    L.err = 0;
+    const int kt[7] = {H, L.KZV, H, H, H, L.KZV, H};
+    for (int i = 0; i < 7; i++) {
+        L.wts_hi[i] = o; o += al((int64_t)H * kt[i]);
+        L.wts_lo[i] = o; o += al((int64_t)H * kt[i]);
+    }
+    const int64_t BH = (int64_t)p->B * H;
+    L.c_de = o; o += al(BH);
+    L.c_ae = o; o += al(BH);
+    L.rows_de = (p->T > 1 ? p->T - 1 : 0) + E;
+    L.rows_ae = dae ? (int64_t)p->T + E : 0;
+    L.pre_de = o; o += al(L.rows_de * BH);
+    L.pre_ae = o; o += al(L.rows_ae * BH);
+    L.x0 = o; o += al(BH); L.k1 = o; o += al(BH); L.k2 = o; o += al(BH); L.k3 = o; o += al(BH);
+    L.ycur = o; o += al(BH); L.a1 = o; o += al(BH); L.hbuf = o; o += al(BH); L.icur = o; o += al(BH); L.G = o; o += al(BH);
+    L.total = o;
+    return L;
+}
+
+bool view_ok(const float* p, int64_t s0, int64_t s1) { return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (s0 & 3) == 0 && (s1 & 3) == 0; }
+
+}  // namespace
+
+bool psn_lg_supports(const psnode_problem* p) {
+    if (p->teacher_x || p->teacher_i) return false;
+    const int H = p->X;
+    if (H != 128 && H != 256) return false;
+    const bool dae = p->kind == PSNODE_DAE;
+    if (p->Z != H) return false;                                   // (the z_dim == 0 script variant runs on the generic kernels)
+    if (dae && (p->V != H || p->I != H)) return false;
+    const int S = p->X + p->Z + p->V + p->I;
+    if (p->de.n_layers != 2 || p->de.in_dim[0] != 3 * S || p->de.out_dim[0] != H || p->de.out_dim[1] != H) return false;
+    if (dae && (p->ae.n_layers != 2 || p->ae.in_dim[0] != S + p->X + p->Z + p->V || p->ae.out_dim[0] != H || p->ae.out_dim[1] != H)) return false;
+    if (!view_ok(p->z.p, p->z.st, p->z.sb)) return false;
+    if (dae && !view_ok(p->v.p, p->v.st, p->v.sb)) return false;
+    if (p->event_idx) {
+        if (!view_ok(p->z_jump, p->zj_sb, p->zj_se)) return false;
+        if (dae && !view_ok(p->v_jump, p->vj_sb, p->vj_se)) return false;
+    }
+    if ((p->x_sol.sb & 3) || (p->x_sol.st & 3)) return false;
+    return lg_encode_fn() != nullptr;
+}
+
+int64_t psn_lg_forward_workspace(const psnode_problem* p) { return lg_layout(p).total * 4; }
+
+int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    const LgLayout L = lg_layout(p);
+    if (ws == nullptr || ws_bytes < L.total * 4) return PSNODE_EWORKSPACE;
+    float* w = static_cast<float*>(ws);
+    int* err = reinterpret_cast<int*>(w + L.err);
+    const bool dae = p->kind == PSNODE_DAE;
+    const int H = L.H, B = p->B, T = p->T, E = p->event_idx ? p->E : 0;
+    const int S = p->X + p->Z + p->V + p->I;
+    const int64_t BH = (int64_t)B * H;
+    const int nstages = psw_nstages(p->method);
+    PSN_CUDA(cudaMemsetAsync(err, 0, 256, stream));
+    // ---- weights: folded, split into tf32 hi / lo planes ----
+    const float* W1 = p->de.W[0];
+    const int ld1 = 3 * S;
+    auto prep = [&](int which, const float* W, int ldw, int col0, int col1, int K) {
+        const int n = H * K;
+        psn_lg_prep_kernel<<<(n + 255) / 256, 256, 0, stream>>>(W, ldw, col0, col1, H, K, w + L.wts_hi[which], w + L.wts_lo[which]);
+        psn_count_launch("psn_lg_prep_kernel");
+    };
+    prep(M_DE1X, W1, ld1, S, 2 * S, H);                                       // F_x = (W_b + W_c)[:, 0:X]
+    prep(M_DE1ZV, W1, ld1, S + p->X, 2 * S + p->X, L.KZV);                    // [F_z | F_v]
+    prep(M_DE2, p->de.W[1], H, 0, -1, H);
+    if (dae) {
+        prep(M_DE1I, W1, ld1, S + p->X + p->Z + p->V, 2 * S + p->X + p->Z + p->V, H);   // F_i
+        const int lda = S + p->X + p->Z + p->V;
+        prep(M_AE1X, p->ae.W[0], lda, S, -1, H);
+        prep(M_AE1ZV, p->ae.W[0], lda, S + p->X, -1, L.KZV);
+        prep(M_AE2, p->ae.W[1], H, 0, -1, H);
+        psn_lg_const_kernel<<<(B + 7) / 8, H, 8 * S * 4, stream>>>(p->ae.W[0], lda, -1, p->ae.b[0], p->a0, p->a0_sb, S, B, H, w + L.c_ae);
+        psn_count_launch("psn_lg_const_kernel");
+    }
+    psn_lg_const_kernel<<<(B + 7) / 8, H, 8 * S * 4, stream>>>(W1, ld1, S, p->de.b[0], p->a0, p->a0_sb, S, B, H, w + L.c_de);
+    psn_count_launch("psn_lg_const_kernel");
+    PSN_CUDA(cudaGetLastError());
+
+    // ---- tensor maps (once per call) ----
+    CUtensorMap mw_hi[7], mw_lo[7], m_z, m_v, m_zj, m_vj, m_y, m_a1, m_h, m_i;
+    const int kt[7] = {H, L.KZV, H, H, H, L.KZV, H};
+    bool ok = true;
+    for (int i = 0; i < 7; i++) {
+        if (!dae && (i == M_DE1I || i >= M_AE1X)) continue;
+        ok = ok && lg_make_map(&mw_hi[i], w + L.wts_hi[i], kt[i], H, kt[i], 1, 0) && lg_make_map(&mw_lo[i], w + L.wts_lo[i], kt[i], H, kt[i], 1, 0);
+    }
+    ok = ok && lg_make_map(&m_z, p->z.p, H, B, p->z.sb, T, p->z.st);
+    if (dae) ok = ok && lg_make_map(&m_v, p->v.p, H, B, p->v.sb, T, p->v.st);
+    if (E > 0) {
+        ok = ok && lg_make_map(&m_zj, p->z_jump, H, B, p->zj_sb, E, p->zj_se);
+        if (dae) ok = ok && lg_make_map(&m_vj, p->v_jump, H, B, p->vj_sb, E, p->vj_se);
+    }
+    ok = ok && lg_make_map(&m_y, w + L.ycur, H, B, H, 1, 0) && lg_make_map(&m_a1, w + L.a1, H, B, H, 1, 0);
+    if (dae) ok = ok && lg_make_map(&m_h, w + L.hbuf, H, B, H, 1, 0) && lg_make_map(&m_i, w + L.icur, H, B, H, 1, 0);
+    if (!ok) return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (layer path)");
+
+    const int smem = (int)sizeof(LgSmem) + 1024;
+    using KernFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const LgParams);
+    static const KernFn kerns[9] = {psn_lg_gemm_kernel<EPI_PLAIN>, psn_lg_gemm_kernel<EPI_HIDDEN>, psn_lg_gemm_kernel<EPI_EULER>,
+                                    psn_lg_gemm_kernel<EPI_MID0>, psn_lg_gemm_kernel<EPI_MID1>, psn_lg_gemm_kernel<EPI_RK0>,
+                                    psn_lg_gemm_kernel<EPI_RK1>, psn_lg_gemm_kernel<EPI_RK2>, psn_lg_gemm_kernel<EPI_RK3>};
+    static bool attr_set = false;
+    if (!attr_set) {
+        for (int i = 0; i < 9; i++) PSN_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    auto epi_of = [&](const LgParams& q) {
+        if (q.mode == LG_PLAIN) return (int)EPI_PLAIN;
+        if (q.mode == LG_HIDDEN) return (int)EPI_HIDDEN;
+        if (q.method == PSNODE_EULER) return (int)EPI_EULER;
+        if (q.method == PSNODE_MIDPOINT) return q.stage == 0 ? (int)EPI_MID0 : (int)EPI_MID1;
+        return (int)EPI_RK0 + q.stage;
+    };
+    const int nbt = (B + TN - 1) / TN;
+    static const int dbg_cta = std::getenv("PSNODE_LG_DBG") ? std::atoi(std::getenv("PSNODE_LG_DBG")) : 0;
+    static const int rotate = std::getenv("PSNODE_LG_ROTATE") ? std::atoi(std::getenv("PSNODE_LG_ROTATE")) : 1;
+    auto base = [&]() {
+        LgParams q;
+        std::memset(&q, 0, sizeof(q));
+        q.N = B; q.R = 1; q.nbt = nbt; q.nsrc = 1; q.kchunks = H / 32; q.mode = LG_PLAIN;
+        q.add1_ld = H; q.add2_ld = H; q.out_ld = H; q.st_ld = H;
+        q.err = err;
+        q.dbg = dbg_cta; q.rotate = rotate;
+        return q;
+    };
+    auto launch = [&](int which, const CUtensorMap& b0, const CUtensorMap& b1, const LgParams& q, const char* name) -> int {
+        dim3 grid((unsigned)(q.R * q.nbt), (unsigned)(H / TM));
+        kerns[epi_of(q)]<<<grid, LG_THREADS, smem, stream>>>(mw_hi[which], mw_lo[which], b0, b1, q);
+        psn_count_launch(name);
+        return PSNODE_OK;
+    };
+    // ---- hoisted layer-1 halves over the whole series ----
+    auto project = [&](int which, const CUtensorMap& bz, const CUtensorMap& bv, int R, const float* cadd, float* out, const char* name) {
+        if (R <= 0) return;
+        LgParams q = base();
+        q.R = R; q.nsrc = dae ? 2 : 1; q.kchunks = H / 32;
+        q.add1 = cadd; q.add1_sr = 0; q.add1_ld = H;
+        q.out = out; q.out_sr = BH; q.out_ld = H;
+        launch(which, bz, dae ? bv : bz, q, name);
+    };
+    project(M_DE1ZV, m_z, m_v, T - 1, w + L.c_de, w + L.pre_de, "psn_lg_gemm_kernel<pre_de>");
+    if (E > 0) project(M_DE1ZV, m_zj, m_vj, E, w + L.c_de, w + L.pre_de + (int64_t)(T - 1) * BH, "psn_lg_gemm_kernel<pre_de_jump>");
+    if (dae) {
+        project(M_AE1ZV, m_z, m_v, T, w + L.c_ae, w + L.pre_ae, "psn_lg_gemm_kernel<pre_ae>");
+        if (E > 0) project(M_AE1ZV, m_zj, m_vj, E, w + L.c_ae, w + L.pre_ae + (int64_t)T * BH, "psn_lg_gemm_kernel<pre_ae_jump>");
+    }
+    // ---- initial state ----
+    {
+        const float* src = dae ? p->x_init : p->x.p;
+        const int64_t sb = dae ? p->x_init_sb : p->x.sb;
+        psn_lg_init_kernel<<<(int)((BH + 255) / 256), 256, 0, stream>>>(src, sb, B, H, w + L.x0, w + L.ycur, p->x_sol.p, p->x_sol.sb);
+        psn_count_launch("psn_lg_init_kernel");
+    }
+    // algebraic evaluation i = ae(x, z, v) on the current state (ycur holds x at step boundaries)
+    auto ae_eval = [&](const float* pre_row, int jrow, bool event_only, int ev_j) {
+        LgParams q = base();
+        q.mode = LG_HIDDEN;
+        q.add1 = pre_row; q.add1_sr = 0;
+        if (event_only) {
+            q.ev = p->event_idx; q.ev_j = ev_j; q.skip_unless_event = 1;
+            q.add1_jump = w + L.pre_ae + (int64_t)T * BH; q.add1_jump_sr = BH;
+        }
+        q.out = w + L.hbuf;
+        launch(M_AE1X, m_y, m_y, q, event_only ? "psn_lg_gemm_kernel<ae1,event>" : "psn_lg_gemm_kernel<ae1>");
+        LgParams q2 = base();
+        q2.bias = p->ae.b[1];
+        if (event_only) { q2.ev = p->event_idx; q2.ev_j = ev_j; q2.skip_unless_event = 1; }
+        q2.out = w + L.icur;
+        if (jrow >= 0) { q2.out2 = p->i_sol.p + (int64_t)jrow * p->i_sol.st; q2.out2_ld = p->i_sol.sb; }
+        launch(M_AE2, m_h, m_h, q2, event_only ? "psn_lg_gemm_kernel<ae2,event>" : "psn_lg_gemm_kernel<ae2>");
+    };
+    if (dae) ae_eval(w + L.pre_ae, 0, false, 0);                               // i_0 = ae(x_0, z[0], v[0])  (my_solvers.py:95)
+
+    for (int j = 1; j < T; j++) {
+        if (dae) {
+            if (E > 0) ae_eval(nullptr, -1, true, j - 1);                      // event: i_0 re-evaluated with the jumped inputs (:108-110)
+            LgParams qg = base();                                              // G = F_i i0
+            qg.out = w + L.G;
+            launch(M_DE1I, m_i, m_i, qg, "psn_lg_gemm_kernel<de1_i>");
+        }
+        for (int e = 0; e < nstages; e++) {
+            LgParams q1 = base();
+            q1.mode = LG_HIDDEN;
+            q1.add1 = w + L.pre_de + (int64_t)(j - 1) * BH;
+            if (E > 0) { q1.ev = p->event_idx; q1.ev_j = j - 1; q1.add1_jump = w + L.pre_de + (int64_t)(T - 1) * BH; q1.add1_jump_sr = BH; }
+            if (dae) q1.add2 = w + L.G;
+            q1.out = w + L.a1;
+            launch(M_DE1X, m_y, m_y, q1, "psn_lg_gemm_kernel<de1>");
+            LgParams q2 = base();
+            q2.mode = LG_RK;
+            q2.bias = p->de.b[1];
+            q2.method = p->method; q2.stage = e;
+            q2.x0 = w + L.x0; q2.k1 = w + L.k1; q2.k2 = w + L.k2; q2.k3 = w + L.k3;
+            q2.t_cur = p->t.p + (int64_t)j * p->t.st; q2.t_prev = p->t.p + (int64_t)(j - 1) * p->t.st; q2.t_sb = p->t.sb;
+            q2.out = w + L.ycur;
+            q2.out2 = p->x_sol.p + (int64_t)j * p->x_sol.st; q2.out2_ld = p->x_sol.sb;
+            launch(M_DE2, m_a1, m_a1, q2, "psn_lg_gemm_kernel<de2,rk>");
+        }
+        if (dae) ae_eval(w + L.pre_ae + (int64_t)j * BH, j, false, 0);          // i_j = ae(x_j, z[j], v[j])  (:121)
+    }
+    PSN_CUDA(cudaGetLastError());
+    if (dbg_cta) {                            // debugging aid only: synchronises
+        long long h[64];
+        cudaStreamSynchronize(stream);
+        cudaMemcpyFromSymbol(h, g_lg_dbg, sizeof(h));
+        std::fprintf(stderr, "psn_lg stamps (cycles since kernel start, last launch, CTA %d):", dbg_cta - 1);
+        for (int i = 1; i < (int)h[63] && i < 32; i++) std::fprintf(stderr, " %lld", h[i] - h[0]);
+        std::fprintf(stderr, "\n");
+    }
+    return PSNODE_OK;
+}
+

@@ -54,6 +54,11 @@ bool psn_wide_bwd_supports(const psnode_problem* p, const psnode_adjoint* a);
 int64_t psn_wide_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);
 int psn_wide_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
 
+// per-layer tcgen05 GEMM launches for the latent nets that do not fit one SM (psnode_lg.cu: DAE_02 / ODE_02 with H = 128 / 256)
+bool psn_lg_supports(const psnode_problem* p);
+int64_t psn_lg_forward_workspace(const psnode_problem* p);
+int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream);
+
 // ---- row GEMM over a whole series (psnode_wide_proj.cu) ------------------------------------------------------------------
 // out[r][b][0:128] = A . in[r][b][0:128] (+ add[b][0:128]),  A[m][k] = W[m*ldw + k] or (transpose) W[k*ldw + m], optionally
 // A = W + W2 (the folded F = W_b + W_c).  `in` is a strided (R, B, 128) view read through a TMA tensor map.

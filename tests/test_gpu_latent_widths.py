@@ -93,7 +93,7 @@ def test_cfg5_shape_latent_dae_h256(native_lib):
         gx, gi = RK4().integrate_DAE(x_init=x_init.to(dev), x_func=de.to(dev), i_func=ae.to(dev), t=t.to(dev), x=x.to(dev), z=z.to(dev),
                                      v=v.to(dev), i=i.to(dev), all_initial=a0.to(dev), event_fn=ev.event_fn,
                                      jump_change_fn=ev.jump_change_fn)
-    assert _native.last_kernel().startswith("psn_generic_fwd_kernel")
+    assert _native.last_kernel().startswith("psn_lg_gemm_kernel")      # round 2: per-layer tcgen05 GEMMs for H = 256
     assert torch.allclose(gx.cpu(), wx, rtol=RTOL, atol=ATOL), "x: " + tol_report(gx.cpu(), wx)
     assert torch.allclose(gi.cpu(), wi, rtol=RTOL, atol=ATOL), "i: " + tol_report(gi.cpu(), wi)
 
