@@ -17,8 +17,9 @@ invocation records them:
   cfg4  RK4 ODE_02 latent net X = Z = H = 128, GLOBAL batch 16384 x 500 steps sharded over the N ranks (strong; BASELINE quotes
         it on 4 GPUs), training leg = adjoint with latent-input gradients + 0.67 MB gradient all-reduce
   cfg5  RK4 DAE_02 latent net H = 256, GLOBAL batch 65536 x 2000 steps sharded over 8 ranks (BASELINE quotes it on 8 GPUs); with
-        fewer than 8 ranks each rank integrates one 1/8 shard (B = 8192).  The H = 256 nets still run on the CUDA-core
-        generic kernel, so the timed call covers a bounded number of grid steps (stated in `sample`).
+        fewer than 8 ranks each rank integrates one 1/8 shard (B = 8192).  Forward: per-layer tcgen05 GEMM launches (impl = layer)
+        over all 2000 steps; the H = 256 reverse sweep still runs on the CUDA-core generic kernel, so the e2e / training legs
+        cover a bounded number of grid steps (stated in `sample`).
 CPU legs: the UNMODIFIED reference from oracle/_ref (vendored by oracle/make_ref.py, executed by oracle/ref_runner.py in a
 subprocess; `kind: "reference"`), or the oracle port when oracle/_ref is absent (`kind: "port"`).
 """
@@ -48,7 +49,7 @@ WORKLOADS = {
                  desc="RK4 fixed-step, ODE_02 latent DE_Func 768-128-128 (x_dim=z_dim=hidden=128), global batch 16384 x 500 steps, "
                       "adjoint training with latent-input gradients"),
     "cfg5": dict(kind="dae", net="02", X=256, Z=256, V=256, I=256, H=256, B=65536, N=2000, scaling="strong", quoted_gpus=8,
-                 bytes_per_unit=4100, flop_per_unit=7864320, sample_steps=40,
+                 bytes_per_unit=4100, flop_per_unit=7864320, aux_steps=40,
                  desc="RK4 fixed-step, DAE_02 latent DE_Func 3072-256-256 + AE_Func 1792-256-256, global batch 65536 x 2000 steps"),
 }
 FP32_PEAK_TFLOPS = 74.4     # nominal: 148 SM x 128 lanes x 2 x 1.965 GHz; measured 72.1 by bench_micro/micro.cu
@@ -360,7 +361,8 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
         return float(tt.item())
 
     B = rank_batch(w, world)
-    n_steps = w.get("sample_steps", w["N"])              # grid steps per timed call (cfg5: a bounded sample, stated)
+    n_steps = w["N"]                                      # grid steps per timed forward call: always the whole grid
+    aux_steps = w.get("aux_steps", n_steps)               # e2e / training legs of cfg5: a bounded number of steps (stated)
     units = B * n_steps
     ways = w["B"] // B if w["scaling"] == "strong" else world
     active = min(world, ways)
@@ -376,8 +378,9 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
         resident = {k: v.to(dev) for k, v in host.items()}
     solver = RK4(impl=args.kernel if main_line else "auto")
     res = {"workload": name + ": " + w["desc"], "batch_per_gpu": B, "grid_steps": n_steps, "scaling": w["scaling"]}
-    if n_steps != w["N"]:
-        res["sample"] = f"each timed call integrates {n_steps} of the {w['N']} grid steps (per-step cost is constant); throughput is per traj-step"
+    if aux_steps != n_steps:
+        res["sample"] = (f"`value` integrates all {n_steps} grid steps; the e2e and training legs integrate {aux_steps} steps per call (the H = 256 "
+                         "reverse sweep still runs on the CUDA-core generic kernel: ~3 s per 40 steps); throughputs are per traj-step")
     if w["scaling"] == "strong":
         res["global_batch"] = w["B"]
         res["shards"] = ways
@@ -389,7 +392,9 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
     if rank == 0 and main_line:
         sampler.start()
     with torch.no_grad():
+        out = None
         for _ in range(max(warmup, 3)):
+            out = None                                     # free the previous trajectory first (cfg5: 2 x 16.8 GB per call)
             out = call_integrate(w, solver, de, ae, resident)
         kernel_name = _native.last_kernel()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -399,6 +404,7 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
         e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_all0.record()
         for a, b in evs:
+            out = None
             a.record()
             out = call_integrate(w, solver, de, ae, resident)
             b.record()
@@ -418,8 +424,15 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
 
     # ---- end-to-end through the host-buffer C ABI (psnode_forward_host): pinned HOST inputs and outputs ------------------
     e2e = None
+    aux_res, aux_host, aux_units = resident, host, units
+    if aux_steps != n_steps:
+        del resident
+        torch.cuda.empty_cache()
+        aux_host = make_data(w, B, aux_steps, seed=rank)
+        aux_res = {k: v.to(dev) for k, v in aux_host.items()}
+        aux_units = B * aux_steps
     try:
-        e2e = _e2e_leg(w, legs, host, resident, solver, de, ae, B, n_steps, units, active, steps, barrier, reduce_max)
+        e2e = _e2e_leg(w, legs, aux_host, aux_res, solver, de, ae, B, aux_steps, aux_units, active, steps, barrier, reduce_max)
     except Exception as exc:
         e2e = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
         torch.cuda.synchronize()
@@ -428,14 +441,14 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
     train = None
     if "train" in legs:
         from py_psnode_b200 import parallel
-        T = n_steps + 1
+        T = aux_steps + 1
         gen = torch.Generator(device=dev).manual_seed(1234 + rank)
         x_target = torch.randn((T, B, w["X"]), device=dev, generator=gen) * 0.1
         mask = torch.ones((T, B, 1), device=dev)       # one value per (trajectory, grid point), as in the scripts
         i_target = torch.randn((T, B, w["I"]), device=dev, generator=gen) * 0.1 if w["kind"] == "dae" else None
         plist = list(de.parameters()) + (list(ae.parameters()) if ae is not None else [])
         bucket = parallel.GradBucket(plist, n_extras=2)
-        tr_data = dict(resident)
+        tr_data = dict(aux_res)
         if w["net"] == "02":        # the latent input series are functions of the encoder weights: they carry gradients
             for k in ("z", "v"):
                 if k in tr_data:
@@ -466,13 +479,13 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
         b.record()
         barrier()
         tr_ms = reduce_max(a.elapsed_time(b)) / steps
-        train = {"value": units * active / (tr_ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": tr_ms,
+        train = {"value": aux_units * active / (tr_ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": tr_ms,
                  "what": "forward + reverse sweep (discrete adjoint: all parameter grads" + (", latent-input grads" if w["net"] == "02" else "")
                          + ") + masked-MSE + one flat gradient all-reduce",
                  "allreduce_bytes": bucket.nbytes, "kernel": bwd_kernel, "gpu_launches": int(_native.launch_count() - l0),
                  "loss": loss_val,
                  # forward + exact reverse mode = 3x the forward's algorithmic FLOPs (the tape-based sweeps do not recompute)
-                 "achieved_tflops_reference_formulation": 3 * w["flop_per_unit"] * units / (tr_ms * 1e-3) / 1e12}
+                 "achieved_tflops_reference_formulation": 3 * w["flop_per_unit"] * aux_units / (tr_ms * 1e-3) / 1e12}
         del x_target, mask, i_target, tr_data
         from py_psnode_b200 import engine
         engine.release_tape_pool()
@@ -497,7 +510,7 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
     hbm = {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
            "traffic": traffic, "peak_source": peak_src,
            "note": "algorithmic (compulsory) bytes per traj-step x units / call time; the path is ~900-1900 FLOP/byte, i.e. compute/latency bound"}
-    if kernel_name.startswith("psn_tc") or kernel_name.startswith("psn_wide"):
+    if kernel_name.startswith("psn_tc") or kernel_name.startswith("psn_wide") or kernel_name.startswith("psn_lg"):
         tc_peak = peaks.get("bf16_tflops", 1590.0)
         tc_src = ("measured (MEASURED_PEAKS.json bf16_tflops, burst: kernel timed alone)" if "bf16_tflops" in peaks
                   else "fallback 1590 TFLOP/s dense bf16 (B200_PROFILING.md)")

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PSNODE_ABI_VERSION 3
+#define PSNODE_ABI_VERSION 4
 #define PSNODE_MAX_LAYERS 8
 
 /* status codes */
@@ -148,6 +148,16 @@ typedef struct psnode_problem {
  *   d_xteach, d_iteach : (T,B,X) / (T,B,I) grads of the teacher-forcing series (only with teacher_x / teacher_i)
  * All outputs are OVERWRITTEN (not accumulated).
  */
+/* One masked squared-error term of the training scripts' loss (neural_00_ODE_01_no_encode.py:353-355,
+ * neural_01_DAE_01_no_encode.py:414-418): sum_{j,b,c} w_c * mask[j,b] * (sol[j,b,c] - target[j,b,c])^2.
+ * target = NULL pointer: term absent. */
+typedef struct psnode_loss_term {
+    psnode_series target;      /* (T,B,width) */
+    psnode_series mask;        /* (T,B,1) */
+    const float* feat_weight;  /* [width] or NULL = ones */
+    const float* scale;        /* device scalar multiplying the term's gradient (upstream / sum(mask)); NULL = 1 */
+} psnode_loss_term;
+
 typedef struct psnode_adjoint {
     psnode_series gx;
     psnode_series gi;
@@ -161,6 +171,12 @@ typedef struct psnode_adjoint {
     float* d_vjump;   int64_t d_vj_sb, d_vj_se;
     psnode_series_out d_xteach;
     psnode_series_out d_iteach;
+    /* Loss fusion: when fuse_x.target.p != NULL the sweep IGNORES gx and forms the upstream gradient
+     *     dL/dx_sol[j,b,c] = scale[0] * 2 * w_c * mask[j,b] * (x_sol[j,b,c] - target[j,b,c])
+     * on the fly from p->x_sol, so the (T,B,X) gradient tensor of the masked MSE is never materialised; fuse_i likewise
+     * replaces gi (DAE).  Supported by the tensor-core sweeps (psnode_sweep_fuses_loss tells); otherwise pass gx / gi. */
+    psnode_loss_term fuse_x;
+    psnode_loss_term fuse_i;
 } psnode_adjoint;
 
 /* library / device introspection */
@@ -194,6 +210,9 @@ int64_t psnode_tape_floats(const psnode_problem* p);
  * the latent `*_02_direct_encode` nets, whose encoders always need them (neural_00_ODE_02_direct_encode.py:75-86);
  * 0: requesting those gradients sends psnode_backward to the recomputing sweep and a tape would be wasted. */
 int psnode_tape_covers_input_grads(const psnode_problem* p);
+
+/* 1 if psnode_backward(p, a) will run a sweep that honours a->fuse_x / a->fuse_i (the tape-based tensor-core sweeps) */
+int psnode_sweep_fuses_loss(const psnode_problem* p, const psnode_adjoint* a);
 
 /* workspace sizes in bytes (0 is possible) */
 int64_t psnode_forward_workspace(const psnode_problem* p);

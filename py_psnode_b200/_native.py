@@ -8,7 +8,7 @@ import os
 import threading
 
 PSNODE_MAX_LAYERS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK, EINVAL, EUNSUPPORTED, EWORKSPACE, ECUDA, ENODEVICE = 0, -1, -2, -3, -4, -5
 EULER, MIDPOINT, RK4 = 0, 1, 2
@@ -47,6 +47,10 @@ class Problem(C.Structure):
                 ("tape", C.c_void_p), ("tape_floats", C.c_int64)]
 
 
+class LossTerm(C.Structure):
+    _fields_ = [("target", Series), ("mask", Series), ("feat_weight", C.c_void_p), ("scale", C.c_void_p)]
+
+
 class Adjoint(C.Structure):
     _fields_ = [("gx", Series), ("gi", Series),
                 ("d_theta", C.c_void_p), ("n_theta", C.c_int64),
@@ -55,7 +59,8 @@ class Adjoint(C.Structure):
                 ("d_z", Series), ("d_v", Series),
                 ("d_zjump", C.c_void_p), ("d_zj_sb", C.c_int64), ("d_zj_se", C.c_int64),
                 ("d_vjump", C.c_void_p), ("d_vj_sb", C.c_int64), ("d_vj_se", C.c_int64),
-                ("d_xteach", Series), ("d_iteach", Series)]
+                ("d_xteach", Series), ("d_iteach", Series),
+                ("fuse_x", LossTerm), ("fuse_i", LossTerm)]
 
 
 # every symbol include/psnode_b200.h declares: (name, restype, argtypes)
@@ -70,6 +75,7 @@ SYMBOLS = [
                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     ("psnode_tape_floats", C.c_int64, [C.POINTER(Problem)]),
     ("psnode_tape_covers_input_grads", C.c_int, [C.POINTER(Problem)]),
+    ("psnode_sweep_fuses_loss", C.c_int, [C.POINTER(Problem), C.POINTER(Adjoint)]),
     ("psnode_forward_workspace", C.c_int64, [C.POINTER(Problem)]),
     ("psnode_backward_workspace", C.c_int64, [C.POINTER(Problem), C.POINTER(Adjoint)]),
     ("psnode_forward", C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_int64, C.c_void_p]),

@@ -67,3 +67,26 @@ int psn_tc8_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStr
 bool psn_tc_dae_bwd_supports(const psnode_problem* p, const psnode_adjoint* a);
 int psn_tc_dae_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
 int64_t psn_tc_dae_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);
+
+// ---- fused masked-MSE upstream gradient (psnode_adjoint.fuse_x / fuse_i) ------------------------------------------------------
+#if defined(__CUDACC__)
+struct PsnFuse {
+    psnode_loss_term term;
+    psnode_series sol;          // the forward result the term refers to (p->x_sol / p->i_sol)
+};
+__device__ __forceinline__ float psn_fuse_scale(const PsnFuse& f) { return f.term.scale ? __ldg(f.term.scale) : 1.0f; }
+// d/d sol[j,b,c] of  scale * sum w_c * mask * (sol - target)^2
+__device__ __forceinline__ float psn_fuse_grad(const PsnFuse& f, float scale, int j, int b, int c) {
+    const float m = __ldg(f.term.mask.p + (int64_t)j * f.term.mask.st + (int64_t)b * f.term.mask.sb);
+    const float d = __ldg(f.sol.p + (int64_t)j * f.sol.st + (int64_t)b * f.sol.sb + c) -
+                    __ldg(f.term.target.p + (int64_t)j * f.term.target.st + (int64_t)b * f.term.target.sb + c);
+    const float w = f.term.feat_weight ? __ldg(f.term.feat_weight + c) : 1.0f;
+    return (scale * (2.0f * w) * m) * d;
+}
+static inline PsnFuse psn_make_fuse(const psnode_loss_term& t, const psnode_series_out& sol) {
+    PsnFuse f;
+    f.term = t;
+    f.sol.p = sol.p; f.sol.st = sol.st; f.sol.sb = sol.sb;
+    return f;
+}
+#endif

@@ -65,6 +65,7 @@ constexpr int G_AREA = TH * TK1;       // floats of the dW1f (folded layer 1) ac
 struct TcBwdParams {
     int B, T, X, Z, S, groups, n_theta;        // X <= 16 state variables (rows / columns X..15 of the tiles are zero padding)
     psnode_series t, z, gx;
+    PsnFuse fx;                                 // fused masked-MSE upstream gradient (fx.term.target.p != NULL: gx is ignored)
     const float* a0; int64_t a0_sb;
     const int32_t* event_idx;
     const float* z_jump; int64_t zj_sb, zj_se;
@@ -411,7 +412,14 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
         float lam, D1[4], dB2[4], dB3[4], dB4 = 0.0f;
 #pragma unroll
         for (int i = 0; i < 4; i++) { D1[i] = 0.f; dB2[i] = 0.f; dB3[i] = 0.f; }
-        lam = (valid && q.gx.p) ? ldser(q.gx, T - 1, bown, srow) : 0.0f;
+        const bool fused = q.fx.term.target.p != nullptr;
+        const float fscale = fused ? psn_fuse_scale(q.fx) : 0.0f;
+        auto up_x = [&](int j) -> float {        // dL/dx_sol[j] of this thread's state element
+            if (!valid) return 0.0f;
+            if (fused) return psn_fuse_grad(q.fx, fscale, j, bown, srow);
+            return q.gx.p ? ldser(q.gx, j, bown, srow) : 0.0f;
+        };
+        lam = up_x(T - 1);
 
         const float c13 = (float)(1.0 / 3.0);
         const float* tp = q.tape + ((int64_t)gid * (T - 1) * NST + (int64_t)(T - 1) * NST - 1) * PSN_TAPE_STAGE;   // last record
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
             float u[TU];
 #pragma unroll
             for (int c = 0; c < TU; c++) u[c] = un[c];
-            const float gxn = (valid && q.gx.p) ? ldser(q.gx, j - 1, bown, srow) : 0.0f;
+            const float gxn = up_x(j - 1);
             if (j > 1) {
                 tan = tbn; tbn = ldser(q.t, j - 2, bbown, 0);
                 if (wk == 4) load_held(j - 1, un);
@@ -623,6 +631,7 @@ int psn_tc_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
     q.B = p->B; q.T = p->T; q.X = p->X; q.Z = p->Z; q.S = p->X + p->Z;
     q.n_theta = (int)n_theta;
     q.t = p->t; q.z = p->z; q.gx = a->gx;
+    q.fx = psn_make_fuse(a->fuse_x, p->x_sol);
     q.a0 = p->a0; q.a0_sb = p->a0_sb;
     q.event_idx = p->event_idx;
     q.z_jump = p->z_jump; q.zj_sb = p->zj_sb; q.zj_se = p->zj_se;

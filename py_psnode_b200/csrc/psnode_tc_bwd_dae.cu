@@ -54,6 +54,7 @@ __host__ __device__ constexpr int slab_floats(int n_de, int n_ae) { return pad4(
 struct DaeBwdParams {
     int B, T, X, Z, V, I, S, E, n_theta, n_theta_de;       // X <= 16 state variables (tile rows / columns X..15 are zero padding)
     psnode_series t, z, v, gx, gi;
+    PsnFuse fx, fi;                             // fused masked-MSE upstream gradients (replace gx / gi when their target is set)
     const float* x_sol; int64_t xs_st, xs_sb;
     const float* i_sol; int64_t is_st, is_sb;
     const float* a0; int64_t a0_sb;
@@ -521,8 +522,18 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
 
         // ---- reverse sweep ---------------------------------------------------------------------------------
         auto own_x = [&](int j) { return own_x_ok ? __ldg(q.x_sol + (int64_t)j * q.xs_st + (int64_t)bbown * q.xs_sb + srow) : 0.0f; };
-        auto own_gx = [&](int j) { return (valid && own_x_ok && q.gx.p) ? ldser(q.gx, j, bown, srow) : 0.0f; };
-        auto own_gi = [&](int j) { return (valid && own_i && q.gi.p) ? ldser(q.gi, j, bown, srow) : 0.0f; };
+        const bool fused_x = q.fx.term.target.p != nullptr, fused_i = q.fi.term.target.p != nullptr;
+        const float fsx = fused_x ? psn_fuse_scale(q.fx) : 0.0f, fsi = fused_i ? psn_fuse_scale(q.fi) : 0.0f;
+        auto own_gx = [&](int j) -> float {
+            if (!(valid && own_x_ok)) return 0.0f;
+            if (fused_x) return psn_fuse_grad(q.fx, fsx, j, bown, srow);
+            return q.gx.p ? ldser(q.gx, j, bown, srow) : 0.0f;
+        };
+        auto own_gi = [&](int j) -> float {
+            if (!(valid && own_i)) return 0.0f;
+            if (fused_i) return psn_fuse_grad(q.fi, fsi, j, bown, srow);
+            return q.gi.p ? ldser(q.gi, j, bown, srow) : 0.0f;
+        };
         float lam = own_gx(T - 1), mu = own_gi(T - 1);
         const float c13 = (float)(1.0 / 3.0);
         float dui_dummy = 0.0f;
@@ -742,6 +753,7 @@ int psn_tc_dae_backward(const psnode_problem* p, const psnode_adjoint* a, void* 
     q.E = p->event_idx ? p->E : 0;
     q.n_theta = (int)n_theta; q.n_theta_de = (int)n_de;
     q.t = p->t; q.z = p->z; q.v = p->v; q.gx = a->gx; q.gi = a->gi;
+    q.fx = psn_make_fuse(a->fuse_x, p->x_sol); q.fi = psn_make_fuse(a->fuse_i, p->i_sol);
     q.x_sol = p->x_sol.p; q.xs_st = p->x_sol.st; q.xs_sb = p->x_sol.sb;
     q.i_sol = p->i_sol.p; q.is_st = p->i_sol.st; q.is_sb = p->i_sol.sb;
     q.a0 = p->a0; q.a0_sb = p->a0_sb;

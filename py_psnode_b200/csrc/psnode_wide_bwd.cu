@@ -28,6 +28,7 @@ constexpr int GROUP_THREADS = PSW_GROUP_THREADS;
 struct WideBwdParams {
     int B, T, ngroups;
     psnode_series t, z, gx;
+    PsnFuse fx;                                   // fused masked-MSE upstream gradient (replaces gx when its target is set)
     const int32_t* event_idx;
     const float* z_jump; int64_t zj_sb, zj_se;
     const float* W1; const float* W2;
@@ -201,11 +202,15 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                 gs.dts[j & 1][lane] = __fsub_rn(__ldg(tp + (int64_t)j * q.t.st), __ldg(tp + (int64_t)(j - 1) * q.t.st));
             }
         };
+        const bool fused = q.fx.term.target.p != nullptr;
+        const float fscale = fused ? psn_fuse_scale(q.fx) : 0.0f;
         auto load_gx = [&](int j, float (&v)[8]) {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int b = b0 + 8 * h + i;
-                v[i] = b < B ? __ldg(q.gx.p + (int64_t)j * q.gx.st + (int64_t)b * q.gx.sb + m) : 0.0f;
+                if (b >= B) v[i] = 0.0f;
+                else if (fused) v[i] = psn_fuse_grad(q.fx, fscale, j, b, m);
+                else v[i] = __ldg(q.gx.p + (int64_t)j * q.gx.st + (int64_t)b * q.gx.sb + m);
             }
         };
 
@@ -333,6 +338,7 @@ int psn_wide_bwd_sweep(const psnode_problem* p, const psnode_adjoint* a, const f
     WideBwdParams q;
     q.B = p->B; q.T = p->T; q.ngroups = psw_ngroups(p->B);
     q.t = p->t; q.z = p->z; q.gx = a->gx;
+    q.fx = psn_make_fuse(a->fuse_x, p->x_sol);
     q.event_idx = p->event_idx;
     q.z_jump = p->z_jump; q.zj_sb = p->zj_sb; q.zj_se = p->zj_se;
     q.W1 = p->de.W[0]; q.W2 = p->de.W[1];

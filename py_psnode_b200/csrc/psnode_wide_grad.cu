@@ -278,7 +278,7 @@ int psn_wide_bwd_sweep(const psnode_problem* p, const psnode_adjoint* a, const f
 bool psn_wide_bwd_supports(const psnode_problem* p, const psnode_adjoint* a) {
     if (!psn_wide_supports(p) || !p->tape || p->tape_floats < psw_tape_floats(p->B, p->T, p->method)) return false;
     if (a->d_xteach.p || a->d_iteach.p) return false;
-    if (!a->gx.p) return false;
+    if (!a->gx.p && !a->fuse_x.target.p) return false;
     return true;
 }
 
