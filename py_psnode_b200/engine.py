@@ -361,9 +361,32 @@ def _backward_chunked(cfg: Config, tens, gx, gi, needs, rows: int) -> List[Optio
     return total
 
 
-def backward_raw(cfg: Config, tens, x_sol, i_sol, gx, gi, needs, tape=None) -> List[Optional[torch.Tensor]]:
+@dataclass
+class LossSpec:
+    """Masked squared-error terms fused with the integration: sum w_c * mask * (sol - target)^2 over the
+    trajectory (x term) and, for a DAE, over the algebraic trajectory (i term).  Time-major (T,B,.) views."""
+    target_x: torch.Tensor
+    mask: torch.Tensor
+    weight_x: Optional[torch.Tensor] = None
+    target_i: Optional[torch.Tensor] = None
+    weight_i: Optional[torch.Tensor] = None
+
+
+def _set_term(term: "N.LossTerm", target, mask, weight, scale, keep) -> None:
+    target, mask = _series(target, "loss target"), _series(mask, "loss mask")
+    keep.extend((target, mask, weight, scale))
+    _set_series(term.target, target)
+    _set_series(term.mask, mask)
+    term.feat_weight = weight.data_ptr() if weight is not None else None
+    term.scale = scale.data_ptr()
+
+
+def backward_raw(cfg: Config, tens, x_sol, i_sol, gx, gi, needs, tape=None, fuse: Optional[LossSpec] = None,
+                 fuse_scale: Optional[torch.Tensor] = None) -> List[Optional[torch.Tensor]]:
     """Reverse sweep through the native library.  `needs[k]` says whether tens[k] wants a gradient; `tape` is what
-    forward_raw(..., want_tape=True) recorded (None: the sweep recomputes the stages from x_sol)."""
+    forward_raw(..., want_tape=True) recorded (None: the sweep recomputes the stages from x_sol).  With `fuse` the upstream
+    gradient is the masked-MSE gradient scaled by the device scalar `fuse_scale`: the tensor-core sweeps form it on the fly
+    (psnode_adjoint.fuse_x / fuse_i), the recomputing sweeps get it materialised by psnode_masked_sse_grad."""
     L = N.lib()
     t = tens[_T]
     dev = t.device
@@ -376,11 +399,19 @@ def backward_raw(cfg: Config, tens, x_sol, i_sol, gx, gi, needs, tape=None) -> L
         keep: list = []
         p = _build_problem(cfg, tens, x_sol, i_sol, keep, tape)
         a = N.Adjoint()
-        gx = torch.zeros_like(x_sol) if gx is None else _series(gx, "grad x_sol")
-        _set_series(a.gx, gx)
-        if dae:
-            gi = torch.zeros_like(i_sol) if gi is None else _series(gi, "grad i_sol")
-            _set_series(a.gi, gi)
+        if fuse is not None:
+            _set_term(a.fuse_x, fuse.target_x, fuse.mask, fuse.weight_x, fuse_scale, keep)
+            if dae and fuse.target_i is not None:
+                _set_term(a.fuse_i, fuse.target_i, fuse.mask, fuse.weight_i, fuse_scale, keep)
+            elif dae:
+                gi = torch.zeros_like(i_sol)
+                _set_series(a.gi, gi)
+        else:
+            gx = torch.zeros_like(x_sol) if gx is None else _series(gx, "grad x_sol")
+            _set_series(a.gx, gx)
+            if dae:
+                gi = torch.zeros_like(i_sol) if gi is None else _series(gi, "grad i_sol")
+                _set_series(a.gi, gi)
         params = tens[_NFIXED:]
         sizes = _theta_sizes(params)
         d_theta = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
@@ -412,6 +443,17 @@ def backward_raw(cfg: Config, tens, x_sol, i_sol, gx, gi, needs, tape=None) -> L
         if cfg.teacher_i and needs[_Is]:
             d_it = torch.empty((T, B, I), dtype=torch.float32, device=dev)
             _set_series(a.d_iteach, d_it)
+        if fuse is not None and not L.psnode_sweep_fuses_loss(C.byref(p), C.byref(a)):
+            # recomputing sweep: materialise the masked-MSE gradient with the fused loss kernel and pass it as gx / gi
+            from .losses import masked_sse_grad_into
+            gx = masked_sse_grad_into(x_sol, fuse.target_x, fuse.mask, fuse.weight_x, fuse_scale)
+            _set_series(a.gx, gx)
+            a.fuse_x = N.LossTerm()
+            if dae:
+                gi = (masked_sse_grad_into(i_sol, fuse.target_i, fuse.mask, fuse.weight_i, fuse_scale) if fuse.target_i is not None
+                      else torch.zeros_like(i_sol))
+                _set_series(a.gi, gi)
+                a.fuse_i = N.LossTerm()
         ws = _workspace(dev, L.psnode_backward_workspace(C.byref(p), C.byref(a)))
         stream = torch.cuda.current_stream(dev).cuda_stream
         N.check(L.psnode_backward(C.byref(p), C.byref(a), ws.data_ptr(), ws.numel(), stream), "psnode_backward")
@@ -434,6 +476,53 @@ def backward_raw(cfg: Config, tens, x_sol, i_sol, gx, gi, needs, tape=None) -> L
             out[_NFIXED + k] = d_theta[off:off + n].view_as(params[k])
         off += n
     return out
+
+
+class _IntegrateLoss(torch.autograd.Function):
+    """num, x_sol, i_sol = integrate_loss(cfg, spec, t, x, ...): the integration fused with the masked squared-error
+    numerator of the scripts' loss.  Only `num` is differentiable; its backward runs the reverse sweep with the loss gradient
+    formed inside the sweep, so dL/dx_sol (T,B,X) never exists (cfg2: 262 MB written and read per step otherwise)."""
+
+    @staticmethod
+    def forward(ctx, cfg: Config, spec: LossSpec, *tens):
+        from .losses import masked_sse
+        needs = ctx.needs_input_grad[2:]
+        input_grads = any(needs[k] for k in (_Zs, _Vs, _Is, _ZJ, _VJ))
+        x_sol, i_sol, tape = forward_raw(cfg, tens, want_tape=not (cfg.teacher_x or cfg.teacher_i), input_grads=input_grads)
+        with torch.no_grad():
+            num = masked_sse(x_sol, spec.target_x, spec.mask, spec.weight_x)
+            if i_sol is not None and spec.target_i is not None:
+                num = num + masked_sse(i_sol, spec.target_i, spec.mask, spec.weight_i)
+        ctx.tape, ctx.cfg, ctx.spec = tape, cfg, spec
+        ctx.save_for_backward(*[q for q in tens if q is not None], x_sol, *([i_sol] if i_sol is not None else []))
+        ctx.present = [q is not None for q in tens]
+        if i_sol is None:
+            i_sol = x_sol.new_empty(0)
+        ctx.mark_non_differentiable(x_sol, i_sol)
+        return num, x_sol, i_sol
+
+    @staticmethod
+    def backward(ctx, gnum, _gx, _gi):
+        cfg: Config = ctx.cfg
+        saved = list(ctx.saved_tensors)
+        it = iter(saved)
+        tens = [next(it) if present else None for present in ctx.present]
+        x_sol = next(it)
+        i_sol = next(it) if cfg.kind == N.DAE else None
+        tape, ctx.tape = ctx.tape, None
+        needs = ctx.needs_input_grad[2:]
+        scale = gnum.detach().to(torch.float32).reshape(1).contiguous()
+        if isinstance(tape, TapeChunks):
+            tape = None                     # chunked re-integration is not combined with loss fusion: recomputing sweep
+        grads = backward_raw(cfg, tens, x_sol, i_sol, None, None, needs, tape, fuse=ctx.spec, fuse_scale=scale)
+        _give_tape(tape)
+        return (None, None, *grads)
+
+
+def integrate_loss(cfg: Config, spec: LossSpec, tens: Sequence[Optional[torch.Tensor]]):
+    """(loss numerator, x_sol, i_sol) -- see _IntegrateLoss."""
+    num, x_sol, i_sol = _IntegrateLoss.apply(cfg, spec, *tens)
+    return num, x_sol, (i_sol if cfg.kind == N.DAE else None)
 
 
 def integrate(cfg: Config, tens: Sequence[Optional[torch.Tensor]]) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:

@@ -83,3 +83,22 @@ def masked_sse(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor,
     place); mask: one value per (trajectory, grid point), shape (.., .., 1); feat_weight: optional X per-feature weights
     (the DAE script counts feature 1 ten times: ones(X) with w[1] = 10)."""
     return _MaskedSSE.apply(pred, target, mask, feat_weight)
+
+
+def masked_sse_grad_into(pred: torch.Tensor, target: torch.Tensor, mask: torch.Tensor, feat_weight: Optional[torch.Tensor],
+                         upstream: torch.Tensor) -> torch.Tensor:
+    """upstream[0] * d/dpred masked_sse(pred, target, mask, feat_weight) as a new tensor shaped like pred (one native pass;
+    used when a reverse sweep cannot form the loss gradient on the fly)."""
+    pred, target = _row_view(pred, "pred"), _row_view(target, "target")
+    mask = _row_view(mask if mask.shape[-1] == 1 else mask[..., :1], "mask")
+    outer, inner = (0, 1) if pred.stride(0) >= pred.stride(1) else (1, 0)
+    grad = torch.empty(pred.shape, device=pred.device, dtype=torch.float32)
+    lib = N.lib()
+    wptr = C.c_void_p(feat_weight.data_ptr()) if feat_weight is not None else None
+    g = _series(grad, outer, inner)
+    a = (_series(pred, outer, inner), _series(target, outer, inner), _series(mask, outer, inner))
+    with torch.cuda.device(pred.device):
+        N.check(lib.psnode_masked_sse_grad(C.byref(a[0]), C.byref(a[1]), C.byref(a[2]), wptr, pred.shape[outer], pred.shape[inner],
+                                           pred.shape[-1], C.c_void_p(upstream.data_ptr()), C.byref(g),
+                                           C.c_void_p(torch.cuda.current_stream(pred.device).cuda_stream)), "psnode_masked_sse_grad")
+    return grad

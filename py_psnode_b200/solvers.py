@@ -107,6 +107,44 @@ class FixedGridODESolver(metaclass=abc.ABCMeta):
         return engine.integrate(cfg, tens)
 
 
+    # ------------------------------------------------------------------ integration fused with the masked loss
+    def integrate_ODE_loss(self, x_func: nn.Module, t, x, z, all_initial, target, mask, feat_weight=None, event_fn=None,
+                           jump_change_fn=None, input_true_x=False):
+        """(loss_numerator, x_solution): integrate_ODE plus `sum(w_c * mask * (x_solution - target)^2)` -- the numerator of the
+        scripts' masked MSE (neural_00_ODE_01_no_encode.py:353-355; divide by mask.sum()).  `target`, `mask` are time-major
+        (T,B,X) / (T,B,1) views like `x`.  Only the numerator carries gradients: its backward runs the reverse sweep with the
+        loss gradient formed inside the sweep, so dL/dx_solution is never materialised.  x_solution is returned detached."""
+        X, Z = x.shape[-1], z.shape[-1]
+        de = pattern.match_de(x_func, X=X, Z=Z, dae=False)
+        ev = pattern.match_event(event_fn, jump_change_fn, dae=False)
+        cfg = engine.Config(kind=N.ODE, method=self._method, impl=N.IMPL_BY_NAME[self.impl], X=X, Z=Z, V=0, I=0,
+                            teacher_x=bool(input_true_x), teacher_i=False, n_de=len(de), n_ae=0,
+                            has_event=ev is not None, check_events=self.check_events)
+        cfg.event_ref = pattern.event_reference(event_fn)
+        tens = [t, x, z, None, None, None, all_initial, ev[0] if ev else None, ev[1] if ev else None, None, *_params(de)]
+        spec = engine.LossSpec(target_x=target, mask=mask, weight_x=feat_weight)
+        num, x_sol, _ = engine.integrate_loss(cfg, spec, tens)
+        return num, x_sol
+
+    def integrate_DAE_loss(self, x_init, x_func: nn.Module, i_func: nn.Module, t, x, z, v, i, all_initial, target_x, target_i, mask,
+                           feat_weight_x=None, feat_weight_i=None, event_fn=None, jump_change_fn=None, input_true_x=False,
+                           input_true_i=False):
+        """(loss_numerator, x_solution, i_solution): integrate_DAE plus the numerator of the DAE scripts' masked loss,
+        sum(wx_c * mask * (x_solution - target_x)^2) + sum(wi_c * mask * (i_solution - target_i)^2)
+        (neural_01_DAE_01_no_encode.py:414-418: wx = ones with wx[1] = 10).  See integrate_ODE_loss."""
+        X, Z, V, I = x_init.shape[-1], z.shape[-1], v.shape[-1], i.shape[-1]
+        de = pattern.match_de(x_func, X=X, Z=Z, V=V, I=I, dae=True)
+        ae = pattern.match_ae(i_func, X=X, Z=Z, V=V, I=I)
+        ev = pattern.match_event(event_fn, jump_change_fn, dae=True)
+        cfg = engine.Config(kind=N.DAE, method=self._method, impl=N.IMPL_BY_NAME[self.impl], X=X, Z=Z, V=V, I=I,
+                            teacher_x=bool(input_true_x), teacher_i=bool(input_true_i), n_de=len(de), n_ae=len(ae),
+                            has_event=ev is not None, check_events=self.check_events)
+        cfg.event_ref = pattern.event_reference(event_fn)
+        tens = [t, x if x.shape[-1] != 0 else None, z, v, i, x_init, all_initial,
+                ev[0] if ev else None, ev[1] if ev else None, ev[2] if ev else None, *_params(de), *_params(ae)]
+        spec = engine.LossSpec(target_x=target_x, mask=mask, weight_x=feat_weight_x, target_i=target_i, weight_i=feat_weight_i)
+        return engine.integrate_loss(cfg, spec, tens)
+
     # ------------------------------------------------------------------ host-buffer variants (C ABI psnode_forward_host)
     def integrate_ODE_host(self, x_func: nn.Module, t, x, z, all_initial, event_fn=None, jump_change_fn=None, input_true_x=False,
                            out=None):
