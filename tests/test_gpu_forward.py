@@ -213,3 +213,45 @@ def test_host_buffer_entry_matches_reference(native_lib, name, pinned):
     assert torch.allclose(xs, torch.from_numpy(d["x_sol"]), rtol=RTOL, atol=ATOL), tol_report(xs, torch.from_numpy(d["x_sol"]))
     if dae:
         assert torch.allclose(is_, torch.from_numpy(d["i_sol"]), rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.parametrize("kind", ["ode", "dae"])
+def test_host_buffer_dma_path_equals_zero_copy_path(native_lib, kind, monkeypatch):
+    """PSNODE_HOST_PATH=dma: the grid is integrated in 8 time chunks whose inputs / trajectory rows move on the copy engines
+    while the neighbouring chunk integrates.  Same kernels, same per-step arithmetic -> bit-identical to the in-place path,
+    including an event that falls on a chunk boundary and the re-evaluated i_0 of every DAE chunk."""
+    from py_psnode_b200 import AE_Func, DAE_Event, DE_Func, ODE_Event, RK4
+    torch.manual_seed(91)
+    B, N, X, Z, V, I, H = 272, 200, 16, 2, 2, 4, 64
+    T = N + 1
+    t = (torch.arange(T, dtype=torch.float32) * 0.01).view(T, 1, 1).repeat(1, B, 1).contiguous().pin_memory()
+    mk = lambda w: (torch.randn(T, B, w) * 0.1).pin_memory()
+    x, z, v, i = mk(X), mk(Z), mk(V), mk(I)
+    event_t = torch.stack((t[25, :, 0], t[113, :, 0]), dim=1).view(B, 2, 1).clone()      # step 25 is the first chunk boundary
+    zj, vj = torch.randn(B, 2, Z) * 0.1, torch.randn(B, 2, V) * 0.1
+    outs = {}
+    for mode in ("inplace", "dma"):
+        if mode == "dma":
+            monkeypatch.setenv("PSNODE_HOST_PATH", "dma")
+        else:
+            monkeypatch.delenv("PSNODE_HOST_PATH", raising=False)
+        torch.manual_seed(92)
+        if kind == "ode":
+            de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H)
+            ev = ODE_Event()
+            ev.set_event(t=event_t, z=zj)
+            a0 = torch.cat((x[0], z[0]), dim=-1)
+            xs = RK4().integrate_ODE_host(x_func=de, t=t, x=x, z=z, all_initial=a0, event_fn=ev.event_fn, jump_change_fn=ev.jump_change_fn)
+            outs[mode] = (xs.clone(),)
+        else:
+            de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H, v_dim=V, i_dim=I)
+            ae = AE_Func(x_dim=X, v_dim=V, i_dim=I, hidden_dim=H, z_dim=Z)
+            ev = DAE_Event()
+            ev.set_event(t=event_t, z=zj, v=vj)
+            x_init = x[0].clone()
+            a0 = torch.cat((x_init, z[0], v[0], i[0]), dim=-1)
+            xs, is_ = RK4().integrate_DAE_host(x_init=x_init, x_func=de, i_func=ae, t=t, x=x, z=z, v=v, i=i, all_initial=a0,
+                                               event_fn=ev.event_fn, jump_change_fn=ev.jump_change_fn)
+            outs[mode] = (xs.clone(), is_.clone())
+    for a, b in zip(outs["dma"], outs["inplace"]):
+        assert torch.isfinite(a).all() and torch.equal(a, b), float((a - b).abs().max())
