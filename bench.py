@@ -268,6 +268,7 @@ def run_reference_arm(args, name, w, rank):
 def _e2e_leg(w, legs, host, resident, solver, de, ae, B, n_steps, units, active, steps, barrier, reduce_max):
     import torch
     e2e = None
+    solver_device = next(de.parameters()).device
     if "e2e" in legs and host is not None:
         import copy
         T = n_steps + 1
@@ -313,12 +314,42 @@ def _e2e_leg(w, legs, host, resident, solver, de, ae, B, n_steps, units, active,
             wall_ms = (time.perf_counter() - t_wall0) * 1e3
             timings[mode] = (reduce_max(max(a.elapsed_time(b), wall_ms)) / steps, moved[0], moved[1])   # the call blocks the host: larger clock
         os.environ.pop("PSNODE_HOST_PATH", None)
+        # platform floor for this leg: the same bytes moved by plain pinned <-> device copies on two streams, all ranks at once
+        # (no integration at all).  At 8 GPUs this is what bounds e2e: the ranks share the host's PCIe / memory bandwidth.
+        copy_ms = None
+        try:
+            dev_in = {k: torch.empty_like(v, device=solver_device) for k, v in pinned.items()}
+            dev_out = torch.empty_like(out_host, device=solver_device)
+            dev_iout = torch.empty_like(iout_host, device=solver_device) if iout_host is not None else None
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def copy_step():
+                with torch.cuda.stream(s_in):
+                    for k in pinned:
+                        dev_in[k].copy_(pinned[k], non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    out_host.copy_(dev_out, non_blocking=True)
+                    if dev_iout is not None:
+                        iout_host.copy_(dev_iout, non_blocking=True)
+                torch.cuda.synchronize()
+
+            copy_step()
+            barrier()
+            t0c = time.perf_counter()
+            for _ in range(steps):
+                copy_step()
+            barrier()
+            copy_ms = reduce_max((time.perf_counter() - t0c) * 1e3) / steps
+            del dev_in, dev_out, dev_iout
+        except Exception:
+            copy_ms = None
         best = min(timings, key=lambda k: timings[k][0])
         e2e_ms = timings[best][0]
         e2e = {"value": units * active / (e2e_ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": timings[best][1], "d2h_bytes_per_step": timings[best][2],
                "path": "psnode_forward_host (C ABI, HOST pointers), mode " + best,
                "modes_ms": {k: v[0] for k, v in timings.items()},
+               "copy_only_ms": copy_ms,
                "modes": "inplace = pinned buffers read/written over PCIe by the kernel itself; dma = chunked cudaMemcpyAsync on two "
                         "side streams overlapped with the integration (PSNODE_HOST_PATH=dma)"}
         del pinned, out_host, iout_host

@@ -12,6 +12,7 @@
 // full-rate M = N = 128 MMAs; sum_e delta1 is also written row-major (`dpre`: gradient of the hoisted layer-1 half), from
 // which psnode_wide_proj.cu produces the input-series / jump gradients d_z = F_z^T dpre the encoders need.
 #include <cstddef>
+#include <cstdlib>
 #include "psnode_wide.cuh"
 
 namespace {
@@ -56,7 +57,7 @@ struct __align__(128) CtaSmem {
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(GROUP_THREADS) : "memory"); }
 __device__ __forceinline__ void st_f32(unsigned char* base, int off, float v) { *reinterpret_cast<float*>(base + off) = v; }
 
-template <int METHOD>
+template <int METHOD, int NP>
 __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wide_bwd_kernel(const __grid_constant__ WideBwdParams q) {
     constexpr int NST = METHOD == PSNODE_EULER ? 1 : (METHOD == PSNODE_MIDPOINT ? 2 : 4);
     extern __shared__ unsigned char smem_raw[];
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
     const int tid = threadIdx.x, lane = tid & 31;
     const int cw = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int g = cw >> 3, wk = cw & 7, wq = wk & 3, h = wk >> 2;
-    const bool issuer = h == 0;
+    const bool issuer = h == 0 && wq < NP;      // NP K-partials, one issuing warp each
+    constexpr int KPI = 16 / NP;                 // K-steps (of 8) per issuer
     GroupSmem& gs = sm.g[g];
     const int B = q.B, T = q.T;
     const int gid = blockIdx.x * PSW_GROUPS_PER_CTA + g;
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
     const int m = 32 * wq + lane;
 
     if (tid == 0) {
-        for (int gg = 0; gg < PSW_GROUPS_PER_CTA; gg++) mbar_init(&sm.g[gg].bar, 4);
+        for (int gg = 0; gg < PSW_GROUPS_PER_CTA; gg++) mbar_init(&sm.g[gg].bar, NP);
         fence_mbar_init();
     }
     if (cw == 0) tmem_alloc(&sm.tmem_base, 512);
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
         const uint64_t d_act_hi = make_desc(smem_u32(gs.act_hi), LBO, SBO_ACT), d_act_lo = d_act_hi + (uint64_t)(ACT_TILE >> 4);
         const uint64_t d_blo = make_desc(smem_u32(sm.fxt_lo), LBO_W, SBO_W);
         constexpr uint64_t KSTEP_B = (uint64_t)((2 * LBO) >> 4), KSTEP_W = (uint64_t)((2 * LBO_W) >> 4);
-        const uint32_t acc_base = tmem + TM_ACC + (uint32_t)(g * 4 * TN);
+        const uint32_t acc_base = tmem + TM_ACC + (uint32_t)(g * 4 * TN);      // (column budget stays 4 x 16 per group)
         const uint32_t my_acc = acc_base + (uint32_t)(wq * TN);
         uint32_t phase = 0;
 
@@ -128,8 +130,8 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                         const uint32_t wa = term == 0 ? TM_A_LO : TM_A_HI;
                         const uint64_t bd = term == 1 ? d_act_lo : d_act_hi;
 #pragma unroll
-                        for (int kk = 0; kk < 4; kk++) {
-                            const int ks = 4 * wq + kk;
+                        for (int kk = 0; kk < KPI; kk++) {
+                            const int ks = KPI * wq + kk;
                             mma_tf32_ts(my_acc, tmem + wa + 8 * ks, bd + KSTEP_B * ks, idesc, accumulate);
                             accumulate = 1;
                         }
@@ -144,16 +146,16 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                 if (elect_one()) {
                     tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 4; kk++) {
-                        const int ks = 4 * wq + kk;
+                    for (int kk = 0; kk < KPI; kk++) {
+                        const int ks = KPI * wq + kk;
                         mma_tf32(my_acc, d_blo + KSTEP_W * ks, d_act_hi + KSTEP_B * ks, idesc, kk > 0 ? 1u : 0u);
                     }
 #pragma unroll
                     for (int term = 1; term < 3; term++) {
                         const uint64_t bd = term == 1 ? d_act_lo : d_act_hi;
 #pragma unroll
-                        for (int kk = 0; kk < 4; kk++) {
-                            const int ks = 4 * wq + kk;
+                        for (int kk = 0; kk < KPI; kk++) {
+                            const int ks = KPI * wq + kk;
                             mma_tf32_ts(my_acc, tmem + TM_B_HI + 8 * ks, bd + KSTEP_B * ks, idesc, 1u);
                         }
                     }
@@ -170,11 +172,16 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
             const uint32_t a = acc_base + lane_base + 8 * h;
             tmem_ld_32x32b_x8(a, t0);
             tmem_ld_32x32b_x8(a + TN, t1);
-            tmem_ld_32x32b_x8(a + 2 * TN, t2);
-            tmem_ld_32x32b_x8(a + 3 * TN, t3);
+            if constexpr (NP == 4) {
+                tmem_ld_32x32b_x8(a + 2 * TN, t2);
+                tmem_ld_32x32b_x8(a + 3 * TN, t3);
+            }
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; i++) d[i] = (t0[i] + t1[i]) + (t2[i] + t3[i]);
+            for (int i = 0; i < 8; i++) {
+                if constexpr (NP == 4) d[i] = (t0[i] + t1[i]) + (t2[i] + t3[i]);
+                else d[i] = t0[i] + t1[i];
+            }
         };
         auto publish = [&]() {
             fence_async_smem();
@@ -356,9 +363,12 @@ int psn_wide_bwd_sweep(const psnode_problem* p, const psnode_adjoint* a, const f
         PSN_CUDA(cudaGetLastError());
         return PSNODE_OK;
     };
+    static const int np = std::getenv("PSNODE_WIDE_NPART") ? std::atoi(std::getenv("PSNODE_WIDE_NPART")) : 4;   // K-partials per GEMM (A/B)
+#define PSW_BWD(METH, NAME) (np == 2 ? launch(psn_wide_bwd_kernel<METH, 2>, NAME) : launch(psn_wide_bwd_kernel<METH, 4>, NAME))
     switch (p->method) {
-        case PSNODE_EULER: return launch(psn_wide_bwd_kernel<PSNODE_EULER>, "psn_wide_bwd_kernel<euler>");
-        case PSNODE_MIDPOINT: return launch(psn_wide_bwd_kernel<PSNODE_MIDPOINT>, "psn_wide_bwd_kernel<midpoint>");
-        default: return launch(psn_wide_bwd_kernel<PSNODE_RK4>, "psn_wide_bwd_kernel<rk4>");
+        case PSNODE_EULER: return PSW_BWD(PSNODE_EULER, "psn_wide_bwd_kernel<euler>");
+        case PSNODE_MIDPOINT: return PSW_BWD(PSNODE_MIDPOINT, "psn_wide_bwd_kernel<midpoint>");
+        default: return PSW_BWD(PSNODE_RK4, "psn_wide_bwd_kernel<rk4>");
     }
+#undef PSW_BWD
 }

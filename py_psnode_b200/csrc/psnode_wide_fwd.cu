@@ -14,6 +14,7 @@
 // reference's operation order, trajectory row (full 128-byte lines) and tape block (psnode_wide.cuh) all use that mapping.
 // Bound: tensor pipe / dependent-layer latency (AI ~ 900 FLOP/B); HBM traffic 1 KB per trajectory-step (+4 KB with the tape).
 #include <cstddef>
+#include <cstdlib>
 #include "psnode_wide.cuh"
 
 namespace {
@@ -56,7 +57,7 @@ struct __align__(128) CtaSmem {
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(GROUP_THREADS) : "memory"); }
 __device__ __forceinline__ void st_f32(unsigned char* base, int off, float v) { *reinterpret_cast<float*>(base + off) = v; }
 
-template <int METHOD, bool TAPE>
+template <int METHOD, bool TAPE, int NP>
 __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wide_fwd_kernel(const __grid_constant__ WideFwdParams q) {
     constexpr int NST = METHOD == PSNODE_EULER ? 1 : (METHOD == PSNODE_MIDPOINT ? 2 : 4);
     extern __shared__ unsigned char smem_raw[];
@@ -65,7 +66,8 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
     const int cw = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform by construction (descriptors stay in uniform registers)
     const int g = cw >> 3, wk = cw & 7, wq = wk & 3, h = wk >> 2;
     const int gt = tid & (GROUP_THREADS - 1);
-    const bool issuer = h == 0;
+    const bool issuer = h == 0 && wq < NP;      // NP K-partials, one issuing warp each
+    constexpr int KPI = 16 / NP;                 // K-steps (of 8) per issuer
     GroupSmem& gs = sm.g[g];
     const int B = q.B, T = q.T;
     const int gid = blockIdx.x * PSW_GROUPS_PER_CTA + g;
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
     // ---- one-time setup ---------------------------------------------------------------------------------------------
     if (tid == 0) {
         for (int gg = 0; gg < PSW_GROUPS_PER_CTA; gg++) {
-            mbar_init(&sm.g[gg].bar, 4);
+            mbar_init(&sm.g[gg].bar, NP);
             mbar_init(&sm.g[gg].pbar[0], 1);
             mbar_init(&sm.g[gg].pbar[1], 1);
         }
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
         const uint64_t d_act_hi = make_desc(smem_u32(gs.act_hi), LBO, SBO_ACT), d_act_lo = d_act_hi + (uint64_t)(ACT_TILE >> 4);
         const uint64_t d_w2lo = make_desc(smem_u32(sm.w2lo), LBO_W, SBO_W);
         constexpr uint64_t KSTEP_B = (uint64_t)((2 * LBO) >> 4), KSTEP_W = (uint64_t)((2 * LBO_W) >> 4);
-        const uint32_t acc_base = tmem + TM_ACC + (uint32_t)(g * 4 * TN);
+        const uint32_t acc_base = tmem + TM_ACC + (uint32_t)(g * 4 * TN);      // (column budget stays 4 x 16 per group)
         const uint32_t my_acc = acc_base + (uint32_t)(wq * TN);           // the K-partial this (issuing) warp accumulates
         uint32_t phase = 0, pphase = 0;
 
@@ -137,8 +139,8 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                         const uint32_t wa = term == 0 ? TM_F_LO : TM_F_HI;
                         const uint64_t bd = term == 1 ? d_act_lo : d_act_hi;
 #pragma unroll
-                        for (int kk = 0; kk < 4; kk++) {
-                            const int ks = 4 * wq + kk;
+                        for (int kk = 0; kk < KPI; kk++) {
+                            const int ks = KPI * wq + kk;
                             mma_tf32_ts(my_acc, tmem + wa + 8 * ks, bd + KSTEP_B * ks, idesc, accumulate);
                             accumulate = 1;
                         }
@@ -153,16 +155,16 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                 if (elect_one()) {
                     tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 4; kk++) {                       // W2_lo . a_hi : A from shared memory
-                        const int ks = 4 * wq + kk;
+                    for (int kk = 0; kk < KPI; kk++) {                       // W2_lo . a_hi : A from shared memory
+                        const int ks = KPI * wq + kk;
                         mma_tf32(my_acc, d_w2lo + KSTEP_W * ks, d_act_hi + KSTEP_B * ks, idesc, kk > 0 ? 1u : 0u);
                     }
 #pragma unroll
                     for (int term = 1; term < 3; term++) {
                         const uint64_t bd = term == 1 ? d_act_lo : d_act_hi;
 #pragma unroll
-                        for (int kk = 0; kk < 4; kk++) {
-                            const int ks = 4 * wq + kk;
+                        for (int kk = 0; kk < KPI; kk++) {
+                            const int ks = KPI * wq + kk;
                             mma_tf32_ts(my_acc, tmem + TM_W2_HI + 8 * ks, bd + KSTEP_B * ks, idesc, 1u);
                         }
                     }
@@ -179,14 +181,20 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
             const uint32_t a = acc_base + lane_base + 8 * h;
             tmem_ld_32x32b_x8(a, t0);
             tmem_ld_32x32b_x8(a + TN, t1);
-            tmem_ld_32x32b_x8(a + 2 * TN, t2);
-            tmem_ld_32x32b_x8(a + 3 * TN, t3);
+            if constexpr (NP == 4) {
+                tmem_ld_32x32b_x8(a + 2 * TN, t2);
+                tmem_ld_32x32b_x8(a + 3 * TN, t3);
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
                 const psn_u64 s01 = psn_add2(psn_pack2(t0[i], t0[i + 1]), psn_pack2(t1[i], t1[i + 1]));
-                const psn_u64 s23 = psn_add2(psn_pack2(t2[i], t2[i + 1]), psn_pack2(t3[i], t3[i + 1]));
-                psn_unpack2(psn_add2(s01, s23), d[i], d[i + 1]);
+                if constexpr (NP == 4) {
+                    const psn_u64 s23 = psn_add2(psn_pack2(t2[i], t2[i + 1]), psn_pack2(t3[i], t3[i + 1]));
+                    psn_unpack2(psn_add2(s01, s23), d[i], d[i + 1]);
+                } else {
+                    psn_unpack2(s01, d[i], d[i + 1]);
+                }
             }
         };
         auto publish = [&]() {
@@ -386,16 +394,19 @@ int psn_wide_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaSt
         PSN_CUDA(cudaGetLastError());
         return PSNODE_OK;
     };
+    static const int np = std::getenv("PSNODE_WIDE_NPART") ? std::atoi(std::getenv("PSNODE_WIDE_NPART")) : 4;   // K-partials per layer (A/B)
+#define PSW_FWD(METH, TAPE_, NAME) (np == 2 ? launch(psn_wide_fwd_kernel<METH, TAPE_, 2>, NAME) : launch(psn_wide_fwd_kernel<METH, TAPE_, 4>, NAME))
     if (q.tape) {
         switch (p->method) {
-            case PSNODE_EULER: return launch(psn_wide_fwd_kernel<PSNODE_EULER, true>, "psn_wide_fwd_kernel<euler,tape>");
-            case PSNODE_MIDPOINT: return launch(psn_wide_fwd_kernel<PSNODE_MIDPOINT, true>, "psn_wide_fwd_kernel<midpoint,tape>");
-            default: return launch(psn_wide_fwd_kernel<PSNODE_RK4, true>, "psn_wide_fwd_kernel<rk4,tape>");
+            case PSNODE_EULER: return PSW_FWD(PSNODE_EULER, true, "psn_wide_fwd_kernel<euler,tape>");
+            case PSNODE_MIDPOINT: return PSW_FWD(PSNODE_MIDPOINT, true, "psn_wide_fwd_kernel<midpoint,tape>");
+            default: return PSW_FWD(PSNODE_RK4, true, "psn_wide_fwd_kernel<rk4,tape>");
         }
     }
     switch (p->method) {
-        case PSNODE_EULER: return launch(psn_wide_fwd_kernel<PSNODE_EULER, false>, "psn_wide_fwd_kernel<euler>");
-        case PSNODE_MIDPOINT: return launch(psn_wide_fwd_kernel<PSNODE_MIDPOINT, false>, "psn_wide_fwd_kernel<midpoint>");
-        default: return launch(psn_wide_fwd_kernel<PSNODE_RK4, false>, "psn_wide_fwd_kernel<rk4>");
+        case PSNODE_EULER: return PSW_FWD(PSNODE_EULER, false, "psn_wide_fwd_kernel<euler>");
+        case PSNODE_MIDPOINT: return PSW_FWD(PSNODE_MIDPOINT, false, "psn_wide_fwd_kernel<midpoint>");
+        default: return PSW_FWD(PSNODE_RK4, false, "psn_wide_fwd_kernel<rk4>");
     }
+#undef PSW_FWD
 }

@@ -18,13 +18,15 @@ namespace {
 using namespace psn_tc;
 
 constexpr int H = PSW_H;
-constexpr int NSLOT = 6;
+constexpr int NSLOT = 3;                           // ring slots; a slot holds a PAIR of records
 constexpr int BLK_BYTES = PSW_BLOCK * 4;           // 8 KB
 constexpr int GRAD_THREADS = 512;
-constexpr int FL = 2;                              // records per accumulator before it is drained
 
+// One slot = two records: per-iteration fixed costs (mbarrier waits, proxy fence, CTA barrier, MMA issue, refill) are ~1400 cycles
+// whatever the amount of work, which held the one-record-per-iteration version at 3.3 TB/s (50 % of the copy bandwidth) with the
+// tensor pipe 29 % busy; a pair halves that overhead per byte.  The two records of a pair are one accumulation chain (12 MMAs).
 struct __align__(128) Slot {
-    float a_hi[PSW_BLOCK], a_lo[PSW_BLOCK], b_hi[PSW_BLOCK], b_lo[PSW_BLOCK];
+    float a_hi[2][PSW_BLOCK], a_lo[2][PSW_BLOCK], b_hi[2][PSW_BLOCK], b_lo[2][PSW_BLOCK];
 };
 struct __align__(128) GradSmem {
     Slot slot[NSLOT];
@@ -54,7 +56,8 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) psn_wide_grad_kernel(const __
     const int ncta = q.cta0[role + 1] - q.cta0[role], me = blockIdx.x - q.cta0[role];
     const int64_t per = (q.nrec[role] + ncta - 1) / ncta;
     const int64_t r0 = per * me, r1 = r0 + per < q.nrec[role] ? r0 + per : q.nrec[role];
-    const int n = r1 > r0 ? (int)(r1 - r0) : 0;
+    const int n = r1 > r0 ? (int)(r1 - r0) : 0;            // records of this CTA
+    const int np = (n + 1) / 2;                            // pairs (the last one may hold a single record)
     const float* abase = q.a_base[role];
     const float* bbase = q.b_base[role];
     const int64_t astr = q.a_stride[role], bstr = q.b_stride[role];
@@ -70,14 +73,17 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) psn_wide_grad_kernel(const __
     const uint32_t tmem = sm.tmem_base;
     const uint32_t lane_base = (uint32_t)(32 * wq) << 16;
 
-    auto load_rec = [&](int i) {            // thread 0
+    auto load_pair = [&](int i) {            // thread 0
         const int s = i % NSLOT;
-        mbar_expect_tx(&sm.full[s], 2 * BLK_BYTES);
-        bulk_g2s(sm.slot[s].a_hi, abase + (r0 + i) * astr, BLK_BYTES, &sm.full[s]);
-        bulk_g2s(sm.slot[s].b_hi, bbase + (r0 + i) * bstr, BLK_BYTES, &sm.full[s]);
+        const int cnt = (2 * i + 1 < n) ? 2 : 1;
+        mbar_expect_tx(&sm.full[s], (uint32_t)(2 * cnt * BLK_BYTES));
+        for (int k = 0; k < cnt; k++) {
+            bulk_g2s(sm.slot[s].a_hi[k], abase + (r0 + 2 * i + k) * astr, BLK_BYTES, &sm.full[s]);
+            bulk_g2s(sm.slot[s].b_hi[k], bbase + (r0 + 2 * i + k) * bstr, BLK_BYTES, &sm.full[s]);
+        }
     };
     if (tid == 0)
-        for (int i = 0; i < NSLOT && i < n; i++) load_rec(i);
+        for (int i = 0; i < NSLOT && i < np; i++) load_pair(i);
 
     float acc[32];
 #pragma unroll
@@ -93,68 +99,68 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) psn_wide_grad_kernel(const __
         for (int i = 0; i < 16; i++) { acc[i] += v0[i]; acc[16 + i] += v1[i]; }
     };
 
-    for (int i = 0; i < n; i++) {
+    for (int i = 0; i < np; i++) {
         const int s = i % NSLOT;
         Slot& sl = sm.slot[s];
+        const int cnt = (2 * i + 1 < n) ? 2 : 1;
         if (!mbar_wait(&sm.full[s], (uint32_t)((i / NSLOT) & 1))) { atomicExch(q.err, 6); __trap(); }
-        {   // tf32 hi (in place) / lo split of both blocks: 2 x 512 float4, one per thread and block
-            float4* ah = reinterpret_cast<float4*>(sl.a_hi); float4* al = reinterpret_cast<float4*>(sl.a_lo);
-            float4* bh = reinterpret_cast<float4*>(sl.b_hi); float4* bl = reinterpret_cast<float4*>(sl.b_lo);
-            float4 lo;
-            float4 hi = split4_hi(ah[tid], lo);
-            ah[tid] = hi; al[tid] = lo;
-            hi = split4_hi(bh[tid], lo);
-            bh[tid] = hi; bl[tid] = lo;
+        {   // tf32 hi (in place) / lo split: 512 float4 per block
+            for (int k = 0; k < cnt; k++) {
+                float4* ah = reinterpret_cast<float4*>(sl.a_hi[k]); float4* al = reinterpret_cast<float4*>(sl.a_lo[k]);
+                float4* bh = reinterpret_cast<float4*>(sl.b_hi[k]); float4* bl = reinterpret_cast<float4*>(sl.b_lo[k]);
+                float4 lo;
+                float4 hi = split4_hi(ah[tid], lo);
+                ah[tid] = hi; al[tid] = lo;
+                hi = split4_hi(bh[tid], lo);
+                bh[tid] = hi; bl[tid] = lo;
+            }
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        const int pair = i / FL;
         if (cw == 0) {
             if (elect_one()) {
                 tc_fence_after();
-                // K-major no-swizzle tiles, rows = 128, K = 16: LBO = 128 B, SBO = 512 B; a K = 8 step advances 256 B
-                const uint64_t da_hi = make_desc(smem_u32(sl.a_hi), 128, 512), da_lo = make_desc(smem_u32(sl.a_lo), 128, 512);
-                const uint64_t db_hi = make_desc(smem_u32(sl.b_hi), 128, 512), db_lo = make_desc(smem_u32(sl.b_lo), 128, 512);
-                const uint32_t d = tmem + (uint32_t)((pair & 1) * H);
-                uint32_t accumulate = (i % FL) != 0 ? 1u : 0u;
+                const uint32_t d = tmem + (uint32_t)((i & 1) * H);
+                uint32_t accumulate = 0;
+                for (int k = 0; k < cnt; k++) {
+                    // K-major no-swizzle tiles, rows = 128, K = 16: LBO = 128 B, SBO = 512 B; a K = 8 step advances 256 B
+                    const uint64_t da_hi = make_desc(smem_u32(sl.a_hi[k]), 128, 512), da_lo = make_desc(smem_u32(sl.a_lo[k]), 128, 512);
+                    const uint64_t db_hi = make_desc(smem_u32(sl.b_hi[k]), 128, 512), db_lo = make_desc(smem_u32(sl.b_lo[k]), 128, 512);
 #pragma unroll
-                for (int term = 0; term < 3; term++) {
-                    const uint64_t ad = term == 0 ? da_lo : da_hi;
-                    const uint64_t bd = term == 1 ? db_lo : db_hi;
+                    for (int term = 0; term < 3; term++) {
+                        const uint64_t ad = term == 0 ? da_lo : da_hi;
+                        const uint64_t bd = term == 1 ? db_lo : db_hi;
 #pragma unroll
-                    for (int ks = 0; ks < 2; ks++) {
-                        mma_tf32(d, ad + (uint64_t)(16 * ks), bd + (uint64_t)(16 * ks), idesc, accumulate);
-                        accumulate = 1;
+                        for (int ks = 0; ks < 2; ks++) {
+                            mma_tf32(d, ad + (uint64_t)(16 * ks), bd + (uint64_t)(16 * ks), idesc, accumulate);
+                            accumulate = 1;
+                        }
                     }
                 }
                 mma_commit(&sm.done[s]);
             }
             __syncwarp();
         }
-        // refill the slot of record i - 1 (its MMAs were issued one iteration ago) with record i + NSLOT - 1
-        if (tid == 0 && i >= 1 && i + NSLOT - 1 < n) {
+        // refill the slot of pair i - 1 (its MMAs were issued one iteration ago) with pair i - 1 + NSLOT
+        if (tid == 0 && i >= 1 && i - 1 + NSLOT < np) {
             const int sp = (i - 1) % NSLOT;
             if (!mbar_wait(&sm.done[sp], (uint32_t)(((i - 1) / NSLOT) & 1))) { atomicExch(q.err, 7); __trap(); }
             fence_async_smem();
-            load_rec(i + NSLOT - 1);
+            load_pair(i - 1 + NSLOT);
         }
-        // drain the PREVIOUS pair's accumulator while this pair's MMAs run
-        if ((i % FL) == FL - 1 && pair >= 1) {
-            const int il = pair * FL - 1;                  // last record of the previous pair
-            if (!mbar_wait(&sm.done[il % NSLOT], (uint32_t)((il / NSLOT) & 1))) { atomicExch(q.err, 8); __trap(); }
+        // drain the PREVIOUS pair's accumulator (round-to-nearest adds in registers) while this pair's MMAs run
+        if (i >= 1) {
+            if (!mbar_wait(&sm.done[(i - 1) % NSLOT], (uint32_t)(((i - 1) / NSLOT) & 1))) { atomicExch(q.err, 8); __trap(); }
             tc_fence_after();
-            drain((pair - 1) & 1);
+            drain((i - 1) & 1);
             tc_fence_before();
         }
     }
-    if (n > 0) {      // tail: the last one or two pairs
-        const int last_pair = (n - 1) / FL;
-        const bool prev_pending = ((n - 1) % FL) != FL - 1 && last_pair >= 1;      // loop drained pair p-1 only at the END of pair p
-        if (!mbar_wait(&sm.done[(n - 1) % NSLOT], (uint32_t)(((n - 1) / NSLOT) & 1))) { atomicExch(q.err, 9); __trap(); }
+    if (np > 0) {
+        if (!mbar_wait(&sm.done[(np - 1) % NSLOT], (uint32_t)(((np - 1) / NSLOT) & 1))) { atomicExch(q.err, 9); __trap(); }
         tc_fence_after();
-        if (prev_pending) drain((last_pair - 1) & 1);
-        drain(last_pair & 1);
+        drain((np - 1) & 1);
         tc_fence_before();
     }
     {
