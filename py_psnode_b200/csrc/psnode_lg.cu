@@ -32,7 +32,7 @@ using namespace psn_tc;
 constexpr int TM = 128, TN = 128;
 constexpr int NST = 3;
 constexpr int SLAB = TN * 128;          // 16 KB: 128 rows x 32 fp32
-constexpr int LG_THREADS = 256;
+constexpr int LG_THREADS = 320;         // 8 split / epilogue warps + TMA producer warp + MMA issuer warp
 constexpr int NPART = 2;                // K-partials (truncating fp32 accumulate: short chains)
 
 enum { LG_PLAIN = 0, LG_HIDDEN = 1, LG_RK = 2 };
@@ -41,7 +41,7 @@ enum { EPI_PLAIN = 0, EPI_HIDDEN, EPI_EULER, EPI_MID0, EPI_MID1, EPI_RK0, EPI_RK
 
 struct __align__(1024) LgSmem {
     unsigned char a_hi[NST][SLAB], a_lo[NST][SLAB], b_hi[NST][SLAB], b_lo[NST][SLAB];
-    uint64_t full[NST], done[NST];
+    uint64_t full[NST], split[NST], done[NST];
     uint32_t tmem_base;
 };
 
@@ -71,6 +71,8 @@ template <int EPI>
 __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                                                                    const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
                                                                    const __grid_constant__ LgParams q) {
+    // programmatic dependent launch: everything above the first read of the previous launch's output may overlap its tail
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int evk = -1;
     if (q.ev) evk = __ldg(q.ev + q.ev_j);
     if (q.skip_unless_event && evk < 0) return;
@@ -87,24 +89,16 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
     int dbg_n = 0;
     auto stamp = [&]() { if (dbg && dbg_n < 32) g_lg_dbg[dbg_n++] = clock64(); };
     stamp();
-    // K chunks are visited in an order rotated by the CTA index: at any moment the 64 CTAs that share a weight block read
-    // different chunks of it instead of all hitting the same L2 lines (fixed, deterministic order per trajectory tile)
+    // Warp roles: warps 0..7 split the B slabs and run the epilogue, warp 8 is the TMA producer, warp 9 the MMA issuer.  Each role
+    // only ever waits on the mbarrier of the role before it (full -> split -> done -> refill), so the three run concurrently
+    // up to the depth of the ring.  (Version 1 had thread 0 do all three in sequence with a CTA barrier per chunk: 1750 cycles
+    // per chunk against 768 of tensor-pipe work.)
+    // K chunks are visited in an order rotated by the CTA index (fixed, deterministic order per trajectory tile).
     const int rot = q.rotate ? (int)(blockIdx.x % (unsigned)nchunk) : 0;
-    auto load_chunk = [&](int c) {          // thread 0; c = position in this CTA's order
-        const int s = c % NST;
-        int ck = c + rot; if (ck >= nchunk) ck -= nchunk;
-        const int src = ck / q.kchunks, kc = ck - src * q.kchunks;
-        mbar_expect_tx(&sm.full[s], 3 * SLAB);
-        tma_load_3d(sm.a_hi[s], &map_a_hi, ck * 32, mblk * TM, 0, &sm.full[s]);
-        tma_load_3d(sm.a_lo[s], &map_a_lo, ck * 32, mblk * TM, 0, &sm.full[s]);
-        tma_load_3d(sm.b_hi[s], src == 0 ? &map_b0 : &map_b1, kc * 32, b0, r, &sm.full[s]);
-    };
-    if (tid == 0) {                         // the first operand chunks are in flight before TMEM is even allocated
-        for (int s = 0; s < NST; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.done[s], 1); }
+    if (tid == 0) {
+        for (int s = 0; s < NST; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.split[s], 8); mbar_init(&sm.done[s], 1); }
         fence_mbar_init();
-        for (int c = 0; c < NST && c < nchunk; c++) load_chunk(c);
     }
-    __syncwarp();
     if (cw == 0) tmem_alloc(&sm.tmem_base, NPART * TN);
     tc_fence_before();
     __syncthreads();
@@ -113,27 +107,27 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
     const uint32_t lane_base = (uint32_t)(32 * wq) << 16;
     stamp();
 
-    const uint32_t idesc = make_idesc_tf32(TM, TN);
-    for (int c = 0; c < nchunk; c++) {
-        const int s = c % NST;
-        if (!mbar_wait(&sm.full[s], (uint32_t)((c / NST) & 1))) { atomicExch(q.err, 11); __trap(); }
-        stamp();
-        {   // B: raw fp32 -> tf32 hi (in place) + lo (elementwise: the swizzled layout is preserved)
-            float4* h4 = reinterpret_cast<float4*>(sm.b_hi[s]);
-            float4* l4 = reinterpret_cast<float4*>(sm.b_lo[s]);
-#pragma unroll
-            for (int e = 0; e < SLAB / 16 / LG_THREADS; e++) {
-                const int idx = tid + e * LG_THREADS;
-                float4 lo;
-                const float4 hi = split4_hi(h4[idx], lo);
-                h4[idx] = hi;
-                l4[idx] = lo;
+    if (cw == 8) {
+        // ---- TMA producer ----
+        if (elect_one()) {
+            for (int c = 0; c < nchunk; c++) {
+                const int s = c % NST;
+                if (c >= NST && !mbar_wait(&sm.done[s], (uint32_t)(((c - NST) / NST) & 1))) { atomicExch(q.err, 12); __trap(); }
+                int ck = c + rot; if (ck >= nchunk) ck -= nchunk;
+                const int src = ck / q.kchunks, kc = ck - src * q.kchunks;
+                mbar_expect_tx(&sm.full[s], 3 * SLAB);
+                tma_load_3d(sm.a_hi[s], &map_a_hi, ck * 32, mblk * TM, 0, &sm.full[s]);
+                tma_load_3d(sm.a_lo[s], &map_a_lo, ck * 32, mblk * TM, 0, &sm.full[s]);
+                tma_load_3d(sm.b_hi[s], src == 0 ? &map_b0 : &map_b1, kc * 32, b0, r, &sm.full[s]);
             }
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (cw == 0) {
+        __syncwarp();
+    } else if (cw == 9) {
+        // ---- MMA issuer ----
+        const uint32_t idesc = make_idesc_tf32(TM, TN);
+        for (int c = 0; c < nchunk; c++) {
+            const int s = c % NST;
+            if (!mbar_wait(&sm.split[s], (uint32_t)((c / NST) & 1))) { atomicExch(q.err, 14); __trap(); }
             if (elect_one()) {
                 tc_fence_after();
                 const uint64_t da_hi = make_desc_sw128(smem_u32(sm.a_hi[s])), da_lo = make_desc_sw128(smem_u32(sm.a_lo[s]));
@@ -155,16 +149,36 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
             }
             __syncwarp();
         }
-        if (tid == 0 && c >= 1 && c - 1 + NST < nchunk) {       // refill the slot of chunk c - 1 once its MMAs have completed
-            const int sp = (c - 1) % NST;
-            if (!mbar_wait(&sm.done[sp], (uint32_t)(((c - 1) / NST) & 1))) { atomicExch(q.err, 12); __trap(); }
+    } else {
+        // ---- splitters: raw fp32 B slab -> tf32 hi (in place) + lo (elementwise: the swizzled layout is preserved) ----
+        for (int c = 0; c < nchunk; c++) {
+            const int s = c % NST;
+            if (!mbar_wait(&sm.full[s], (uint32_t)((c / NST) & 1))) { atomicExch(q.err, 11); __trap(); }
+            stamp();
+            float4* h4 = reinterpret_cast<float4*>(sm.b_hi[s]);
+            float4* l4 = reinterpret_cast<float4*>(sm.b_lo[s]);
+#pragma unroll
+            for (int e = 0; e < SLAB / 16 / 256; e++) {
+                const int idx = tid + e * 256;
+                float4 lo;
+                const float4 hi = split4_hi(h4[idx], lo);
+                h4[idx] = hi;
+                l4[idx] = lo;
+            }
             fence_async_smem();
-            load_chunk(c - 1 + NST);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.split[s]);
         }
+    }
+    if (cw >= 8) {          // producer / issuer are done; they only join the final barrier
+        tc_fence_before();
+        __syncthreads();
+        return;
     }
     stamp();
     if (!mbar_wait(&sm.done[(nchunk - 1) % NST], (uint32_t)(((nchunk - 1) / NST) & 1))) { atomicExch(q.err, 13); __trap(); }
     tc_fence_after();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the next layer's grid may be set up while this epilogue runs
     stamp();
 
     // ---- epilogue: lane = output feature, columns = trajectories ---------------------------------------------------------
@@ -181,20 +195,35 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
         const float bias = q.bias ? __ldg(q.bias + m) : 0.0f;
         const float c13 = (float)(1.0 / 3.0);
         struct Buf { float p0[16], p1[16], p2[16], p3[16], dt[16]; };
+        // per-thread base pointers (element (column c of this thread's 64, feature m) at base + c * ld): no 64-bit index
+        // arithmetic and no per-element bounds test on full tiles
+        const int ncol0 = b0 + 64 * hh;
+        const bool full_tile = b0 + TN <= q.N;
+        const float* pa1 = add1 ? add1 + add1_row + (int64_t)ncol0 * q.add1_ld + m : nullptr;
+        const float* pa2 = q.add2 ? q.add2 + (int64_t)ncol0 * q.add2_ld + m : nullptr;
+        float* pout = q.out + (int64_t)r * q.out_sr + (int64_t)ncol0 * q.out_ld + m;
+        float* pout2 = q.out2 ? q.out2 + (int64_t)ncol0 * q.out2_ld + m : nullptr;
+        float* px0 = rk ? q.x0 + (int64_t)ncol0 * q.st_ld + m : nullptr;
+        float* pk1 = rk ? q.k1 + (int64_t)ncol0 * q.st_ld + m : nullptr;
+        float* pk2 = rk ? q.k2 + (int64_t)ncol0 * q.st_ld + m : nullptr;
+        float* pk3 = rk ? q.k3 + (int64_t)ncol0 * q.st_ld + m : nullptr;
+        const float* ptc = rk ? q.t_cur + (int64_t)ncol0 * q.t_sb : nullptr;
+        const float* ptp = rk ? q.t_prev + (int64_t)ncol0 * q.t_sb : nullptr;
+        const int a1ld = (int)q.add1_ld, a2ld = (int)q.add2_ld, old = (int)q.out_ld, o2ld = (int)q.out2_ld, sld = (int)q.st_ld, tsb = (int)q.t_sb;
+        const int nlive = full_tile ? 64 : max(0, min(64, q.N - ncol0));      // live columns of this thread
         auto fetch = [&](int bt, Buf& e) {
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                const int nn = min(b0 + 64 * hh + 16 * bt + i, q.N - 1);
+                const int c = full_tile ? 16 * bt + i : min(16 * bt + i, max(nlive - 1, 0));
                 if constexpr (rk) {
-                    const int64_t so = (int64_t)nn * q.st_ld + m;
-                    e.p0[i] = q.x0[so];
-                    if constexpr (EPI >= EPI_RK1) e.p1[i] = q.k1[so];
-                    if constexpr (EPI >= EPI_RK2) e.p2[i] = q.k2[so];
-                    if constexpr (EPI >= EPI_RK3) e.p3[i] = q.k3[so];
-                    e.dt[i] = __fsub_rn(__ldg(q.t_cur + (int64_t)nn * q.t_sb), __ldg(q.t_prev + (int64_t)nn * q.t_sb));
+                    e.p0[i] = px0[c * sld];
+                    if constexpr (EPI >= EPI_RK1) e.p1[i] = pk1[c * sld];
+                    if constexpr (EPI >= EPI_RK2) e.p2[i] = pk2[c * sld];
+                    if constexpr (EPI >= EPI_RK3) e.p3[i] = pk3[c * sld];
+                    e.dt[i] = __fsub_rn(__ldg(ptc + c * tsb), __ldg(ptp + c * tsb));
                 } else {
-                    e.p0[i] = add1 ? __ldg(add1 + add1_row + (int64_t)nn * q.add1_ld + m) : 0.0f;
-                    e.p1[i] = q.add2 ? __ldg(q.add2 + (int64_t)nn * q.add2_ld + m) : 0.0f;
+                    e.p0[i] = pa1 ? __ldg(pa1 + c * a1ld) : 0.0f;
+                    e.p1[i] = pa2 ? __ldg(pa2 + c * a2ld) : 0.0f;
                 }
             }
         };
@@ -206,33 +235,32 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-                const int n = b0 + n0 + i;
-                if (n >= q.N) continue;
+                const int c = 16 * bt + i;
+                if (!full_tile && c >= nlive) continue;
                 float v = (t0[i] + t1[i]) + bias;
                 if constexpr (!rk) {
                     v = (v + e.p0[i]) + e.p1[i];
                     if constexpr (EPI == EPI_HIDDEN) v = psn_elu(v);
-                    q.out[(int64_t)r * q.out_sr + (int64_t)n * q.out_ld + m] = v;
-                    if (q.out2) q.out2[(int64_t)n * q.out2_ld + m] = v;
+                    pout[c * old] = v;
+                    if (pout2) pout2[c * o2ld] = v;
                 } else {
                     // reference operation order (neural_dae/my_fixed_grid.py:15-59)
-                    const int64_t so = (int64_t)n * q.st_ld + m;
                     const float dt = e.dt[i], x0 = e.p0[i], kk = v;
                     float xn;
                     constexpr bool last = EPI == EPI_EULER || EPI == EPI_MID1 || EPI == EPI_RK3;
                     if constexpr (EPI == EPI_EULER || EPI == EPI_MID1) xn = __fadd_rn(x0, __fmul_rn(dt, kk));
                     else if constexpr (EPI == EPI_MID0) xn = __fadd_rn(x0, __fmul_rn(kk, __fmul_rn(0.5f, dt)));
-                    else if constexpr (EPI == EPI_RK0) { q.k1[so] = kk; xn = __fadd_rn(x0, __fmul_rn(__fmul_rn(dt, kk), c13)); }
-                    else if constexpr (EPI == EPI_RK1) { q.k2[so] = kk; xn = __fadd_rn(x0, __fmul_rn(dt, __fsub_rn(kk, __fmul_rn(e.p1[i], c13)))); }
-                    else if constexpr (EPI == EPI_RK2) { q.k3[so] = kk; xn = __fadd_rn(x0, __fmul_rn(dt, __fadd_rn(__fsub_rn(e.p1[i], e.p2[i]), kk))); }
+                    else if constexpr (EPI == EPI_RK0) { pk1[c * sld] = kk; xn = __fadd_rn(x0, __fmul_rn(__fmul_rn(dt, kk), c13)); }
+                    else if constexpr (EPI == EPI_RK1) { pk2[c * sld] = kk; xn = __fadd_rn(x0, __fmul_rn(dt, __fsub_rn(kk, __fmul_rn(e.p1[i], c13)))); }
+                    else if constexpr (EPI == EPI_RK2) { pk3[c * sld] = kk; xn = __fadd_rn(x0, __fmul_rn(dt, __fadd_rn(__fsub_rn(e.p1[i], e.p2[i]), kk))); }
                     else {
                         const float ksum = __fadd_rn(__fadd_rn(e.p1[i], __fmul_rn(3.0f, __fadd_rn(e.p2[i], e.p3[i]))), kk);
                         xn = __fadd_rn(x0, __fmul_rn(__fmul_rn(ksum, dt), 0.125f));
                     }
-                    q.out[(int64_t)n * q.out_ld + m] = xn;                       // next stage input / x_j
+                    pout[c * old] = xn;                                          // next stage input / x_j
                     if constexpr (last) {
-                        q.x0[so] = xn;
-                        if (q.out2) q.out2[(int64_t)n * q.out2_ld + m] = xn;     // trajectory row j
+                        px0[c * sld] = xn;
+                        if (pout2) pout2[c * o2ld] = xn;                         // trajectory row j
                     }
                 }
             }
@@ -462,6 +490,7 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
     };
     const int nbt = (B + TN - 1) / TN;
     static const int dbg_cta = std::getenv("PSNODE_LG_DBG") ? std::atoi(std::getenv("PSNODE_LG_DBG")) : 0;
+    static const bool use_pdl = std::getenv("PSNODE_LG_PDL") ? std::atoi(std::getenv("PSNODE_LG_PDL")) != 0 : true;
     static const int rotate = std::getenv("PSNODE_LG_ROTATE") ? std::atoi(std::getenv("PSNODE_LG_ROTATE")) : 1;
     auto base = [&]() {
         LgParams q;
@@ -474,7 +503,17 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
     };
     auto launch = [&](int which, const CUtensorMap& b0, const CUtensorMap& b1, const LgParams& q, const char* name) -> int {
         dim3 grid((unsigned)(q.R * q.nbt), (unsigned)(H / TM));
-        kerns[epi_of(q)]<<<grid, LG_THREADS, smem, stream>>>(mw_hi[which], mw_lo[which], b0, b1, q);
+        if (use_pdl) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid; cfg.blockDim = dim3(LG_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, kerns[epi_of(q)], mw_hi[which], mw_lo[which], b0, b1, q);
+        } else {
+            kerns[epi_of(q)]<<<grid, LG_THREADS, smem, stream>>>(mw_hi[which], mw_lo[which], b0, b1, q);
+        }
         psn_count_launch(name);
         return PSNODE_OK;
     };
