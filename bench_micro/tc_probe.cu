@@ -130,7 +130,24 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ W,
     long long t0 = clock64();
     for (int it = 0; it < iters && ok; it++) {
         const long long s0 = clock64();
-        if (nacc == -5) {       // as -4, but the weights (A operand) live in TMEM: only B is fetched from shared memory
+        if (nacc == -6) {       // ONE issuing warp, weights in TMEM, all 24 MMAs fully unrolled into ONE accumulator (round 2:
+                                // re-measures the single-issuer cost after the elect_one + uniform-descriptor fixes)
+            if (warp == 0) {
+                if (elect_one()) {
+                    tc_fence_after();
+#pragma unroll
+                    for (int term = 0; term < 3; term++) {
+                        const uint32_t ta = tmem + 128 + (term == 0 ? 64 : 0);
+                        const uint64_t db = term == 1 ? dalo : dahi;
+#pragma unroll
+                        for (int ks = 0; ks < K / 8; ks++)
+                            mma_tf32_ts(tmem, ta + 8 * ks, db + (uint64_t)((ks * 2 * LBO_B) >> 4), idesc, (term | ks) ? 1 : 0);
+                    }
+                    mma_commit(&bar);
+                }
+                __syncwarp();
+            }
+        } else if (nacc == -5) {       // as -4, but the weights (A operand) live in TMEM: only B is fetched from shared memory
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
@@ -172,11 +189,11 @@ __global__ void __launch_bounds__(128) probe_kernel(const float* __restrict__ W,
             }
         }
         const long long s1 = clock64();
-        ok = mbar_wait(nacc <= -4 ? &bar4 : &bar, phase); phase ^= 1;
+        ok = mbar_wait((nacc == -4 || nacc == -5) ? &bar4 : &bar, phase); phase ^= 1;
         tc_fence_after();
         const long long s2 = clock64();
         load_d();
-        if (nacc <= -4) {       // sum the 4 partial accumulators
+        if (nacc == -4 || nacc == -5) {       // sum the 4 partial accumulators
             float vv[N / 2 < 4 ? 4 : N / 2];
             for (int i = 0; i < (N / 2 < 4 ? 4 : N / 2); i++) vv[i] = v[i];
             for (int a = 1; a < 4; a++) {
@@ -262,5 +279,8 @@ int main() {
     run<8>(2000, 3, -5);
     run<16>(2000, 3, -5);
     run<32>(2000, 3, -5);
+    run<8>(2000, 3, -6);
+    run<16>(2000, 3, -6);
+    run<32>(2000, 3, -6);
     return 0;
 }
