@@ -101,7 +101,9 @@ __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %
 __device__ __forceinline__ void st_f32(unsigned char* base, int off, float v) { *reinterpret_cast<float*>(base + off) = v; }
 __device__ __forceinline__ void st_f32x2(unsigned char* base, int off, float a, float b) { *reinterpret_cast<float2*>(base + off) = make_float2(a, b); }
 
-template <int METHOD>
+// FUSED: the upstream gradient is the masked-MSE gradient formed from the stored trajectory (psnode_adjoint.fuse_x); a separate
+// instantiation so that the plain-gx kernel keeps its register allocation (tools/sass_r2ur_check.py)
+template <int METHOD, bool FUSED>
 __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const __grid_constant__ TcBwdParams q) {
     constexpr int NST = METHOD == PSNODE_EULER ? 1 : (METHOD == PSNODE_MIDPOINT ? 2 : 4);
     extern __shared__ unsigned char smem_raw[];
@@ -412,12 +414,10 @@ __global__ void __launch_bounds__(2 * GROUP_THREADS, 1) psn_tc_bwd_kernel(const 
         float lam, D1[4], dB2[4], dB3[4], dB4 = 0.0f;
 #pragma unroll
         for (int i = 0; i < 4; i++) { D1[i] = 0.f; dB2[i] = 0.f; dB3[i] = 0.f; }
-        const bool fused = q.fx.term.target.p != nullptr;
-        const float fscale = fused ? psn_fuse_scale(q.fx) : 0.0f;
-        auto up_x = [&](int j) -> float {        // dL/dx_sol[j] of this thread's state element
+        auto up_x = [&](int j) -> float {        // dL/dx_sol[j] of this thread's state element (operands re-read from the parameters)
             if (!valid) return 0.0f;
-            if (fused) return psn_fuse_grad(q.fx, fscale, j, bown, srow);
-            return q.gx.p ? ldser(q.gx, j, bown, srow) : 0.0f;
+            if constexpr (FUSED) return psn_fuse_grad(q.fx, psn_fuse_scale(q.fx), j, bown, srow);
+            else return q.gx.p ? ldser(q.gx, j, bown, srow) : 0.0f;
         };
         lam = up_x(T - 1);
 
@@ -655,9 +655,12 @@ int psn_tc_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
     };
     int st;
     switch (p->method) {
-        case PSNODE_EULER: st = launch(psn_tc_bwd_kernel<PSNODE_EULER>, "psn_tc_bwd_kernel<euler>"); break;
-        case PSNODE_MIDPOINT: st = launch(psn_tc_bwd_kernel<PSNODE_MIDPOINT>, "psn_tc_bwd_kernel<midpoint>"); break;
-        default: st = launch(psn_tc_bwd_kernel<PSNODE_RK4>, "psn_tc_bwd_kernel<rk4>"); break;
+        case PSNODE_EULER: st = a->fuse_x.target.p ? launch(psn_tc_bwd_kernel<PSNODE_EULER, true>, "psn_tc_bwd_kernel<euler,fused-loss>")
+                                                   : launch(psn_tc_bwd_kernel<PSNODE_EULER, false>, "psn_tc_bwd_kernel<euler>"); break;
+        case PSNODE_MIDPOINT: st = a->fuse_x.target.p ? launch(psn_tc_bwd_kernel<PSNODE_MIDPOINT, true>, "psn_tc_bwd_kernel<midpoint,fused-loss>")
+                                                      : launch(psn_tc_bwd_kernel<PSNODE_MIDPOINT, false>, "psn_tc_bwd_kernel<midpoint>"); break;
+        default: st = a->fuse_x.target.p ? launch(psn_tc_bwd_kernel<PSNODE_RK4, true>, "psn_tc_bwd_kernel<rk4,fused-loss>")
+                                         : launch(psn_tc_bwd_kernel<PSNODE_RK4, false>, "psn_tc_bwd_kernel<rk4>"); break;
     }
     if (st != PSNODE_OK) return st;
     psn_tc_grad_reduce_kernel<<<32, 256, 0, stream>>>(q.slab, ngroups, (int)n_theta, pad4((int)n_theta) + G_AREA, a->d_theta);

@@ -93,7 +93,9 @@ __device__ __forceinline__ void st_f32x2(unsigned char* base, int off, float a, 
 using DE_NET = std::integral_constant<bool, false>;
 using AE_NET = std::integral_constant<bool, true>;
 
-template <int METHOD>
+// FUSED: upstream gradients formed from the stored trajectories (psnode_adjoint.fuse_x / fuse_i); separate instantiation so the
+// plain gx / gi kernel keeps its register allocation
+template <int METHOD, bool FUSED>
 __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const __grid_constant__ DaeBwdParams q) {
     constexpr int NST = METHOD == PSNODE_EULER ? 1 : (METHOD == PSNODE_MIDPOINT ? 2 : 4);
     extern __shared__ unsigned char smem_raw[];
@@ -522,16 +524,16 @@ __global__ void __launch_bounds__(GROUP_THREADS, 1) psn_tc_bwd_dae_kernel(const 
 
         // ---- reverse sweep ---------------------------------------------------------------------------------
         auto own_x = [&](int j) { return own_x_ok ? __ldg(q.x_sol + (int64_t)j * q.xs_st + (int64_t)bbown * q.xs_sb + srow) : 0.0f; };
-        const bool fused_x = q.fx.term.target.p != nullptr, fused_i = q.fi.term.target.p != nullptr;
-        const float fsx = fused_x ? psn_fuse_scale(q.fx) : 0.0f, fsi = fused_i ? psn_fuse_scale(q.fi) : 0.0f;
+        // fused masked-MSE upstream gradients: nothing is kept in registers between calls (every operand is re-read from the
+        // kernel parameters), so the MMA descriptors stay in uniform registers (tools/sass_r2ur_check.py)
         auto own_gx = [&](int j) -> float {
             if (!(valid && own_x_ok)) return 0.0f;
-            if (fused_x) return psn_fuse_grad(q.fx, fsx, j, bown, srow);
+            if (FUSED && q.fx.term.target.p) return psn_fuse_grad(q.fx, psn_fuse_scale(q.fx), j, bown, srow);
             return q.gx.p ? ldser(q.gx, j, bown, srow) : 0.0f;
         };
         auto own_gi = [&](int j) -> float {
             if (!(valid && own_i)) return 0.0f;
-            if (fused_i) return psn_fuse_grad(q.fi, fsi, j, bown, srow);
+            if (FUSED && q.fi.term.target.p) return psn_fuse_grad(q.fi, psn_fuse_scale(q.fi), j, bown, srow);
             return q.gi.p ? ldser(q.gi, j, bown, srow) : 0.0f;
         };
         float lam = own_gx(T - 1), mu = own_gi(T - 1);
@@ -778,10 +780,14 @@ int psn_tc_dae_backward(const psnode_problem* p, const psnode_adjoint* a, void* 
         return PSNODE_OK;
     };
     int st;
+    const bool fused = a->fuse_x.target.p || a->fuse_i.target.p;
     switch (p->method) {
-        case PSNODE_EULER: st = launch(psn_tc_bwd_dae_kernel<PSNODE_EULER>, "psn_tc_bwd_dae_kernel<euler>"); break;
-        case PSNODE_MIDPOINT: st = launch(psn_tc_bwd_dae_kernel<PSNODE_MIDPOINT>, "psn_tc_bwd_dae_kernel<midpoint>"); break;
-        default: st = launch(psn_tc_bwd_dae_kernel<PSNODE_RK4>, "psn_tc_bwd_dae_kernel<rk4>"); break;
+        case PSNODE_EULER: st = fused ? launch(psn_tc_bwd_dae_kernel<PSNODE_EULER, true>, "psn_tc_bwd_dae_kernel<euler,fused-loss>")
+                                      : launch(psn_tc_bwd_dae_kernel<PSNODE_EULER, false>, "psn_tc_bwd_dae_kernel<euler>"); break;
+        case PSNODE_MIDPOINT: st = fused ? launch(psn_tc_bwd_dae_kernel<PSNODE_MIDPOINT, true>, "psn_tc_bwd_dae_kernel<midpoint,fused-loss>")
+                                         : launch(psn_tc_bwd_dae_kernel<PSNODE_MIDPOINT, false>, "psn_tc_bwd_dae_kernel<midpoint>"); break;
+        default: st = fused ? launch(psn_tc_bwd_dae_kernel<PSNODE_RK4, true>, "psn_tc_bwd_dae_kernel<rk4,fused-loss>")
+                            : launch(psn_tc_bwd_dae_kernel<PSNODE_RK4, false>, "psn_tc_bwd_dae_kernel<rk4>"); break;
     }
     if (st != PSNODE_OK) return st;
     psn_tc_dae_grad_reduce_kernel<<<32, 256, 0, stream>>>(q.slab, ngroups, (int)n_theta, (int)n_de, slab_floats((int)n_de, (int)(n_theta - n_de)), a->d_theta);

@@ -363,8 +363,8 @@ int psn_wide_bwd_sweep(const psnode_problem* p, const psnode_adjoint* a, const f
         PSN_CUDA(cudaGetLastError());
         return PSNODE_OK;
     };
-    static const int np = std::getenv("PSNODE_WIDE_NPART") ? std::atoi(std::getenv("PSNODE_WIDE_NPART")) : 4;   // K-partials per GEMM (A/B)
-#define PSW_BWD(METH, NAME) (np == 2 ? launch(psn_wide_bwd_kernel<METH, 2>, NAME) : launch(psn_wide_bwd_kernel<METH, 4>, NAME))
+    // NP = 4 K-partials; the NP = 2 instantiation lost its A/B and is not built
+#define PSW_BWD(METH, NAME) launch(psn_wide_bwd_kernel<METH, 4>, NAME)
     switch (p->method) {
         case PSNODE_EULER: return PSW_BWD(PSNODE_EULER, "psn_wide_bwd_kernel<euler>");
         case PSNODE_MIDPOINT: return PSW_BWD(PSNODE_MIDPOINT, "psn_wide_bwd_kernel<midpoint>");

@@ -394,8 +394,8 @@ int psn_wide_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaSt
         PSN_CUDA(cudaGetLastError());
         return PSNODE_OK;
     };
-    static const int np = std::getenv("PSNODE_WIDE_NPART") ? std::atoi(std::getenv("PSNODE_WIDE_NPART")) : 4;   // K-partials per layer (A/B)
-#define PSW_FWD(METH, TAPE_, NAME) (np == 2 ? launch(psn_wide_fwd_kernel<METH, TAPE_, 2>, NAME) : launch(psn_wide_fwd_kernel<METH, TAPE_, 4>, NAME))
+    // NP = 4 K-partials; the NP = 2 instantiation lost its A/B and is not built
+#define PSW_FWD(METH, TAPE_, NAME) launch(psn_wide_fwd_kernel<METH, TAPE_, 4>, NAME)
     if (q.tape) {
         switch (p->method) {
             case PSNODE_EULER: return PSW_FWD(PSNODE_EULER, true, "psn_wide_fwd_kernel<euler,tape>");

@@ -135,7 +135,8 @@ def test_mma_descriptors_stay_in_uniform_registers(native_lib):
     if shutil.which("cuobjdump") is None:
         pytest.skip("cuobjdump not available")
     lib_dir = os.path.join(ROOT, "py_psnode_b200", "_lib")
-    for unit, allowed in (("psnode_tc8_fwd.o", 0), ("psnode_tc_bwd.o", 2), ("psnode_tc_bwd_dae.o", 4)):
+    for unit, allowed in (("psnode_tc8_fwd.o", 0), ("psnode_tc_bwd.o", 2), ("psnode_tc_bwd_dae.o", 4), ("psnode_wide_fwd.o", 0),
+                          ("psnode_wide_bwd.o", 0), ("psnode_wide_grad.o", 0), ("psnode_wide_proj.o", 0), ("psnode_lg.o", 1)):
         obj = os.path.join(lib_dir, unit)
         if not os.path.exists(obj):
             pytest.skip(f"{unit} not built")
@@ -149,3 +150,23 @@ def test_mma_descriptors_stay_in_uniform_registers(native_lib):
                 continue
             near = sum(1 for i, o in enumerate(ops) if "R2UR" in o and any(0 < j - i <= 14 for j in mma))
             assert near <= allowed, f"{unit}: {near} R2UR in front of UTCHMMA in {f.splitlines()[0][:80]}"
+
+
+def test_blackwell_native_sass_of_the_latent_width_kernels(native_lib):
+    """What proves the round-2 kernels are Blackwell-native (B200_PROFILING.md): tcgen05.mma -> UTCHMMA, tcgen05.ld / st -> LDTM / STTM,
+    cp.async.bulk.tensor (the TMA-staged input series) -> UTMALDG, cp.async.bulk -> UBLKCP, in the objects that ship."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    lib_dir = os.path.join(ROOT, "py_psnode_b200", "_lib")
+    want = {"psnode_wide_proj.o": ("UTCHMMA", "UTMALDG", "LDTM", "STTM"), "psnode_wide_fwd.o": ("UTCHMMA", "UBLKCP", "LDTM", "STTM"),
+            "psnode_wide_bwd.o": ("UTCHMMA", "LDTM", "STTM"), "psnode_wide_grad.o": ("UTCHMMA", "UBLKCP", "LDTM"),
+            "psnode_lg.o": ("UTCHMMA", "UTMALDG", "LDTM")}
+    for unit, mnemonics in want.items():
+        obj = os.path.join(lib_dir, unit)
+        if not os.path.exists(obj):
+            pytest.skip(f"{unit} not built")
+        txt = subprocess.run(["cuobjdump", "-sass", obj], stdout=subprocess.PIPE, text=True, check=True).stdout
+        for mn in mnemonics:
+            assert mn in txt, f"{unit}: no {mn} in the SASS"
