@@ -356,6 +356,244 @@ bool lg_make_map(CUtensorMap* map, const float* p, int width, int64_t rows, int6
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- weight-gradient products of the layer path -----------------------------------------------------------------------------
+// D[m][k] = sum_{slot, n} P[slot][n][m] * Q[slot][n][k]      (dW = sum over trajectories / stages / steps of delta (x) activation)
+// Both operands are consumed in their natural (trajectory, feature) row-major layout: the reduction index n is the ROW index, i.e.
+// they are MN-major UMMA operands.  A TMA box {32 features, 32 rows} with SWIZZLE_128B is exactly the canonical MN-major atom stack
+// (8 K-rows x 128 B per atom): a K = 8 step advances the start by 1024 B (one atom), feature blocks of 32 are 4096 B apart (LBO).
+// CTA tile 128 x 128, split-K over (slot, row-chunk) ranges; 3xTF32; the accumulator alternates between two TMEM buffers and is
+// drained into registers (round-to-nearest) every 2 chunks (24 accumulations); per-split slabs are reduced in a fixed order.
+constexpr int WG_THREADS = 320;
+struct __align__(1024) WgSmem {
+    unsigned char p_hi[NST][SLAB], p_lo[NST][SLAB], q_hi[NST][SLAB], q_lo[NST][SLAB];
+    uint64_t full[NST], split[NST], done[NST], drained[2];
+    uint32_t tmem_base;
+};
+struct WgParams {
+    int nslots, N, nsplit;          // rows per slot N; split-K ways
+    int mblks, kblks;
+    float* slabs;                   // [split][tile][128][128]
+    int* err;
+    int dbg, lbo, sbo, kadv;        // debugging / probing of the MN-major descriptor fields (bytes)
+};
+// MN-major tf32 operands exist in ONE shared-memory layout only: 128-byte swizzle with 32-byte atomicity (UMMA layout type 1,
+// SWIZZLE_128B_BASE32B; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  The swizzle pattern repeats every 4 rows of 128 B, so the
+// stride between K groups (SBO) is 512 B; with the plain 128B swizzle the tensor core returns zeros.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, int lbo, int sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                    // SWIZZLE_128B_BASE32B
+    return d;
+}
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)(4096 >> 4) << 16;          // LBO: next block of 32 features (one TMA box of 32 rows x 128 B)
+    d |= (uint64_t)(1024 >> 4) << 32;          // SBO: next group of 8 reduction rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) psn_lg_wgrad_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
+                                                                    const __grid_constant__ WgParams q) {
+    extern __shared__ unsigned char smem_raw[];
+    WgSmem& sm = *reinterpret_cast<WgSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cw = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int wq = cw & 3, hh = (cw >> 2) & 1;
+    const int tile = blockIdx.x, split = blockIdx.y;
+    const int mblk = tile / q.kblks, kblk = tile - mblk * q.kblks;
+    const int cps = (q.N + 31) / 32;                       // row chunks per slot
+    const int64_t total = (int64_t)q.nslots * cps;
+    const int64_t c0 = total * split / q.nsplit, c1 = total * (split + 1) / q.nsplit;
+    const int n = (int)(c1 - c0);
+
+    if (tid == 0) {
+        for (int s = 0; s < NST; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.split[s], 8); mbar_init(&sm.done[s], 1); }
+        mbar_init(&sm.drained[0], 8); mbar_init(&sm.drained[1], 8);
+        fence_mbar_init();
+    }
+    if (cw == 0) tmem_alloc(&sm.tmem_base, 2 * TN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    const uint32_t lane_base = (uint32_t)(32 * wq) << 16;
+
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++) acc[i] = 0.0f;
+
+    if (cw == 8) {
+        if (elect_one()) {
+            for (int c = 0; c < n; c++) {
+                const int s = c % NST;
+                if (c >= NST && !mbar_wait(&sm.done[s], (uint32_t)(((c - NST) / NST) & 1))) { atomicExch(q.err, 21); __trap(); }
+                const int64_t cc = c0 + c;
+                const int slot = (int)(cc / cps), row0 = (int)(cc - (int64_t)slot * cps) * 32;
+                mbar_expect_tx(&sm.full[s], 2 * SLAB);
+#pragma unroll
+                for (int fb = 0; fb < 4; fb++) {
+                    tma_load_3d(sm.p_hi[s] + fb * 4096, &map_p, mblk * TM + fb * 32, row0, slot, &sm.full[s]);
+                    tma_load_3d(sm.q_hi[s] + fb * 4096, &map_q, kblk * TN + fb * 32, row0, slot, &sm.full[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (cw == 9) {
+        const uint32_t idesc = q.dbg == 4 ? make_idesc_tf32(TM, TN) : (q.dbg == 5 ? (make_idesc_tf32(TM, TN) | (1u << 15)) : (q.dbg == 6 ? (make_idesc_tf32(TM, TN) | (1u << 16)) : make_idesc_tf32_mn(TM, TN)));
+        for (int c = 0; c < n; c++) {
+            const int s = c % NST;
+            const int pair = c >> 1;
+            if ((c & 1) == 0 && pair >= 2 && !mbar_wait(&sm.drained[pair & 1], (uint32_t)(((pair - 2) >> 1) & 1))) { atomicExch(q.err, 22); __trap(); }
+            if (!mbar_wait(&sm.split[s], (uint32_t)((c / NST) & 1))) { atomicExch(q.err, 23); __trap(); }
+            if (elect_one()) {
+                tc_fence_after();
+                const uint64_t dp_hi = make_desc_mn(smem_u32(sm.p_hi[s]), q.lbo, q.sbo), dp_lo = make_desc_mn(smem_u32(sm.p_lo[s]), q.lbo, q.sbo);
+                const uint64_t dq_hi = make_desc_mn(smem_u32(sm.q_hi[s]), q.lbo, q.sbo), dq_lo = make_desc_mn(smem_u32(sm.q_lo[s]), q.lbo, q.sbo);
+                const uint64_t kadv = (uint64_t)(q.kadv >> 4);
+                uint32_t accumulate = (c & 1) ? 1u : 0u;
+#pragma unroll
+                for (int term = 0; term < 3; term++) {
+                    const uint64_t ad = term == 0 ? dp_lo : dp_hi;
+                    const uint64_t bd = term == 1 ? dq_lo : dq_hi;
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        mma_tf32(tmem + (uint32_t)((pair & 1) * TN), ad + kadv * kk, bd + kadv * kk, idesc, accumulate);
+                        accumulate = 1;
+                    }
+                }
+                mma_commit(&sm.done[s]);
+            }
+            __syncwarp();
+        }
+    } else {
+        auto drain = [&](int pair, int last_chunk) {
+            if (!mbar_wait(&sm.done[last_chunk % NST], (uint32_t)((last_chunk / NST) & 1))) { atomicExch(q.err, 24); __trap(); }
+            tc_fence_after();
+#pragma unroll
+            for (int b4 = 0; b4 < 4; b4++) {
+                float v[16];
+                tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)((pair & 1) * TN + 64 * hh + 16 * b4), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i++) acc[16 * b4 + i] += v[i];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.drained[pair & 1]);
+        };
+        for (int c = 0; c < n; c++) {
+            const int s = c % NST;
+            if (!mbar_wait(&sm.full[s], (uint32_t)((c / NST) & 1))) { atomicExch(q.err, 25); __trap(); }
+            float4* ph = reinterpret_cast<float4*>(sm.p_hi[s]); float4* pl = reinterpret_cast<float4*>(sm.p_lo[s]);
+            float4* qh = reinterpret_cast<float4*>(sm.q_hi[s]); float4* ql = reinterpret_cast<float4*>(sm.q_lo[s]);
+#pragma unroll
+            for (int e = 0; e < SLAB / 16 / 256; e++) {
+                const int idx = tid + e * 256;
+                float4 lo;
+                float4 hi = split4_hi(ph[idx], lo);
+                ph[idx] = hi; pl[idx] = lo;
+                hi = split4_hi(qh[idx], lo);
+                qh[idx] = hi; ql[idx] = lo;
+            }
+            if (q.dbg == 3 && c == 0 && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {      // debugging aid
+                float* f = reinterpret_cast<float*>(q.err);
+                q.err[1] = n; q.err[2] = cps; q.err[3] = (int)total;
+                f[4] = reinterpret_cast<const float*>(sm.p_hi[s])[0]; f[5] = reinterpret_cast<const float*>(sm.p_hi[s])[33];
+                f[6] = reinterpret_cast<const float*>(sm.q_hi[s])[0]; f[7] = reinterpret_cast<const float*>(sm.p_lo[s])[0];
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.split[s]);
+            // drain the previous pair once this pair's second chunk has been handed to the issuer
+            if ((c & 1) == 1 && c >= 3) drain((c >> 1) - 1, c - 2);
+        }
+        if (n > 0) {        // pairs the loop has not drained (it drains pair p - 1 when it hands the second chunk of pair p over)
+            const int last_pair = (n - 1) >> 1;
+            const int cmax = ((n - 1) & 1) ? n - 1 : n - 2;                 // last odd chunk index
+            const int upto = cmax >= 3 ? (cmax >> 1) - 1 : -1;             // last pair drained in the loop
+            for (int pp = upto + 1; pp <= last_pair; pp++) drain(pp, min(2 * pp + 1, n - 1));
+        }
+        if (q.dbg == 3 && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+            float* f = reinterpret_cast<float*>(q.err);
+            f[8] = acc[0]; f[9] = acc[1]; f[10] = acc[63];
+        }
+        float* slab = q.slabs + ((int64_t)split * gridDim.x + tile) * TM * TN + (int64_t)(32 * wq + lane) * TN + 64 * hh;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(slab + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (cw == 0) tmem_dealloc(tmem, 2 * TN);
+}
+
+// out[m][k] (+)= sum_s slabs[s][tile(m,k)][m%128][k%128]   (out row stride ld, fixed summation order)
+__global__ void psn_lg_wgrad_reduce_kernel(const float* __restrict__ slabs, int nsplit, int ntiles, int kblks, int M, int K, float* __restrict__ out,
+                                           int64_t ld, int accumulate) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * K) return;
+    const int m = idx / K, k = idx - m * K;
+    const int tile = (m / TM) * kblks + k / TN;
+    const float* src = slabs + (int64_t)tile * TM * TN + (m % TM) * TN + (k % TN);
+    float s = 0.0f;
+    for (int sp = 0; sp < nsplit; sp++) s += src[(int64_t)sp * ntiles * TM * TN];
+    float* dst = out + (int64_t)m * ld + k;
+    *dst = accumulate ? *dst + s : s;
+}
+
+bool lg_make_map32(CUtensorMap* map, const float* p, int width, int64_t rows, int64_t s_row, int64_t outer, int64_t s_outer) {
+    if (!lg_encode_fn() || (reinterpret_cast<uintptr_t>(p) & 15) || (s_row & 3) || (outer > 1 && (s_outer & 3))) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)width, (cuuint64_t)rows, (cuuint64_t)(outer > 0 ? outer : 1)};
+    const cuuint64_t gstr[2] = {(cuuint64_t)s_row * 4, (cuuint64_t)(outer > 1 ? s_outer : s_row * rows) * 4};
+    const cuuint32_t box[3] = {32, 32, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return lg_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(p), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+constexpr int WG_NSPLIT_MAX = 37;
+int64_t lg_wgrad_slab_floats(int M, int K) { return (int64_t)WG_NSPLIT_MAX * (M / TM) * (K / TN) * TM * TN; }
+
+// out[M x K] (+)= sum over slots and rows of P^T Q.  P: (nslots, N, M) with strides (p_ss, p_sn, 1); Q: (nslots, N, K) likewise.
+int lg_wgrad(const float* P, int64_t p_sn, int64_t p_ss, int M, const float* Q, int64_t q_sn, int64_t q_ss, int K, int nslots, int N, float* out,
+             int64_t out_ld, int accumulate, float* slabs, int* err, cudaStream_t stream) {
+    CUtensorMap mp, mq;
+    if (!lg_make_map32(&mp, P, M, N, p_sn, nslots, p_ss) || !lg_make_map32(&mq, Q, K, N, q_sn, nslots, q_ss))
+        return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (layer weight gradients)");
+    WgParams q;
+    q.nslots = nslots; q.N = N;
+    q.mblks = M / TM; q.kblks = K / TN;
+    const int ntiles = q.mblks * q.kblks;
+    const int64_t total = (int64_t)nslots * ((N + 31) / 32);
+    int nsplit = 148 / ntiles;
+    if (nsplit > WG_NSPLIT_MAX) nsplit = WG_NSPLIT_MAX;
+    if (nsplit > total) nsplit = (int)total;
+    if (nsplit < 1) nsplit = 1;
+    q.nsplit = nsplit;
+    q.slabs = slabs; q.err = err;
+    q.dbg = std::getenv("PSNODE_WG_DBG") ? std::atoi(std::getenv("PSNODE_WG_DBG")) : 0;
+    q.lbo = std::getenv("PSNODE_WG_LBO") ? std::atoi(std::getenv("PSNODE_WG_LBO")) : 4096;
+    q.sbo = std::getenv("PSNODE_WG_SBO") ? std::atoi(std::getenv("PSNODE_WG_SBO")) : 512;
+    q.kadv = std::getenv("PSNODE_WG_KADV") ? std::atoi(std::getenv("PSNODE_WG_KADV")) : 1024;
+    const int smem = (int)sizeof(WgSmem) + 1024;
+    static bool attr = false;
+    if (!attr) { PSN_CUDA(cudaFuncSetAttribute(psn_lg_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
+    psn_lg_wgrad_kernel<<<dim3((unsigned)ntiles, (unsigned)nsplit), WG_THREADS, smem, stream>>>(mp, mq, q);
+    psn_count_launch("psn_lg_wgrad_kernel");
+    psn_lg_wgrad_reduce_kernel<<<(M * K + 255) / 256, 256, 0, stream>>>(slabs, nsplit, ntiles, q.kblks, M, K, out, out_ld, accumulate);
+    psn_count_launch("psn_lg_wgrad_reduce_kernel");
+    PSN_CUDA(cudaGetLastError());
+    return PSNODE_OK;
+}
+
 int64_t al(int64_t floats) { return (floats + 63) & ~(int64_t)63; }
 
 struct LgLayout {
@@ -598,3 +836,16 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
     return PSNODE_OK;
 }
 
+
+
+// Test hook (not part of the public header): the MN-major weight-gradient GEMM alone.  out[M x K] = sum_{slot, n} P[slot][n][:]^T Q[slot][n][:].
+extern "C" int psnode_debug_lg_wgrad(const float* P, int64_t p_sn, int64_t p_ss, int M, const float* Q, int64_t q_sn, int64_t q_ss, int K, int nslots,
+                                     int N, float* out, void* ws, int64_t ws_bytes, void* stream) {
+    if ((M != 128 && M != 256 && M != 512) || (K % 128) != 0 || K < 128) return PSNODE_EINVAL;
+    if (ws_bytes < 256 + lg_wgrad_slab_floats(M, K) * 4) return PSNODE_EWORKSPACE;
+    int* err = static_cast<int*>(ws);
+    float* slabs = reinterpret_cast<float*>(static_cast<unsigned char*>(ws) + 256);
+    PSN_CUDA(cudaMemsetAsync(err, 0, 256, static_cast<cudaStream_t>(stream)));
+    return lg_wgrad(P, p_sn, p_ss, M, Q, q_sn, q_ss, K, nslots, N, out, K, 0, slabs, err, static_cast<cudaStream_t>(stream));
+}
+extern "C" int64_t psnode_debug_lg_wgrad_workspace(int M, int K) { return 256 + lg_wgrad_slab_floats(M, K) * 4; }
