@@ -35,9 +35,10 @@ constexpr int SLAB = TN * 128;          // 16 KB: 128 rows x 32 fp32
 constexpr int LG_THREADS = 320;         // 8 split / epilogue warps + TMA producer warp + MMA issuer warp
 constexpr int NPART = 2;                // K-partials (truncating fp32 accumulate: short chains)
 
-enum { LG_PLAIN = 0, LG_HIDDEN = 1, LG_RK = 2 };
+enum { LG_PLAIN = 0, LG_HIDDEN = 1, LG_RK = 2, LG_DELTA = 3 };
 // epilogue kinds (template parameter of the GEMM kernel)
-enum { EPI_PLAIN = 0, EPI_HIDDEN, EPI_EULER, EPI_MID0, EPI_MID1, EPI_RK0, EPI_RK1, EPI_RK2, EPI_RK3 };
+enum { EPI_PLAIN = 0, EPI_HIDDEN, EPI_EULER, EPI_MID0, EPI_MID1, EPI_RK0, EPI_RK1, EPI_RK2, EPI_RK3, EPI_DELTA };
+// EPI_DELTA (reverse pass): out = D * ELU'(act) with act = the recorded post-ELU activation (add1 operand); out2 (+)= out
 
 struct __align__(1024) LgSmem {
     unsigned char a_hi[NST][SLAB], a_lo[NST][SLAB], b_hi[NST][SLAB], b_lo[NST][SLAB];
@@ -53,7 +54,10 @@ struct LgParams {
     int nsrc, kchunks;                  // B sources (K segments) and 32-wide chunks per source
     int mode;
     // event handling (neural_base.py:52-65, 180-196): ev[ev_j] = index of the event that fires when leaving grid point ev_j, or -1
-    const int32_t* ev; int ev_j; int skip_unless_event;
+    const int32_t* ev; int ev_j; int skip_unless_event; int skip_if_event;
+    int b_r0;                           // added to the row coordinate of the B operand (slot of a ring of activation buffers)
+    int out2_acc;                       // EPI_DELTA: out2 += out instead of out2 = out
+    float* out2_jump; int64_t out2_jump_sr;   // when an event fires at ev_j, out2 = out2_jump + k * out2_jump_sr (row of the event)
     const float* add1; int64_t add1_sr, add1_ld;             // [r][n][m]  (hoisted layer-1 half / per-trajectory constant)
     const float* add1_jump; int64_t add1_jump_sr;            // event rows of add1 (selected when ev[ev_j] >= 0)
     const float* add2; int64_t add2_ld;                      // [n][m]
@@ -76,6 +80,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
     int evk = -1;
     if (q.ev) evk = __ldg(q.ev + q.ev_j);
     if (q.skip_unless_event && evk < 0) return;
+    if (q.skip_if_event && evk >= 0) return;
     extern __shared__ unsigned char smem_raw[];
     LgSmem& sm = *reinterpret_cast<LgSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, lane = tid & 31;
@@ -118,7 +123,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                 mbar_expect_tx(&sm.full[s], 3 * SLAB);
                 tma_load_3d(sm.a_hi[s], &map_a_hi, ck * 32, mblk * TM, 0, &sm.full[s]);
                 tma_load_3d(sm.a_lo[s], &map_a_lo, ck * 32, mblk * TM, 0, &sm.full[s]);
-                tma_load_3d(sm.b_hi[s], src == 0 ? &map_b0 : &map_b1, kc * 32, b0, r, &sm.full[s]);
+                tma_load_3d(sm.b_hi[s], src == 0 ? &map_b0 : &map_b1, kc * 32, b0, r + q.b_r0, &sm.full[s]);
             }
         }
         __syncwarp();
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
     // rolled: the first version (run-time mode switch inside fully unrolled loops) was 16 000 instructions of straight-line
     // code executed once per CTA and spent 38 000 of its 54 000 cycles waiting for instruction fetches (`no_inst` stalls).
     {
-        constexpr bool rk = EPI >= EPI_EULER;
+        constexpr bool rk = EPI >= EPI_EULER && EPI <= EPI_RK3;
         const int m = mblk * TM + 32 * wq + lane;
         const float* add1 = q.add1;
         int64_t add1_row = (int64_t)r * q.add1_sr;
@@ -203,6 +208,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
         const float* pa2 = q.add2 ? q.add2 + (int64_t)ncol0 * q.add2_ld + m : nullptr;
         float* pout = q.out + (int64_t)r * q.out_sr + (int64_t)ncol0 * q.out_ld + m;
         float* pout2 = q.out2 ? q.out2 + (int64_t)ncol0 * q.out2_ld + m : nullptr;
+        if (evk >= 0 && q.out2_jump) pout2 = q.out2_jump + (int64_t)evk * q.out2_jump_sr + (int64_t)ncol0 * q.out2_ld + m;
         float* px0 = rk ? q.x0 + (int64_t)ncol0 * q.st_ld + m : nullptr;
         float* pk1 = rk ? q.k1 + (int64_t)ncol0 * q.st_ld + m : nullptr;
         float* pk2 = rk ? q.k2 + (int64_t)ncol0 * q.st_ld + m : nullptr;
@@ -238,7 +244,11 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                 const int c = 16 * bt + i;
                 if (!full_tile && c >= nlive) continue;
                 float v = (t0[i] + t1[i]) + bias;
-                if constexpr (!rk) {
+                if constexpr (EPI == EPI_DELTA) {
+                    v = (t0[i] + t1[i]) * psn_elu_grad_from_out(e.p0[i]);
+                    pout[c * old] = v;
+                    if (pout2) pout2[c * o2ld] = q.out2_acc ? pout2[c * o2ld] + v : v;
+                } else if constexpr (!rk) {
                     v = (v + e.p0[i]) + e.p1[i];
                     if constexpr (EPI == EPI_HIDDEN) v = psn_elu(v);
                     pout[c * old] = v;
@@ -374,6 +384,7 @@ struct WgParams {
     int mblks, kblks;
     float* slabs;                   // [split][tile][128][128]
     int* err;
+    const int32_t* ev; int ev_j;    // skip (early exit) unless an event fires at ev_j (ev == NULL: never skip)
     int dbg, lbo, sbo, kadv;        // debugging / probing of the MN-major descriptor fields (bytes)
 };
 // MN-major tf32 operands exist in ONE shared-memory layout only: 128-byte swizzle with 32-byte atomicity (UMMA layout type 1,
@@ -403,6 +414,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
 
 __global__ void __launch_bounds__(WG_THREADS, 1) psn_lg_wgrad_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q,
                                                                     const __grid_constant__ WgParams q) {
+    if (q.ev && __ldg(q.ev + q.ev_j) < 0) return;
     extern __shared__ unsigned char smem_raw[];
     WgSmem& sm = *reinterpret_cast<WgSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, lane = tid & 31;
@@ -537,7 +549,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) psn_lg_wgrad_kernel(const __gri
 
 // out[m][k] (+)= sum_s slabs[s][tile(m,k)][m%128][k%128]   (out row stride ld, fixed summation order)
 __global__ void psn_lg_wgrad_reduce_kernel(const float* __restrict__ slabs, int nsplit, int ntiles, int kblks, int M, int K, float* __restrict__ out,
-                                           int64_t ld, int accumulate) {
+                                           int64_t ld, int accumulate, const int32_t* ev, int ev_j) {
+    if (ev && __ldg(ev + ev_j) < 0) return;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * K) return;
     const int m = idx / K, k = idx - m * K;
@@ -564,7 +577,7 @@ int64_t lg_wgrad_slab_floats(int M, int K) { return (int64_t)WG_NSPLIT_MAX * (M 
 
 // out[M x K] (+)= sum over slots and rows of P^T Q.  P: (nslots, N, M) with strides (p_ss, p_sn, 1); Q: (nslots, N, K) likewise.
 int lg_wgrad(const float* P, int64_t p_sn, int64_t p_ss, int M, const float* Q, int64_t q_sn, int64_t q_ss, int K, int nslots, int N, float* out,
-             int64_t out_ld, int accumulate, float* slabs, int* err, cudaStream_t stream) {
+             int64_t out_ld, int accumulate, float* slabs, int* err, cudaStream_t stream, const int32_t* ev = nullptr, int ev_j = 0) {
     CUtensorMap mp, mq;
     if (!lg_make_map32(&mp, P, M, N, p_sn, nslots, p_ss) || !lg_make_map32(&mq, Q, K, N, q_sn, nslots, q_ss))
         return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (layer weight gradients)");
@@ -579,6 +592,7 @@ int lg_wgrad(const float* P, int64_t p_sn, int64_t p_ss, int M, const float* Q, 
     if (nsplit < 1) nsplit = 1;
     q.nsplit = nsplit;
     q.slabs = slabs; q.err = err;
+    q.ev = ev; q.ev_j = ev_j;
     q.dbg = std::getenv("PSNODE_WG_DBG") ? std::atoi(std::getenv("PSNODE_WG_DBG")) : 0;
     q.lbo = std::getenv("PSNODE_WG_LBO") ? std::atoi(std::getenv("PSNODE_WG_LBO")) : 4096;
     q.sbo = std::getenv("PSNODE_WG_SBO") ? std::atoi(std::getenv("PSNODE_WG_SBO")) : 512;
@@ -588,9 +602,58 @@ int lg_wgrad(const float* P, int64_t p_sn, int64_t p_ss, int M, const float* Q, 
     if (!attr) { PSN_CUDA(cudaFuncSetAttribute(psn_lg_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
     psn_lg_wgrad_kernel<<<dim3((unsigned)ntiles, (unsigned)nsplit), WG_THREADS, smem, stream>>>(mp, mq, q);
     psn_count_launch("psn_lg_wgrad_kernel");
-    psn_lg_wgrad_reduce_kernel<<<(M * K + 255) / 256, 256, 0, stream>>>(slabs, nsplit, ntiles, q.kblks, M, K, out, out_ld, accumulate);
+    psn_lg_wgrad_reduce_kernel<<<(M * K + 255) / 256, 256, 0, stream>>>(slabs, nsplit, ntiles, q.kblks, M, K, out, out_ld, accumulate, ev, ev_j);
     psn_count_launch("psn_lg_wgrad_reduce_kernel");
     PSN_CUDA(cudaGetLastError());
+    return PSNODE_OK;
+}
+
+using LgKernFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const LgParams);
+const LgKernFn* lg_kernels() {
+    static const LgKernFn kerns[10] = {psn_lg_gemm_kernel<EPI_PLAIN>, psn_lg_gemm_kernel<EPI_HIDDEN>, psn_lg_gemm_kernel<EPI_EULER>,
+                                       psn_lg_gemm_kernel<EPI_MID0>, psn_lg_gemm_kernel<EPI_MID1>, psn_lg_gemm_kernel<EPI_RK0>,
+                                       psn_lg_gemm_kernel<EPI_RK1>, psn_lg_gemm_kernel<EPI_RK2>, psn_lg_gemm_kernel<EPI_RK3>,
+                                       psn_lg_gemm_kernel<EPI_DELTA>};
+    return kerns;
+}
+int lg_gemm_smem() { return (int)sizeof(LgSmem) + 1024; }
+int lg_prepare_kernels() {
+    static bool attr_set = false;
+    if (!attr_set) {
+        for (int i = 0; i < 10; i++) PSN_CUDA(cudaFuncSetAttribute(lg_kernels()[i], cudaFuncAttributeMaxDynamicSharedMemorySize, lg_gemm_smem()));
+        attr_set = true;
+    }
+    return PSNODE_OK;
+}
+int lg_epi_of(const LgParams& q) {
+    if (q.mode == LG_PLAIN) return (int)EPI_PLAIN;
+    if (q.mode == LG_HIDDEN) return (int)EPI_HIDDEN;
+    if (q.mode == LG_DELTA) return (int)EPI_DELTA;
+    if (q.method == PSNODE_EULER) return (int)EPI_EULER;
+    if (q.method == PSNODE_MIDPOINT) return q.stage == 0 ? (int)EPI_MID0 : (int)EPI_MID1;
+    return (int)EPI_RK0 + q.stage;
+}
+bool lg_use_pdl() {
+    static const bool v = std::getenv("PSNODE_LG_PDL") ? std::atoi(std::getenv("PSNODE_LG_PDL")) != 0 : true;
+    return v;
+}
+// one GEMM launch: A planes (hi, lo maps), one or two B sources
+int lg_launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b0, const CUtensorMap& b1, const LgParams& q, int mblks,
+                   cudaStream_t stream, const char* name) {
+    dim3 grid((unsigned)(q.R * q.nbt), (unsigned)mblks);
+    const LgKernFn kern = lg_kernels()[lg_epi_of(q)];
+    if (lg_use_pdl()) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(LG_THREADS); cfg.dynamicSmemBytes = (size_t)lg_gemm_smem(); cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kern, a_hi, a_lo, b0, b1, q);
+    } else {
+        kern<<<grid, LG_THREADS, lg_gemm_smem(), stream>>>(a_hi, a_lo, b0, b1, q);
+    }
+    psn_count_launch(name);
     return PSNODE_OK;
 }
 
@@ -711,24 +774,11 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
 
     const int smem = (int)sizeof(LgSmem) + 1024;
     using KernFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const LgParams);
-    static const KernFn kerns[9] = {psn_lg_gemm_kernel<EPI_PLAIN>, psn_lg_gemm_kernel<EPI_HIDDEN>, psn_lg_gemm_kernel<EPI_EULER>,
-                                    psn_lg_gemm_kernel<EPI_MID0>, psn_lg_gemm_kernel<EPI_MID1>, psn_lg_gemm_kernel<EPI_RK0>,
-                                    psn_lg_gemm_kernel<EPI_RK1>, psn_lg_gemm_kernel<EPI_RK2>, psn_lg_gemm_kernel<EPI_RK3>};
-    static bool attr_set = false;
-    if (!attr_set) {
-        for (int i = 0; i < 9; i++) PSN_CUDA(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
-    auto epi_of = [&](const LgParams& q) {
-        if (q.mode == LG_PLAIN) return (int)EPI_PLAIN;
-        if (q.mode == LG_HIDDEN) return (int)EPI_HIDDEN;
-        if (q.method == PSNODE_EULER) return (int)EPI_EULER;
-        if (q.method == PSNODE_MIDPOINT) return q.stage == 0 ? (int)EPI_MID0 : (int)EPI_MID1;
-        return (int)EPI_RK0 + q.stage;
-    };
+    if (lg_prepare_kernels() != PSNODE_OK) return PSNODE_ECUDA;
+    const LgKernFn* kerns = lg_kernels();
+    auto epi_of = [&](const LgParams& q) { return lg_epi_of(q); };
     const int nbt = (B + TN - 1) / TN;
     static const int dbg_cta = std::getenv("PSNODE_LG_DBG") ? std::atoi(std::getenv("PSNODE_LG_DBG")) : 0;
-    static const bool use_pdl = std::getenv("PSNODE_LG_PDL") ? std::atoi(std::getenv("PSNODE_LG_PDL")) != 0 : true;
     static const int rotate = std::getenv("PSNODE_LG_ROTATE") ? std::atoi(std::getenv("PSNODE_LG_ROTATE")) : 1;
     auto base = [&]() {
         LgParams q;
@@ -740,20 +790,7 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
         return q;
     };
     auto launch = [&](int which, const CUtensorMap& b0, const CUtensorMap& b1, const LgParams& q, const char* name) -> int {
-        dim3 grid((unsigned)(q.R * q.nbt), (unsigned)(H / TM));
-        if (use_pdl) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = grid; cfg.blockDim = dim3(LG_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            cudaLaunchKernelEx(&cfg, kerns[epi_of(q)], mw_hi[which], mw_lo[which], b0, b1, q);
-        } else {
-            kerns[epi_of(q)]<<<grid, LG_THREADS, smem, stream>>>(mw_hi[which], mw_lo[which], b0, b1, q);
-        }
-        psn_count_launch(name);
-        return PSNODE_OK;
+        return lg_launch_gemm(mw_hi[which], mw_lo[which], b0, b1, q, H / TM, stream, name);
     };
     // ---- hoisted layer-1 halves over the whole series ----
     auto project = [&](int which, const CUtensorMap& bz, const CUtensorMap& bv, int R, const float* cadd, float* out, const char* name) {
