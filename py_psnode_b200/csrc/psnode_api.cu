@@ -192,6 +192,7 @@ int64_t psnode_backward_workspace(const psnode_problem* p, const psnode_adjoint*
     { const int64_t g2 = psn_generic_backward_workspace_tb2(p, a); if (g2 > g) g = g2; }
     const int64_t t = !psn_tc_supports(p) ? 0 : (p->kind == PSNODE_ODE ? psn_tc_backward_workspace(p, a) : psn_tc_dae_backward_workspace(p, a));
     if (psn_wide_bwd_supports(p, a)) { const int64_t w = psn_wide_backward_workspace(p, a); if (w > g) g = w; }
+    if (psn_lg_bwd_supports(p, a)) { const int64_t w = psn_lg_backward_workspace(p, a); if (w > g) g = w; }
     return g > t ? g : t;
 }
 
@@ -207,6 +208,8 @@ int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* work
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC8) && psn_tc_dae_bwd_supports(p, a))
         return psn_tc_dae_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if (a->fuse_x.target.p || a->fuse_i.target.p) return PSNODE_EUNSUPPORTED;      // the recomputing sweeps take gx / gi only
+    if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_LAYER) && psn_lg_bwd_supports(p, a))
+        return psn_lg_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     const int gst = psn_generic_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if (gst != PSNODE_EUNSUPPORTED) return gst;
     return psn_generic_backward_tb2(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));

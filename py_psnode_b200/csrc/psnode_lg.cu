@@ -35,10 +35,15 @@ constexpr int SLAB = TN * 128;          // 16 KB: 128 rows x 32 fp32
 constexpr int LG_THREADS = 320;         // 8 split / epilogue warps + TMA producer warp + MMA issuer warp
 constexpr int NPART = 2;                // K-partials (truncating fp32 accumulate: short chains)
 
-enum { LG_PLAIN = 0, LG_HIDDEN = 1, LG_RK = 2, LG_DELTA = 3 };
+enum { LG_PLAIN = 0, LG_HIDDEN = 1, LG_RK = 2, LG_DELTA = 3, LG_BRK = 4 };      // LG_BRK: LgParams::stage = the EPI_B* kind
 // epilogue kinds (template parameter of the GEMM kernel)
-enum { EPI_PLAIN = 0, EPI_HIDDEN, EPI_EULER, EPI_MID0, EPI_MID1, EPI_RK0, EPI_RK1, EPI_RK2, EPI_RK3, EPI_DELTA };
-// EPI_DELTA (reverse pass): out = D * ELU'(act) with act = the recorded post-ELU activation (add1 operand); out2 (+)= out
+enum { EPI_PLAIN = 0, EPI_HIDDEN, EPI_EULER, EPI_MID0, EPI_MID1, EPI_RK0, EPI_RK1, EPI_RK2, EPI_RK3, EPI_DELTA,
+       EPI_BRK3, EPI_BRK2, EPI_BRK1, EPI_BMID1, EPI_BSUM, EPI_COUNT };
+// Reverse pass (psn_lg_backward):
+// EPI_DELTA: out = D * ELU'(act), act = the recomputed post-ELU activation (add1 operand); out2 (+)= out; acc += out.
+// EPI_B*:    D = dy_e = F_x^T delta1_e of stage e; the Runge-Kutta adjoint (transpose of my_fixed_grid.py:15-59) turns it into the slope
+//            adjoint of the stage before (out = dk_{e-1}, acc += dk_{e-1}; dy_e kept in k1 / k2 / k3), and after stage 0 into the
+//            state adjoint of the previous grid point: out = x0 + k1 + k2 + k3 + D + add1  (x0 = gx_j, k* = the kept dy, add1 = dL/dx_sol[j-1]).
 
 struct __align__(1024) LgSmem {
     unsigned char a_hi[NST][SLAB], a_lo[NST][SLAB], b_hi[NST][SLAB], b_lo[NST][SLAB];
@@ -67,6 +72,7 @@ struct LgParams {
     // Runge-Kutta epilogue
     int method, stage;
     float* x0; float* k1; float* k2; float* k3; int64_t st_ld;
+    float* acc;                                              // reverse pass: acc[n][m] += out (row stride st_ld)
     const float* t_cur; const float* t_prev; int64_t t_sb;   // t[j], t[j-1] rows (element n at n * t_sb)
     int* err;
 };
@@ -193,6 +199,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
     // code executed once per CTA and spent 38 000 of its 54 000 cycles waiting for instruction fetches (`no_inst` stalls).
     {
         constexpr bool rk = EPI >= EPI_EULER && EPI <= EPI_RK3;
+        constexpr bool brk = EPI >= EPI_BRK3 && EPI <= EPI_BSUM;
         const int m = mblk * TM + 32 * wq + lane;
         const float* add1 = q.add1;
         int64_t add1_row = (int64_t)r * q.add1_sr;
@@ -209,12 +216,13 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
         float* pout = q.out + (int64_t)r * q.out_sr + (int64_t)ncol0 * q.out_ld + m;
         float* pout2 = q.out2 ? q.out2 + (int64_t)ncol0 * q.out2_ld + m : nullptr;
         if (evk >= 0 && q.out2_jump) pout2 = q.out2_jump + (int64_t)evk * q.out2_jump_sr + (int64_t)ncol0 * q.out2_ld + m;
-        float* px0 = rk ? q.x0 + (int64_t)ncol0 * q.st_ld + m : nullptr;
-        float* pk1 = rk ? q.k1 + (int64_t)ncol0 * q.st_ld + m : nullptr;
-        float* pk2 = rk ? q.k2 + (int64_t)ncol0 * q.st_ld + m : nullptr;
-        float* pk3 = rk ? q.k3 + (int64_t)ncol0 * q.st_ld + m : nullptr;
-        const float* ptc = rk ? q.t_cur + (int64_t)ncol0 * q.t_sb : nullptr;
-        const float* ptp = rk ? q.t_prev + (int64_t)ncol0 * q.t_sb : nullptr;
+        float* px0 = (rk || brk) ? q.x0 + (int64_t)ncol0 * q.st_ld + m : nullptr;
+        float* pk1 = (rk || brk) ? q.k1 + (int64_t)ncol0 * q.st_ld + m : nullptr;
+        float* pk2 = (rk || brk) ? q.k2 + (int64_t)ncol0 * q.st_ld + m : nullptr;
+        float* pk3 = (rk || brk) ? q.k3 + (int64_t)ncol0 * q.st_ld + m : nullptr;
+        float* pacc = q.acc ? q.acc + (int64_t)ncol0 * q.st_ld + m : nullptr;
+        const float* ptc = (rk || (brk && EPI != EPI_BSUM)) ? q.t_cur + (int64_t)ncol0 * q.t_sb : nullptr;
+        const float* ptp = (rk || (brk && EPI != EPI_BSUM)) ? q.t_prev + (int64_t)ncol0 * q.t_sb : nullptr;
         const int a1ld = (int)q.add1_ld, a2ld = (int)q.add2_ld, old = (int)q.out_ld, o2ld = (int)q.out2_ld, sld = (int)q.st_ld, tsb = (int)q.t_sb;
         const int nlive = full_tile ? 64 : max(0, min(64, q.N - ncol0));      // live columns of this thread
         auto fetch = [&](int bt, Buf& e) {
@@ -227,6 +235,16 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                     if constexpr (EPI >= EPI_RK2) e.p2[i] = pk2[c * sld];
                     if constexpr (EPI >= EPI_RK3) e.p3[i] = pk3[c * sld];
                     e.dt[i] = __fsub_rn(__ldg(ptc + c * tsb), __ldg(ptp + c * tsb));
+                } else if constexpr (brk) {
+                    e.p0[i] = px0[c * sld];
+                    if constexpr (EPI == EPI_BRK2 || EPI == EPI_BRK1 || EPI == EPI_BSUM) e.p1[i] = pk1[c * sld];
+                    if constexpr (EPI == EPI_BRK1 || EPI == EPI_BSUM) e.p2[i] = pk2[c * sld];
+                    if constexpr (EPI == EPI_BSUM) {
+                        e.p3[i] = pk3[c * sld];
+                        e.dt[i] = pa1 ? __ldg(pa1 + c * a1ld) : 0.0f;               // upstream gradient row
+                    } else {
+                        e.dt[i] = __fsub_rn(__ldg(ptc + c * tsb), __ldg(ptp + c * tsb));
+                    }
                 } else {
                     e.p0[i] = pa1 ? __ldg(pa1 + c * a1ld) : 0.0f;
                     e.p1[i] = pa2 ? __ldg(pa2 + c * a2ld) : 0.0f;
@@ -248,6 +266,21 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                     v = (t0[i] + t1[i]) * psn_elu_grad_from_out(e.p0[i]);
                     pout[c * old] = v;
                     if (pout2) pout2[c * o2ld] = q.out2_acc ? pout2[c * o2ld] + v : v;
+                    if (pacc) pacc[c * sld] += v;
+                } else if constexpr (brk) {
+                    const float D = t0[i] + t1[i], gx = e.p0[i];
+                    if constexpr (EPI == EPI_BSUM) {
+                        pout[c * old] = ((((gx + e.p1[i]) + e.p2[i]) + e.p3[i]) + D) + e.dt[i];
+                    } else {
+                        const float dt = e.dt[i];
+                        float dk;
+                        if constexpr (EPI == EPI_BRK3) { pk1[c * sld] = D; dk = dt * fmaf(0.375f, gx, D); }
+                        else if constexpr (EPI == EPI_BRK2) { pk2[c * sld] = D; dk = dt * (fmaf(0.375f, gx, D) - e.p1[i]); }
+                        else if constexpr (EPI == EPI_BRK1) { pk3[c * sld] = D; dk = dt * (fmaf(0.125f, gx, e.p1[i]) + c13 * (D - e.p2[i])); }
+                        else { pk1[c * sld] = D; dk = (0.5f * dt) * D; }
+                        pout[c * old] = dk;
+                        if (pacc) pacc[c * sld] += dk;
+                    }
                 } else if constexpr (!rk) {
                     v = (v + e.p0[i]) + e.p1[i];
                     if constexpr (EPI == EPI_HIDDEN) v = psn_elu(v);
@@ -293,18 +326,6 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
 }
 
 // ---- one-time preparation per call ------------------------------------------------------------------------------------------
-// dst_hi / dst_lo [m][k] (k < K) = split_tf32(W[m * ldw + col0 + k] (+ W[m * ldw + col1 + k] if col1 >= 0))
-__global__ void psn_lg_prep_kernel(const float* __restrict__ W, int ldw, int col0, int col1, int M, int K, float* __restrict__ hi, float* __restrict__ lo) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= M * K) return;
-    const int m = idx / K, k = idx - m * K;
-    float w = __ldg(W + (int64_t)m * ldw + col0 + k);
-    if (col1 >= 0) w += __ldg(W + (int64_t)m * ldw + col1 + k);
-    float h, l;
-    split_tf32(w, h, l);
-    hi[idx] = h;
-    lo[idx] = l;
-}
 // c[b][m] = bias[m] + sum_{k < S} (W[m][k] - (sub >= 0 ? W[m][sub + k] : 0)) a0[b][k]; block = 8 trajectories, thread = m (blockDim = H)
 __global__ void psn_lg_const_kernel(const float* __restrict__ W, int ldw, int sub, const float* __restrict__ bias, const float* __restrict__ a0,
                                     int64_t a0_sb, int S, int B, int H, float* __restrict__ c) {
@@ -397,15 +418,6 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr, int lbo, in
     d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)1 << 61;                    // SWIZZLE_128B_BASE32B
-    return d;
-}
-__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)(4096 >> 4) << 16;          // LBO: next block of 32 features (one TMA box of 32 rows x 128 B)
-    d |= (uint64_t)(1024 >> 4) << 32;          // SBO: next group of 8 reduction rows
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
     return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
@@ -610,17 +622,18 @@ int lg_wgrad(const float* P, int64_t p_sn, int64_t p_ss, int M, const float* Q, 
 
 using LgKernFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const LgParams);
 const LgKernFn* lg_kernels() {
-    static const LgKernFn kerns[10] = {psn_lg_gemm_kernel<EPI_PLAIN>, psn_lg_gemm_kernel<EPI_HIDDEN>, psn_lg_gemm_kernel<EPI_EULER>,
-                                       psn_lg_gemm_kernel<EPI_MID0>, psn_lg_gemm_kernel<EPI_MID1>, psn_lg_gemm_kernel<EPI_RK0>,
-                                       psn_lg_gemm_kernel<EPI_RK1>, psn_lg_gemm_kernel<EPI_RK2>, psn_lg_gemm_kernel<EPI_RK3>,
-                                       psn_lg_gemm_kernel<EPI_DELTA>};
+    static const LgKernFn kerns[EPI_COUNT] = {psn_lg_gemm_kernel<EPI_PLAIN>, psn_lg_gemm_kernel<EPI_HIDDEN>, psn_lg_gemm_kernel<EPI_EULER>,
+                                              psn_lg_gemm_kernel<EPI_MID0>, psn_lg_gemm_kernel<EPI_MID1>, psn_lg_gemm_kernel<EPI_RK0>,
+                                              psn_lg_gemm_kernel<EPI_RK1>, psn_lg_gemm_kernel<EPI_RK2>, psn_lg_gemm_kernel<EPI_RK3>,
+                                              psn_lg_gemm_kernel<EPI_DELTA>, psn_lg_gemm_kernel<EPI_BRK3>, psn_lg_gemm_kernel<EPI_BRK2>,
+                                              psn_lg_gemm_kernel<EPI_BRK1>, psn_lg_gemm_kernel<EPI_BMID1>, psn_lg_gemm_kernel<EPI_BSUM>};
     return kerns;
 }
 int lg_gemm_smem() { return (int)sizeof(LgSmem) + 1024; }
 int lg_prepare_kernels() {
     static bool attr_set = false;
     if (!attr_set) {
-        for (int i = 0; i < 10; i++) PSN_CUDA(cudaFuncSetAttribute(lg_kernels()[i], cudaFuncAttributeMaxDynamicSharedMemorySize, lg_gemm_smem()));
+        for (int i = 0; i < EPI_COUNT; i++) PSN_CUDA(cudaFuncSetAttribute(lg_kernels()[i], cudaFuncAttributeMaxDynamicSharedMemorySize, lg_gemm_smem()));
         attr_set = true;
     }
     return PSNODE_OK;
@@ -629,6 +642,7 @@ int lg_epi_of(const LgParams& q) {
     if (q.mode == LG_PLAIN) return (int)EPI_PLAIN;
     if (q.mode == LG_HIDDEN) return (int)EPI_HIDDEN;
     if (q.mode == LG_DELTA) return (int)EPI_DELTA;
+    if (q.mode == LG_BRK) return q.stage;
     if (q.method == PSNODE_EULER) return (int)EPI_EULER;
     if (q.method == PSNODE_MIDPOINT) return q.stage == 0 ? (int)EPI_MID0 : (int)EPI_MID1;
     return (int)EPI_RK0 + q.stage;
@@ -659,41 +673,306 @@ int lg_launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUten
 
 int64_t al(int64_t floats) { return (floats + 63) & ~(int64_t)63; }
 
-struct LgLayout {
-    int H, KZV, nmat;
-    int64_t err, wts_hi[7], wts_lo[7], c_de, c_ae, pre_de, pre_ae, x0, k1, k2, k3, ycur, a1, hbuf, icur, G, total;
-    int64_t rows_de, rows_ae;
-};
-enum { M_DE1X = 0, M_DE1ZV, M_DE1I, M_DE2, M_AE1X, M_AE1ZV, M_AE2 };
+// prepared weight planes: the forward's seven (A = weights as they multiply activations) and the reverse pass's transposes
+enum { M_DE1X = 0, M_DE1ZV, M_DE1I, M_DE2, M_AE1X, M_AE1ZV, M_AE2,
+       M_T_DE2, M_T_DE1X, M_T_DE1I, M_T_AE2, M_T_AE1X, M_T_DZ, M_T_DV, M_T_DA0, NMAT };
+constexpr int NMAT_FWD = M_AE2 + 1;
 
-LgLayout lg_layout(const psnode_problem* p) {
+// BH-sized work buffers of the reverse pass (one contiguous array, one tensor map, addressed by index)
+enum { BUF_GX = 0, BUF_DY3, BUF_DY2, BUF_DY1, BUF_GI0, BUF_HEV, BUF_DHEV, BUF_G, BUF_K1, BUF_K2, BUF_K3, BUF_DCDE, BUF_DCAE, BUF_ACCDK, BUF_ACCGI,
+       BUF_SINGLES };
+
+struct LgLayout {
+    int H, KZV, S, nmat, bwd;
+    int mrows[NMAT], mcols[NMAT];
+    int64_t err, wts_hi[NMAT], wts_lo[NMAT], c_de, c_ae, pre_de, pre_ae, x0, k1, k2, k3, ycur, a1, hbuf, icur, G, total;
+    int64_t rows_de, rows_ae;
+    // reverse pass
+    int ring, nst, nbufs;
+    int64_t dpj_de, dpj_ae, bufs, slabs;
+    int ring_y(int s, int e) const { return BUF_SINGLES + (0 * ring + s) * nst + e; }
+    int ring_a1(int s, int e) const { return BUF_SINGLES + (1 * ring + s) * nst + e; }
+    int ring_dk(int s, int e) const { return BUF_SINGLES + (2 * ring + s) * nst + e; }
+    int ring_d1(int s, int e) const { return BUF_SINGLES + (3 * ring + s) * nst + e; }
+    int ring_one(int kind, int s) const { return BUF_SINGLES + 4 * ring * nst + kind * ring + s; }      // kind: 0 i0, 1 dsum, 2 gi, 3 h, 4 dh
+};
+enum { R_I0 = 0, R_DSUM, R_GI, R_H, R_DH };
+
+int lg_ring_depth() {
+    static const int v = std::getenv("PSNODE_LG_RING") ? std::atoi(std::getenv("PSNODE_LG_RING")) : 8;
+    return v < 1 ? 1 : (v > 64 ? 64 : v);
+}
+
+LgLayout lg_layout(const psnode_problem* p, bool bwd) {
     LgLayout L;
+    std::memset(&L, 0, sizeof(L));
     const bool dae = p->kind == PSNODE_DAE;
     const int H = p->X, E = p->event_idx ? p->E : 0;
     L.H = H;
     L.KZV = p->Z + p->V;
-    L.nmat = dae ? 7 : 4;
+    L.S = p->X + p->Z + p->V + p->I;
+    L.bwd = bwd ? 1 : 0;
+    L.nmat = bwd ? NMAT : NMAT_FWD;
+    const int k2 = dae ? 2 * H : H;
+    const int rows[NMAT] = {H, H, H, H, H, H, H, H, H, H, H, H, H, H, L.S};
+    const int cols[NMAT] = {H, L.KZV, H, H, H, L.KZV, H, H, H, H, H, H, k2, k2, k2};
     int64_t o = 64;
     L.err = 0;
-    const int kt[7] = {H, L.KZV, H, H, H, L.KZV, H};
-    for (int i = 0; i < 7; i++) {
-        L.wts_hi[i] = o; o += al((int64_t)H * kt[i]);
-        L.wts_lo[i] = o; o += al((int64_t)H * kt[i]);
+    for (int i = 0; i < NMAT; i++) {
+        L.mrows[i] = rows[i]; L.mcols[i] = cols[i];
+        if (i >= L.nmat) continue;
+        const bool used = dae || (i == M_DE1X || i == M_DE1ZV || i == M_DE2 || i == M_T_DE2 || i == M_T_DE1X || i == M_T_DZ || i == M_T_DA0);
+        if (!used) continue;
+        L.wts_hi[i] = o; o += al((int64_t)rows[i] * cols[i]);
+        L.wts_lo[i] = o; o += al((int64_t)rows[i] * cols[i]);
     }
     const int64_t BH = (int64_t)p->B * H;
     L.c_de = o; o += al(BH);
     L.c_ae = o; o += al(BH);
-    L.rows_de = (p->T > 1 ? p->T - 1 : 0) + E;
+    // (the reverse pass overwrites pre[r] with d pre[r] in place)
+    L.rows_de = (p->T > 1 ? p->T - 1 : 0) + E ;
     L.rows_ae = dae ? (int64_t)p->T + E : 0;
     L.pre_de = o; o += al(L.rows_de * BH);
     L.pre_ae = o; o += al(L.rows_ae * BH);
     L.x0 = o; o += al(BH); L.k1 = o; o += al(BH); L.k2 = o; o += al(BH); L.k3 = o; o += al(BH);
     L.ycur = o; o += al(BH); L.a1 = o; o += al(BH); L.hbuf = o; o += al(BH); L.icur = o; o += al(BH); L.G = o; o += al(BH);
+    if (bwd) {
+        L.ring = lg_ring_depth();
+        if (p->T - 1 < L.ring) L.ring = p->T > 1 ? p->T - 1 : 1;
+        L.nst = psw_nstages(p->method);
+        L.nbufs = BUF_SINGLES + L.ring * (4 * L.nst + 5);
+        L.dpj_de = o; o += al((int64_t)(E > 0 ? E : 1) * BH);
+        L.dpj_ae = o; o += al((int64_t)(E > 0 ? E : 1) * BH);
+        L.bufs = o; o += (int64_t)L.nbufs * al(BH);
+        L.slabs = o; o += al(lg_wgrad_slab_floats(H, L.S));
+    }
     L.total = o;
     return L;
 }
 
 bool view_ok(const float* p, int64_t s0, int64_t s1) { return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (s0 & 3) == 0 && (s1 & 3) == 0; }
+
+// dst[m * ldd + k] (m < M, k < K) = split_tf32(A[m][k]),  A[m][k] = W[m * ldw + col0 + k] (+ sgn * W[m * ldw + col1 + k] if col1 >= 0), or with
+// `transpose` the same expression with m and k exchanged on the right-hand side (A = the transposed block)
+__global__ void psn_lg_prep2_kernel(const float* __restrict__ W, int ldw, int col0, int col1, float sgn, int transpose, int M, int K, int ldd,
+                                    float* __restrict__ hi, float* __restrict__ lo) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * K) return;
+    const int m = idx / K, k = idx - m * K;
+    const int r = transpose ? k : m, c = transpose ? m : k;
+    float w = __ldg(W + (int64_t)r * ldw + col0 + c);
+    if (col1 >= 0) w = fmaf(sgn, __ldg(W + (int64_t)r * ldw + col1 + c), w);
+    float h, l;
+    split_tf32(w, h, l);
+    hi[(int64_t)m * ldd + k] = h;
+    lo[(int64_t)m * ldd + k] = l;
+}
+
+// Everything the forward pass and the reverse pass share: prepared planes, tensor maps, hoisted projections, launch helpers.
+struct LgCtx {
+    const psnode_problem* p;
+    LgLayout L;
+    float* w;
+    int* err;
+    cudaStream_t stream;
+    bool dae;
+    int H, B, T, E, S, nbt, nstages;
+    int64_t BH;
+    CUtensorMap mw_hi[NMAT], mw_lo[NMAT], m_z, m_v, m_zj, m_vj, m_y, m_a1, m_h, m_i;
+    int dbg_cta, rotate;
+
+    LgParams base() const {
+        LgParams q;
+        std::memset(&q, 0, sizeof(q));
+        q.N = B; q.R = 1; q.nbt = nbt; q.nsrc = 1; q.kchunks = H / 32; q.mode = LG_PLAIN;
+        q.add1_ld = H; q.add2_ld = H; q.out_ld = H; q.st_ld = H;
+        q.err = err;
+        q.dbg = dbg_cta; q.rotate = rotate;
+        return q;
+    }
+    int launch(int which, const CUtensorMap& b0, const CUtensorMap& b1, const LgParams& q, const char* name) const {
+        return lg_launch_gemm(mw_hi[which], mw_lo[which], b0, b1, q, L.mrows[which] / TM, stream, name);
+    }
+    void prep(int which, const float* W, int ldw, int col0, int col1, float sgn, int transpose, int M, int K, int dcol) const {
+        const int n = M * K;
+        psn_lg_prep2_kernel<<<(n + 255) / 256, 256, 0, stream>>>(W, ldw, col0, col1, sgn, transpose, M, K, L.mcols[which],
+                                                                 w + L.wts_hi[which] + dcol, w + L.wts_lo[which] + dcol);
+        psn_count_launch("psn_lg_prep_kernel");
+    }
+    void project(int which, const CUtensorMap& bz, const CUtensorMap& bv, int R, const float* cadd, float* out, const char* name) const {
+        if (R <= 0) return;
+        LgParams q = base();
+        q.R = R; q.nsrc = dae ? 2 : 1; q.kchunks = H / 32;
+        q.add1 = cadd; q.add1_sr = 0; q.add1_ld = H;
+        q.out = out; q.out_sr = BH; q.out_ld = H;
+        launch(which, bz, dae ? bv : bz, q, name);
+    }
+};
+
+// weights -> planes, per-trajectory constants, tensor maps, hoisted layer-1 halves over the whole series
+int lg_setup(LgCtx& c, const psnode_problem* p, bool bwd, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    c.p = p;
+    c.L = lg_layout(p, bwd);
+    const LgLayout& L = c.L;
+    if (ws == nullptr || ws_bytes < L.total * 4) return PSNODE_EWORKSPACE;
+    float* w = c.w = static_cast<float*>(ws);
+    c.err = reinterpret_cast<int*>(w + L.err);
+    c.stream = stream;
+    const bool dae = c.dae = p->kind == PSNODE_DAE;
+    const int H = c.H = L.H, B = c.B = p->B, T = c.T = p->T, E = c.E = p->event_idx ? p->E : 0;
+    const int S = c.S = L.S;
+    c.BH = (int64_t)B * H;
+    c.nstages = psw_nstages(p->method);
+    c.nbt = (B + TN - 1) / TN;
+    static const int dbg_cta = std::getenv("PSNODE_LG_DBG") ? std::atoi(std::getenv("PSNODE_LG_DBG")) : 0;
+    static const int rotate = std::getenv("PSNODE_LG_ROTATE") ? std::atoi(std::getenv("PSNODE_LG_ROTATE")) : 1;
+    c.dbg_cta = dbg_cta; c.rotate = rotate;
+    PSN_CUDA(cudaMemsetAsync(c.err, 0, 256, stream));
+    // ---- weights: folded, split into tf32 hi / lo planes ----
+    const float* W1 = p->de.W[0];
+    const int ld1 = 3 * S;
+    const int X = p->X, Z = p->Z, V = p->V;
+    const float* A1 = dae ? p->ae.W[0] : nullptr;
+    const int lda = S + X + Z + V;
+    c.prep(M_DE1X, W1, ld1, S, 2 * S, 1.0f, 0, H, H, 0);                              // F_x = (W_b + W_c)[:, 0:X]
+    c.prep(M_DE1ZV, W1, ld1, S + X, 2 * S + X, 1.0f, 0, H, L.KZV, 0);                 // [F_z | F_v]
+    c.prep(M_DE2, p->de.W[1], H, 0, -1, 0.0f, 0, H, H, 0);
+    if (dae) {
+        c.prep(M_DE1I, W1, ld1, S + X + Z + V, 2 * S + X + Z + V, 1.0f, 0, H, H, 0);   // F_i
+        c.prep(M_AE1X, A1, lda, S, -1, 0.0f, 0, H, H, 0);
+        c.prep(M_AE1ZV, A1, lda, S + X, -1, 0.0f, 0, H, L.KZV, 0);
+        c.prep(M_AE2, p->ae.W[1], H, 0, -1, 0.0f, 0, H, H, 0);
+        psn_lg_const_kernel<<<(B + 7) / 8, H, 8 * S * 4, stream>>>(A1, lda, -1, p->ae.b[0], p->a0, p->a0_sb, S, B, H, w + L.c_ae);
+        psn_count_launch("psn_lg_const_kernel");
+    }
+    if (bwd) {
+        c.prep(M_T_DE2, p->de.W[1], H, 0, -1, 0.0f, 1, H, H, 0);                      // W2^T
+        c.prep(M_T_DE1X, W1, ld1, S, 2 * S, 1.0f, 1, H, H, 0);                        // F_x^T
+        c.prep(M_T_DZ, W1, ld1, S + X, 2 * S + X, 1.0f, 1, H, H, 0);                  // [F_z^T | A1z^T]
+        c.prep(M_T_DA0, W1, ld1, 0, S, -1.0f, 1, S, H, 0);                            // [(W_a - W_b)^T | A1a^T]
+        if (dae) {
+            c.prep(M_T_DE1I, W1, ld1, S + X + Z + V, 2 * S + X + Z + V, 1.0f, 1, H, H, 0);
+            c.prep(M_T_AE2, p->ae.W[1], H, 0, -1, 0.0f, 1, H, H, 0);
+            c.prep(M_T_AE1X, A1, lda, S, -1, 0.0f, 1, H, H, 0);
+            c.prep(M_T_DZ, A1, lda, S + X, -1, 0.0f, 1, H, H, H);
+            c.prep(M_T_DV, W1, ld1, S + X + Z, 2 * S + X + Z, 1.0f, 1, H, H, 0);      // [F_v^T | A1v^T]
+            c.prep(M_T_DV, A1, lda, S + X + Z, -1, 0.0f, 1, H, H, H);
+            c.prep(M_T_DA0, A1, lda, 0, -1, 0.0f, 1, S, H, H);
+        }
+    }
+    psn_lg_const_kernel<<<(B + 7) / 8, H, 8 * S * 4, stream>>>(W1, ld1, S, p->de.b[0], p->a0, p->a0_sb, S, B, H, w + L.c_de);
+    psn_count_launch("psn_lg_const_kernel");
+    PSN_CUDA(cudaGetLastError());
+
+    // ---- tensor maps (once per call) ----
+    bool ok = true;
+    for (int i = 0; i < L.nmat; i++) {
+        if (L.wts_hi[i] == 0) continue;
+        ok = ok && lg_make_map(&c.mw_hi[i], w + L.wts_hi[i], L.mcols[i], L.mrows[i], L.mcols[i], 1, 0) &&
+             lg_make_map(&c.mw_lo[i], w + L.wts_lo[i], L.mcols[i], L.mrows[i], L.mcols[i], 1, 0);
+    }
+    ok = ok && lg_make_map(&c.m_z, p->z.p, H, B, p->z.sb, T, p->z.st);
+    if (dae) ok = ok && lg_make_map(&c.m_v, p->v.p, H, B, p->v.sb, T, p->v.st);
+    if (E > 0) {
+        ok = ok && lg_make_map(&c.m_zj, p->z_jump, H, B, p->zj_sb, E, p->zj_se);
+        if (dae) ok = ok && lg_make_map(&c.m_vj, p->v_jump, H, B, p->vj_sb, E, p->vj_se);
+    }
+    ok = ok && lg_make_map(&c.m_y, w + L.ycur, H, B, H, 1, 0) && lg_make_map(&c.m_a1, w + L.a1, H, B, H, 1, 0);
+    if (dae) ok = ok && lg_make_map(&c.m_h, w + L.hbuf, H, B, H, 1, 0) && lg_make_map(&c.m_i, w + L.icur, H, B, H, 1, 0);
+    if (!ok) return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (layer path)");
+    if (lg_prepare_kernels() != PSNODE_OK) return PSNODE_ECUDA;
+
+    // ---- hoisted layer-1 halves over the whole series ----
+    const int64_t BH = c.BH;
+    const int64_t jump_de = (int64_t)(T > 1 ? T - 1 : 0) * BH;
+    c.project(M_DE1ZV, c.m_z, c.m_v, T - 1, w + L.c_de, w + L.pre_de, "psn_lg_gemm_kernel<pre_de>");
+    if (E > 0) c.project(M_DE1ZV, c.m_zj, c.m_vj, E, w + L.c_de, w + L.pre_de + jump_de, "psn_lg_gemm_kernel<pre_de_jump>");
+    if (dae) {
+        c.project(M_AE1ZV, c.m_z, c.m_v, T, w + L.c_ae, w + L.pre_ae, "psn_lg_gemm_kernel<pre_ae>");
+        if (E > 0) c.project(M_AE1ZV, c.m_zj, c.m_vj, E, w + L.c_ae, w + L.pre_ae + (int64_t)T * BH, "psn_lg_gemm_kernel<pre_ae_jump>");
+    }
+    return PSNODE_OK;
+}
+
+// ---- small fp32 kernels of the reverse pass (element-wise over one (B, H) buffer) --------------------------------------------
+// start of the sweep: gx = dL/dx_sol[T-1], gi = dL/di_sol[T-1], acc_gi = gi
+__global__ void psn_lg_bwd_init_kernel(int B, int H, const float* __restrict__ gx_up, int64_t gx_sb, const float* __restrict__ gi_up, int64_t gi_sb,
+                                       float* __restrict__ gx, float* __restrict__ gi, float* __restrict__ acc_gi) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * H) return;
+    const int b = idx / H, m = idx - b * H;
+    gx[idx] = __ldg(gx_up + (int64_t)b * gx_sb + m);
+    if (gi_up) {
+        const float g = __ldg(gi_up + (int64_t)b * gi_sb + m);
+        gi[idx] = g;
+        acc_gi[idx] = g;
+    }
+}
+// head of step j: stage-0 input y0 = x_sol[j-1], held i0 = i_sol[j-1], slope adjoint of the last stage dk = gx * dt * c
+__global__ void psn_lg_bwd_head_kernel(int B, int H, const float* __restrict__ xprev, int64_t x_sb, const float* __restrict__ iprev, int64_t i_sb,
+                                       float* __restrict__ y0, float* __restrict__ i0, const float* __restrict__ gx, const float* __restrict__ tcur,
+                                       const float* __restrict__ tprev, int64_t t_sb, float c, float* __restrict__ dk, float* __restrict__ acc_dk) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * H) return;
+    const int b = idx / H, m = idx - b * H;
+    y0[idx] = __ldg(xprev + (int64_t)b * x_sb + m);
+    if (iprev) i0[idx] = __ldg(iprev + (int64_t)b * i_sb + m);
+    const float dt = __fsub_rn(__ldg(tcur + (int64_t)b * t_sb), __ldg(tprev + (int64_t)b * t_sb));
+    const float v = gx[idx] * (dt * c);
+    dk[idx] = v;
+    acc_dk[idx] += v;
+}
+// tail of step j: d pre_de row (the row of the event when one fired at j-1, and then zeros in the grid row), and the adjoint of
+// i_{j-1}: dL/di_sol[j-1] (+ F_i^T dsum when i_{j-1} itself was the held i0, i.e. no event re-evaluated it)
+__global__ void psn_lg_bwd_tail_kernel(int B, int H, const int32_t* __restrict__ ev, int ev_j, const float* __restrict__ dsum, float* __restrict__ dpre_row,
+                                       float* __restrict__ dpre_jump, int64_t jump_sr, const float* __restrict__ gi0, const float* __restrict__ gi_up,
+                                       int64_t gi_sb, float* __restrict__ gi_next, float* __restrict__ acc_gi) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * H) return;
+    const int b = idx / H, m = idx - b * H;
+    const int evk = ev ? __ldg(ev + ev_j) : -1;
+    const float d = dsum[idx];
+    if (evk < 0) dpre_row[idx] = d;
+    else { dpre_row[idx] = 0.0f; dpre_jump[(int64_t)evk * jump_sr + idx] = d; }
+    if (gi_next) {
+        const float up = __ldg(gi_up + (int64_t)b * gi_sb + m), g0 = gi0[idx];
+        gi_next[idx] = evk < 0 ? up + g0 : up;
+        acc_gi[idx] += up + g0;
+    }
+}
+// out[m] = sum_b src[b][m]: block = 32 features, 32 row lanes
+__global__ void __launch_bounds__(1024) psn_lg_colsum_kernel(const float* __restrict__ src, int B, int H, float* __restrict__ out) {
+    __shared__ float part[32][33];
+    const int c = threadIdx.x & 31, r = threadIdx.x >> 5, m = blockIdx.x * 32 + c;
+    float s = 0.0f;
+    for (int b = r; b < B; b += 32) s += src[(int64_t)b * H + m];
+    part[r][c] = s;
+    __syncthreads();
+    if (r == 0) {
+        float t = 0.0f;
+        for (int i = 0; i < 32; i++) t += part[i][c];
+        out[m] = t;
+    }
+}
+// dW1 = [dW_a | dW_b | dW_c] with dW_a = dc (x) a0 (already in place), dW_c = dF (already in place), dW_b = dF - dW_a
+__global__ void psn_lg_unfold_w1_kernel(float* __restrict__ dW1, int H, int S) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * S) return;
+    const int m = idx / S, k = idx - m * S;
+    float* row = dW1 + (int64_t)m * 3 * S;
+    row[S + k] = row[2 * S + k] - row[k];
+}
+__global__ void psn_lg_copy_rows_kernel(int B, int H, const float* __restrict__ src, float* __restrict__ dst, int64_t dst_sb) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * H) return;
+    dst[(int64_t)(idx / H) * dst_sb + (idx % H)] = src[idx];
+}
+__global__ void psn_lg_zero_rows_kernel(int R, int B, int H, float* __restrict__ dst, int64_t dst_sr, int64_t dst_sb) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)R * B * H) return;
+    const int64_t r = idx / ((int64_t)B * H), rem = idx - r * (int64_t)B * H;
+    dst[r * dst_sr + (rem / H) * dst_sb + (rem % H)] = 0.0f;
+}
 
 }  // namespace
 
@@ -717,96 +996,17 @@ bool psn_lg_supports(const psnode_problem* p) {
     return lg_encode_fn() != nullptr;
 }
 
-int64_t psn_lg_forward_workspace(const psnode_problem* p) { return lg_layout(p).total * 4; }
+int64_t psn_lg_forward_workspace(const psnode_problem* p) { return lg_layout(p, false).total * 4; }
 
 int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream) {
-    const LgLayout L = lg_layout(p);
-    if (ws == nullptr || ws_bytes < L.total * 4) return PSNODE_EWORKSPACE;
-    float* w = static_cast<float*>(ws);
-    int* err = reinterpret_cast<int*>(w + L.err);
-    const bool dae = p->kind == PSNODE_DAE;
-    const int H = L.H, B = p->B, T = p->T, E = p->event_idx ? p->E : 0;
-    const int S = p->X + p->Z + p->V + p->I;
-    const int64_t BH = (int64_t)B * H;
-    const int nstages = psw_nstages(p->method);
-    PSN_CUDA(cudaMemsetAsync(err, 0, 256, stream));
-    // ---- weights: folded, split into tf32 hi / lo planes ----
-    const float* W1 = p->de.W[0];
-    const int ld1 = 3 * S;
-    auto prep = [&](int which, const float* W, int ldw, int col0, int col1, int K) {
-        const int n = H * K;
-        psn_lg_prep_kernel<<<(n + 255) / 256, 256, 0, stream>>>(W, ldw, col0, col1, H, K, w + L.wts_hi[which], w + L.wts_lo[which]);
-        psn_count_launch("psn_lg_prep_kernel");
-    };
-    prep(M_DE1X, W1, ld1, S, 2 * S, H);                                       // F_x = (W_b + W_c)[:, 0:X]
-    prep(M_DE1ZV, W1, ld1, S + p->X, 2 * S + p->X, L.KZV);                    // [F_z | F_v]
-    prep(M_DE2, p->de.W[1], H, 0, -1, H);
-    if (dae) {
-        prep(M_DE1I, W1, ld1, S + p->X + p->Z + p->V, 2 * S + p->X + p->Z + p->V, H);   // F_i
-        const int lda = S + p->X + p->Z + p->V;
-        prep(M_AE1X, p->ae.W[0], lda, S, -1, H);
-        prep(M_AE1ZV, p->ae.W[0], lda, S + p->X, -1, L.KZV);
-        prep(M_AE2, p->ae.W[1], H, 0, -1, H);
-        psn_lg_const_kernel<<<(B + 7) / 8, H, 8 * S * 4, stream>>>(p->ae.W[0], lda, -1, p->ae.b[0], p->a0, p->a0_sb, S, B, H, w + L.c_ae);
-        psn_count_launch("psn_lg_const_kernel");
-    }
-    psn_lg_const_kernel<<<(B + 7) / 8, H, 8 * S * 4, stream>>>(W1, ld1, S, p->de.b[0], p->a0, p->a0_sb, S, B, H, w + L.c_de);
-    psn_count_launch("psn_lg_const_kernel");
-    PSN_CUDA(cudaGetLastError());
-
-    // ---- tensor maps (once per call) ----
-    CUtensorMap mw_hi[7], mw_lo[7], m_z, m_v, m_zj, m_vj, m_y, m_a1, m_h, m_i;
-    const int kt[7] = {H, L.KZV, H, H, H, L.KZV, H};
-    bool ok = true;
-    for (int i = 0; i < 7; i++) {
-        if (!dae && (i == M_DE1I || i >= M_AE1X)) continue;
-        ok = ok && lg_make_map(&mw_hi[i], w + L.wts_hi[i], kt[i], H, kt[i], 1, 0) && lg_make_map(&mw_lo[i], w + L.wts_lo[i], kt[i], H, kt[i], 1, 0);
-    }
-    ok = ok && lg_make_map(&m_z, p->z.p, H, B, p->z.sb, T, p->z.st);
-    if (dae) ok = ok && lg_make_map(&m_v, p->v.p, H, B, p->v.sb, T, p->v.st);
-    if (E > 0) {
-        ok = ok && lg_make_map(&m_zj, p->z_jump, H, B, p->zj_sb, E, p->zj_se);
-        if (dae) ok = ok && lg_make_map(&m_vj, p->v_jump, H, B, p->vj_sb, E, p->vj_se);
-    }
-    ok = ok && lg_make_map(&m_y, w + L.ycur, H, B, H, 1, 0) && lg_make_map(&m_a1, w + L.a1, H, B, H, 1, 0);
-    if (dae) ok = ok && lg_make_map(&m_h, w + L.hbuf, H, B, H, 1, 0) && lg_make_map(&m_i, w + L.icur, H, B, H, 1, 0);
-    if (!ok) return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (layer path)");
-
-    const int smem = (int)sizeof(LgSmem) + 1024;
-    using KernFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const LgParams);
-    if (lg_prepare_kernels() != PSNODE_OK) return PSNODE_ECUDA;
-    const LgKernFn* kerns = lg_kernels();
-    auto epi_of = [&](const LgParams& q) { return lg_epi_of(q); };
-    const int nbt = (B + TN - 1) / TN;
-    static const int dbg_cta = std::getenv("PSNODE_LG_DBG") ? std::atoi(std::getenv("PSNODE_LG_DBG")) : 0;
-    static const int rotate = std::getenv("PSNODE_LG_ROTATE") ? std::atoi(std::getenv("PSNODE_LG_ROTATE")) : 1;
-    auto base = [&]() {
-        LgParams q;
-        std::memset(&q, 0, sizeof(q));
-        q.N = B; q.R = 1; q.nbt = nbt; q.nsrc = 1; q.kchunks = H / 32; q.mode = LG_PLAIN;
-        q.add1_ld = H; q.add2_ld = H; q.out_ld = H; q.st_ld = H;
-        q.err = err;
-        q.dbg = dbg_cta; q.rotate = rotate;
-        return q;
-    };
-    auto launch = [&](int which, const CUtensorMap& b0, const CUtensorMap& b1, const LgParams& q, const char* name) -> int {
-        return lg_launch_gemm(mw_hi[which], mw_lo[which], b0, b1, q, H / TM, stream, name);
-    };
-    // ---- hoisted layer-1 halves over the whole series ----
-    auto project = [&](int which, const CUtensorMap& bz, const CUtensorMap& bv, int R, const float* cadd, float* out, const char* name) {
-        if (R <= 0) return;
-        LgParams q = base();
-        q.R = R; q.nsrc = dae ? 2 : 1; q.kchunks = H / 32;
-        q.add1 = cadd; q.add1_sr = 0; q.add1_ld = H;
-        q.out = out; q.out_sr = BH; q.out_ld = H;
-        launch(which, bz, dae ? bv : bz, q, name);
-    };
-    project(M_DE1ZV, m_z, m_v, T - 1, w + L.c_de, w + L.pre_de, "psn_lg_gemm_kernel<pre_de>");
-    if (E > 0) project(M_DE1ZV, m_zj, m_vj, E, w + L.c_de, w + L.pre_de + (int64_t)(T - 1) * BH, "psn_lg_gemm_kernel<pre_de_jump>");
-    if (dae) {
-        project(M_AE1ZV, m_z, m_v, T, w + L.c_ae, w + L.pre_ae, "psn_lg_gemm_kernel<pre_ae>");
-        if (E > 0) project(M_AE1ZV, m_zj, m_vj, E, w + L.c_ae, w + L.pre_ae + (int64_t)T * BH, "psn_lg_gemm_kernel<pre_ae_jump>");
-    }
+    LgCtx c;
+    const int st = lg_setup(c, p, false, ws, ws_bytes, stream);
+    if (st != PSNODE_OK) return st;
+    const LgLayout& L = c.L;
+    float* w = c.w;
+    const bool dae = c.dae;
+    const int H = c.H, B = c.B, T = c.T, E = c.E;
+    const int64_t BH = c.BH;
     // ---- initial state ----
     {
         const float* src = dae ? p->x_init : p->x.p;
@@ -816,7 +1016,7 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
     }
     // algebraic evaluation i = ae(x, z, v) on the current state (ycur holds x at step boundaries)
     auto ae_eval = [&](const float* pre_row, int jrow, bool event_only, int ev_j) {
-        LgParams q = base();
+        LgParams q = c.base();
         q.mode = LG_HIDDEN;
         q.add1 = pre_row; q.add1_sr = 0;
         if (event_only) {
@@ -824,32 +1024,32 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
             q.add1_jump = w + L.pre_ae + (int64_t)T * BH; q.add1_jump_sr = BH;
         }
         q.out = w + L.hbuf;
-        launch(M_AE1X, m_y, m_y, q, event_only ? "psn_lg_gemm_kernel<ae1,event>" : "psn_lg_gemm_kernel<ae1>");
-        LgParams q2 = base();
+        c.launch(M_AE1X, c.m_y, c.m_y, q, event_only ? "psn_lg_gemm_kernel<ae1,event>" : "psn_lg_gemm_kernel<ae1>");
+        LgParams q2 = c.base();
         q2.bias = p->ae.b[1];
         if (event_only) { q2.ev = p->event_idx; q2.ev_j = ev_j; q2.skip_unless_event = 1; }
         q2.out = w + L.icur;
         if (jrow >= 0) { q2.out2 = p->i_sol.p + (int64_t)jrow * p->i_sol.st; q2.out2_ld = p->i_sol.sb; }
-        launch(M_AE2, m_h, m_h, q2, event_only ? "psn_lg_gemm_kernel<ae2,event>" : "psn_lg_gemm_kernel<ae2>");
+        c.launch(M_AE2, c.m_h, c.m_h, q2, event_only ? "psn_lg_gemm_kernel<ae2,event>" : "psn_lg_gemm_kernel<ae2>");
     };
     if (dae) ae_eval(w + L.pre_ae, 0, false, 0);                               // i_0 = ae(x_0, z[0], v[0])  (my_solvers.py:95)
 
     for (int j = 1; j < T; j++) {
         if (dae) {
             if (E > 0) ae_eval(nullptr, -1, true, j - 1);                      // event: i_0 re-evaluated with the jumped inputs (:108-110)
-            LgParams qg = base();                                              // G = F_i i0
+            LgParams qg = c.base();                                            // G = F_i i0
             qg.out = w + L.G;
-            launch(M_DE1I, m_i, m_i, qg, "psn_lg_gemm_kernel<de1_i>");
+            c.launch(M_DE1I, c.m_i, c.m_i, qg, "psn_lg_gemm_kernel<de1_i>");
         }
-        for (int e = 0; e < nstages; e++) {
-            LgParams q1 = base();
+        for (int e = 0; e < c.nstages; e++) {
+            LgParams q1 = c.base();
             q1.mode = LG_HIDDEN;
             q1.add1 = w + L.pre_de + (int64_t)(j - 1) * BH;
             if (E > 0) { q1.ev = p->event_idx; q1.ev_j = j - 1; q1.add1_jump = w + L.pre_de + (int64_t)(T - 1) * BH; q1.add1_jump_sr = BH; }
             if (dae) q1.add2 = w + L.G;
             q1.out = w + L.a1;
-            launch(M_DE1X, m_y, m_y, q1, "psn_lg_gemm_kernel<de1>");
-            LgParams q2 = base();
+            c.launch(M_DE1X, c.m_y, c.m_y, q1, "psn_lg_gemm_kernel<de1>");
+            LgParams q2 = c.base();
             q2.mode = LG_RK;
             q2.bias = p->de.b[1];
             q2.method = p->method; q2.stage = e;
@@ -857,23 +1057,371 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
             q2.t_cur = p->t.p + (int64_t)j * p->t.st; q2.t_prev = p->t.p + (int64_t)(j - 1) * p->t.st; q2.t_sb = p->t.sb;
             q2.out = w + L.ycur;
             q2.out2 = p->x_sol.p + (int64_t)j * p->x_sol.st; q2.out2_ld = p->x_sol.sb;
-            launch(M_DE2, m_a1, m_a1, q2, "psn_lg_gemm_kernel<de2,rk>");
+            c.launch(M_DE2, c.m_a1, c.m_a1, q2, "psn_lg_gemm_kernel<de2,rk>");
         }
         if (dae) ae_eval(w + L.pre_ae + (int64_t)j * BH, j, false, 0);          // i_j = ae(x_j, z[j], v[j])  (:121)
     }
     PSN_CUDA(cudaGetLastError());
-    if (dbg_cta) {                            // debugging aid only: synchronises
+    if (c.dbg_cta) {                          // debugging aid only: synchronises
         long long h[64];
         cudaStreamSynchronize(stream);
         cudaMemcpyFromSymbol(h, g_lg_dbg, sizeof(h));
-        std::fprintf(stderr, "psn_lg stamps (cycles since kernel start, last launch, CTA %d):", dbg_cta - 1);
+        std::fprintf(stderr, "psn_lg stamps (cycles since kernel start, last launch, CTA %d):", c.dbg_cta - 1);
         for (int i = 1; i < (int)h[63] && i < 32; i++) std::fprintf(stderr, " %lld", h[i] - h[0]);
         std::fprintf(stderr, "\n");
     }
     return PSNODE_OK;
 }
 
+// ---- reverse sweep (discrete adjoint) on the same per-layer GEMM kernel --------------------------------------------------------
+// Exact reverse mode of the loop above (what loss.backward() replays in the reference, neural_01_DAE_02_direct_encode.py training
+// loop -> my_solvers.py:82-131).  Nothing of the forward pass is kept except the trajectory: x_sol / i_sol are the checkpoints, and
+// every step's stage inputs y_e and hidden activations a1_e are recomputed from x_sol[j-1] / i_sol[j-1] by the forward's own GEMM
+// launches (the cfg5 activation tape would be 150 GB per shard).  Per step, walking j = T-1 .. 1:
+//     AE at j:    h_j recomputed;  dh = (A2^T gi_j) * ELU'(h_j);  gx_j += A1x^T dh;  d pre_ae[j] = dh
+//     DE step j:  stages recomputed;  for e = last .. 0:  delta1_e = (W2^T dk_e) * ELU'(a1_e);  dy_e = F_x^T delta1_e -> Runge-Kutta
+//                 adjoint -> dk_{e-1} / gx_{j-1};  dsum = sum_e delta1_e = d pre_de[j-1] = dG;  gi0 = F_i^T dsum -> gi_{j-1}
+//                 (or, when an event re-evaluated i0 at j-1, through that evaluation into gx_{j-1} and the jump rows)
+// Weight-gradient products (delta (x) activation, summed over trajectories, stages and steps) run as big-K MN-major GEMMs
+// (psn_lg_wgrad_kernel) once per `ring` steps on a ring of recomputed activations / deltas; input-series, jump, all_initial
+// gradients and the layer-1 constants are hoisted to the end exactly as the forward hoists the corresponding products.
+bool psn_lg_bwd_supports(const psnode_problem* p, const psnode_adjoint* a) {
+    if (!psn_lg_supports(p)) return false;
+    if (a->d_xteach.p || a->d_iteach.p) return false;
+    if (a->fuse_x.target.p || a->fuse_i.target.p) return false;
+    const bool dae = p->kind == PSNODE_DAE;
+    if (!a->gx.p || (dae && !a->gi.p)) return false;
+    if (!view_ok(p->a0, p->a0_sb, 0)) return false;
+    if (!view_ok(p->x_sol.p, p->x_sol.st, p->x_sol.sb)) return false;
+    if (dae && !view_ok(p->i_sol.p, p->i_sol.st, p->i_sol.sb)) return false;
+    static const bool off = std::getenv("PSNODE_LG_BWD") && std::atoi(std::getenv("PSNODE_LG_BWD")) == 0;
+    return !off;
+}
 
+int64_t psn_lg_backward_workspace(const psnode_problem* p, const psnode_adjoint* a) {
+    (void)a;
+    return lg_layout(p, true).total * 4;
+}
+
+int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    LgCtx c;
+    int st = lg_setup(c, p, true, ws, ws_bytes, stream);
+    if (st != PSNODE_OK) return st;
+    const LgLayout& L = c.L;
+    float* w = c.w;
+    const bool dae = c.dae;
+    const int H = c.H, B = c.B, T = c.T, E = c.E, S = c.S, NS = c.nstages;
+    const int X = p->X, Z = p->Z, V = p->V;
+    const int64_t BH = c.BH, BHa = al(BH);
+    const int ring = L.ring;
+    const int nblk = (int)((BH + 255) / 256);
+    auto buf = [&](int i) { return w + L.bufs + (int64_t)i * BHa; };
+    float* slabs = w + L.slabs;
+
+    // ---- d_theta layout (psnode_b200.h): de: W1 (H x 3S), b1, W2 (H x H), b2; ae: A1 (H x (S + X + Z + V)), ab1, A2, ab2 ----
+    const int lda = S + X + Z + V;
+    const int64_t o_W1 = 0, o_b1 = o_W1 + (int64_t)H * 3 * S, o_W2 = o_b1 + H, o_b2 = o_W2 + (int64_t)H * H;
+    const int64_t o_A1 = o_b2 + H, o_ab1 = o_A1 + (int64_t)H * lda, o_A2 = o_ab1 + H, o_ab2 = o_A2 + (int64_t)H * H;
+    const int64_t ntheta = dae ? o_ab2 + H : o_A1;
+    if (a->n_theta < ntheta) return PSNODE_EINVAL;
+    float* th = a->d_theta;
+    PSN_CUDA(cudaMemsetAsync(th, 0, (size_t)ntheta * 4, stream));
+    // zero: kept dy buffers (schemes with fewer stages read them as zeros), accumulators, jump-row gradients, last d pre_de row
+    for (int i : {BUF_DY3, BUF_DY2, BUF_DY1, BUF_DCDE, BUF_DCAE, BUF_ACCDK, BUF_ACCGI, BUF_GI0})
+        PSN_CUDA(cudaMemsetAsync(buf(i), 0, (size_t)BH * 4, stream));
+    PSN_CUDA(cudaMemsetAsync(w + L.dpj_de, 0, (size_t)(E > 0 ? E : 1) * BH * 4, stream));
+    PSN_CUDA(cudaMemsetAsync(w + L.dpj_ae, 0, (size_t)(E > 0 ? E : 1) * BH * 4, stream));
+    float* dpre_de = w + L.pre_de;                                            // rows 0 .. T-2 overwritten in place, row T-1 = 0
+    float* dpre_ae = w + L.pre_ae;
+    const int64_t jump_de = (int64_t)(T > 1 ? T - 1 : 0) * BH;                // forward's event rows of pre_de (read only here)
+
+    // ---- tensor maps of the reverse pass ----
+    CUtensorMap m_buf, m_xsol, m_isol, m_dpde, m_dpae, m_dpjde, m_dpjae, m_zero;
+    bool ok = lg_make_map(&m_buf, w + L.bufs, H, B, H, L.nbufs, BHa) && lg_make_map(&m_xsol, p->x_sol.p, H, B, p->x_sol.sb, T, p->x_sol.st);
+    if (dae) ok = ok && lg_make_map(&m_isol, p->i_sol.p, H, B, p->i_sol.sb, T, p->i_sol.st);
+    if (T > 1) ok = ok && lg_make_map(&m_dpde, dpre_de, H, B, H, T - 1, BH);
+    if (dae) ok = ok && lg_make_map(&m_dpae, dpre_ae, H, B, H, T, BH);
+    ok = ok && lg_make_map(&m_dpjde, w + L.dpj_de, H, B, H, E > 0 ? E : 1, BH) && lg_make_map(&m_dpjae, w + L.dpj_ae, H, B, H, E > 0 ? E : 1, BH);
+    ok = ok && lg_make_map(&m_zero, buf(BUF_DY1), H, B, H, 1, 0);
+    if (!ok) return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (layer path, reverse)");
+
+    auto gemm = [&](int which, int bidx, LgParams& q, const char* name) {      // B operand = work buffer `bidx`
+        q.b_r0 = bidx;
+        c.launch(which, m_buf, m_buf, q, name);
+    };
+    auto gated = [&](LgParams& q, int ev_j) { q.ev = p->event_idx; q.ev_j = ev_j; q.skip_unless_event = 1; };
+    const float* t = p->t.p;
+    const float c_last = p->method == PSNODE_RK4 ? 0.125f : 1.0f;
+
+    // AE at grid point j: gi (ring slot s) -> dh, gx, d pre_ae[j]
+    auto ae_backward = [&](int j, int s) {
+        LgParams q1 = c.base();                                                // h_j = ELU(A1x x_j + pre_ae[j])
+        q1.mode = LG_HIDDEN;
+        q1.add1 = dpre_ae + (int64_t)j * BH;
+        q1.out = buf(L.ring_one(R_H, s));
+        q1.b_r0 = j;
+        c.launch(M_AE1X, m_xsol, m_xsol, q1, "psn_lg_gemm_kernel<bwd:ae1>");
+        LgParams q2 = c.base();                                                // dh = (A2^T gi_j) * ELU'(h_j)
+        q2.mode = LG_DELTA;
+        q2.add1 = buf(L.ring_one(R_H, s));
+        q2.out = buf(L.ring_one(R_DH, s));
+        q2.out2 = dpre_ae + (int64_t)j * BH; q2.out2_ld = H;
+        q2.acc = buf(BUF_DCAE);
+        gemm(M_T_AE2, L.ring_one(R_GI, s), q2, "psn_lg_gemm_kernel<bwd:ae2^T>");
+        LgParams q3 = c.base();                                                // gx += A1x^T dh
+        q3.add1 = buf(BUF_GX);
+        q3.out = buf(BUF_GX);
+        gemm(M_T_AE1X, L.ring_one(R_DH, s), q3, "psn_lg_gemm_kernel<bwd:ae1x^T>");
+    };
+    // weight-gradient products of the steps / grid points of one ring batch: grid points [j_lo, j_hi)
+    auto flush = [&](int j_lo, int j_hi) -> int {
+        const int de_lo = j_lo < 1 ? 1 : j_lo, n_de = j_hi - de_lo;            // DE steps in the batch
+        int rc = PSNODE_OK;
+        if (n_de > 0) {
+            const int s0 = de_lo % ring;
+            rc = lg_wgrad(buf(L.ring_dk(s0, 0)), H, BHa, H, buf(L.ring_a1(s0, 0)), H, BHa, H, n_de * NS, B, th + o_W2, H, 1, slabs, c.err, stream);
+            if (rc != PSNODE_OK) return rc;
+            rc = lg_wgrad(buf(L.ring_d1(s0, 0)), H, BHa, H, buf(L.ring_y(s0, 0)), H, BHa, H, n_de * NS, B, th + o_W1 + 2 * S, 3 * S, 1, slabs, c.err, stream);
+            if (rc != PSNODE_OK) return rc;
+            if (dae) {
+                rc = lg_wgrad(buf(L.ring_one(R_DSUM, s0)), H, BHa, H, buf(L.ring_one(R_I0, s0)), H, BHa, H, n_de, B, th + o_W1 + 2 * S + X + Z + V, 3 * S, 1,
+                              slabs, c.err, stream);
+                if (rc != PSNODE_OK) return rc;
+            }
+        }
+        if (dae && j_hi > j_lo) {
+            const int s0 = j_lo % ring, n = j_hi - j_lo;
+            rc = lg_wgrad(buf(L.ring_one(R_GI, s0)), H, BHa, H, buf(L.ring_one(R_H, s0)), H, BHa, H, n, B, th + o_A2, H, 1, slabs, c.err, stream);
+            if (rc != PSNODE_OK) return rc;
+            rc = lg_wgrad(buf(L.ring_one(R_DH, s0)), H, BHa, H, p->x_sol.p + (int64_t)j_lo * p->x_sol.st, p->x_sol.sb, p->x_sol.st, H, n, B,
+                          th + o_A1 + S, lda, 1, slabs, c.err, stream);
+            if (rc != PSNODE_OK) return rc;
+        }
+        return PSNODE_OK;
+    };
+
+    // ---- start: adjoints of the last grid point ----
+    {
+        const int s = (T - 1) % ring;
+        psn_lg_bwd_init_kernel<<<nblk, 256, 0, stream>>>(B, H, a->gx.p + (int64_t)(T - 1) * a->gx.st, a->gx.sb,
+                                                         dae ? a->gi.p + (int64_t)(T - 1) * a->gi.st : nullptr, a->gi.sb, buf(BUF_GX),
+                                                         buf(L.ring_one(R_GI, s)), buf(BUF_ACCGI));
+        psn_count_launch("psn_lg_bwd_init_kernel");
+    }
+    for (int j = T - 1; j >= 0; j--) {
+        const int s = j % ring;
+        if (dae) ae_backward(j, s);
+        if (j >= 1) {
+            const float* tc = t + (int64_t)j * p->t.st;
+            const float* tp = t + (int64_t)(j - 1) * p->t.st;
+            psn_lg_bwd_head_kernel<<<nblk, 256, 0, stream>>>(B, H, p->x_sol.p + (int64_t)(j - 1) * p->x_sol.st, p->x_sol.sb,
+                                                             dae ? p->i_sol.p + (int64_t)(j - 1) * p->i_sol.st : nullptr, p->i_sol.sb,
+                                                             buf(L.ring_y(s, 0)), buf(L.ring_one(R_I0, s)), buf(BUF_GX), tc, tp, p->t.sb, c_last,
+                                                             buf(L.ring_dk(s, NS - 1)), buf(BUF_ACCDK));
+            psn_count_launch("psn_lg_bwd_head_kernel");
+            // ---- recompute the stages of step j ----
+            if (dae) {
+                if (E > 0) {                                                   // event at j-1: i0 = ae(x_{j-1}, jumped inputs)  (my_solvers.py:108-110)
+                    LgParams q = c.base();
+                    q.mode = LG_HIDDEN;
+                    gated(q, j - 1);
+                    q.add1_jump = w + L.pre_ae + (int64_t)T * BH; q.add1_jump_sr = BH;
+                    q.out = buf(BUF_HEV);
+                    gemm(M_AE1X, L.ring_y(s, 0), q, "psn_lg_gemm_kernel<bwd:ae1,event>");
+                    LgParams q2 = c.base();
+                    q2.bias = p->ae.b[1];
+                    gated(q2, j - 1);
+                    q2.out = buf(L.ring_one(R_I0, s));
+                    gemm(M_AE2, BUF_HEV, q2, "psn_lg_gemm_kernel<bwd:ae2,event>");
+                }
+                LgParams qg = c.base();                                        // G = F_i i0
+                qg.out = buf(BUF_G);
+                gemm(M_DE1I, L.ring_one(R_I0, s), qg, "psn_lg_gemm_kernel<bwd:de1_i>");
+            }
+            for (int e = 0; e < NS; e++) {
+                LgParams q1 = c.base();
+                q1.mode = LG_HIDDEN;
+                q1.add1 = w + L.pre_de + (int64_t)(j - 1) * BH;
+                if (E > 0) { q1.ev = p->event_idx; q1.ev_j = j - 1; q1.add1_jump = w + L.pre_de + jump_de; q1.add1_jump_sr = BH; }
+                if (dae) q1.add2 = buf(BUF_G);
+                q1.out = buf(L.ring_a1(s, e));
+                gemm(M_DE1X, L.ring_y(s, e), q1, "psn_lg_gemm_kernel<bwd:de1>");
+                if (e + 1 < NS) {                                              // next stage input (the last stage's slope is not needed)
+                    LgParams q2 = c.base();
+                    q2.mode = LG_RK;
+                    q2.bias = p->de.b[1];
+                    q2.method = p->method; q2.stage = e;
+                    q2.x0 = buf(L.ring_y(s, 0)); q2.k1 = buf(BUF_K1); q2.k2 = buf(BUF_K2); q2.k3 = buf(BUF_K3);
+                    q2.t_cur = tc; q2.t_prev = tp; q2.t_sb = p->t.sb;
+                    q2.out = buf(L.ring_y(s, e + 1));
+                    gemm(M_DE2, L.ring_a1(s, e), q2, "psn_lg_gemm_kernel<bwd:de2,rk>");
+                }
+            }
+            // ---- reverse through the stages ----
+            for (int e = NS - 1; e >= 0; e--) {
+                LgParams q1 = c.base();                                        // delta1_e = (W2^T dk_e) * ELU'(a1_e); dsum (+)= delta1_e
+                q1.mode = LG_DELTA;
+                q1.add1 = buf(L.ring_a1(s, e));
+                q1.out = buf(L.ring_d1(s, e));
+                q1.out2 = buf(L.ring_one(R_DSUM, s)); q1.out2_ld = H; q1.out2_acc = e == NS - 1 ? 0 : 1;
+                q1.acc = buf(BUF_DCDE);
+                gemm(M_T_DE2, L.ring_dk(s, e), q1, "psn_lg_gemm_kernel<bwd:de2^T>");
+                LgParams q2 = c.base();                                        // dy_e = F_x^T delta1_e -> Runge-Kutta adjoint
+                q2.mode = LG_BRK;
+                q2.x0 = buf(BUF_GX); q2.k1 = buf(BUF_DY3); q2.k2 = buf(BUF_DY2); q2.k3 = buf(BUF_DY1);
+                q2.t_cur = tc; q2.t_prev = tp; q2.t_sb = p->t.sb;
+                if (e == 0) {
+                    q2.stage = EPI_BSUM;
+                    q2.add1 = a->gx.p + (int64_t)(j - 1) * a->gx.st; q2.add1_ld = a->gx.sb;
+                    q2.out = buf(BUF_GX);
+                } else {
+                    q2.stage = p->method == PSNODE_MIDPOINT ? (int)EPI_BMID1 : (e == 3 ? (int)EPI_BRK3 : (e == 2 ? (int)EPI_BRK2 : (int)EPI_BRK1));
+                    q2.out = buf(L.ring_dk(s, e - 1));
+                    q2.acc = buf(BUF_ACCDK);
+                }
+                gemm(M_T_DE1X, L.ring_d1(s, e), q2, "psn_lg_gemm_kernel<bwd:de1x^T>");
+            }
+            if (dae) {
+                LgParams qi = c.base();                                        // gi0 = F_i^T dsum
+                qi.out = buf(BUF_GI0);
+                gemm(M_T_DE1I, L.ring_one(R_DSUM, s), qi, "psn_lg_gemm_kernel<bwd:de1i^T>");
+                if (E > 0) {                                                   // the event's own evaluation of i0: back into x_{j-1} and the jump rows
+                    LgParams q1 = c.base();
+                    q1.mode = LG_DELTA;
+                    gated(q1, j - 1);
+                    q1.add1 = buf(BUF_HEV);
+                    q1.out = buf(BUF_DHEV);
+                    q1.out2_jump = w + L.dpj_ae; q1.out2_jump_sr = BH; q1.out2_ld = H;
+                    q1.acc = buf(BUF_DCAE);
+                    gemm(M_T_AE2, BUF_GI0, q1, "psn_lg_gemm_kernel<bwd:ae2^T,event>");
+                    LgParams q2 = c.base();
+                    gated(q2, j - 1);
+                    q2.add1 = buf(BUF_GX);
+                    q2.out = buf(BUF_GX);
+                    gemm(M_T_AE1X, BUF_DHEV, q2, "psn_lg_gemm_kernel<bwd:ae1x^T,event>");
+                    st = lg_wgrad(buf(BUF_GI0), H, BHa, H, buf(BUF_HEV), H, BHa, H, 1, B, th + o_A2, H, 1, slabs, c.err, stream, p->event_idx, j - 1);
+                    if (st != PSNODE_OK) return st;
+                    st = lg_wgrad(buf(BUF_DHEV), H, BHa, H, buf(L.ring_y(s, 0)), H, BHa, H, 1, B, th + o_A1 + S, lda, 1, slabs, c.err, stream, p->event_idx,
+                                  j - 1);
+                    if (st != PSNODE_OK) return st;
+                }
+            }
+        }
+        if (j % ring == 0) {
+            st = flush(j, j + ring < T ? j + ring : T);
+            if (st != PSNODE_OK) return st;
+        }
+        if (j >= 1) {
+            const int sn = (j - 1) % ring;
+            psn_lg_bwd_tail_kernel<<<nblk, 256, 0, stream>>>(B, H, E > 0 ? p->event_idx : nullptr, j - 1, buf(L.ring_one(R_DSUM, s)),
+                                                             dpre_de + (int64_t)(j - 1) * BH, w + L.dpj_de, BH, dae ? buf(BUF_GI0) : nullptr,
+                                                             dae ? a->gi.p + (int64_t)(j - 1) * a->gi.st : nullptr, a->gi.sb,
+                                                             dae ? buf(L.ring_one(R_GI, sn)) : nullptr, buf(BUF_ACCGI));
+            psn_count_launch("psn_lg_bwd_tail_kernel");
+        }
+    }
+    PSN_CUDA(cudaGetLastError());
+
+    // ---- gradient of the initial state ----
+    if (a->d_x0) {
+        psn_lg_copy_rows_kernel<<<nblk, 256, 0, stream>>>(B, H, buf(BUF_GX), a->d_x0, a->d_x0_sb);
+        psn_count_launch("psn_lg_copy_rows_kernel");
+    }
+    // ---- input-series / jump gradients: d_z[r] = F_z^T d pre_de[r] + A1z^T d pre_ae[r]  (d pre_de[T-1] = 0: z[T-1] only enters the AE) ----
+    auto series_grad = [&](int which, float* out, int64_t out_sr, int64_t out_sb, const char* name) {
+        if (!out) return;
+        if (T > 1) {
+            LgParams q = c.base();
+            q.R = T - 1; q.nsrc = dae ? 2 : 1;
+            q.out = out; q.out_sr = out_sr; q.out_ld = out_sb;
+            c.launch(which, m_dpde, dae ? m_dpae : m_dpde, q, name);
+        }
+        if (dae) {                                                             // last grid row: the AE half only
+            LgParams q = c.base();
+            q.R = 1; q.nsrc = 2; q.b_r0 = 0;
+            q.out = out + (int64_t)(T - 1) * out_sr; q.out_sr = 0; q.out_ld = out_sb;
+            CUtensorMap m_last;
+            if (!lg_make_map(&m_last, dpre_ae + (int64_t)(T - 1) * BH, H, B, H, 1, 0)) return;
+            c.launch(which, m_zero, m_last, q, name);
+        } else {
+            psn_lg_zero_rows_kernel<<<nblk, 256, 0, stream>>>(1, B, H, out + (int64_t)(T - 1) * out_sr, 0, out_sb);
+            psn_count_launch("psn_lg_zero_rows_kernel");
+        }
+    };
+    auto jump_grad = [&](int which, float* out, int64_t out_se, int64_t out_sb, const char* name) {
+        if (!out || E <= 0) return;
+        LgParams q = c.base();
+        q.R = E; q.nsrc = dae ? 2 : 1;
+        q.out = out; q.out_sr = out_se; q.out_ld = out_sb;
+        c.launch(which, m_dpjde, dae ? m_dpjae : m_dpjde, q, name);
+    };
+    // BUF_DY1 doubles as the zero operand of the last row: clear it (the sweep used it)
+    PSN_CUDA(cudaMemsetAsync(buf(BUF_DY1), 0, (size_t)BH * 4, stream));
+    series_grad(M_T_DZ, a->d_z.p, a->d_z.st, a->d_z.sb, "psn_lg_gemm_kernel<bwd:d_z>");
+    if (dae) series_grad(M_T_DV, a->d_v.p, a->d_v.st, a->d_v.sb, "psn_lg_gemm_kernel<bwd:d_v>");
+    jump_grad(M_T_DZ, a->d_zjump, a->d_zj_se, a->d_zj_sb, "psn_lg_gemm_kernel<bwd:d_zjump>");
+    if (dae) jump_grad(M_T_DV, a->d_vjump, a->d_vj_se, a->d_vj_sb, "psn_lg_gemm_kernel<bwd:d_vjump>");
+
+    // ---- hoisted weight gradients: dF_z, dF_v (and dA1z, dA1v) over the whole series and the jump rows ----
+    if (T > 1) {
+        st = lg_wgrad(dpre_de, H, BH, H, p->z.p, p->z.sb, p->z.st, H, T - 1, B, th + o_W1 + 2 * S + X, 3 * S, 1, slabs, c.err, stream);
+        if (st != PSNODE_OK) return st;
+        if (dae) {
+            st = lg_wgrad(dpre_de, H, BH, H, p->v.p, p->v.sb, p->v.st, H, T - 1, B, th + o_W1 + 2 * S + X + Z, 3 * S, 1, slabs, c.err, stream);
+            if (st != PSNODE_OK) return st;
+        }
+    }
+    if (E > 0) {
+        st = lg_wgrad(w + L.dpj_de, H, BH, H, p->z_jump, p->zj_sb, p->zj_se, H, E, B, th + o_W1 + 2 * S + X, 3 * S, 1, slabs, c.err, stream);
+        if (st != PSNODE_OK) return st;
+        if (dae) {
+            st = lg_wgrad(w + L.dpj_de, H, BH, H, p->v_jump, p->vj_sb, p->vj_se, H, E, B, th + o_W1 + 2 * S + X + Z, 3 * S, 1, slabs, c.err, stream);
+            if (st != PSNODE_OK) return st;
+        }
+    }
+    if (dae) {
+        st = lg_wgrad(dpre_ae, H, BH, H, p->z.p, p->z.sb, p->z.st, H, T, B, th + o_A1 + S + X, lda, 1, slabs, c.err, stream);
+        if (st != PSNODE_OK) return st;
+        st = lg_wgrad(dpre_ae, H, BH, H, p->v.p, p->v.sb, p->v.st, H, T, B, th + o_A1 + S + X + Z, lda, 1, slabs, c.err, stream);
+        if (st != PSNODE_OK) return st;
+        if (E > 0) {
+            st = lg_wgrad(w + L.dpj_ae, H, BH, H, p->z_jump, p->zj_sb, p->zj_se, H, E, B, th + o_A1 + S + X, lda, 1, slabs, c.err, stream);
+            if (st != PSNODE_OK) return st;
+            st = lg_wgrad(w + L.dpj_ae, H, BH, H, p->v_jump, p->vj_sb, p->vj_se, H, E, B, th + o_A1 + S + X + Z, lda, 1, slabs, c.err, stream);
+            if (st != PSNODE_OK) return st;
+        }
+    }
+    // ---- per-trajectory layer-1 constants: c_de = (W_a - W_b) a0 + b1, c_ae = A1a a0 + ab1 ----
+    st = lg_wgrad(buf(BUF_DCDE), H, BH, H, p->a0, p->a0_sb, 0, S, 1, B, th + o_W1, 3 * S, 1, slabs, c.err, stream);      // dW_a = dc (x) a0
+    if (st != PSNODE_OK) return st;
+    if (dae) {
+        st = lg_wgrad(buf(BUF_DCAE), H, BH, H, p->a0, p->a0_sb, 0, S, 1, B, th + o_A1, lda, 1, slabs, c.err, stream);
+        if (st != PSNODE_OK) return st;
+    }
+    psn_lg_unfold_w1_kernel<<<(H * S + 255) / 256, 256, 0, stream>>>(th + o_W1, H, S);
+    psn_count_launch("psn_lg_unfold_w1_kernel");
+    psn_lg_colsum_kernel<<<H / 32, 1024, 0, stream>>>(buf(BUF_DCDE), B, H, th + o_b1);
+    psn_lg_colsum_kernel<<<H / 32, 1024, 0, stream>>>(buf(BUF_ACCDK), B, H, th + o_b2);
+    psn_count_launch("psn_lg_colsum_kernel"); psn_count_launch("psn_lg_colsum_kernel");
+    if (dae) {
+        psn_lg_colsum_kernel<<<H / 32, 1024, 0, stream>>>(buf(BUF_DCAE), B, H, th + o_ab1);
+        psn_lg_colsum_kernel<<<H / 32, 1024, 0, stream>>>(buf(BUF_ACCGI), B, H, th + o_ab2);
+        psn_count_launch("psn_lg_colsum_kernel"); psn_count_launch("psn_lg_colsum_kernel");
+    }
+    if (a->d_a0) {                                                             // d_a0 = (W_a - W_b)^T dc_de + A1a^T dc_ae
+        LgParams q = c.base();
+        q.nsrc = dae ? 2 : 1;
+        q.out = a->d_a0; q.out_ld = a->d_a0_sb;
+        LgParams qq = q;
+        qq.b_r0 = 0;
+        CUtensorMap m_dcde, m_dcae;
+        if (!lg_make_map(&m_dcde, buf(BUF_DCDE), H, B, H, 1, 0) || !lg_make_map(&m_dcae, buf(BUF_DCAE), H, B, H, 1, 0))
+            return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (layer path, d_a0)");
+        c.launch(M_T_DA0, m_dcde, m_dcae, qq, "psn_lg_gemm_kernel<bwd:d_a0>");
+    }
+    PSN_CUDA(cudaGetLastError());
+    return PSNODE_OK;
+}
 
 // Test hook (not part of the public header): the MN-major weight-gradient GEMM alone.  out[M x K] = sum_{slot, n} P[slot][n][:]^T Q[slot][n][:].
 extern "C" int psnode_debug_lg_wgrad(const float* P, int64_t p_sn, int64_t p_ss, int M, const float* Q, int64_t q_sn, int64_t q_ss, int K, int nslots,

@@ -58,6 +58,10 @@ int psn_wide_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws
 bool psn_lg_supports(const psnode_problem* p);
 int64_t psn_lg_forward_workspace(const psnode_problem* p);
 int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream);
+// recomputing reverse sweep on the same GEMM kernel (all parameter, initial-state, all_initial, input-series and jump gradients)
+bool psn_lg_bwd_supports(const psnode_problem* p, const psnode_adjoint* a);
+int64_t psn_lg_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);
+int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
 
 // ---- row GEMM over a whole series (psnode_wide_proj.cu) ------------------------------------------------------------------
 // out[r][b][0:128] = A . in[r][b][0:128] (+ add[b][0:128]),  A[m][k] = W[m*ldw + k] or (transpose) W[k*ldw + m], optionally

@@ -109,3 +109,143 @@ def test_layer_ode_h256_vs_oracle(native_lib, solver):
                                 jump_change_fn=ev.jump_change_fn).cpu()
     assert _native.last_kernel().startswith("psn_lg_gemm_kernel"), _native.last_kernel()
     assert torch.allclose(got, want, rtol=RTOL, atol=ATOL), tol_report(got, want)
+
+
+def _dae_grads_fp64(solver, de, ae, d, ev, wx, wi):
+    """All gradient sinks of the encoded DAE model by float64 autograd through the oracle."""
+    from oracle import psnode_oracle as O
+    pde = [(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in _params(de.cpu().x_dot)]
+    pae = [(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in _params(ae.cpu().i_calculator)]
+    z64, v64 = d["z"].double().requires_grad_(True), d["v"].double().requires_grad_(True)
+    xi64, a064 = d["x_init"].double().requires_grad_(True), d["a0"].double().requires_grad_(True)
+    args = (solver, pde, pae, xi64, d["t"].double(), d["x"].double(), z64, v64, d["i"].double(), a064)
+    zj64 = vj64 = None
+    if ev is not None:
+        zj64, vj64 = ev[1].double().requires_grad_(True), ev[2].double().requires_grad_(True)
+        xs, is_ = O.integrate_dae(*args, ev[0].double(), zj64, vj64)
+    else:
+        xs, is_ = O.integrate_dae(*args)
+    ((xs * wx.double()).sum() + (is_ * wi.double()).sum()).backward()
+    out = {"W1": pde[0][0].grad, "b1": pde[0][1].grad, "W2": pde[1][0].grad, "b2": pde[1][1].grad,
+           "A1": pae[0][0].grad, "ab1": pae[0][1].grad, "A2": pae[1][0].grad, "ab2": pae[1][1].grad,
+           "z": z64.grad, "v": v64.grad, "x_init": xi64.grad, "a0": a064.grad}
+    if ev is not None:
+        out["z_jump"], out["v_jump"] = zj64.grad, vj64.grad
+    return out
+
+
+def _dae_grads_gpu(solver, de, ae, d, ev, wx, wi, impl, dev="cuda:0"):
+    from py_psnode_b200 import DAE_Event, Euler, Midpoint, RK4, _native
+    import copy
+    S = {"euler": Euler, "midpoint": Midpoint, "rk4": RK4}[solver]
+    de_d, ae_d = copy.deepcopy(de).to(dev), copy.deepcopy(ae).to(dev)
+    leaf = lambda q: q.to(dev).requires_grad_(True)
+    z, v, xi, a0 = leaf(d["z"]), leaf(d["v"]), leaf(d["x_init"]), leaf(d["a0"])
+    kw, zj, vj = {}, None, None
+    if ev is not None:
+        zj, vj = leaf(ev[1]), leaf(ev[2])
+        e = DAE_Event()
+        e.set_event(t=ev[0].to(dev), z=zj, v=vj)
+        kw = dict(event_fn=e.event_fn, jump_change_fn=e.jump_change_fn)
+    xs, is_ = S(impl=impl).integrate_DAE(x_init=xi, x_func=de_d, i_func=ae_d, t=d["t"].to(dev), x=d["x"].to(dev), z=z, v=v, i=d["i"].to(dev),
+                                        all_initial=a0, **kw)
+    fwd_kernel = _native.last_kernel()
+    ((xs * wx.to(dev)).sum() + (is_ * wi.to(dev)).sum()).backward()
+    bwd_kernel = _native.last_kernel()
+    ld = [m for m in de_d.x_dot if isinstance(m, torch.nn.Linear)]
+    la = [m for m in ae_d.i_calculator if isinstance(m, torch.nn.Linear)]
+    out = {"W1": ld[0].weight.grad, "b1": ld[0].bias.grad, "W2": ld[1].weight.grad, "b2": ld[1].bias.grad,
+           "A1": la[0].weight.grad, "ab1": la[0].bias.grad, "A2": la[1].weight.grad, "ab2": la[1].bias.grad,
+           "z": z.grad, "v": v.grad, "x_init": xi.grad, "a0": a0.grad}
+    if ev is not None:
+        out["z_jump"], out["v_jump"] = zj.grad, vj.grad
+    return {k: g.detach().cpu() for k, g in out.items()}, fwd_kernel, bwd_kernel
+
+
+def _compare_grads(got, want, tol=2e-5):
+    bad = []
+    for name, g64 in want.items():
+        g = got[name]
+        scale = float(g64.abs().max())
+        err = float((g.double() - g64.double()).abs().max())
+        print(f"grad {name}: max err {err:.3e} scale {scale:.3e} rel {err / max(scale, 1e-30):.2e}")
+        if not err <= tol * scale + 1e-7:
+            bad.append((name, err, scale))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("H,solver,events,B,N", [(256, "rk4", 1, 40, 11), (128, "euler", 0, 24, 9), (128, "midpoint", 2, 24, 10),
+                                                  (256, "rk4", 2, 150, 19)])
+def test_layer_dae_gradients_vs_fp64_autograd(native_lib, H, solver, events, B, N):
+    """The recomputing reverse sweep of the layer path (psn_lg_backward: transposed-weight GEMM launches with delta / Runge-Kutta
+    adjoint epilogues + MN-major weight-gradient GEMMs) against float64 autograd: parameters of both nets, x_init, all_initial, the
+    latent input series z / v and the jump tensors.  N is not a multiple of the ring depth (8), B not a multiple of the tile."""
+    de, ae, d, ev = _dae_problem(B=B, N=N, H=H, seed=61 + H + N, events=events)
+    torch.manual_seed(5)
+    wx, wi = torch.randn(N + 1, B, H) * 0.1, torch.randn(N + 1, B, H) * 0.1
+    want = _dae_grads_fp64(solver, de, ae, d, ev, wx, wi)
+    got, fk, bk = _dae_grads_gpu(solver, de, ae, d, ev, wx, wi, "auto")
+    assert fk.startswith("psn_lg_gemm_kernel"), fk
+    assert bk.startswith("psn_lg_"), bk
+    _compare_grads(got, want)
+
+
+def test_layer_dae_gradients_vs_generic_sweep(native_lib):
+    """Same sweep against the CUDA-core generic reverse sweep (itself pinned to the reference's autograd goldens) at a batch of
+    several n-tiles and more steps than the ring holds; deterministic across two runs."""
+    B, N, H = 300, 21, 256
+    de, ae, d, ev = _dae_problem(B=B, N=N, H=H, seed=77, events=1)
+    torch.manual_seed(6)
+    wx, wi = torch.randn(N + 1, B, H) * 0.1, torch.randn(N + 1, B, H) * 0.1
+    got, fk, bk = _dae_grads_gpu("rk4", de, ae, d, ev, wx, wi, "layer")
+    assert bk.startswith("psn_lg_"), bk
+    ref, _, bk0 = _dae_grads_gpu("rk4", de, ae, d, ev, wx, wi, "generic")
+    assert bk0.startswith("psn_g"), bk0
+    _compare_grads(got, ref, tol=3e-5)
+    again, _, _ = _dae_grads_gpu("rk4", de, ae, d, ev, wx, wi, "layer")
+    for k in got:
+        assert torch.equal(got[k], again[k]), k
+
+
+@pytest.mark.parametrize("solver,events", [("rk4", 1), ("midpoint", 0)])
+def test_layer_ode_h256_gradients_vs_fp64_autograd(native_lib, solver, events):
+    from oracle import psnode_oracle as O
+    from py_psnode_b200 import DE_Func, Midpoint, ODE_Event, RK4, _native
+    torch.manual_seed(52)
+    dev = "cuda:0"
+    B, N, H = 40, 12, 256
+    T = N + 1
+    de = DE_Func(x_dim=H, z_dim=H, hidden_dim=H, depth=2)
+    t = (torch.arange(T, dtype=torch.float32) * 0.01).view(T, 1, 1).repeat(1, B, 1)
+    x, z = torch.randn(T, B, H) * 0.05, torch.randn(T, B, H) * 0.05
+    w = torch.randn(T, B, H) * 0.1
+    event_t = t[N // 2].view(B, 1, 1).clone()
+    z_jump = torch.randn(B, 1, H) * 0.05
+    p64 = [(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in _params(de.x_dot)]
+    x64, z64 = x.double().requires_grad_(True), z.double().requires_grad_(True)
+    a064 = torch.cat((x64[0], z64[0]), dim=-1)
+    zj64 = z_jump.double().requires_grad_(True)
+    if events:
+        sol64 = O.integrate_ode(solver, p64, t.double(), x64, z64, a064, event_t.double(), zj64)
+    else:
+        sol64 = O.integrate_ode(solver, p64, t.double(), x64, z64, a064)
+    (sol64 * w.double()).sum().backward()
+    de_d = de.to(dev)
+    xd, zd = x.to(dev).requires_grad_(True), z.to(dev).requires_grad_(True)
+    a0d = torch.cat((xd[0], zd[0]), dim=-1)
+    kw, zjd = {}, None
+    if events:
+        zjd = z_jump.to(dev).requires_grad_(True)
+        ev = ODE_Event()
+        ev.set_event(t=event_t.to(dev), z=zjd)
+        kw = dict(event_fn=ev.event_fn, jump_change_fn=ev.jump_change_fn)
+    S = {"midpoint": Midpoint, "rk4": RK4}[solver]
+    sol = S().integrate_ODE(x_func=de_d, t=t.to(dev), x=xd, z=zd, all_initial=a0d, **kw)
+    (sol * w.to(dev)).sum().backward()
+    assert _native.last_kernel().startswith("psn_lg_"), _native.last_kernel()
+    lin = [m for m in de_d.x_dot if isinstance(m, torch.nn.Linear)]
+    got = {"W1": lin[0].weight.grad, "b1": lin[0].bias.grad, "W2": lin[1].weight.grad, "b2": lin[1].bias.grad, "x": xd.grad, "z": zd.grad}
+    want = {"W1": p64[0][0].grad, "b1": p64[0][1].grad, "W2": p64[1][0].grad, "b2": p64[1][1].grad, "x": x64.grad, "z": z64.grad}
+    if events:
+        got["z_jump"], want["z_jump"] = zjd.grad, zj64.grad
+    _compare_grads({k: g.detach().cpu() for k, g in got.items()}, want)
