@@ -49,7 +49,7 @@ WORKLOADS = {
                  desc="RK4 fixed-step, ODE_02 latent DE_Func 768-128-128 (x_dim=z_dim=hidden=128), global batch 16384 x 500 steps, "
                       "adjoint training with latent-input gradients"),
     "cfg5": dict(kind="dae", net="02", X=256, Z=256, V=256, I=256, H=256, B=65536, N=2000, scaling="strong", quoted_gpus=8,
-                 bytes_per_unit=4100, flop_per_unit=7864320, aux_steps=40,
+                 bytes_per_unit=4100, flop_per_unit=7864320, aux_steps=200,
                  desc="RK4 fixed-step, DAE_02 latent DE_Func 3072-256-256 + AE_Func 1792-256-256, global batch 65536 x 2000 steps"),
 }
 FP32_PEAK_TFLOPS = 74.4     # nominal: 148 SM x 128 lanes x 2 x 1.965 GHz; measured 72.1 by bench_micro/micro.cu

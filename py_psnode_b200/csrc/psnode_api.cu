@@ -183,6 +183,7 @@ int psnode_sweep_fuses_loss(const psnode_problem* p, const psnode_adjoint* a) {
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_WIDE) && psn_wide_bwd_supports(p, a)) return 1;
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC || p->impl == PSNODE_IMPL_TC8) && psn_tc_bwd_supports(p, a)) return 1;
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC8) && psn_tc_dae_bwd_supports(p, a)) return 1;
+    if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_LAYER) && psn_lg_bwd_supports(p, a)) return 1;
     return 0;
 }
 
@@ -207,9 +208,9 @@ int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* work
         return psn_tc_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC8) && psn_tc_dae_bwd_supports(p, a))
         return psn_tc_dae_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
-    if (a->fuse_x.target.p || a->fuse_i.target.p) return PSNODE_EUNSUPPORTED;      // the recomputing sweeps take gx / gi only
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_LAYER) && psn_lg_bwd_supports(p, a))
         return psn_lg_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    if (a->fuse_x.target.p || a->fuse_i.target.p) return PSNODE_EUNSUPPORTED;      // the generic recomputing sweeps take gx / gi only
     const int gst = psn_generic_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if (gst != PSNODE_EUNSUPPORTED) return gst;
     return psn_generic_backward_tb2(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));

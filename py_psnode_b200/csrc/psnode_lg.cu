@@ -244,7 +244,12 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                         e.dt[i] = pa1 ? __ldg(pa1 + c * a1ld) : 0.0f;               // upstream gradient row
                     } else {
                         e.dt[i] = __fsub_rn(__ldg(ptc + c * tsb), __ldg(ptp + c * tsb));
+                        e.p3[i] = pacc ? pacc[c * sld] : 0.0f;                      // read-modify-write operands are fetched ahead too
                     }
+                } else if constexpr (EPI == EPI_DELTA) {
+                    e.p0[i] = __ldg(pa1 + c * a1ld);
+                    e.p1[i] = (pout2 && q.out2_acc) ? pout2[c * o2ld] : 0.0f;
+                    e.p2[i] = pacc ? pacc[c * sld] : 0.0f;
                 } else {
                     e.p0[i] = pa1 ? __ldg(pa1 + c * a1ld) : 0.0f;
                     e.p1[i] = pa2 ? __ldg(pa2 + c * a2ld) : 0.0f;
@@ -265,8 +270,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                 if constexpr (EPI == EPI_DELTA) {
                     v = (t0[i] + t1[i]) * psn_elu_grad_from_out(e.p0[i]);
                     pout[c * old] = v;
-                    if (pout2) pout2[c * o2ld] = q.out2_acc ? pout2[c * o2ld] + v : v;
-                    if (pacc) pacc[c * sld] += v;
+                    if (pout2) pout2[c * o2ld] = e.p1[i] + v;
+                    if (pacc) pacc[c * sld] = e.p2[i] + v;
                 } else if constexpr (brk) {
                     const float D = t0[i] + t1[i], gx = e.p0[i];
                     if constexpr (EPI == EPI_BSUM) {
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                         else if constexpr (EPI == EPI_BRK1) { pk3[c * sld] = D; dk = dt * (fmaf(0.125f, gx, e.p1[i]) + c13 * (D - e.p2[i])); }
                         else { pk1[c * sld] = D; dk = (0.5f * dt) * D; }
                         pout[c * old] = dk;
-                        if (pacc) pacc[c * sld] += dk;
+                        if (pacc) pacc[c * sld] = e.p3[i] + dk;
                     }
                 } else if constexpr (!rk) {
                     v = (v + e.p0[i]) + e.p1[i];
@@ -674,13 +679,13 @@ int lg_launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUten
 int64_t al(int64_t floats) { return (floats + 63) & ~(int64_t)63; }
 
 // prepared weight planes: the forward's seven (A = weights as they multiply activations) and the reverse pass's transposes
-enum { M_DE1X = 0, M_DE1ZV, M_DE1I, M_DE2, M_AE1X, M_AE1ZV, M_AE2,
+enum { M_DE1X = 0, M_DE1ZV, M_DE1I, M_DE2, M_AE1X, M_AE1ZV, M_AE2, M_C_DE, M_C_AE,
        M_T_DE2, M_T_DE1X, M_T_DE1I, M_T_AE2, M_T_AE1X, M_T_DZ, M_T_DV, M_T_DA0, NMAT };
-constexpr int NMAT_FWD = M_AE2 + 1;
+constexpr int NMAT_FWD = M_C_AE + 1;
 
 // BH-sized work buffers of the reverse pass (one contiguous array, one tensor map, addressed by index)
 enum { BUF_GX = 0, BUF_DY3, BUF_DY2, BUF_DY1, BUF_GI0, BUF_HEV, BUF_DHEV, BUF_G, BUF_K1, BUF_K2, BUF_K3, BUF_DCDE, BUF_DCAE, BUF_ACCDK, BUF_ACCGI,
-       BUF_SINGLES };
+       BUF_UPX, BUF_UPI, BUF_SINGLES };
 
 struct LgLayout {
     int H, KZV, S, nmat, bwd;
@@ -714,14 +719,14 @@ LgLayout lg_layout(const psnode_problem* p, bool bwd) {
     L.bwd = bwd ? 1 : 0;
     L.nmat = bwd ? NMAT : NMAT_FWD;
     const int k2 = dae ? 2 * H : H;
-    const int rows[NMAT] = {H, H, H, H, H, H, H, H, H, H, H, H, H, H, L.S};
-    const int cols[NMAT] = {H, L.KZV, H, H, H, L.KZV, H, H, H, H, H, H, k2, k2, k2};
+    const int rows[NMAT] = {H, H, H, H, H, H, H, H, H, H, H, H, H, H, H, H, L.S};
+    const int cols[NMAT] = {H, L.KZV, H, H, H, L.KZV, H, L.S, L.S, H, H, H, H, H, k2, k2, k2};
     int64_t o = 64;
     L.err = 0;
     for (int i = 0; i < NMAT; i++) {
         L.mrows[i] = rows[i]; L.mcols[i] = cols[i];
         if (i >= L.nmat) continue;
-        const bool used = dae || (i == M_DE1X || i == M_DE1ZV || i == M_DE2 || i == M_T_DE2 || i == M_T_DE1X || i == M_T_DZ || i == M_T_DA0);
+        const bool used = dae || (i == M_DE1X || i == M_DE1ZV || i == M_DE2 || i == M_C_DE || i == M_T_DE2 || i == M_T_DE1X || i == M_T_DZ || i == M_T_DA0);
         if (!used) continue;
         L.wts_hi[i] = o; o += al((int64_t)rows[i] * cols[i]);
         L.wts_lo[i] = o; o += al((int64_t)rows[i] * cols[i]);
@@ -842,7 +847,19 @@ int lg_setup(LgCtx& c, const psnode_problem* p, bool bwd, void* ws, int64_t ws_b
         c.prep(M_AE1X, A1, lda, S, -1, 0.0f, 0, H, H, 0);
         c.prep(M_AE1ZV, A1, lda, S + X, -1, 0.0f, 0, H, L.KZV, 0);
         c.prep(M_AE2, p->ae.W[1], H, 0, -1, 0.0f, 0, H, H, 0);
-        psn_lg_const_kernel<<<(B + 7) / 8, H, 8 * S * 4, stream>>>(A1, lda, -1, p->ae.b[0], p->a0, p->a0_sb, S, B, H, w + L.c_ae);
+    }
+    // per-trajectory layer-1 constants c = (W_a - W_b) a0 + b1 (and A1a a0 + ab1): a K = S GEMM on the same kernel when all_initial can be
+    // a TMA operand, else a CUDA-core kernel
+    const bool a0_tma = view_ok(p->a0, p->a0_sb, 0);
+    if (a0_tma) {
+        c.prep(M_C_DE, W1, ld1, 0, S, -1.0f, 0, H, S, 0);
+        if (dae) c.prep(M_C_AE, A1, lda, 0, -1, 0.0f, 0, H, S, 0);
+    } else {
+        if (dae) {
+            psn_lg_const_kernel<<<(B + 7) / 8, H, 8 * S * 4, stream>>>(A1, lda, -1, p->ae.b[0], p->a0, p->a0_sb, S, B, H, w + L.c_ae);
+            psn_count_launch("psn_lg_const_kernel");
+        }
+        psn_lg_const_kernel<<<(B + 7) / 8, H, 8 * S * 4, stream>>>(W1, ld1, S, p->de.b[0], p->a0, p->a0_sb, S, B, H, w + L.c_de);
         psn_count_launch("psn_lg_const_kernel");
     }
     if (bwd) {
@@ -860,8 +877,6 @@ int lg_setup(LgCtx& c, const psnode_problem* p, bool bwd, void* ws, int64_t ws_b
             c.prep(M_T_DA0, A1, lda, 0, -1, 0.0f, 1, S, H, H);
         }
     }
-    psn_lg_const_kernel<<<(B + 7) / 8, H, 8 * S * 4, stream>>>(W1, ld1, S, p->de.b[0], p->a0, p->a0_sb, S, B, H, w + L.c_de);
-    psn_count_launch("psn_lg_const_kernel");
     PSN_CUDA(cudaGetLastError());
 
     // ---- tensor maps (once per call) ----
@@ -881,6 +896,20 @@ int lg_setup(LgCtx& c, const psnode_problem* p, bool bwd, void* ws, int64_t ws_b
     if (dae) ok = ok && lg_make_map(&c.m_h, w + L.hbuf, H, B, H, 1, 0) && lg_make_map(&c.m_i, w + L.icur, H, B, H, 1, 0);
     if (!ok) return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (layer path)");
     if (lg_prepare_kernels() != PSNODE_OK) return PSNODE_ECUDA;
+    if (a0_tma) {
+        CUtensorMap m_a0;
+        if (!lg_make_map(&m_a0, p->a0, S, B, p->a0_sb, 1, 0)) return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (all_initial)");
+        LgParams q = c.base();
+        q.kchunks = S / 32;
+        q.bias = p->de.b[0];
+        q.out = w + L.c_de;
+        c.launch(M_C_DE, m_a0, m_a0, q, "psn_lg_gemm_kernel<c_de>");
+        if (dae) {
+            q.bias = p->ae.b[0];
+            q.out = w + L.c_ae;
+            c.launch(M_C_AE, m_a0, m_a0, q, "psn_lg_gemm_kernel<c_ae>");
+        }
+    }
 
     // ---- hoisted layer-1 halves over the whole series ----
     const int64_t BH = c.BH;
@@ -939,6 +968,14 @@ __global__ void psn_lg_bwd_tail_kernel(int B, int H, const int32_t* __restrict__
         gi_next[idx] = evk < 0 ? up + g0 : up;
         acc_gi[idx] += up + g0;
     }
+}
+// one grid row of the fused masked-MSE upstream gradient (psnode_adjoint.fuse_x / fuse_i): up[b][m] = dL/dsol[j][b][m]
+__global__ void psn_lg_fuse_row_kernel(int B, int H, int j, PsnFuse fx, float* __restrict__ upx, PsnFuse fi, float* __restrict__ upi) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * H) return;
+    const int b = idx / H, m = idx - b * H;
+    if (upx) upx[idx] = psn_fuse_grad(fx, psn_fuse_scale(fx), j, b, m);
+    if (upi) upi[idx] = psn_fuse_grad(fi, psn_fuse_scale(fi), j, b, m);
 }
 // out[m] = sum_b src[b][m]: block = 32 features, 32 row lanes
 __global__ void __launch_bounds__(1024) psn_lg_colsum_kernel(const float* __restrict__ src, int B, int H, float* __restrict__ out) {
@@ -1088,9 +1125,9 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
 bool psn_lg_bwd_supports(const psnode_problem* p, const psnode_adjoint* a) {
     if (!psn_lg_supports(p)) return false;
     if (a->d_xteach.p || a->d_iteach.p) return false;
-    if (a->fuse_x.target.p || a->fuse_i.target.p) return false;
     const bool dae = p->kind == PSNODE_DAE;
-    if (!a->gx.p || (dae && !a->gi.p)) return false;
+    if (!a->gx.p && !a->fuse_x.target.p) return false;
+    if (dae && !a->gi.p && !a->fuse_i.target.p) return false;
     if (!view_ok(p->a0, p->a0_sb, 0)) return false;
     if (!view_ok(p->x_sol.p, p->x_sol.st, p->x_sol.sb)) return false;
     if (dae && !view_ok(p->i_sol.p, p->i_sol.st, p->i_sol.sb)) return false;
@@ -1200,18 +1237,32 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
         return PSNODE_OK;
     };
 
+    // upstream gradient rows dL/dx_sol[j], dL/di_sol[j]: the caller's tensors, or formed on the fly from the trajectory (fused masked MSE)
+    const bool fuse_x = a->fuse_x.target.p != nullptr, fuse_i = dae && a->fuse_i.target.p != nullptr;
+    const PsnFuse fx = psn_make_fuse(a->fuse_x, p->x_sol), fi = psn_make_fuse(a->fuse_i, p->i_sol);
+    const float* upx = nullptr; const float* upi = nullptr;
+    int64_t upx_sb = H, upi_sb = H;
+    auto upstream_row = [&](int j) {
+        if (fuse_x || fuse_i) {
+            psn_lg_fuse_row_kernel<<<nblk, 256, 0, stream>>>(B, H, j, fx, fuse_x ? buf(BUF_UPX) : nullptr, fi, fuse_i ? buf(BUF_UPI) : nullptr);
+            psn_count_launch("psn_lg_fuse_row_kernel");
+        }
+        if (fuse_x) { upx = buf(BUF_UPX); upx_sb = H; } else { upx = a->gx.p + (int64_t)j * a->gx.st; upx_sb = a->gx.sb; }
+        if (fuse_i) { upi = buf(BUF_UPI); upi_sb = H; } else if (dae) { upi = a->gi.p + (int64_t)j * a->gi.st; upi_sb = a->gi.sb; }
+    };
     // ---- start: adjoints of the last grid point ----
     {
         const int s = (T - 1) % ring;
-        psn_lg_bwd_init_kernel<<<nblk, 256, 0, stream>>>(B, H, a->gx.p + (int64_t)(T - 1) * a->gx.st, a->gx.sb,
-                                                         dae ? a->gi.p + (int64_t)(T - 1) * a->gi.st : nullptr, a->gi.sb, buf(BUF_GX),
-                                                         buf(L.ring_one(R_GI, s)), buf(BUF_ACCGI));
+        upstream_row(T - 1);
+        psn_lg_bwd_init_kernel<<<nblk, 256, 0, stream>>>(B, H, upx, upx_sb, dae ? upi : nullptr, upi_sb, buf(BUF_GX), buf(L.ring_one(R_GI, s)),
+                                                         buf(BUF_ACCGI));
         psn_count_launch("psn_lg_bwd_init_kernel");
     }
     for (int j = T - 1; j >= 0; j--) {
         const int s = j % ring;
         if (dae) ae_backward(j, s);
         if (j >= 1) {
+            upstream_row(j - 1);
             const float* tc = t + (int64_t)j * p->t.st;
             const float* tp = t + (int64_t)(j - 1) * p->t.st;
             psn_lg_bwd_head_kernel<<<nblk, 256, 0, stream>>>(B, H, p->x_sol.p + (int64_t)(j - 1) * p->x_sol.st, p->x_sol.sb,
@@ -1272,7 +1323,7 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
                 q2.t_cur = tc; q2.t_prev = tp; q2.t_sb = p->t.sb;
                 if (e == 0) {
                     q2.stage = EPI_BSUM;
-                    q2.add1 = a->gx.p + (int64_t)(j - 1) * a->gx.st; q2.add1_ld = a->gx.sb;
+                    q2.add1 = upx; q2.add1_ld = upx_sb;
                     q2.out = buf(BUF_GX);
                 } else {
                     q2.stage = p->method == PSNODE_MIDPOINT ? (int)EPI_BMID1 : (e == 3 ? (int)EPI_BRK3 : (e == 2 ? (int)EPI_BRK2 : (int)EPI_BRK1));
@@ -1315,8 +1366,7 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
             const int sn = (j - 1) % ring;
             psn_lg_bwd_tail_kernel<<<nblk, 256, 0, stream>>>(B, H, E > 0 ? p->event_idx : nullptr, j - 1, buf(L.ring_one(R_DSUM, s)),
                                                              dpre_de + (int64_t)(j - 1) * BH, w + L.dpj_de, BH, dae ? buf(BUF_GI0) : nullptr,
-                                                             dae ? a->gi.p + (int64_t)(j - 1) * a->gi.st : nullptr, a->gi.sb,
-                                                             dae ? buf(L.ring_one(R_GI, sn)) : nullptr, buf(BUF_ACCGI));
+                                                             dae ? upi : nullptr, upi_sb, dae ? buf(L.ring_one(R_GI, sn)) : nullptr, buf(BUF_ACCGI));
             psn_count_launch("psn_lg_bwd_tail_kernel");
         }
     }

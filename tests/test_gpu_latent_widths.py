@@ -126,7 +126,8 @@ def test_cfg5_shape_gradients_h256(native_lib):
     xid = x_init.to(dev).requires_grad_(True)
     zd, vd = z.to(dev).requires_grad_(True), v.to(dev).requires_grad_(True)
     a0d = torch.cat((xid, zd[0], vd[0], i.to(dev)[0]), dim=-1)
-    gx, gi = RK4().integrate_DAE(x_init=xid, x_func=de_d, i_func=ae_d, t=t.to(dev), x=x.to(dev), z=zd, v=vd, i=i.to(dev), all_initial=a0d)
+    # impl = generic: the CUDA-core sweep stays covered at these widths (auto takes the layer path's tensor-core sweep, test_gpu_layer.py)
+    gx, gi = RK4(impl="generic").integrate_DAE(x_init=xid, x_func=de_d, i_func=ae_d, t=t.to(dev), x=x.to(dev), z=zd, v=vd, i=i.to(dev), all_initial=a0d)
     ((gx * wx.to(dev)).sum() + (gi * wi.to(dev)).sum()).backward()
     assert _native.last_kernel() == "psn_grad_reduce_kernel"
     lin_d = [m for m in de_d.x_dot if isinstance(m, torch.nn.Linear)]

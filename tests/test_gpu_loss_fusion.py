@@ -95,3 +95,43 @@ def test_dae_loss_fusion_matches_unfused(native_lib):
     assert torch.allclose(res["fused"][0], res["unfused"][0], rtol=1e-6)
     for k, (a, b) in enumerate(zip(res["fused"][1], res["unfused"][1])):
         _close(f"tensor {k}", a, b)
+
+
+def test_layer_dae_loss_fusion_matches_unfused(native_lib):
+    """Latent DAE_02 net on the layer path (H = 128): the recomputing sweep forms the upstream rows of both loss terms on the fly."""
+    from py_psnode_b200 import AE_Func, DAE_Event, DE_Func, RK4, _native
+    from py_psnode_b200.losses import masked_sse
+    torch.manual_seed(83)
+    B, N, H = 36, 13, 128
+    T = N + 1
+    de = DE_Func(x_dim=H, z_dim=H, hidden_dim=H, v_dim=H, i_dim=H, depth=2).to(DEV)
+    ae = AE_Func(x_dim=H, v_dim=H, i_dim=H, hidden_dim=H, z_dim=H, depth=2).to(DEV)
+    t = (torch.arange(T, dtype=torch.float32, device=DEV) * 0.01).view(T, 1, 1).repeat(1, B, 1)
+    mk = lambda: torch.randn(T, B, H, device=DEV) * 0.05
+    z0, v0, i, tx, ti = mk(), mk(), mk(), mk(), mk()
+    mask = torch.ones(T, B, 1, device=DEV)
+    mask[T - 2:] = 0.0
+    fwx = torch.ones(H, device=DEV)
+    fwx[1] = 10.0
+    ev = DAE_Event()
+    ev.set_event(t=t[N // 2].view(B, 1, 1).clone(), z=torch.randn(B, 1, H, device=DEV) * 0.05, v=torch.randn(B, 1, H, device=DEV) * 0.05)
+    plist = list(de.parameters()) + list(ae.parameters())
+    res = {}
+    for mode in ("unfused", "fused"):
+        for p in plist:
+            p.grad = None
+        z, v = z0.clone().requires_grad_(True), v0.clone().requires_grad_(True)
+        x0 = (tx[0].clone() * 0.5).requires_grad_(True)
+        a0 = torch.cat((x0.detach(), z0[0], v0[0], i[0]), dim=-1).requires_grad_(True)
+        kw = dict(x_init=x0, x_func=de, i_func=ae, t=t, x=tx, z=z, v=v, i=i, all_initial=a0, event_fn=ev.event_fn, jump_change_fn=ev.jump_change_fn)
+        if mode == "unfused":
+            sx, si = RK4().integrate_DAE(**kw)
+            num = masked_sse(sx, tx, mask, fwx) + masked_sse(si, ti, mask)
+        else:
+            num, sx, si = RK4().integrate_DAE_loss(target_x=tx, target_i=ti, mask=mask, feat_weight_x=fwx, **kw)
+        (num / mask.sum()).backward()
+        assert _native.last_kernel().startswith("psn_lg_"), _native.last_kernel()
+        res[mode] = (num.detach().clone(), _grads(plist, [x0, a0, z, v]))
+    assert torch.allclose(res["fused"][0], res["unfused"][0], rtol=1e-6)
+    for k, (a, b) in enumerate(zip(res["fused"][1], res["unfused"][1])):
+        _close(f"tensor {k}", a, b)
