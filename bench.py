@@ -18,8 +18,9 @@ invocation records them:
         it on 4 GPUs), training leg = adjoint with latent-input gradients + 0.67 MB gradient all-reduce
   cfg5  RK4 DAE_02 latent net H = 256, GLOBAL batch 65536 x 2000 steps sharded over 8 ranks (BASELINE quotes it on 8 GPUs); with
         fewer than 8 ranks each rank integrates one 1/8 shard (B = 8192).  Forward: per-layer tcgen05 GEMM launches (impl = layer)
-        over all 2000 steps; the H = 256 reverse sweep still runs on the CUDA-core generic kernel, so the e2e / training legs
-        cover a bounded number of grid steps (stated in `sample`).
+        over all 2000 steps; the reverse sweep recomputes every step on the same GEMM kernel (psn_lg_backward).  The e2e leg (GBs of
+        pinned host memory) and the training leg (series, targets and latent-input gradients are (T, B, 256) tensors of 16.8 GB
+        each at T = 2001) cover a bounded number of grid steps, stated in `sample`.
 CPU legs: the UNMODIFIED reference from oracle/_ref (vendored by oracle/make_ref.py, executed by oracle/ref_runner.py in a
 subprocess; `kind: "reference"`), or the oracle port when oracle/_ref is absent (`kind: "port"`).
 """
@@ -49,7 +50,7 @@ WORKLOADS = {
                  desc="RK4 fixed-step, ODE_02 latent DE_Func 768-128-128 (x_dim=z_dim=hidden=128), global batch 16384 x 500 steps, "
                       "adjoint training with latent-input gradients"),
     "cfg5": dict(kind="dae", net="02", X=256, Z=256, V=256, I=256, H=256, B=65536, N=2000, scaling="strong", quoted_gpus=8,
-                 bytes_per_unit=4100, flop_per_unit=7864320, aux_steps=200,
+                 bytes_per_unit=4100, flop_per_unit=7864320, aux_steps=200, train_steps=1000,
                  desc="RK4 fixed-step, DAE_02 latent DE_Func 3072-256-256 + AE_Func 1792-256-256, global batch 65536 x 2000 steps"),
 }
 FP32_PEAK_TFLOPS = 74.4     # nominal: 148 SM x 128 lanes x 2 x 1.965 GHz; measured 72.1 by bench_micro/micro.cu
@@ -425,8 +426,9 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
     solver = RK4(impl=args.kernel if main_line else "auto")
     res = {"workload": name + ": " + w["desc"], "batch_per_gpu": B, "grid_steps": n_steps, "scaling": w["scaling"]}
     if aux_steps != n_steps:
-        res["sample"] = (f"`value` integrates all {n_steps} grid steps; the e2e and training legs integrate {aux_steps} steps per call (the H = 256 "
-                         "reverse sweep still runs on the CUDA-core generic kernel: ~3 s per 40 steps); throughputs are per traj-step")
+        res["sample"] = (f"`value` integrates all {n_steps} grid steps; the e2e leg integrates {aux_steps} steps per call (pinned host buffers of "
+                         f"{aux_steps + 1} x {B} x {w['Z']} floats per series) and the training leg {w.get('train_steps', aux_steps)} steps per call (its "
+                         "series, targets and latent-input gradients are separate (T, B, 256) tensors); throughputs are per traj-step")
     if w["scaling"] == "strong":
         res["global_batch"] = w["B"]
         res["shards"] = ways
@@ -487,7 +489,13 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
     train = None
     if "train" in legs:
         from py_psnode_b200 import parallel
-        T = aux_steps + 1
+        train_steps = w.get("train_steps", aux_steps)
+        if train_steps != aux_steps:
+            aux_res = aux_host = None
+            torch.cuda.empty_cache()
+            aux_res = make_data(w, B, train_steps, seed=rank, device=dev)
+            aux_units = B * train_steps
+        T = train_steps + 1
         gen = torch.Generator(device=dev).manual_seed(1234 + rank)
         x_target = torch.randn((T, B, w["X"]), device=dev, generator=gen) * 0.1
         mask = torch.ones((T, B, 1), device=dev)       # one value per (trajectory, grid point), as in the scripts
