@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PSNODE_ABI_VERSION 4
+#define PSNODE_ABI_VERSION 5
 #define PSNODE_MAX_LAYERS 8
 
 /* status codes */
@@ -253,6 +253,37 @@ int psnode_masked_sse(const psnode_series* pred, const psnode_series* target, co
 int psnode_masked_sse_grad(const psnode_series* pred, const psnode_series* target, const psnode_series* mask,
                            const float* feat_weight, int32_t n_outer, int32_t n_inner, int32_t X,
                            const float* upstream, const psnode_series_out* grad, void* stream);
+
+/*
+ * Encoder / decoder fusion for the `*_02_direct_encode` models (ODE_Model.forward,
+ * neural_00_ODE_02_direct_encode.py:75-89; DAE_Model.forward, neural_01_DAE_02_direct_encode.py:126-153).  The scripts encode the raw
+ * input series with 2-layer ELU MLPs into (T,B,H) latent tensors, call integrate_ODE / integrate_DAE on them and decode the latent
+ * trajectory with 2-layer MLPs.  psnode_forward_encoded does the three steps in one call, time chunk by time chunk, so that no
+ * (T,B,H) tensor ever exists in HBM:
+ *   - z_enc / v_enc: Linear(raw -> H) . ELU . Linear(H -> H).  The second Linear is folded into the held-input half of layer 1
+ *     (F_z E2) and the hidden layer ELU(E1 raw + e1) is generated in shared memory as the GEMM operand from the raw
+ *     (T,B,<=8) series;
+ *   - the integration runs on `chunk_rows` grid rows at a time (latent rows live in a chunk-sized scratch);
+ *   - x_dec / i_dec: Linear(H -> H) . ELU . Linear(H -> raw width <= 128) applied to every latent row before the store.
+ * In `p`: z.p / v.p / z_jump / v_jump / x_sol.p / i_sol.p are ignored (NULL); Z = V = I = X = H in {128, 256}; x_init (DAE) or x.p
+ * row 0 (ODE) is the LATENT initial state and a0 the latent all_initial (the caller encodes those B rows); event_idx as usual.
+ * Forward / evaluation only (no reverse sweep through the fused codecs: training uses the unfused calls).
+ */
+typedef struct psnode_codec {
+    int32_t ZR, VR, XR, IR;            /* raw widths: inputs z_raw, v_raw (1..8); decoded outputs (1..128); VR = IR = 0 for an ODE */
+    psnode_series z_raw, v_raw;        /* (T,B,ZR), (T,B,VR) */
+    const float* zj_raw;               /* (B,E,ZR) raw jump values (events) */
+    int64_t zjr_sb, zjr_se;
+    const float* vj_raw;               /* (B,E,VR) */
+    int64_t vjr_sb, vjr_se;
+    psnode_mlp z_enc, v_enc;           /* 2 layers each */
+    psnode_mlp x_dec, i_dec;           /* 2 layers each */
+    psnode_series_out x_out, i_out;    /* decoded trajectories (T,B,XR), (T,B,IR) */
+    int32_t chunk_rows;                /* grid rows per time chunk; 0 = default (64) */
+} psnode_codec;
+
+int64_t psnode_forward_encoded_workspace(const psnode_problem* p, const psnode_codec* c);
+int psnode_forward_encoded(const psnode_problem* p, const psnode_codec* c, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

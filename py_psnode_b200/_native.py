@@ -8,7 +8,7 @@ import os
 import threading
 
 PSNODE_MAX_LAYERS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OK, EINVAL, EUNSUPPORTED, EWORKSPACE, ECUDA, ENODEVICE = 0, -1, -2, -3, -4, -5
 EULER, MIDPOINT, RK4 = 0, 1, 2
@@ -63,6 +63,16 @@ class Adjoint(C.Structure):
                 ("fuse_x", LossTerm), ("fuse_i", LossTerm)]
 
 
+class Codec(C.Structure):
+    _fields_ = [("ZR", C.c_int32), ("VR", C.c_int32), ("XR", C.c_int32), ("IR", C.c_int32),
+                ("z_raw", Series), ("v_raw", Series),
+                ("zj_raw", C.c_void_p), ("zjr_sb", C.c_int64), ("zjr_se", C.c_int64),
+                ("vj_raw", C.c_void_p), ("vjr_sb", C.c_int64), ("vjr_se", C.c_int64),
+                ("z_enc", Mlp), ("v_enc", Mlp), ("x_dec", Mlp), ("i_dec", Mlp),
+                ("x_out", Series), ("i_out", Series),
+                ("chunk_rows", C.c_int32)]
+
+
 # every symbol include/psnode_b200.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("psnode_abi_version", C.c_int, []),
@@ -86,6 +96,8 @@ SYMBOLS = [
                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     ("psnode_masked_sse_grad", C.c_int, [C.POINTER(Series), C.POINTER(Series), C.POINTER(Series), C.c_void_p, C.c_int32,
                                          C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Series), C.c_void_p]),
+    ("psnode_forward_encoded_workspace", C.c_int64, [C.POINTER(Problem), C.POINTER(Codec)]),
+    ("psnode_forward_encoded", C.c_int, [C.POINTER(Problem), C.POINTER(Codec), C.c_void_p, C.c_int64, C.c_void_p]),
 ]
 
 # PSNODE_B200_LIB selects an alternative build of the SAME library (A/B kernel experiments); never a different backend.

@@ -34,6 +34,7 @@ constexpr int NST = 3;
 constexpr int SLAB = TN * 128;          // 16 KB: 128 rows x 32 fp32
 constexpr int LG_THREADS = 320;         // 8 split / epilogue warps + TMA producer warp + MMA issuer warp
 constexpr int NPART = 2;                // K-partials (truncating fp32 accumulate: short chains)
+constexpr int GEN_W = 8;                // widest raw input of a generated B source
 
 enum { LG_PLAIN = 0, LG_HIDDEN = 1, LG_RK = 2, LG_DELTA = 3, LG_BRK = 4 };      // LG_BRK: LgParams::stage = the EPI_B* kind
 // epilogue kinds (template parameter of the GEMM kernel)
@@ -49,6 +50,7 @@ struct __align__(1024) LgSmem {
     unsigned char a_hi[NST][SLAB], a_lo[NST][SLAB], b_hi[NST][SLAB], b_lo[NST][SLAB];
     uint64_t full[NST], split[NST], done[NST];
     uint32_t tmem_base;
+    float raw[2][TN][GEN_W];            // encoder fusion: the raw input rows of this trajectory tile (B-generator mode)
 };
 
 __device__ long long g_lg_dbg[64];        // clock64 stamps of one CTA (PSNODE_LG_DBG=<cta index + 1>): phase breakdown on the device
@@ -74,6 +76,13 @@ struct LgParams {
     float* x0; float* k1; float* k2; float* k3; int64_t st_ld;
     float* acc;                                              // reverse pass: acc[n][m] += out (row stride st_ld)
     const float* t_cur; const float* t_prev; int64_t t_sb;   // t[j], t[j-1] rows (element n at n * t_sb)
+    // B-generator (encoder fusion): bit s of `gen` set = source s of the B operand is not loaded but computed in
+    // shared memory as the hidden layer of an input encoder, b[n][k] = ELU(sum_c gen_W[k][c] * raw[r][n][c] + gen_b[k]), from the raw
+    // (rows, trajectories, gen_w <= 8) series: the encoded (T, B, H) latent series never exists in HBM
+    int gen;
+    const float* gen_raw[2]; int64_t gen_sr[2], gen_sb[2]; int gen_w[2];
+    const float* gen_W[2]; const float* gen_b[2];
+    int m_live;                                              // > 0: output features m >= m_live are padding (not stored)
     int* err;
 };
 
@@ -111,6 +120,15 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
         fence_mbar_init();
     }
     if (cw == 0) tmem_alloc(&sm.tmem_base, NPART * TN);
+    if (q.gen) {
+        for (int e = tid; e < 2 * TN * GEN_W; e += LG_THREADS) {
+            const int src = e / (TN * GEN_W), n = (e / GEN_W) % TN, cc = e % GEN_W;
+            float v = 0.0f;
+            if (((q.gen >> src) & 1) && cc < q.gen_w[src] && b0 + n < q.N)
+                v = __ldg(q.gen_raw[src] + (int64_t)r * q.gen_sr[src] + (int64_t)(b0 + n) * q.gen_sb[src] + cc);
+            sm.raw[src][n][cc] = v;
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -126,10 +144,11 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                 if (c >= NST && !mbar_wait(&sm.done[s], (uint32_t)(((c - NST) / NST) & 1))) { atomicExch(q.err, 12); __trap(); }
                 int ck = c + rot; if (ck >= nchunk) ck -= nchunk;
                 const int src = ck / q.kchunks, kc = ck - src * q.kchunks;
-                mbar_expect_tx(&sm.full[s], 3 * SLAB);
+                const bool generated = (q.gen >> src) & 1;
+                mbar_expect_tx(&sm.full[s], (generated ? 2 : 3) * SLAB);
                 tma_load_3d(sm.a_hi[s], &map_a_hi, ck * 32, mblk * TM, 0, &sm.full[s]);
                 tma_load_3d(sm.a_lo[s], &map_a_lo, ck * 32, mblk * TM, 0, &sm.full[s]);
-                tma_load_3d(sm.b_hi[s], src == 0 ? &map_b0 : &map_b1, kc * 32, b0, r + q.b_r0, &sm.full[s]);
+                if (!generated) tma_load_3d(sm.b_hi[s], src == 0 ? &map_b0 : &map_b1, kc * 32, b0, r + q.b_r0, &sm.full[s]);
             }
         }
         __syncwarp();
@@ -168,13 +187,42 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
             stamp();
             float4* h4 = reinterpret_cast<float4*>(sm.b_hi[s]);
             float4* l4 = reinterpret_cast<float4*>(sm.b_lo[s]);
+            int gsrc = -1, gkc = 0;
+            if (q.gen) {
+                int ck = c + rot; if (ck >= nchunk) ck -= nchunk;
+                const int src = ck / q.kchunks;
+                if ((q.gen >> src) & 1) { gsrc = src; gkc = ck - src * q.kchunks; }
+            }
+            if (gsrc >= 0) {
+                // the slab is written as TMA would have delivered it: 128-byte row n, 16-byte unit u at position u ^ (n & 7)
+                const float* gW = q.gen_W[gsrc];
+                const float* gb = q.gen_b[gsrc];
+                const int gw = q.gen_w[gsrc];
+#pragma unroll 1
+                for (int e = 0; e < SLAB / 16 / 256; e++) {
+                    const int idx = tid + e * 256;
+                    const int n = idx >> 3, k0 = gkc * 32 + (((idx & 7) ^ (n & 7)) << 2);
+                    float v[4];
 #pragma unroll
-            for (int e = 0; e < SLAB / 16 / 256; e++) {
-                const int idx = tid + e * 256;
-                float4 lo;
-                const float4 hi = split4_hi(h4[idx], lo);
-                h4[idx] = hi;
-                l4[idx] = lo;
+                    for (int u = 0; u < 4; u++) {
+                        float pre = __ldg(gb + k0 + u);
+                        for (int cc = 0; cc < gw; cc++) pre = fmaf(__ldg(gW + (k0 + u) * gw + cc), sm.raw[gsrc][n][cc], pre);
+                        v[u] = psn_elu(pre);
+                    }
+                    float4 lo;
+                    const float4 hi = split4_hi(make_float4(v[0], v[1], v[2], v[3]), lo);
+                    h4[idx] = hi;
+                    l4[idx] = lo;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < SLAB / 16 / 256; e++) {
+                    const int idx = tid + e * 256;
+                    float4 lo;
+                    const float4 hi = split4_hi(h4[idx], lo);
+                    h4[idx] = hi;
+                    l4[idx] = lo;
+                }
             }
             fence_async_smem();
             __syncwarp();
@@ -204,7 +252,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
         const float* add1 = q.add1;
         int64_t add1_row = (int64_t)r * q.add1_sr;
         if (evk >= 0 && q.add1_jump) { add1 = q.add1_jump; add1_row = (int64_t)evk * q.add1_jump_sr; }
-        const float bias = q.bias ? __ldg(q.bias + m) : 0.0f;
+        const bool m_ok = q.m_live <= 0 || m < q.m_live;
+        const float bias = (q.bias && m_ok) ? __ldg(q.bias + m) : 0.0f;
         const float c13 = (float)(1.0 / 3.0);
         struct Buf { float p0[16], p1[16], p2[16], p3[16], dt[16]; };
         // per-thread base pointers (element (column c of this thread's 64, feature m) at base + c * ld): no 64-bit index
@@ -289,7 +338,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                 } else if constexpr (!rk) {
                     v = (v + e.p0[i]) + e.p1[i];
                     if constexpr (EPI == EPI_HIDDEN) v = psn_elu(v);
-                    pout[c * old] = v;
+                    if (m_ok) pout[c * old] = v;
                     if (pout2) pout2[c * o2ld] = v;
                 } else {
                     // reference operation order (neural_dae/my_fixed_grid.py:15-59)
@@ -411,7 +460,6 @@ struct WgParams {
     float* slabs;                   // [split][tile][128][128]
     int* err;
     const int32_t* ev; int ev_j;    // skip (early exit) unless an event fires at ev_j (ev == NULL: never skip)
-    int dbg, lbo, sbo, kadv;        // debugging / probing of the MN-major descriptor fields (bytes)
 };
 // MN-major tf32 operands exist in ONE shared-memory layout only: 128-byte swizzle with 32-byte atomicity (UMMA layout type 1,
 // SWIZZLE_128B_BASE32B; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  The swizzle pattern repeats every 4 rows of 128 B, so the
@@ -477,7 +525,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) psn_lg_wgrad_kernel(const __gri
         }
         __syncwarp();
     } else if (cw == 9) {
-        const uint32_t idesc = q.dbg == 4 ? make_idesc_tf32(TM, TN) : (q.dbg == 5 ? (make_idesc_tf32(TM, TN) | (1u << 15)) : (q.dbg == 6 ? (make_idesc_tf32(TM, TN) | (1u << 16)) : make_idesc_tf32_mn(TM, TN)));
+        const uint32_t idesc = make_idesc_tf32_mn(TM, TN);
         for (int c = 0; c < n; c++) {
             const int s = c % NST;
             const int pair = c >> 1;
@@ -485,9 +533,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) psn_lg_wgrad_kernel(const __gri
             if (!mbar_wait(&sm.split[s], (uint32_t)((c / NST) & 1))) { atomicExch(q.err, 23); __trap(); }
             if (elect_one()) {
                 tc_fence_after();
-                const uint64_t dp_hi = make_desc_mn(smem_u32(sm.p_hi[s]), q.lbo, q.sbo), dp_lo = make_desc_mn(smem_u32(sm.p_lo[s]), q.lbo, q.sbo);
-                const uint64_t dq_hi = make_desc_mn(smem_u32(sm.q_hi[s]), q.lbo, q.sbo), dq_lo = make_desc_mn(smem_u32(sm.q_lo[s]), q.lbo, q.sbo);
-                const uint64_t kadv = (uint64_t)(q.kadv >> 4);
+                // LBO = 4096 B (next block of 32 features = one TMA box), SBO = 512 B (next group of 4 reduction rows), K = 8 step = 1024 B
+                const uint64_t dp_hi = make_desc_mn(smem_u32(sm.p_hi[s]), 4096, 512), dp_lo = make_desc_mn(smem_u32(sm.p_lo[s]), 4096, 512);
+                const uint64_t dq_hi = make_desc_mn(smem_u32(sm.q_hi[s]), 4096, 512), dq_lo = make_desc_mn(smem_u32(sm.q_lo[s]), 4096, 512);
+                constexpr uint64_t kadv = 1024 >> 4;
                 uint32_t accumulate = (c & 1) ? 1u : 0u;
 #pragma unroll
                 for (int term = 0; term < 3; term++) {
@@ -533,12 +582,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) psn_lg_wgrad_kernel(const __gri
                 hi = split4_hi(qh[idx], lo);
                 qh[idx] = hi; ql[idx] = lo;
             }
-            if (q.dbg == 3 && c == 0 && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {      // debugging aid
-                float* f = reinterpret_cast<float*>(q.err);
-                q.err[1] = n; q.err[2] = cps; q.err[3] = (int)total;
-                f[4] = reinterpret_cast<const float*>(sm.p_hi[s])[0]; f[5] = reinterpret_cast<const float*>(sm.p_hi[s])[33];
-                f[6] = reinterpret_cast<const float*>(sm.q_hi[s])[0]; f[7] = reinterpret_cast<const float*>(sm.p_lo[s])[0];
-            }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.split[s]);
@@ -550,10 +593,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) psn_lg_wgrad_kernel(const __gri
             const int cmax = ((n - 1) & 1) ? n - 1 : n - 2;                 // last odd chunk index
             const int upto = cmax >= 3 ? (cmax >> 1) - 1 : -1;             // last pair drained in the loop
             for (int pp = upto + 1; pp <= last_pair; pp++) drain(pp, min(2 * pp + 1, n - 1));
-        }
-        if (q.dbg == 3 && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
-            float* f = reinterpret_cast<float*>(q.err);
-            f[8] = acc[0]; f[9] = acc[1]; f[10] = acc[63];
         }
         float* slab = q.slabs + ((int64_t)split * gridDim.x + tile) * TM * TN + (int64_t)(32 * wq + lane) * TN + 64 * hh;
 #pragma unroll
@@ -610,10 +649,6 @@ int lg_wgrad(const float* P, int64_t p_sn, int64_t p_ss, int M, const float* Q, 
     q.nsplit = nsplit;
     q.slabs = slabs; q.err = err;
     q.ev = ev; q.ev_j = ev_j;
-    q.dbg = std::getenv("PSNODE_WG_DBG") ? std::atoi(std::getenv("PSNODE_WG_DBG")) : 0;
-    q.lbo = std::getenv("PSNODE_WG_LBO") ? std::atoi(std::getenv("PSNODE_WG_LBO")) : 4096;
-    q.sbo = std::getenv("PSNODE_WG_SBO") ? std::atoi(std::getenv("PSNODE_WG_SBO")) : 512;
-    q.kadv = std::getenv("PSNODE_WG_KADV") ? std::atoi(std::getenv("PSNODE_WG_KADV")) : 1024;
     const int smem = (int)sizeof(WgSmem) + 1024;
     static bool attr = false;
     if (!attr) { PSN_CUDA(cudaFuncSetAttribute(psn_lg_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = true; }
@@ -680,15 +715,21 @@ int64_t al(int64_t floats) { return (floats + 63) & ~(int64_t)63; }
 
 // prepared weight planes: the forward's seven (A = weights as they multiply activations) and the reverse pass's transposes
 enum { M_DE1X = 0, M_DE1ZV, M_DE1I, M_DE2, M_AE1X, M_AE1ZV, M_AE2, M_C_DE, M_C_AE,
-       M_T_DE2, M_T_DE1X, M_T_DE1I, M_T_AE2, M_T_AE1X, M_T_DZ, M_T_DV, M_T_DA0, NMAT };
+       M_T_DE2, M_T_DE1X, M_T_DE1I, M_T_AE2, M_T_AE1X, M_T_DZ, M_T_DV, M_T_DA0,
+       M_XD1, M_XD2, M_ID1, M_ID2, NMAT };                                      // decoders of the encoded entry (M_?D2: rows padded to 128)
+constexpr int NMAT_BWD = M_T_DA0 + 1;
 constexpr int NMAT_FWD = M_C_AE + 1;
 
 // BH-sized work buffers of the reverse pass (one contiguous array, one tensor map, addressed by index)
 enum { BUF_GX = 0, BUF_DY3, BUF_DY2, BUF_DY1, BUF_GI0, BUF_HEV, BUF_DHEV, BUF_G, BUF_K1, BUF_K2, BUF_K3, BUF_DCDE, BUF_DCAE, BUF_ACCDK, BUF_ACCGI,
        BUF_UPX, BUF_UPI, BUF_SINGLES };
 
+enum { LG_FWD = 0, LG_BWD = 1, LG_ENC = 2 };
 struct LgLayout {
-    int H, KZV, S, nmat, bwd;
+    int H, KZV, S, nmat, bwd, enc;
+    // encoded entry: time-chunk scratch (rows of B x H floats)
+    int rc;
+    int64_t encb_de, encb_ae, pj_de, pj_ae, xs, is, dtmp;
     int mrows[NMAT], mcols[NMAT];
     int64_t err, wts_hi[NMAT], wts_lo[NMAT], c_de, c_ae, pre_de, pre_ae, x0, k1, k2, k3, ycur, a1, hbuf, icur, G, total;
     int64_t rows_de, rows_ae;
@@ -708,25 +749,28 @@ int lg_ring_depth() {
     return v < 1 ? 1 : (v > 64 ? 64 : v);
 }
 
-LgLayout lg_layout(const psnode_problem* p, bool bwd) {
+LgLayout lg_layout(const psnode_problem* p, int mode, int chunk_rows = 0) {
     LgLayout L;
     std::memset(&L, 0, sizeof(L));
+    const bool bwd = mode == LG_BWD, enc = mode == LG_ENC;
     const bool dae = p->kind == PSNODE_DAE;
     const int H = p->X, E = p->event_idx ? p->E : 0;
     L.H = H;
     L.KZV = p->Z + p->V;
     L.S = p->X + p->Z + p->V + p->I;
     L.bwd = bwd ? 1 : 0;
-    L.nmat = bwd ? NMAT : NMAT_FWD;
+    L.enc = enc ? 1 : 0;
+    L.nmat = bwd ? NMAT_BWD : NMAT_FWD;
     const int k2 = dae ? 2 * H : H;
-    const int rows[NMAT] = {H, H, H, H, H, H, H, H, H, H, H, H, H, H, H, H, L.S};
-    const int cols[NMAT] = {H, L.KZV, H, H, H, L.KZV, H, L.S, L.S, H, H, H, H, H, k2, k2, k2};
+    const int rows[NMAT] = {H, H, H, H, H, H, H, H, H, H, H, H, H, H, H, H, L.S, H, 128, H, 128};
+    const int cols[NMAT] = {H, L.KZV, H, H, H, L.KZV, H, L.S, L.S, H, H, H, H, H, k2, k2, k2, H, H, H, H};
     int64_t o = 64;
     L.err = 0;
     for (int i = 0; i < NMAT; i++) {
         L.mrows[i] = rows[i]; L.mcols[i] = cols[i];
-        if (i >= L.nmat) continue;
-        const bool used = dae || (i == M_DE1X || i == M_DE1ZV || i == M_DE2 || i == M_C_DE || i == M_T_DE2 || i == M_T_DE1X || i == M_T_DZ || i == M_T_DA0);
+        const bool dec = enc && (i == M_XD1 || i == M_XD2 || (dae && (i == M_ID1 || i == M_ID2)));
+        if (i >= L.nmat && !dec) continue;
+        const bool used = dec || dae || (i == M_DE1X || i == M_DE1ZV || i == M_DE2 || i == M_C_DE || i == M_T_DE2 || i == M_T_DE1X || i == M_T_DZ || i == M_T_DA0);
         if (!used) continue;
         L.wts_hi[i] = o; o += al((int64_t)rows[i] * cols[i]);
         L.wts_lo[i] = o; o += al((int64_t)rows[i] * cols[i]);
@@ -737,6 +781,19 @@ LgLayout lg_layout(const psnode_problem* p, bool bwd) {
     // (the reverse pass overwrites pre[r] with d pre[r] in place)
     L.rows_de = (p->T > 1 ? p->T - 1 : 0) + E ;
     L.rows_ae = dae ? (int64_t)p->T + E : 0;
+    if (enc) {                                                  // one time chunk of rows instead of the whole series
+        L.rc = chunk_rows > 0 ? chunk_rows : 64;
+        if (L.rc > p->T) L.rc = p->T;
+        L.rows_de = L.rc;
+        L.rows_ae = dae ? L.rc + 1 : 0;
+        L.encb_de = o; o += al(H);
+        L.encb_ae = o; o += al(H);
+        L.pj_de = o; o += al((int64_t)(E > 0 ? E : 1) * BH);
+        L.pj_ae = o; o += al((int64_t)(E > 0 ? E : 1) * BH);
+        L.xs = o; o += al((int64_t)(L.rc + 1) * BH);
+        L.is = o; o += al(dae ? (int64_t)(L.rc + 1) * BH : 64);
+        L.dtmp = o; o += al((int64_t)(L.rc + 1) * BH);
+    }
     L.pre_de = o; o += al(L.rows_de * BH);
     L.pre_ae = o; o += al(L.rows_ae * BH);
     L.x0 = o; o += al(BH); L.k1 = o; o += al(BH); L.k2 = o; o += al(BH); L.k3 = o; o += al(BH);
@@ -771,6 +828,27 @@ __global__ void psn_lg_prep2_kernel(const float* __restrict__ W, int ldw, int co
     split_tf32(w, h, l);
     hi[(int64_t)m * ldd + k] = h;
     lo[(int64_t)m * ldd + k] = l;
+}
+
+// encoder fusion: out[m][dcol + k] = split_tf32(sum_h F[m][h] * E2[h][k]),  F[m][h] = W[m * ldw + col0 + h] (+ W[m * ldw + col1 + h]); and the
+// matching bias  pb[m] (+)= sum_h F[m][h] * e2[h]   (the encoder's second Linear folded into the held-input half of layer 1)
+__global__ void psn_lg_fold_enc_kernel(const float* __restrict__ W, int ldw, int col0, int col1, const float* __restrict__ E2, const float* __restrict__ e2,
+                                       int H, int ldd, int dcol, float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ pb, int pb_acc) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * H) return;
+    const int m = idx / H, k = idx - m * H;
+    float acc = 0.0f, accb = 0.0f;
+    for (int h = 0; h < H; h++) {
+        float f = __ldg(W + (int64_t)m * ldw + col0 + h);
+        if (col1 >= 0) f += __ldg(W + (int64_t)m * ldw + col1 + h);
+        acc = fmaf(f, __ldg(E2 + (int64_t)h * H + k), acc);
+        if (k == 0) accb = fmaf(f, __ldg(e2 + h), accb);
+    }
+    float hh, ll;
+    split_tf32(acc, hh, ll);
+    hi[(int64_t)m * ldd + dcol + k] = hh;
+    lo[(int64_t)m * ldd + dcol + k] = ll;
+    if (k == 0) pb[m] = pb_acc ? pb[m] + accb : accb;
 }
 
 // Everything the forward pass and the reverse pass share: prepared planes, tensor maps, hoisted projections, launch helpers.
@@ -815,9 +893,10 @@ struct LgCtx {
 };
 
 // weights -> planes, per-trajectory constants, tensor maps, hoisted layer-1 halves over the whole series
-int lg_setup(LgCtx& c, const psnode_problem* p, bool bwd, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+int lg_setup(LgCtx& c, const psnode_problem* p, int mode, void* ws, int64_t ws_bytes, cudaStream_t stream, const psnode_codec* codec = nullptr) {
+    const bool bwd = mode == LG_BWD, enc = mode == LG_ENC;
     c.p = p;
-    c.L = lg_layout(p, bwd);
+    c.L = lg_layout(p, mode, codec ? codec->chunk_rows : 0);
     const LgLayout& L = c.L;
     if (ws == nullptr || ws_bytes < L.total * 4) return PSNODE_EWORKSPACE;
     float* w = c.w = static_cast<float*>(ws);
@@ -840,13 +919,37 @@ int lg_setup(LgCtx& c, const psnode_problem* p, bool bwd, void* ws, int64_t ws_b
     const float* A1 = dae ? p->ae.W[0] : nullptr;
     const int lda = S + X + Z + V;
     c.prep(M_DE1X, W1, ld1, S, 2 * S, 1.0f, 0, H, H, 0);                              // F_x = (W_b + W_c)[:, 0:X]
-    c.prep(M_DE1ZV, W1, ld1, S + X, 2 * S + X, 1.0f, 0, H, L.KZV, 0);                 // [F_z | F_v]
+    if (!enc) c.prep(M_DE1ZV, W1, ld1, S + X, 2 * S + X, 1.0f, 0, H, L.KZV, 0);       // [F_z | F_v]
     c.prep(M_DE2, p->de.W[1], H, 0, -1, 0.0f, 0, H, H, 0);
     if (dae) {
         c.prep(M_DE1I, W1, ld1, S + X + Z + V, 2 * S + X + Z + V, 1.0f, 0, H, H, 0);   // F_i
         c.prep(M_AE1X, A1, lda, S, -1, 0.0f, 0, H, H, 0);
-        c.prep(M_AE1ZV, A1, lda, S + X, -1, 0.0f, 0, H, L.KZV, 0);
+        if (!enc) c.prep(M_AE1ZV, A1, lda, S + X, -1, 0.0f, 0, H, L.KZV, 0);
         c.prep(M_AE2, p->ae.W[1], H, 0, -1, 0.0f, 0, H, H, 0);
+    }
+    if (enc) {
+        // [F_z E2z | F_v E2v] and [A1z E2z | A1v E2v]: the held-input halves act on the encoders' HIDDEN layers; decoder planes
+        auto fold = [&](int which, const float* W, int ldw, int col0, int col1, const psnode_mlp& en, int dcol, float* pb, int pb_acc) {
+            psn_lg_fold_enc_kernel<<<(H * H + 255) / 256, 256, 0, stream>>>(W, ldw, col0, col1, en.W[1], en.b[1], H, L.mcols[which], dcol,
+                                                                            w + L.wts_hi[which], w + L.wts_lo[which], pb, pb_acc);
+            psn_count_launch("psn_lg_fold_enc_kernel");
+        };
+        fold(M_DE1ZV, W1, ld1, S + X, 2 * S + X, codec->z_enc, 0, w + L.encb_de, 0);
+        if (dae) {
+            fold(M_DE1ZV, W1, ld1, S + X + Z, 2 * S + X + Z, codec->v_enc, H, w + L.encb_de, 1);
+            fold(M_AE1ZV, A1, lda, S + X, -1, codec->z_enc, 0, w + L.encb_ae, 0);
+            fold(M_AE1ZV, A1, lda, S + X + Z, -1, codec->v_enc, H, w + L.encb_ae, 1);
+        }
+        c.prep(M_XD1, codec->x_dec.W[0], H, 0, -1, 0.0f, 0, H, H, 0);
+        PSN_CUDA(cudaMemsetAsync(w + L.wts_hi[M_XD2], 0, (size_t)128 * H * 4, stream));
+        PSN_CUDA(cudaMemsetAsync(w + L.wts_lo[M_XD2], 0, (size_t)128 * H * 4, stream));
+        c.prep(M_XD2, codec->x_dec.W[1], H, 0, -1, 0.0f, 0, codec->XR, H, 0);
+        if (dae) {
+            c.prep(M_ID1, codec->i_dec.W[0], H, 0, -1, 0.0f, 0, H, H, 0);
+            PSN_CUDA(cudaMemsetAsync(w + L.wts_hi[M_ID2], 0, (size_t)128 * H * 4, stream));
+            PSN_CUDA(cudaMemsetAsync(w + L.wts_lo[M_ID2], 0, (size_t)128 * H * 4, stream));
+            c.prep(M_ID2, codec->i_dec.W[1], H, 0, -1, 0.0f, 0, codec->IR, H, 0);
+        }
     }
     // per-trajectory layer-1 constants c = (W_a - W_b) a0 + b1 (and A1a a0 + ab1): a K = S GEMM on the same kernel when all_initial can be
     // a TMA operand, else a CUDA-core kernel
@@ -881,16 +984,18 @@ int lg_setup(LgCtx& c, const psnode_problem* p, bool bwd, void* ws, int64_t ws_b
 
     // ---- tensor maps (once per call) ----
     bool ok = true;
-    for (int i = 0; i < L.nmat; i++) {
+    for (int i = 0; i < NMAT; i++) {
         if (L.wts_hi[i] == 0) continue;
         ok = ok && lg_make_map(&c.mw_hi[i], w + L.wts_hi[i], L.mcols[i], L.mrows[i], L.mcols[i], 1, 0) &&
              lg_make_map(&c.mw_lo[i], w + L.wts_lo[i], L.mcols[i], L.mrows[i], L.mcols[i], 1, 0);
     }
-    ok = ok && lg_make_map(&c.m_z, p->z.p, H, B, p->z.sb, T, p->z.st);
-    if (dae) ok = ok && lg_make_map(&c.m_v, p->v.p, H, B, p->v.sb, T, p->v.st);
-    if (E > 0) {
-        ok = ok && lg_make_map(&c.m_zj, p->z_jump, H, B, p->zj_sb, E, p->zj_se);
-        if (dae) ok = ok && lg_make_map(&c.m_vj, p->v_jump, H, B, p->vj_sb, E, p->vj_se);
+    if (!enc) {
+        ok = ok && lg_make_map(&c.m_z, p->z.p, H, B, p->z.sb, T, p->z.st);
+        if (dae) ok = ok && lg_make_map(&c.m_v, p->v.p, H, B, p->v.sb, T, p->v.st);
+        if (E > 0) {
+            ok = ok && lg_make_map(&c.m_zj, p->z_jump, H, B, p->zj_sb, E, p->zj_se);
+            if (dae) ok = ok && lg_make_map(&c.m_vj, p->v_jump, H, B, p->vj_sb, E, p->vj_se);
+        }
     }
     ok = ok && lg_make_map(&c.m_y, w + L.ycur, H, B, H, 1, 0) && lg_make_map(&c.m_a1, w + L.a1, H, B, H, 1, 0);
     if (dae) ok = ok && lg_make_map(&c.m_h, w + L.hbuf, H, B, H, 1, 0) && lg_make_map(&c.m_i, w + L.icur, H, B, H, 1, 0);
@@ -911,6 +1016,7 @@ int lg_setup(LgCtx& c, const psnode_problem* p, bool bwd, void* ws, int64_t ws_b
         }
     }
 
+    if (enc) return PSNODE_OK;                                   // the encoded entry projects chunk by chunk
     // ---- hoisted layer-1 halves over the whole series ----
     const int64_t BH = c.BH;
     const int64_t jump_de = (int64_t)(T > 1 ? T - 1 : 0) * BH;
@@ -1033,16 +1139,87 @@ bool psn_lg_supports(const psnode_problem* p) {
     return lg_encode_fn() != nullptr;
 }
 
-int64_t psn_lg_forward_workspace(const psnode_problem* p) { return lg_layout(p, false).total * 4; }
+int64_t psn_lg_forward_workspace(const psnode_problem* p) { return lg_layout(p, LG_FWD).total * 4; }
+
+namespace {
+// one grid step of the forward pass (shared by psn_lg_forward and the encoded entry)
+struct LgStepIO {
+    const float* pre_de_row;        // hoisted DE half of grid row j-1
+    const float* pre_de_jump;       // its event rows (row stride B * H)
+    const float* pre_ae_row;        // hoisted AE half of grid row j
+    const float* pre_ae_jump;
+    float* xrow; int64_t xld;       // where x_j goes (row stride xld)
+    float* irow; int64_t ild;       // where i_j goes
+};
+// algebraic evaluation i = ae(x, z, v) on the current state (ycur holds x at step boundaries)
+void lg_ae_eval(const LgCtx& c, const float* pre_row, const float* pre_jump, float* irow, int64_t ild, bool event_only, int ev_j) {
+    const psnode_problem* p = c.p;
+    float* w = c.w;
+    LgParams q = c.base();
+    q.mode = LG_HIDDEN;
+    q.add1 = pre_row; q.add1_sr = 0;
+    if (event_only) {
+        q.ev = p->event_idx; q.ev_j = ev_j; q.skip_unless_event = 1;
+        q.add1_jump = pre_jump; q.add1_jump_sr = c.BH;
+    }
+    q.out = w + c.L.hbuf;
+    c.launch(M_AE1X, c.m_y, c.m_y, q, event_only ? "psn_lg_gemm_kernel<ae1,event>" : "psn_lg_gemm_kernel<ae1>");
+    LgParams q2 = c.base();
+    q2.bias = p->ae.b[1];
+    if (event_only) { q2.ev = p->event_idx; q2.ev_j = ev_j; q2.skip_unless_event = 1; }
+    q2.out = w + c.L.icur;
+    if (irow) { q2.out2 = irow; q2.out2_ld = ild; }
+    c.launch(M_AE2, c.m_h, c.m_h, q2, event_only ? "psn_lg_gemm_kernel<ae2,event>" : "psn_lg_gemm_kernel<ae2>");
+}
+void lg_step(const LgCtx& c, int j, const LgStepIO& io) {
+    const psnode_problem* p = c.p;
+    float* w = c.w;
+    const LgLayout& L = c.L;
+    if (c.dae) {
+        if (c.E > 0) lg_ae_eval(c, nullptr, io.pre_ae_jump, nullptr, 0, true, j - 1);   // event: i_0 re-evaluated with the jumped inputs (:108-110)
+        LgParams qg = c.base();                                                          // G = F_i i0
+        qg.out = w + L.G;
+        c.launch(M_DE1I, c.m_i, c.m_i, qg, "psn_lg_gemm_kernel<de1_i>");
+    }
+    for (int e = 0; e < c.nstages; e++) {
+        LgParams q1 = c.base();
+        q1.mode = LG_HIDDEN;
+        q1.add1 = io.pre_de_row;
+        if (c.E > 0) { q1.ev = p->event_idx; q1.ev_j = j - 1; q1.add1_jump = io.pre_de_jump; q1.add1_jump_sr = c.BH; }
+        if (c.dae) q1.add2 = w + L.G;
+        q1.out = w + L.a1;
+        c.launch(M_DE1X, c.m_y, c.m_y, q1, "psn_lg_gemm_kernel<de1>");
+        LgParams q2 = c.base();
+        q2.mode = LG_RK;
+        q2.bias = p->de.b[1];
+        q2.method = p->method; q2.stage = e;
+        q2.x0 = w + L.x0; q2.k1 = w + L.k1; q2.k2 = w + L.k2; q2.k3 = w + L.k3;
+        q2.t_cur = p->t.p + (int64_t)j * p->t.st; q2.t_prev = p->t.p + (int64_t)(j - 1) * p->t.st; q2.t_sb = p->t.sb;
+        q2.out = w + L.ycur;
+        q2.out2 = io.xrow; q2.out2_ld = io.xld;
+        c.launch(M_DE2, c.m_a1, c.m_a1, q2, "psn_lg_gemm_kernel<de2,rk>");
+    }
+    if (c.dae) lg_ae_eval(c, io.pre_ae_row, nullptr, io.irow, io.ild, false, 0);         // i_j = ae(x_j, z[j], v[j])  (:121)
+}
+void lg_dump_stamps(const LgCtx& c) {
+    if (!c.dbg_cta) return;                  // debugging aid only: synchronises
+    long long h[64];
+    cudaStreamSynchronize(c.stream);
+    cudaMemcpyFromSymbol(h, g_lg_dbg, sizeof(h));
+    std::fprintf(stderr, "psn_lg stamps (cycles since kernel start, last launch, CTA %d):", c.dbg_cta - 1);
+    for (int i = 1; i < (int)h[63] && i < 32; i++) std::fprintf(stderr, " %lld", h[i] - h[0]);
+    std::fprintf(stderr, "\n");
+}
+}  // namespace
 
 int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream) {
     LgCtx c;
-    const int st = lg_setup(c, p, false, ws, ws_bytes, stream);
+    const int st = lg_setup(c, p, LG_FWD, ws, ws_bytes, stream);
     if (st != PSNODE_OK) return st;
     const LgLayout& L = c.L;
     float* w = c.w;
     const bool dae = c.dae;
-    const int H = c.H, B = c.B, T = c.T, E = c.E;
+    const int H = c.H, B = c.B, T = c.T;
     const int64_t BH = c.BH;
     // ---- initial state ----
     {
@@ -1051,62 +1228,140 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
         psn_lg_init_kernel<<<(int)((BH + 255) / 256), 256, 0, stream>>>(src, sb, B, H, w + L.x0, w + L.ycur, p->x_sol.p, p->x_sol.sb);
         psn_count_launch("psn_lg_init_kernel");
     }
-    // algebraic evaluation i = ae(x, z, v) on the current state (ycur holds x at step boundaries)
-    auto ae_eval = [&](const float* pre_row, int jrow, bool event_only, int ev_j) {
-        LgParams q = c.base();
-        q.mode = LG_HIDDEN;
-        q.add1 = pre_row; q.add1_sr = 0;
-        if (event_only) {
-            q.ev = p->event_idx; q.ev_j = ev_j; q.skip_unless_event = 1;
-            q.add1_jump = w + L.pre_ae + (int64_t)T * BH; q.add1_jump_sr = BH;
-        }
-        q.out = w + L.hbuf;
-        c.launch(M_AE1X, c.m_y, c.m_y, q, event_only ? "psn_lg_gemm_kernel<ae1,event>" : "psn_lg_gemm_kernel<ae1>");
-        LgParams q2 = c.base();
-        q2.bias = p->ae.b[1];
-        if (event_only) { q2.ev = p->event_idx; q2.ev_j = ev_j; q2.skip_unless_event = 1; }
-        q2.out = w + L.icur;
-        if (jrow >= 0) { q2.out2 = p->i_sol.p + (int64_t)jrow * p->i_sol.st; q2.out2_ld = p->i_sol.sb; }
-        c.launch(M_AE2, c.m_h, c.m_h, q2, event_only ? "psn_lg_gemm_kernel<ae2,event>" : "psn_lg_gemm_kernel<ae2>");
-    };
-    if (dae) ae_eval(w + L.pre_ae, 0, false, 0);                               // i_0 = ae(x_0, z[0], v[0])  (my_solvers.py:95)
-
+    const float* ae_jump = w + L.pre_ae + (int64_t)T * BH;
+    const float* de_jump = w + L.pre_de + (int64_t)(T - 1) * BH;
+    if (dae) lg_ae_eval(c, w + L.pre_ae, nullptr, p->i_sol.p, p->i_sol.sb, false, 0);     // i_0 = ae(x_0, z[0], v[0])  (my_solvers.py:95)
     for (int j = 1; j < T; j++) {
-        if (dae) {
-            if (E > 0) ae_eval(nullptr, -1, true, j - 1);                      // event: i_0 re-evaluated with the jumped inputs (:108-110)
-            LgParams qg = c.base();                                            // G = F_i i0
-            qg.out = w + L.G;
-            c.launch(M_DE1I, c.m_i, c.m_i, qg, "psn_lg_gemm_kernel<de1_i>");
-        }
-        for (int e = 0; e < c.nstages; e++) {
-            LgParams q1 = c.base();
-            q1.mode = LG_HIDDEN;
-            q1.add1 = w + L.pre_de + (int64_t)(j - 1) * BH;
-            if (E > 0) { q1.ev = p->event_idx; q1.ev_j = j - 1; q1.add1_jump = w + L.pre_de + (int64_t)(T - 1) * BH; q1.add1_jump_sr = BH; }
-            if (dae) q1.add2 = w + L.G;
-            q1.out = w + L.a1;
-            c.launch(M_DE1X, c.m_y, c.m_y, q1, "psn_lg_gemm_kernel<de1>");
-            LgParams q2 = c.base();
-            q2.mode = LG_RK;
-            q2.bias = p->de.b[1];
-            q2.method = p->method; q2.stage = e;
-            q2.x0 = w + L.x0; q2.k1 = w + L.k1; q2.k2 = w + L.k2; q2.k3 = w + L.k3;
-            q2.t_cur = p->t.p + (int64_t)j * p->t.st; q2.t_prev = p->t.p + (int64_t)(j - 1) * p->t.st; q2.t_sb = p->t.sb;
-            q2.out = w + L.ycur;
-            q2.out2 = p->x_sol.p + (int64_t)j * p->x_sol.st; q2.out2_ld = p->x_sol.sb;
-            c.launch(M_DE2, c.m_a1, c.m_a1, q2, "psn_lg_gemm_kernel<de2,rk>");
-        }
-        if (dae) ae_eval(w + L.pre_ae + (int64_t)j * BH, j, false, 0);          // i_j = ae(x_j, z[j], v[j])  (:121)
+        LgStepIO io;
+        io.pre_de_row = w + L.pre_de + (int64_t)(j - 1) * BH; io.pre_de_jump = de_jump;
+        io.pre_ae_row = w + L.pre_ae + (int64_t)j * BH; io.pre_ae_jump = ae_jump;
+        io.xrow = p->x_sol.p + (int64_t)j * p->x_sol.st; io.xld = p->x_sol.sb;
+        io.irow = dae ? p->i_sol.p + (int64_t)j * p->i_sol.st : nullptr; io.ild = p->i_sol.sb;
+        lg_step(c, j, io);
     }
     PSN_CUDA(cudaGetLastError());
-    if (c.dbg_cta) {                          // debugging aid only: synchronises
-        long long h[64];
-        cudaStreamSynchronize(stream);
-        cudaMemcpyFromSymbol(h, g_lg_dbg, sizeof(h));
-        std::fprintf(stderr, "psn_lg stamps (cycles since kernel start, last launch, CTA %d):", c.dbg_cta - 1);
-        for (int i = 1; i < (int)h[63] && i < 32; i++) std::fprintf(stderr, " %lld", h[i] - h[0]);
-        std::fprintf(stderr, "\n");
+    lg_dump_stamps(c);
+    return PSNODE_OK;
+}
+
+// ---- encoded entry (psnode_forward_encoded): encoders fused into the hoisted projections, time chunks, decoders before the store ----
+bool psn_lg_encoded_supports(const psnode_problem* p, const psnode_codec* cd) {
+    if (!p || !cd) return false;
+    const int H = p->X;
+    const bool dae = p->kind == PSNODE_DAE;
+    if (H != 128 && H != 256) return false;
+    if (p->teacher_x || p->teacher_i || p->Z != H || (dae && (p->V != H || p->I != H)) || (!dae && (p->V || p->I))) return false;
+    const int S = p->X + p->Z + p->V + p->I;
+    if (p->de.n_layers != 2 || p->de.in_dim[0] != 3 * S || p->de.out_dim[0] != H || p->de.out_dim[1] != H) return false;
+    if (dae && (p->ae.n_layers != 2 || p->ae.in_dim[0] != S + p->X + p->Z + p->V || p->ae.out_dim[0] != H || p->ae.out_dim[1] != H)) return false;
+    auto enc_ok = [&](const psnode_mlp& m, int raw) {
+        return m.n_layers == 2 && raw >= 1 && raw <= GEN_W && m.in_dim[0] == raw && m.out_dim[0] == H && m.in_dim[1] == H && m.out_dim[1] == H &&
+               m.W[0] && m.b[0] && m.W[1] && m.b[1];
+    };
+    auto dec_ok = [&](const psnode_mlp& m, int raw) {
+        return m.n_layers == 2 && raw >= 1 && raw <= 128 && m.in_dim[0] == H && m.out_dim[0] == H && m.in_dim[1] == H && m.out_dim[1] == raw &&
+               m.W[0] && m.b[0] && m.W[1] && m.b[1];
+    };
+    if (!enc_ok(cd->z_enc, cd->ZR) || !cd->z_raw.p || !dec_ok(cd->x_dec, cd->XR) || !cd->x_out.p) return false;
+    if (dae && (!enc_ok(cd->v_enc, cd->VR) || !cd->v_raw.p || !dec_ok(cd->i_dec, cd->IR) || !cd->i_out.p)) return false;
+    if (p->event_idx && (p->E < 1 || !cd->zj_raw || (dae && !cd->vj_raw))) return false;
+    if (!p->t.p || !p->a0 || (dae ? !p->x_init : !p->x.p)) return false;
+    if (p->method < PSNODE_EULER || p->method > PSNODE_RK4 || p->B < 1 || p->T < 1) return false;
+    return lg_encode_fn() != nullptr;
+}
+
+int64_t psn_lg_encoded_workspace(const psnode_problem* p, const psnode_codec* cd) { return lg_layout(p, LG_ENC, cd->chunk_rows).total * 4; }
+
+int psn_lg_forward_encoded(const psnode_problem* p, const psnode_codec* cd, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    LgCtx c;
+    const int st = lg_setup(c, p, LG_ENC, ws, ws_bytes, stream, cd);
+    if (st != PSNODE_OK) return st;
+    const LgLayout& L = c.L;
+    float* w = c.w;
+    const bool dae = c.dae;
+    const int H = c.H, B = c.B, T = c.T, E = c.E, RC = L.rc;
+    const int64_t BH = c.BH;
+    CUtensorMap m_xs, m_is, m_tmp;
+    bool ok = lg_make_map(&m_xs, w + L.xs, H, B, H, RC + 1, BH) && lg_make_map(&m_tmp, w + L.dtmp, H, B, H, RC + 1, BH);
+    if (dae) ok = ok && lg_make_map(&m_is, w + L.is, H, B, H, RC + 1, BH);
+    if (!ok) return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (encoded entry)");
+    // hoisted halves of `rows` grid rows starting at raw row r0 (or of the E event rows): the B operand is generated from the raw series
+    auto project = [&](int which, int rows, const float* zraw, int64_t z_sr, int64_t z_sb, const float* vraw, int64_t v_sr, int64_t v_sb,
+                       const float* cadd, const float* bias, float* out, const char* name) {
+        if (rows <= 0) return;
+        LgParams q = c.base();
+        q.R = rows; q.nsrc = dae ? 2 : 1;
+        q.add1 = cadd; q.add1_sr = 0;
+        q.bias = bias;
+        q.out = out; q.out_sr = BH;
+        q.gen = dae ? 3 : 1;
+        q.gen_raw[0] = zraw; q.gen_sr[0] = z_sr; q.gen_sb[0] = z_sb; q.gen_w[0] = cd->ZR; q.gen_W[0] = cd->z_enc.W[0]; q.gen_b[0] = cd->z_enc.b[0];
+        if (dae) {
+            q.gen_raw[1] = vraw; q.gen_sr[1] = v_sr; q.gen_sb[1] = v_sb; q.gen_w[1] = cd->VR; q.gen_W[1] = cd->v_enc.W[0]; q.gen_b[1] = cd->v_enc.b[0];
+        }
+        c.launch(which, c.m_y, c.m_y, q, name);          // (the tensor maps of the B operand are not used in generator mode)
+    };
+    // decoder over `rows` latent rows of a chunk scratch, first chunk row `row0`, into grid rows j0.. of the decoded output
+    auto decode = [&](int d1, int d2, const psnode_mlp& dec, const CUtensorMap& m_src, int row0, int rows, const psnode_series_out& out, int j0, int width) {
+        LgParams q = c.base();
+        q.mode = LG_HIDDEN;
+        q.R = rows; q.b_r0 = row0;
+        q.bias = dec.b[0];
+        q.out = w + L.dtmp; q.out_sr = BH;
+        c.launch(d1, m_src, m_src, q, "psn_lg_gemm_kernel<dec1>");
+        LgParams q2 = c.base();
+        q2.R = rows;
+        q2.bias = dec.b[1];
+        q2.m_live = width;
+        q2.out = out.p + (int64_t)j0 * out.st; q2.out_sr = out.st; q2.out_ld = out.sb;
+        c.launch(d2, m_tmp, m_tmp, q2, "psn_lg_gemm_kernel<dec2>");
+    };
+    if (E > 0) {
+        project(M_DE1ZV, E, cd->zj_raw, cd->zjr_se, cd->zjr_sb, cd->vj_raw, cd->vjr_se, cd->vjr_sb, w + L.c_de, w + L.encb_de, w + L.pj_de,
+                "psn_lg_gemm_kernel<pre_de_jump,enc>");
+        if (dae) project(M_AE1ZV, E, cd->zj_raw, cd->zjr_se, cd->zjr_sb, cd->vj_raw, cd->vjr_se, cd->vjr_sb, w + L.c_ae, w + L.encb_ae, w + L.pj_ae,
+                         "psn_lg_gemm_kernel<pre_ae_jump,enc>");
     }
+    // ---- initial state: latent x_0 into chunk row 0 ----
+    {
+        const float* src = dae ? p->x_init : p->x.p;
+        const int64_t sb = dae ? p->x_init_sb : p->x.sb;
+        psn_lg_init_kernel<<<(int)((BH + 255) / 256), 256, 0, stream>>>(src, sb, B, H, w + L.x0, w + L.ycur, w + L.xs, H);
+        psn_count_launch("psn_lg_init_kernel");
+    }
+    auto raw_row = [](const psnode_series& s, int r) { return s.p + (int64_t)r * s.st; };
+    if (dae) {                                                  // i_0 = ae(x_0, z[0], v[0])
+        project(M_AE1ZV, 1, raw_row(cd->z_raw, 0), cd->z_raw.st, cd->z_raw.sb, raw_row(cd->v_raw, 0), cd->v_raw.st, cd->v_raw.sb, w + L.c_ae,
+                w + L.encb_ae, w + L.pre_ae, "psn_lg_gemm_kernel<pre_ae,enc>");
+        lg_ae_eval(c, w + L.pre_ae, nullptr, w + L.is, H, false, 0);
+    }
+    if (T == 1) {
+        decode(M_XD1, M_XD2, cd->x_dec, m_xs, 0, 1, cd->x_out, 0, cd->XR);
+        if (dae) decode(M_ID1, M_ID2, cd->i_dec, m_is, 0, 1, cd->i_out, 0, cd->IR);
+    }
+    // ---- time chunks: steps j = r0 + 1 .. r1 ----
+    for (int r0 = 0; r0 < T - 1; r0 += RC) {
+        const int r1 = r0 + RC < T - 1 ? r0 + RC : T - 1, n = r1 - r0;
+        project(M_DE1ZV, n, raw_row(cd->z_raw, r0), cd->z_raw.st, cd->z_raw.sb, dae ? raw_row(cd->v_raw, r0) : nullptr, cd->v_raw.st, cd->v_raw.sb,
+                w + L.c_de, w + L.encb_de, w + L.pre_de, "psn_lg_gemm_kernel<pre_de,enc>");
+        if (dae) project(M_AE1ZV, n, raw_row(cd->z_raw, r0 + 1), cd->z_raw.st, cd->z_raw.sb, raw_row(cd->v_raw, r0 + 1), cd->v_raw.st, cd->v_raw.sb,
+                         w + L.c_ae, w + L.encb_ae, w + L.pre_ae + BH, "psn_lg_gemm_kernel<pre_ae,enc>");
+        for (int j = r0 + 1; j <= r1; j++) {
+            const int k = j - r0;                               // chunk row of grid point j (row 0 = the chunk's start state)
+            LgStepIO io;
+            io.pre_de_row = w + L.pre_de + (int64_t)(k - 1) * BH; io.pre_de_jump = w + L.pj_de;
+            io.pre_ae_row = w + L.pre_ae + (int64_t)k * BH; io.pre_ae_jump = w + L.pj_ae;
+            io.xrow = w + L.xs + (int64_t)k * BH; io.xld = H;
+            io.irow = dae ? w + L.is + (int64_t)k * BH : nullptr; io.ild = H;
+            lg_step(c, j, io);
+        }
+        // decoders: rows 1..n of the chunk (and row 0 = the initial state in the first chunk)
+        const int row0 = r0 == 0 ? 0 : 1, rows = r0 == 0 ? n + 1 : n, j0 = r0 == 0 ? 0 : r0 + 1;
+        decode(M_XD1, M_XD2, cd->x_dec, m_xs, row0, rows, cd->x_out, j0, cd->XR);
+        if (dae) decode(M_ID1, M_ID2, cd->i_dec, m_is, row0, rows, cd->i_out, j0, cd->IR);
+    }
+    PSN_CUDA(cudaGetLastError());
+    lg_dump_stamps(c);
     return PSNODE_OK;
 }
 
@@ -1137,12 +1392,12 @@ bool psn_lg_bwd_supports(const psnode_problem* p, const psnode_adjoint* a) {
 
 int64_t psn_lg_backward_workspace(const psnode_problem* p, const psnode_adjoint* a) {
     (void)a;
-    return lg_layout(p, true).total * 4;
+    return lg_layout(p, LG_BWD).total * 4;
 }
 
 int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream) {
     LgCtx c;
-    int st = lg_setup(c, p, true, ws, ws_bytes, stream);
+    int st = lg_setup(c, p, LG_BWD, ws, ws_bytes, stream);
     if (st != PSNODE_OK) return st;
     const LgLayout& L = c.L;
     float* w = c.w;

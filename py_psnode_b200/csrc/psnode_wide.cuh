@@ -62,6 +62,10 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
 bool psn_lg_bwd_supports(const psnode_problem* p, const psnode_adjoint* a);
 int64_t psn_lg_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);
 int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
+// encoders / decoders of the `*_02_direct_encode` models fused with the integration, time chunk by time chunk (psnode_forward_encoded)
+bool psn_lg_encoded_supports(const psnode_problem* p, const psnode_codec* c);
+int64_t psn_lg_encoded_workspace(const psnode_problem* p, const psnode_codec* c);
+int psn_lg_forward_encoded(const psnode_problem* p, const psnode_codec* c, void* ws, int64_t ws_bytes, cudaStream_t stream);
 
 // ---- row GEMM over a whole series (psnode_wide_proj.cu) ------------------------------------------------------------------
 // out[r][b][0:128] = A . in[r][b][0:128] (+ add[b][0:128]),  A[m][k] = W[m*ldw + k] or (transpose) W[k*ldw + m], optionally

@@ -534,6 +534,92 @@ def integrate(cfg: Config, tens: Sequence[Optional[torch.Tensor]]) -> Tuple[torc
     return x_sol, (i_sol if cfg.kind == N.DAE else None)
 
 
+# ------------------------------------------------------------------------------------------------ encoded entry
+def forward_encoded(cfg: Config, t, x0, a0, z_raw, v_raw, event_t, zj_raw, vj_raw, de_params, ae_params, z_enc, v_enc, x_dec, i_dec,
+                    chunk_rows: int = 0):
+    """`psnode_forward_encoded`: raw (T,B,<=8) input series in, decoded (T,B,x_dim) trajectories out; the
+    encoders run inside the hoisted projection GEMMs, the integration in time chunks, the decoders before the store -- no
+    (T,B,H) tensor exists.  `x0` / `a0` are the LATENT initial state (B,H) and all_initial (B,S).  Forward / evaluation only."""
+    L = N.lib()
+    _require_cuda_f32("t", t)
+    dev = t.device
+    T, B = t.shape[0], t.shape[1]
+    dae = cfg.kind == N.DAE
+    keep: list = []
+    with torch.cuda.device(dev):
+        p = N.Problem()
+        p.kind, p.method, p.impl = cfg.kind, cfg.method, N.IMPL_LAYER
+        p.B, p.T = B, T
+        p.X, p.Z, p.V, p.I = cfg.X, cfg.Z, cfg.V, cfg.I
+        ts = _series(t, "t")
+        _set_series(p.t, ts)
+        x0 = _rows(x0, "latent initial state")
+        a0 = _rows(a0, "all_initial")
+        keep.extend((ts, x0, a0))
+        if dae:
+            p.x_init, p.x_init_sb = x0.data_ptr(), x0.stride(0)
+        else:
+            p.x.p, p.x.st, p.x.sb = x0.data_ptr(), 0, x0.stride(0)
+        p.a0, p.a0_sb = a0.data_ptr(), a0.stride(0)
+        c = N.Codec()
+        zr = _series(z_raw, "z_raw")
+        keep.append(zr)
+        _set_series(c.z_raw, zr)
+        c.ZR = zr.shape[2]
+        if dae:
+            vr = _series(v_raw, "v_raw")
+            keep.append(vr)
+            _set_series(c.v_raw, vr)
+            c.VR = vr.shape[2]
+        p.E = 0
+        if event_t is not None:
+            _require_cuda_f32("event_t", event_t)
+            E = event_t.shape[1]
+            ev0, t00 = event_t[0].reshape(E), ts[:, 0, 0]
+            if cfg.event_ref is not None:
+                t00, ev0 = cfg.event_ref
+            idx = torch.empty(max(T - 1, 1), dtype=torch.int32, device=dev)
+            err = torch.zeros(1, dtype=torch.int32, device=dev)
+            keep.extend((ev0, t00, idx, err))
+            N.check(L.psnode_event_table(t00.data_ptr(), t00.stride(0), T, ev0.data_ptr(), ev0.stride(0), E, idx.data_ptr(), err.data_ptr(),
+                                         torch.cuda.current_stream(dev).cuda_stream), "psnode_event_table")
+            if cfg.check_events and int(err.item()) != 0:
+                raise RuntimeError("more than one event matches the same grid time (the reference raises here too)")
+            p.event_idx, p.E = idx.data_ptr(), E
+            zj = zj_raw if zj_raw.stride(-1) == 1 or zj_raw.shape[-1] == 1 else zj_raw.contiguous()
+            _require_cuda_f32("z_jump", zj)
+            keep.append(zj)
+            c.zj_raw, c.zjr_sb, c.zjr_se = zj.data_ptr(), zj.stride(0), zj.stride(1)
+            if dae:
+                vj = vj_raw if vj_raw.stride(-1) == 1 or vj_raw.shape[-1] == 1 else vj_raw.contiguous()
+                _require_cuda_f32("v_jump", vj)
+                keep.append(vj)
+                c.vj_raw, c.vjr_sb, c.vjr_se = vj.data_ptr(), vj.stride(0), vj.stride(1)
+        _fill_mlp(p.de, de_params, keep)
+        _fill_mlp(c.z_enc, z_enc, keep)
+        _fill_mlp(c.x_dec, x_dec, keep)
+        c.XR = x_dec[2].shape[0]
+        x_out = torch.empty((T, B, c.XR), dtype=torch.float32, device=dev)
+        _set_series(c.x_out, x_out)
+        i_out = None
+        if dae:
+            _fill_mlp(p.ae, ae_params, keep)
+            _fill_mlp(c.v_enc, v_enc, keep)
+            _fill_mlp(c.i_dec, i_dec, keep)
+            c.IR = i_dec[2].shape[0]
+            i_out = torch.empty((T, B, c.IR), dtype=torch.float32, device=dev)
+            _set_series(c.i_out, i_out)
+        c.chunk_rows = int(chunk_rows)
+        nbytes = L.psnode_forward_encoded_workspace(C.byref(p), C.byref(c))
+        if nbytes <= 0:
+            raise RuntimeError("psnode_forward_encoded: unsupported problem (latent width must be 128 or 256, 2-layer nets, raw inputs <= 8 "
+                               "wide, decoded outputs <= 128 wide)")
+        ws = _workspace(dev, nbytes)
+        N.check(L.psnode_forward_encoded(C.byref(p), C.byref(c), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream),
+                "psnode_forward_encoded")
+    return x_out, i_out
+
+
 # ------------------------------------------------------------------------------------------------ host-buffer entry
 def _host_series(ten: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
     if ten is None or ten.shape[-1] == 0:

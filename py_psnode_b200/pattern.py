@@ -57,6 +57,19 @@ def linear_chain(module: nn.Module, preferred_attr: str) -> List[nn.Linear]:
     return layers
 
 
+def codec_chain(seq: nn.Module, what: str) -> List[nn.Linear]:
+    """The two Linear layers of an encoder / decoder of the `*_02_direct_encode` models: nn.Sequential(Linear, ELU, Linear)
+    (neural_00_ODE_02_direct_encode.py:63-68, neural_01_DAE_02_direct_encode.py:107-119)."""
+    if not isinstance(seq, nn.Sequential):
+        raise UnsupportedModuleError(f"{what}: expected nn.Sequential(Linear, ELU, Linear), got {type(seq).__name__}")
+    holder = nn.Module()
+    holder.seq = seq
+    layers = linear_chain(holder, "seq")
+    if len(layers) != 2:
+        raise UnsupportedModuleError(f"{what}: expected exactly two Linear layers, found {len(layers)}")
+    return layers
+
+
 def _mlp(layers: Sequence[nn.Linear], u: torch.Tensor) -> torch.Tensor:
     for k, lin in enumerate(layers):
         u = torch.nn.functional.linear(u, lin.weight, lin.bias)

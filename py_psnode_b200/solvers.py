@@ -145,6 +145,40 @@ class FixedGridODESolver(metaclass=abc.ABCMeta):
         spec = engine.LossSpec(target_x=target_x, mask=mask, weight_x=feat_weight_x, target_i=target_i, weight_i=feat_weight_i)
         return engine.integrate_loss(cfg, spec, tens)
 
+    # ------------------------------------------------------------------ encoders / decoders fused (C ABI psnode_forward_encoded)
+    def integrate_ODE_encoded(self, x_func: nn.Module, t, x0, z, all_initial, z_encoder: nn.Module, x_decoder: nn.Module, event_t=None,
+                              z_jump=None, chunk_rows: int = 0):
+        """Decoded trajectory (T,B,x_dim) of the `ODE_Model.forward` pipeline (neural_00_ODE_02_direct_encode.py:75-89) in one call:
+        `z` is the RAW (T,B,z_dim) input series (time-major view), `z_jump` the raw (B,E,z_dim) jump values, `x0` = x_encoder(x[:,0]) and
+        `all_initial` = cat(x0, z_encoder(z)[0]) the latent (B,H) / (B,2H) rows.  z_encoder runs inside the hoisted projection GEMM, the
+        latent trajectory lives in a `chunk_rows`-row scratch and x_decoder is applied before the store: no (T,B,H) tensor is ever
+        materialised.  Forward / evaluation only (returns tensors without autograd history); latent width 128 or 256."""
+        H = x0.shape[-1]
+        de = pattern.match_de(x_func, X=H, Z=H, dae=False)
+        cfg = engine.Config(kind=N.ODE, method=self._method, impl=N.IMPL_LAYER, X=H, Z=H, V=0, I=0, teacher_x=False, teacher_i=False,
+                            n_de=len(de), n_ae=0, has_event=event_t is not None, check_events=self.check_events)
+        with torch.no_grad():
+            x_out, _ = engine.forward_encoded(cfg, t, x0, all_initial, z, None, event_t, z_jump, None, _params(de), None,
+                                              _params(pattern.codec_chain(z_encoder, "z_encoder")), None,
+                                              _params(pattern.codec_chain(x_decoder, "x_decoder")), None, chunk_rows)
+        return x_out
+
+    def integrate_DAE_encoded(self, x_init, x_func: nn.Module, i_func: nn.Module, t, z, v, all_initial, z_encoder: nn.Module,
+                              v_encoder: nn.Module, x_decoder: nn.Module, i_decoder: nn.Module, event_t=None, z_jump=None, v_jump=None,
+                              chunk_rows: int = 0):
+        """(decoded x (T,B,x_dim), decoded i (T,B,i_dim)) of the `DAE_Model.forward` pipeline (neural_01_DAE_02_direct_encode.py:126-153)
+        from the RAW z / v series; see integrate_ODE_encoded.  `x_init` = x_encoder(init_func(...)) and `all_initial` are latent rows."""
+        H = x_init.shape[-1]
+        de = pattern.match_de(x_func, X=H, Z=H, V=H, I=H, dae=True)
+        ae = pattern.match_ae(i_func, X=H, Z=H, V=H, I=H)
+        cfg = engine.Config(kind=N.DAE, method=self._method, impl=N.IMPL_LAYER, X=H, Z=H, V=H, I=H, teacher_x=False, teacher_i=False,
+                            n_de=len(de), n_ae=len(ae), has_event=event_t is not None, check_events=self.check_events)
+        with torch.no_grad():
+            return engine.forward_encoded(cfg, t, x_init, all_initial, z, v, event_t, z_jump, v_jump, _params(de), _params(ae),
+                                          _params(pattern.codec_chain(z_encoder, "z_encoder")), _params(pattern.codec_chain(v_encoder, "v_encoder")),
+                                          _params(pattern.codec_chain(x_decoder, "x_decoder")), _params(pattern.codec_chain(i_decoder, "i_decoder")),
+                                          chunk_rows)
+
     # ------------------------------------------------------------------ host-buffer variants (C ABI psnode_forward_host)
     def integrate_ODE_host(self, x_func: nn.Module, t, x, z, all_initial, event_fn=None, jump_change_fn=None, input_true_x=False,
                            out=None):

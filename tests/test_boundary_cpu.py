@@ -34,8 +34,9 @@ def test_ctypes_structs_match_header_sizes():
     import subprocess
     import tempfile
     from py_psnode_b200 import _native
-    src = ('#include <stdio.h>\n#include "psnode_b200.h"\nint main(void){printf("%zu %zu %zu %zu %d %d\\n", sizeof(psnode_mlp), '
-           'sizeof(psnode_series), sizeof(psnode_problem), sizeof(psnode_adjoint), PSNODE_IMPL_TC, PSNODE_MAX_LAYERS);return 0;}\n')
+    src = ('#include <stdio.h>\n#include "psnode_b200.h"\nint main(void){printf("%zu %zu %zu %zu %d %d %zu\\n", sizeof(psnode_mlp), '
+           'sizeof(psnode_series), sizeof(psnode_problem), sizeof(psnode_adjoint), PSNODE_IMPL_TC, PSNODE_MAX_LAYERS, sizeof(psnode_codec));'
+           'return 0;}\n')
     with tempfile.TemporaryDirectory() as td:
         cfile, exe = os.path.join(td, "s.c"), os.path.join(td, "s")
         open(cfile, "w").write(src)
@@ -44,6 +45,7 @@ def test_ctypes_structs_match_header_sizes():
     sizes = [int(q) for q in out]
     assert sizes[:4] == [C.sizeof(_native.Mlp), C.sizeof(_native.Series), C.sizeof(_native.Problem), C.sizeof(_native.Adjoint)]
     assert sizes[4] == _native.IMPL_TC and sizes[5] == _native.PSNODE_MAX_LAYERS
+    assert sizes[6] == C.sizeof(_native.Codec)
 
 
 def test_param_count_helper(native_lib):
