@@ -389,6 +389,58 @@ def _e2e_leg(w, legs, host, resident, solver, de, ae, B, n_steps, units, active,
     return e2e
 
 
+def _encoded_leg(w, solver, de, ae, resident, B, n_steps, units, active, barrier, reduce_max):
+    """integrate_{ODE,DAE}_encoded at the workload's batch and ALL grid steps: raw (T,B,<=2) series in, decoded trajectories out; no
+    (T,B,H) latent tensor exists (encoders inside the projection GEMMs, time chunks, decoders before the store)."""
+    import torch
+    import torch.nn as nn
+    from py_psnode_b200 import _native
+    dev = resident["t"].device
+    H, T = w["H"], n_steps + 1
+    dae = w["kind"] == "dae"
+    XR, ZR, VR, IR = (32, 1, 2, 2) if dae else (8, 2, 0, 0)          # physical widths of SURVEY 8d (cfg5 / cfg4)
+    torch.manual_seed(7)
+    codec = lambda i, o: nn.Sequential(nn.Linear(i, H), nn.ELU(), nn.Linear(H, o)).to(dev)
+    z_enc, x_dec = codec(ZR, H), codec(H, XR)
+    v_enc, i_dec = (codec(VR, H), codec(H, IR)) if dae else (None, None)
+    z_raw = torch.randn(T, B, ZR, device=dev) * 0.1
+    v_raw = torch.randn(T, B, VR, device=dev) * 0.1 if dae else None
+    x0 = resident["x0"]
+    with torch.no_grad():
+        a0 = torch.cat((x0, z_enc(z_raw[0])) + ((v_enc(v_raw[0]), resident["i0"]) if dae else ()), dim=-1)
+
+    def call():
+        if dae:
+            return solver.integrate_DAE_encoded(x_init=x0, x_func=de, i_func=ae, t=resident["t"], z=z_raw, v=v_raw, all_initial=a0, z_encoder=z_enc,
+                                                v_encoder=v_enc, x_decoder=x_dec, i_decoder=i_dec)
+        return solver.integrate_ODE_encoded(x_func=de, t=resident["t"], x0=x0, z=z_raw, all_initial=a0, z_encoder=z_enc, x_decoder=x_dec)
+    from py_psnode_b200 import engine
+    torch.cuda.synchronize()
+    engine._workspaces.clear()                       # so that the peak below includes this entry's own workspace, not a larger cached one
+    torch.cuda.empty_cache()
+    base = torch.cuda.memory_allocated()
+    call()
+    call()
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(2):
+        out = None
+        out = call()
+    b.record()
+    barrier()
+    ms = reduce_max(a.elapsed_time(b)) / 2
+    del out
+    return {"value": units * active / (ms * 1e-3), "unit": "traj-steps/s", "ms_per_step": ms, "kernel": _native.last_kernel(),
+            "raw_widths": {"x": XR, "z": ZR, "v": VR, "i": IR},
+            "peak_hbm_gib_above_inputs": (torch.cuda.max_memory_allocated() - base) / 2 ** 30,
+            "latent_series_gib_unfused": (4 if dae else 2) * T * B * H * 4 / 2 ** 30,
+            "what": "Model.forward pipeline of the *_02 scripts in one call from the raw series: encoders generated inside the hoisted projection "
+                    "GEMMs, integration in 64-row time chunks, decoders before the store (psnode_forward_encoded); outputs decoded (T,B,x_dim)"}
+
+
 def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
     """Measure one workload on this rank's GPU; returns the result dict (rank 0) or None."""
     import torch
@@ -469,6 +521,14 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
     kern_ms = statistics.mean(per_call_ms)
     res.update(value=value, unit="traj-steps/s", ms_per_step=ms_per_step, kernel=kernel_name, kernel_ms=kern_ms,
                gpu_launches=int(launches))
+
+    # ---- `*_02` models: the whole Model.forward pipeline from the RAW series (encoders + integration + decoders fused) ----
+    if w["net"] == "02" and "e2e" in legs:
+        try:
+            res["encoded"] = _encoded_leg(w, solver, de, ae, resident, B, n_steps, units, active, barrier, reduce_max)
+        except Exception as exc:
+            res["encoded"] = {"error": f"{type(exc).__name__}: {str(exc)[:300]}"}
+            torch.cuda.synchronize()
 
     # ---- end-to-end through the host-buffer C ABI (psnode_forward_host): pinned HOST inputs and outputs ------------------
     e2e = None
