@@ -54,6 +54,14 @@ struct __align__(1024) LgSmem {
 };
 
 __device__ long long g_lg_dbg[64];        // clock64 stamps of one CTA (PSNODE_LG_DBG=<cta index + 1>): phase breakdown on the device
+// PSNODE_LG_TRACE=1: per launch, over all CTAs: earliest entry / earliest and latest return of griddepcontrol.wait / latest exit (%globaltimer, ns)
+constexpr int LG_TRACE_N = 4096;
+__device__ unsigned long long g_lg_tmin[LG_TRACE_N][2], g_lg_tmax[LG_TRACE_N][2];
+__device__ __forceinline__ unsigned long long lg_gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct LgParams {
     int dbg, rotate;
@@ -83,6 +91,7 @@ struct LgParams {
     const float* gen_raw[2]; int64_t gen_sr[2], gen_sb[2]; int gen_w[2];
     const float* gen_W[2]; const float* gen_b[2];
     int m_live;                                              // > 0: output features m >= m_live are padding (not stored)
+    int trace;                                               // >= 0: slot of the launch trace (debugging aid)
     int* err;
 };
 
@@ -91,7 +100,9 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                                                                    const __grid_constant__ CUtensorMap map_b0, const __grid_constant__ CUtensorMap map_b1,
                                                                    const __grid_constant__ LgParams q) {
     // programmatic dependent launch: everything above the first read of the previous launch's output may overlap its tail
+    if (q.trace >= 0 && threadIdx.x == 0) atomicMin(&g_lg_tmin[q.trace][0], lg_gtime());
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (q.trace >= 0 && threadIdx.x == 0) { const unsigned long long tt = lg_gtime(); atomicMin(&g_lg_tmin[q.trace][1], tt); atomicMax(&g_lg_tmax[q.trace][1], tt); }
     int evk = -1;
     if (q.ev) evk = __ldg(q.ev + q.ev_j);
     if (q.skip_unless_event && evk < 0) return;
@@ -235,10 +246,6 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
         return;
     }
     stamp();
-    if (!mbar_wait(&sm.done[(nchunk - 1) % NST], (uint32_t)(((nchunk - 1) / NST) & 1))) { atomicExch(q.err, 13); __trap(); }
-    tc_fence_after();
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the next layer's grid may be set up while this epilogue runs
-    stamp();
 
     // ---- epilogue: lane = output feature, columns = trajectories ---------------------------------------------------------
     // Operands of the fused epilogue (hoisted layer-1 half, G, or the Runge-Kutta state) are fetched 16 columns ahead of the
@@ -363,7 +370,11 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
             }
         };
         Buf cur, nxt;
-        fetch(0, cur);
+        fetch(0, cur);                      // issued BEFORE the wait for the last MMAs: the first operand batch's L2 / HBM latency hides under them
+        if (!mbar_wait(&sm.done[(nchunk - 1) % NST], (uint32_t)(((nchunk - 1) / NST) & 1))) { atomicExch(q.err, 13); __trap(); }
+        tc_fence_after();
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the next layer's grid may be set up while this epilogue runs
+        stamp();
 #pragma unroll 1
         for (int bt = 0; bt < 4; bt++) {
             if (bt + 1 < 4) fetch(bt + 1, nxt);
@@ -377,6 +388,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
     if (cw == 0) tmem_dealloc(tmem, NPART * TN);
     stamp();
     if (dbg) g_lg_dbg[63] = dbg_n;
+    if (q.trace >= 0 && threadIdx.x == 0) atomicMax(&g_lg_tmax[q.trace][0], lg_gtime());
 }
 
 // ---- one-time preparation per call ------------------------------------------------------------------------------------------
@@ -692,8 +704,13 @@ bool lg_use_pdl() {
     return v;
 }
 // one GEMM launch: A planes (hi, lo maps), one or two B sources
-int lg_launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b0, const CUtensorMap& b1, const LgParams& q, int mblks,
+int g_lg_trace_next = -1;                   // host side of PSNODE_LG_TRACE: next free trace slot (-1: tracing off)
+const char* g_lg_trace_name[LG_TRACE_N];
+int lg_launch_gemm(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b0, const CUtensorMap& b1, const LgParams& q_in, int mblks,
                    cudaStream_t stream, const char* name) {
+    LgParams q = q_in;
+    q.trace = -1;
+    if (g_lg_trace_next >= 0 && g_lg_trace_next < LG_TRACE_N) { g_lg_trace_name[g_lg_trace_next] = name; q.trace = g_lg_trace_next++; }
     dim3 grid((unsigned)(q.R * q.nbt), (unsigned)mblks);
     const LgKernFn kern = lg_kernels()[lg_epi_of(q)];
     if (lg_use_pdl()) {
@@ -912,6 +929,14 @@ int lg_setup(LgCtx& c, const psnode_problem* p, int mode, void* ws, int64_t ws_b
     static const int rotate = std::getenv("PSNODE_LG_ROTATE") ? std::atoi(std::getenv("PSNODE_LG_ROTATE")) : 1;
     c.dbg_cta = dbg_cta; c.rotate = rotate;
     PSN_CUDA(cudaMemsetAsync(c.err, 0, 256, stream));
+    static const bool trace = std::getenv("PSNODE_LG_TRACE") && std::atoi(std::getenv("PSNODE_LG_TRACE")) != 0;
+    if (trace) {
+        void *pmin = nullptr, *pmax = nullptr;
+        cudaGetSymbolAddress(&pmin, g_lg_tmin); cudaGetSymbolAddress(&pmax, g_lg_tmax);
+        cudaMemsetAsync(pmin, 0xFF, sizeof(unsigned long long) * LG_TRACE_N * 2, stream);
+        cudaMemsetAsync(pmax, 0, sizeof(unsigned long long) * LG_TRACE_N * 2, stream);
+        g_lg_trace_next = 0;
+    }
     // ---- weights: folded, split into tf32 hi / lo planes ----
     const float* W1 = p->de.W[0];
     const int ld1 = 3 * S;
@@ -1201,7 +1226,27 @@ void lg_step(const LgCtx& c, int j, const LgStepIO& io) {
     }
     if (c.dae) lg_ae_eval(c, io.pre_ae_row, nullptr, io.irow, io.ild, false, 0);         // i_j = ae(x_j, z[j], v[j])  (:121)
 }
+void lg_dump_trace(const LgCtx& c) {
+    if (g_lg_trace_next < 0) return;         // debugging aid only: synchronises
+    static unsigned long long tmin[LG_TRACE_N][2], tmax[LG_TRACE_N][2];
+    cudaStreamSynchronize(c.stream);
+    cudaMemcpyFromSymbol(tmin, g_lg_tmin, sizeof(tmin));
+    cudaMemcpyFromSymbol(tmax, g_lg_tmax, sizeof(tmax));
+    const int n = g_lg_trace_next;
+    const int from = n > 120 ? n / 2 : 1, to = from + 60 < n ? from + 60 : n;
+    std::fprintf(stderr, "psn_lg trace (ns): launch | first entry - prev end | first wait-return - prev end | last wait-return - prev end | duration (last exit - first wait-return)\n");
+    double g0 = 0, g1 = 0, g2 = 0, d = 0; int cnt = 0;
+    for (int k = from; k < to; k++) {
+        const long long pe = (long long)tmax[k - 1][0];
+        const long long a = (long long)tmin[k][0] - pe, b = (long long)tmin[k][1] - pe, cc = (long long)tmax[k][1] - pe, dur = (long long)tmax[k][0] - (long long)tmin[k][1];
+        std::fprintf(stderr, "  %4d %-40s %8lld %8lld %8lld %8lld\n", k, g_lg_trace_name[k], a, b, cc, dur);
+        g0 += a; g1 += b; g2 += cc; d += dur; cnt++;
+    }
+    if (cnt) std::fprintf(stderr, "  mean over %d launches: entry gap %.0f, wait gap %.0f .. %.0f, duration %.0f ns\n", cnt, g0 / cnt, g1 / cnt, g2 / cnt, d / cnt);
+    g_lg_trace_next = -1;
+}
 void lg_dump_stamps(const LgCtx& c) {
+    lg_dump_trace(c);
     if (!c.dbg_cta) return;                  // debugging aid only: synchronises
     long long h[64];
     cudaStreamSynchronize(c.stream);

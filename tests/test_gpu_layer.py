@@ -175,7 +175,7 @@ def _compare_grads(got, want, tol=2e-5):
 
 
 @pytest.mark.parametrize("H,solver,events,B,N", [(256, "rk4", 1, 40, 11), (128, "euler", 0, 24, 9), (128, "midpoint", 2, 24, 10),
-                                                  (256, "rk4", 2, 150, 19)])
+                                                  (256, "rk4", 2, 150, 19), (128, "rk4", 1, 20, 3), (128, "rk4", 0, 20, 1)])
 def test_layer_dae_gradients_vs_fp64_autograd(native_lib, H, solver, events, B, N):
     """The recomputing reverse sweep of the layer path (psn_lg_backward: transposed-weight GEMM launches with delta / Runge-Kutta
     adjoint epilogues + MN-major weight-gradient GEMMs) against float64 autograd: parameters of both nets, x_init, all_initial, the
