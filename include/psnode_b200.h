@@ -285,6 +285,23 @@ typedef struct psnode_codec {
 int64_t psnode_forward_encoded_workspace(const psnode_problem* p, const psnode_codec* c);
 int psnode_forward_encoded(const psnode_problem* p, const psnode_codec* c, void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * Init_Func + all_initial construction in one launch (DAE_Model.forward, neural_01_DAE_01_no_encode.py:50-58, :98-99;
+ * neural_01_DAE_02_direct_encode.py:126-127):
+ *     x0 = init(cat(z0, v0, i0))   (Linear/ELU chain),     all_initial = cat(x0, z0, v0, i0)
+ * z0 / v0 / i0 are the first grid rows of the series, (B, width) with row stride *_sb (unit feature stride).
+ * psnode_init_state_backward is the exact reverse mode: d_x0 (B,X) = gradient of the initial state (psnode_adjoint.d_x0) and d_a0 (B,S)
+ * = gradient of all_initial (either may be NULL) -> d_theta (Init_Func parameters, layout as psnode_adjoint.d_theta for one net) and
+ * the gradients of the three rows (each may be NULL).  Deterministic.
+ */
+int psnode_init_state(const psnode_mlp* init, const float* z0, int64_t z_sb, const float* v0, int64_t v_sb, const float* i0, int64_t i_sb,
+                      int32_t B, int32_t Z, int32_t V, int32_t I, float* x0, int64_t x0_sb, float* a0, int64_t a0_sb, void* stream);
+int64_t psnode_init_state_backward_workspace(const psnode_mlp* init, int32_t B);
+int psnode_init_state_backward(const psnode_mlp* init, const float* z0, int64_t z_sb, const float* v0, int64_t v_sb, const float* i0, int64_t i_sb,
+                               int32_t B, int32_t Z, int32_t V, int32_t I, const float* d_x0, int64_t d_x0_sb, const float* d_a0, int64_t d_a0_sb,
+                               float* d_theta, float* d_z0, int64_t d_z0_sb, float* d_v0, int64_t d_v0_sb, float* d_i0, int64_t d_i0_sb,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,12 @@ SYMBOLS = [
                                          C.c_int32, C.c_int32, C.c_void_p, C.POINTER(Series), C.c_void_p]),
     ("psnode_forward_encoded_workspace", C.c_int64, [C.POINTER(Problem), C.POINTER(Codec)]),
     ("psnode_forward_encoded", C.c_int, [C.POINTER(Problem), C.POINTER(Codec), C.c_void_p, C.c_int64, C.c_void_p]),
+    ("psnode_init_state", C.c_int, [C.POINTER(Mlp), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    ("psnode_init_state_backward_workspace", C.c_int64, [C.POINTER(Mlp), C.c_int32]),
+    ("psnode_init_state_backward", C.c_int, [C.POINTER(Mlp), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32,
+                                             C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                             C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
 ]
 
 # PSNODE_B200_LIB selects an alternative build of the SAME library (A/B kernel experiments); never a different backend.

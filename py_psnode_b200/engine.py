@@ -534,6 +534,84 @@ def integrate(cfg: Config, tens: Sequence[Optional[torch.Tensor]]) -> Tuple[torc
     return x_sol, (i_sol if cfg.kind == N.DAE else None)
 
 
+# ------------------------------------------------------------------------------------------------ Init_Func + all_initial in one launch
+def _row(ten: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if ten is None or ten.shape[-1] == 0:
+        return None
+    _require_cuda_f32(name, ten)
+    if ten.dim() != 2:
+        raise ValueError(f"`{name}` must be (B, width), got {tuple(ten.shape)}")
+    return ten if ten.stride(1) == 1 or ten.shape[1] == 1 else ten.contiguous()
+
+
+class _InitState(torch.autograd.Function):
+    """x0, all_initial = init_state(z0, v0, i0, *init_params): `psnode_init_state` / `psnode_init_state_backward`."""
+
+    @staticmethod
+    def forward(ctx, z0, v0, i0, *params):
+        L = N.lib()
+        rows = [_row(z0, "z0"), _row(v0, "v0"), _row(i0, "i0")]
+        ref = next(r for r in rows if r is not None)
+        dev, B = ref.device, ref.shape[0]
+        keep: list = []
+        mlp = N.Mlp()
+        _fill_mlp(mlp, params, keep)
+        X = params[-2].shape[0]
+        widths = [0 if r is None else r.shape[1] for r in rows]
+        S = X + sum(widths)
+        with torch.cuda.device(dev):
+            x0 = torch.empty((B, X), dtype=torch.float32, device=dev)
+            a0 = torch.empty((B, S), dtype=torch.float32, device=dev)
+            ptr = lambda r: (None, 0) if r is None else (r.data_ptr(), r.stride(0))
+            (zp, zs), (vp, vs), (ip, is_) = ptr(rows[0]), ptr(rows[1]), ptr(rows[2])
+            N.check(L.psnode_init_state(C.byref(mlp), zp, zs, vp, vs, ip, is_, B, widths[0], widths[1], widths[2], x0.data_ptr(), X, a0.data_ptr(), S,
+                                        torch.cuda.current_stream(dev).cuda_stream), "psnode_init_state")
+        ctx.save_for_backward(*[r for r in rows if r is not None], *params)
+        ctx.present = [r is not None for r in rows]
+        ctx.n_params = len(params)
+        return x0, a0
+
+    @staticmethod
+    def backward(ctx, gx0, ga0):
+        L = N.lib()
+        saved = list(ctx.saved_tensors)
+        it = iter(saved)
+        rows = [next(it) if pr else None for pr in ctx.present]
+        params = [next(it) for _ in range(ctx.n_params)]
+        ref = next(r for r in rows if r is not None)
+        dev, B = ref.device, ref.shape[0]
+        keep: list = []
+        mlp = N.Mlp()
+        _fill_mlp(mlp, params, keep)
+        widths = [0 if r is None else r.shape[1] for r in rows]
+        gx0 = None if gx0 is None else gx0.contiguous()
+        ga0 = None if ga0 is None else ga0.contiguous()
+        if gx0 is None and ga0 is None:
+            return (None,) * (3 + ctx.n_params)
+        with torch.cuda.device(dev):
+            sizes = _theta_sizes(params)
+            d_theta = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            d_rows = [None if r is None else torch.empty((B, r.shape[1]), dtype=torch.float32, device=dev) for r in rows]
+            ws = _workspace(dev, L.psnode_init_state_backward_workspace(C.byref(mlp), B))
+            ptr = lambda r: (None, 0) if r is None else (r.data_ptr(), r.stride(0))
+            (zp, zs), (vp, vs), (ip, is_) = ptr(rows[0]), ptr(rows[1]), ptr(rows[2])
+            (dzp, dzs), (dvp, dvs), (dip, dis) = ptr(d_rows[0]), ptr(d_rows[1]), ptr(d_rows[2])
+            gxp, gxs = ptr(gx0)
+            gap, gas = ptr(ga0)
+            N.check(L.psnode_init_state_backward(C.byref(mlp), zp, zs, vp, vs, ip, is_, B, widths[0], widths[1], widths[2], gxp, gxs, gap, gas,
+                                                 d_theta.data_ptr(), dzp, dzs, dvp, dvs, dip, dis, ws.data_ptr(), ws.numel(),
+                                                 torch.cuda.current_stream(dev).cuda_stream), "psnode_init_state_backward")
+        grads, off = [], 0
+        for k, n in enumerate(sizes):
+            grads.append(d_theta[off:off + n].view_as(params[k]) if ctx.needs_input_grad[3 + k] else None)
+            off += n
+        return (*[g if ctx.needs_input_grad[k] else None for k, g in enumerate(d_rows)], *grads)
+
+
+def init_state(params: Sequence[torch.Tensor], z0, v0, i0):
+    return _InitState.apply(z0, v0, i0, *params)
+
+
 # ------------------------------------------------------------------------------------------------ encoded entry
 def forward_encoded(cfg: Config, t, x0, a0, z_raw, v_raw, event_t, zj_raw, vj_raw, de_params, ae_params, z_enc, v_enc, x_dec, i_dec,
                     chunk_rows: int = 0):

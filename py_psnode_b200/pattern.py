@@ -57,6 +57,23 @@ def linear_chain(module: nn.Module, preferred_attr: str) -> List[nn.Linear]:
     return layers
 
 
+def match_init(module: nn.Module, Z: int, V: int, I: int) -> List[nn.Linear]:
+    """Linear layers of an `Init_Func` (neural_01_DAE_01_no_encode.py:50-58): forward(z0, v0, i0) = mlp(cat(z0, v0, i0)), verified once per
+    module instance on a random probe."""
+    layers = linear_chain(module, "init_fun")
+    if layers[0].in_features != Z + V + I:
+        raise UnsupportedModuleError(f"{type(module).__name__}: first Linear takes {layers[0].in_features} inputs, expected Z+V+I = {Z + V + I}")
+
+    def probe():
+        p = layers[0].weight
+        g = torch.Generator(device="cpu").manual_seed(0)
+        mk = lambda w: torch.randn(3, w, generator=g).to(device=p.device, dtype=p.dtype)
+        z0, v0, i0 = mk(Z), mk(V), mk(I)
+        return module(z0, v0, i0), _mlp(layers, torch.cat((z0, v0, i0), dim=-1))
+    _probe_ok(module, ("init", Z, V, I), probe)
+    return layers
+
+
 def codec_chain(seq: nn.Module, what: str) -> List[nn.Linear]:
     """The two Linear layers of an encoder / decoder of the `*_02_direct_encode` models: nn.Sequential(Linear, ELU, Linear)
     (neural_00_ODE_02_direct_encode.py:63-68, neural_01_DAE_02_direct_encode.py:107-119)."""

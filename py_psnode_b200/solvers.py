@@ -145,6 +145,16 @@ class FixedGridODESolver(metaclass=abc.ABCMeta):
         spec = engine.LossSpec(target_x=target_x, mask=mask, weight_x=feat_weight_x, target_i=target_i, weight_i=feat_weight_i)
         return engine.integrate_loss(cfg, spec, tens)
 
+    # ------------------------------------------------------------------ Init_Func + all_initial (C ABI psnode_init_state)
+    @staticmethod
+    def init_state(init_func: nn.Module, z0, v0, i0):
+        """(x0, all_initial) = (init_func(z0, v0, i0), cat(x0, z0, v0, i0)) in ONE launch, differentiable (one more launch + a reduce in
+        the backward): the first two lines of `DAE_Model.forward` (neural_01_DAE_01_no_encode.py:98-99).  `z0`, `v0`, `i0` are the first
+        grid rows (B, width) of the series -- views such as `z.permute(1, 0, 2)[0]` are read in place."""
+        layers = pattern.match_init(init_func, Z=0 if z0 is None else z0.shape[-1], V=0 if v0 is None else v0.shape[-1],
+                                    I=0 if i0 is None else i0.shape[-1])
+        return engine.init_state(_params(layers), z0, v0, i0)
+
     # ------------------------------------------------------------------ encoders / decoders fused (SURVEY 8f next-1; C ABI psnode_forward_encoded)
     def integrate_ODE_encoded(self, x_func: nn.Module, t, x0, z, all_initial, z_encoder: nn.Module, x_decoder: nn.Module, event_t=None,
                               z_jump=None, chunk_rows: int = 0):
