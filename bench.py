@@ -18,9 +18,9 @@ invocation records them:
         it on 4 GPUs), training leg = adjoint with latent-input gradients + 0.67 MB gradient all-reduce
   cfg5  RK4 DAE_02 latent net H = 256, GLOBAL batch 65536 x 2000 steps sharded over 8 ranks (BASELINE quotes it on 8 GPUs); with
         fewer than 8 ranks each rank integrates one 1/8 shard (B = 8192).  Forward: per-layer tcgen05 GEMM launches (impl = layer)
-        over all 2000 steps; the reverse sweep recomputes every step on the same GEMM kernel (psn_lg_backward).  The e2e leg (GBs of
-        pinned host memory) and the training leg (series, targets and latent-input gradients are (T, B, 256) tensors of 16.8 GB
-        each at T = 2001) cover a bounded number of grid steps, stated in `sample`.
+        over all 2000 steps; the reverse sweep recomputes every step on the same GEMM kernel (psn_lg_backward) and the training leg
+        also covers all 2000 steps (131 GiB of HBM: series, targets, trajectories and latent-input gradients are 16.8 GB each).  Only the
+        e2e leg (GBs of pinned host memory per series) integrates a bounded number of grid steps, stated in `sample`.
 CPU legs: the UNMODIFIED reference from oracle/_ref (vendored by oracle/make_ref.py, executed by oracle/ref_runner.py in a
 subprocess; `kind: "reference"`), or the oracle port when oracle/_ref is absent (`kind: "port"`).
 """
@@ -50,7 +50,7 @@ WORKLOADS = {
                  desc="RK4 fixed-step, ODE_02 latent DE_Func 768-128-128 (x_dim=z_dim=hidden=128), global batch 16384 x 500 steps, "
                       "adjoint training with latent-input gradients"),
     "cfg5": dict(kind="dae", net="02", X=256, Z=256, V=256, I=256, H=256, B=65536, N=2000, scaling="strong", quoted_gpus=8,
-                 bytes_per_unit=4100, flop_per_unit=7864320, aux_steps=200, train_steps=1000,
+                 bytes_per_unit=4100, flop_per_unit=7864320, aux_steps=200, train_steps=2000,
                  desc="RK4 fixed-step, DAE_02 latent DE_Func 3072-256-256 + AE_Func 1792-256-256, global batch 65536 x 2000 steps"),
 }
 FP32_PEAK_TFLOPS = 74.4     # nominal: 148 SM x 128 lanes x 2 x 1.965 GHz; measured 72.1 by bench_micro/micro.cu
@@ -479,8 +479,8 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
     res = {"workload": name + ": " + w["desc"], "batch_per_gpu": B, "grid_steps": n_steps, "scaling": w["scaling"]}
     if aux_steps != n_steps:
         res["sample"] = (f"`value` integrates all {n_steps} grid steps; the e2e leg integrates {aux_steps} steps per call (pinned host buffers of "
-                         f"{aux_steps + 1} x {B} x {w['Z']} floats per series) and the training leg {w.get('train_steps', aux_steps)} steps per call (its "
-                         "series, targets and latent-input gradients are separate (T, B, 256) tensors); throughputs are per traj-step")
+                         f"{aux_steps + 1} x {B} x {w['Z']} floats per series), the training leg {w.get('train_steps', aux_steps)} steps per call; "
+                         "throughputs are per traj-step")
     if w["scaling"] == "strong":
         res["global_batch"] = w["B"]
         res["shards"] = ways
@@ -556,6 +556,9 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
             aux_res = make_data(w, B, train_steps, seed=rank, device=dev)
             aux_units = B * train_steps
         T = train_steps + 1
+        memdbg = (lambda tag: print(f"[mem] {tag}: {torch.cuda.memory_allocated() / 2 ** 30:.1f} GiB allocated", file=sys.stderr, flush=True)) \
+            if os.environ.get("PSNODE_BENCH_MEMDBG") else (lambda tag: None)
+        memdbg("train leg, inputs ready")
         gen = torch.Generator(device=dev).manual_seed(1234 + rank)
         x_target = torch.randn((T, B, w["X"]), device=dev, generator=gen) * 0.1
         mask = torch.ones((T, B, 1), device=dev)       # one value per (trajectory, grid point), as in the scripts
@@ -582,14 +585,17 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
                 a0 = torch.cat((d["x0"], d["z"][0], d["v"][0], d["i0"]), dim=-1)
                 num, _, _ = solver.integrate_DAE_loss(x_init=d["x0"], x_func=de, i_func=ae, t=d["t"], x=x_view, z=d["z"], v=d["v"], i=i_view,
                                                       all_initial=a0, target_x=x_target, target_i=i_target, mask=mask)
+            memdbg("after the fused forward")
             return num, mask.sum()
 
         def train_step():
             for k in ("z", "v"):
                 if k in tr_data and tr_data[k].requires_grad:
                     tr_data[k].grad = None
+            memdbg("train step start")
             return parallel.sharded_training_step(fused_forward, plist, bucket, lambda out: out)
 
+        torch.cuda.reset_peak_memory_stats()
         for _ in range(max(min(warmup, 3), 2)):
             train_step()
         bwd_kernel = _native.last_kernel()
@@ -606,6 +612,7 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
                  "what": "forward + reverse sweep (discrete adjoint: all parameter grads" + (", latent-input grads" if w["net"] == "02" else "")
                          + ") with the masked-MSE loss fused into the sweep + one flat gradient all-reduce",
                  "allreduce_bytes": bucket.nbytes, "kernel": bwd_kernel, "gpu_launches": int(_native.launch_count() - l0),
+                 "grid_steps": train_steps, "peak_hbm_gib": torch.cuda.max_memory_allocated() / 2 ** 30,
                  "loss": loss_val,
                  # forward + exact reverse mode = 3x the forward's algorithmic FLOPs (the tape-based sweeps do not recompute)
                  "achieved_tflops_reference_formulation": 3 * w["flop_per_unit"] * aux_units / (tr_ms * 1e-3) / 1e12}
@@ -743,7 +750,7 @@ def main():
             "kernel_ms": res["kernel_ms"], "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
             "host_affinity": affinity,
         }
-        for k in ("e2e", "train", "cpu_baseline", "sample", "note"):
+        for k in ("e2e", "train", "encoded", "cpu_baseline", "sample", "note"):
             if k in res:
                 line[k] = res[k]
         if others:

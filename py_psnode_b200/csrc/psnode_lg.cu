@@ -71,6 +71,7 @@ struct LgParams {
     // event handling (neural_base.py:52-65, 180-196): ev[ev_j] = index of the event that fires when leaving grid point ev_j, or -1
     const int32_t* ev; int ev_j; int skip_unless_event; int skip_if_event;
     int b_r0;                           // added to the row coordinate of the B operand (slot of a ring of activation buffers)
+    int a_c0;                           // added to the K coordinate of the A operand (second half of a [P | Q] plane used on its own)
     int out2_acc;                       // EPI_DELTA: out2 += out instead of out2 = out
     float* out2_jump; int64_t out2_jump_sr;   // when an event fires at ev_j, out2 = out2_jump + k * out2_jump_sr (row of the event)
     const float* add1; int64_t add1_sr, add1_ld;             // [r][n][m]  (hoisted layer-1 half / per-trajectory constant)
@@ -157,8 +158,8 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                 const int src = ck / q.kchunks, kc = ck - src * q.kchunks;
                 const bool generated = (q.gen >> src) & 1;
                 mbar_expect_tx(&sm.full[s], (generated ? 2 : 3) * SLAB);
-                tma_load_3d(sm.a_hi[s], &map_a_hi, ck * 32, mblk * TM, 0, &sm.full[s]);
-                tma_load_3d(sm.a_lo[s], &map_a_lo, ck * 32, mblk * TM, 0, &sm.full[s]);
+                tma_load_3d(sm.a_hi[s], &map_a_hi, ck * 32 + q.a_c0, mblk * TM, 0, &sm.full[s]);
+                tma_load_3d(sm.a_lo[s], &map_a_lo, ck * 32 + q.a_c0, mblk * TM, 0, &sm.full[s]);
                 if (!generated) tma_load_3d(sm.b_hi[s], src == 0 ? &map_b0 : &map_b1, kc * 32, b0, r + q.b_r0, &sm.full[s]);
             }
         }
@@ -761,6 +762,10 @@ struct LgLayout {
 };
 enum { R_I0 = 0, R_DSUM, R_GI, R_H, R_DH };
 
+int lg_chunk_rows() {
+    static const int v = std::getenv("PSNODE_LG_CHUNK") ? std::atoi(std::getenv("PSNODE_LG_CHUNK")) : 64;
+    return v < 1 ? 1 : v;
+}
 int lg_ring_depth() {
     static const int v = std::getenv("PSNODE_LG_RING") ? std::atoi(std::getenv("PSNODE_LG_RING")) : 8;
     return v < 1 ? 1 : (v > 64 ? 64 : v);
@@ -796,17 +801,17 @@ LgLayout lg_layout(const psnode_problem* p, int mode, int chunk_rows = 0) {
     L.c_de = o; o += al(BH);
     L.c_ae = o; o += al(BH);
     // (the reverse pass overwrites pre[r] with d pre[r] in place)
-    L.rows_de = (p->T > 1 ? p->T - 1 : 0) + E ;
-    L.rows_ae = dae ? (int64_t)p->T + E : 0;
-    if (enc) {                                                  // one time chunk of rows instead of the whole series
-        L.rc = chunk_rows > 0 ? chunk_rows : 64;
-        if (L.rc > p->T) L.rc = p->T;
-        L.rows_de = L.rc;
-        L.rows_ae = dae ? L.rc + 1 : 0;
+    // hoisted layer-1 halves live in a time-chunk scratch (rc grid rows) in every mode: projections, steps and -- in the reverse pass --
+    // the chunk's share of the hoisted gradients run chunk by chunk, so the workspace is O(chunk), not O(T)
+    L.rc = chunk_rows > 0 ? chunk_rows : lg_chunk_rows();
+    if (L.rc > p->T) L.rc = p->T;
+    L.rows_de = L.rc;
+    L.rows_ae = dae ? L.rc + 1 : 0;
+    L.pj_de = o; o += al((int64_t)(E > 0 ? E : 1) * BH);
+    L.pj_ae = o; o += al((int64_t)(E > 0 ? E : 1) * BH);
+    if (enc) {
         L.encb_de = o; o += al(H);
         L.encb_ae = o; o += al(H);
-        L.pj_de = o; o += al((int64_t)(E > 0 ? E : 1) * BH);
-        L.pj_ae = o; o += al((int64_t)(E > 0 ? E : 1) * BH);
         L.xs = o; o += al((int64_t)(L.rc + 1) * BH);
         L.is = o; o += al(dae ? (int64_t)(L.rc + 1) * BH : 64);
         L.dtmp = o; o += al((int64_t)(L.rc + 1) * BH);
@@ -899,10 +904,12 @@ struct LgCtx {
                                                                  w + L.wts_hi[which] + dcol, w + L.wts_lo[which] + dcol);
         psn_count_launch("psn_lg_prep_kernel");
     }
-    void project(int which, const CUtensorMap& bz, const CUtensorMap& bv, int R, const float* cadd, float* out, const char* name) const {
+    // hoisted half of R series rows starting at row r_first: out[r] = [F_z | F_v] [z[r_first + r]; v[r_first + r]] + cadd
+    void project(int which, const CUtensorMap& bz, const CUtensorMap& bv, int r_first, int R, const float* cadd, float* out, const char* name) const {
         if (R <= 0) return;
         LgParams q = base();
         q.R = R; q.nsrc = dae ? 2 : 1; q.kchunks = H / 32;
+        q.b_r0 = r_first;
         q.add1 = cadd; q.add1_sr = 0; q.add1_ld = H;
         q.out = out; q.out_sr = BH; q.out_ld = H;
         launch(which, bz, dae ? bv : bz, q, name);
@@ -1041,15 +1048,11 @@ int lg_setup(LgCtx& c, const psnode_problem* p, int mode, void* ws, int64_t ws_b
         }
     }
 
-    if (enc) return PSNODE_OK;                                   // the encoded entry projects chunk by chunk
-    // ---- hoisted layer-1 halves over the whole series ----
-    const int64_t BH = c.BH;
-    const int64_t jump_de = (int64_t)(T > 1 ? T - 1 : 0) * BH;
-    c.project(M_DE1ZV, c.m_z, c.m_v, T - 1, w + L.c_de, w + L.pre_de, "psn_lg_gemm_kernel<pre_de>");
-    if (E > 0) c.project(M_DE1ZV, c.m_zj, c.m_vj, E, w + L.c_de, w + L.pre_de + jump_de, "psn_lg_gemm_kernel<pre_de_jump>");
-    if (dae) {
-        c.project(M_AE1ZV, c.m_z, c.m_v, T, w + L.c_ae, w + L.pre_ae, "psn_lg_gemm_kernel<pre_ae>");
-        if (E > 0) c.project(M_AE1ZV, c.m_zj, c.m_vj, E, w + L.c_ae, w + L.pre_ae + (int64_t)T * BH, "psn_lg_gemm_kernel<pre_ae_jump>");
+    if (enc) return PSNODE_OK;                                   // the encoded entry generates its projections from the raw series
+    // ---- hoisted layer-1 halves of the event rows (the grid rows are projected chunk by chunk by the callers) ----
+    if (E > 0) {
+        c.project(M_DE1ZV, c.m_zj, c.m_vj, 0, E, w + L.c_de, w + L.pj_de, "psn_lg_gemm_kernel<pre_de_jump>");
+        if (dae) c.project(M_AE1ZV, c.m_zj, c.m_vj, 0, E, w + L.c_ae, w + L.pj_ae, "psn_lg_gemm_kernel<pre_ae_jump>");
     }
     return PSNODE_OK;
 }
@@ -1273,16 +1276,25 @@ int psn_lg_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStre
         psn_lg_init_kernel<<<(int)((BH + 255) / 256), 256, 0, stream>>>(src, sb, B, H, w + L.x0, w + L.ycur, p->x_sol.p, p->x_sol.sb);
         psn_count_launch("psn_lg_init_kernel");
     }
-    const float* ae_jump = w + L.pre_ae + (int64_t)T * BH;
-    const float* de_jump = w + L.pre_de + (int64_t)(T - 1) * BH;
-    if (dae) lg_ae_eval(c, w + L.pre_ae, nullptr, p->i_sol.p, p->i_sol.sb, false, 0);     // i_0 = ae(x_0, z[0], v[0])  (my_solvers.py:95)
-    for (int j = 1; j < T; j++) {
-        LgStepIO io;
-        io.pre_de_row = w + L.pre_de + (int64_t)(j - 1) * BH; io.pre_de_jump = de_jump;
-        io.pre_ae_row = w + L.pre_ae + (int64_t)j * BH; io.pre_ae_jump = ae_jump;
-        io.xrow = p->x_sol.p + (int64_t)j * p->x_sol.st; io.xld = p->x_sol.sb;
-        io.irow = dae ? p->i_sol.p + (int64_t)j * p->i_sol.st : nullptr; io.ild = p->i_sol.sb;
-        lg_step(c, j, io);
+    const int RC = L.rc;
+    if (dae) {                                                                 // i_0 = ae(x_0, z[0], v[0])  (my_solvers.py:95)
+        c.project(M_AE1ZV, c.m_z, c.m_v, 0, 1, w + L.c_ae, w + L.pre_ae, "psn_lg_gemm_kernel<pre_ae>");
+        lg_ae_eval(c, w + L.pre_ae, nullptr, p->i_sol.p, p->i_sol.sb, false, 0);
+    }
+    // ---- time chunks: the hoisted halves of rc grid rows at a time, then the chunk's steps j = r0 + 1 .. r1 ----
+    for (int r0 = 0; r0 < T - 1; r0 += RC) {
+        const int r1 = r0 + RC < T - 1 ? r0 + RC : T - 1, n = r1 - r0;
+        c.project(M_DE1ZV, c.m_z, c.m_v, r0, n, w + L.c_de, w + L.pre_de, "psn_lg_gemm_kernel<pre_de>");
+        if (dae) c.project(M_AE1ZV, c.m_z, c.m_v, r0 + 1, n, w + L.c_ae, w + L.pre_ae + BH, "psn_lg_gemm_kernel<pre_ae>");
+        for (int j = r0 + 1; j <= r1; j++) {
+            const int k = j - r0;
+            LgStepIO io;
+            io.pre_de_row = w + L.pre_de + (int64_t)(k - 1) * BH; io.pre_de_jump = w + L.pj_de;
+            io.pre_ae_row = w + L.pre_ae + (int64_t)k * BH; io.pre_ae_jump = w + L.pj_ae;
+            io.xrow = p->x_sol.p + (int64_t)j * p->x_sol.st; io.xld = p->x_sol.sb;
+            io.irow = dae ? p->i_sol.p + (int64_t)j * p->i_sol.st : nullptr; io.ild = p->i_sol.sb;
+            lg_step(c, j, io);
+        }
     }
     PSN_CUDA(cudaGetLastError());
     lg_dump_stamps(c);
@@ -1468,18 +1480,21 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
         PSN_CUDA(cudaMemsetAsync(buf(i), 0, (size_t)BH * 4, stream));
     PSN_CUDA(cudaMemsetAsync(w + L.dpj_de, 0, (size_t)(E > 0 ? E : 1) * BH * 4, stream));
     PSN_CUDA(cudaMemsetAsync(w + L.dpj_ae, 0, (size_t)(E > 0 ? E : 1) * BH * 4, stream));
-    float* dpre_de = w + L.pre_de;                                            // rows 0 .. T-2 overwritten in place, row T-1 = 0
+    // time-chunk scratch: pre_de[k] = hoisted DE half of grid row r0 + k, pre_ae[k] = hoisted AE half of grid row r0 + k; both are
+    // overwritten in place by their gradients as the sweep passes, and the chunk's share of the hoisted gradients is taken before the
+    // next (earlier) chunk reuses the scratch
+    float* dpre_de = w + L.pre_de;
     float* dpre_ae = w + L.pre_ae;
-    const int64_t jump_de = (int64_t)(T > 1 ? T - 1 : 0) * BH;                // forward's event rows of pre_de (read only here)
+    const int RC = L.rc;
+    int r0 = 0;                                                                // first grid row of the current chunk
 
     // ---- tensor maps of the reverse pass ----
-    CUtensorMap m_buf, m_xsol, m_isol, m_dpde, m_dpae, m_dpjde, m_dpjae, m_zero;
+    CUtensorMap m_buf, m_xsol, m_isol, m_dpde, m_dpae, m_dpjde, m_dpjae;
     bool ok = lg_make_map(&m_buf, w + L.bufs, H, B, H, L.nbufs, BHa) && lg_make_map(&m_xsol, p->x_sol.p, H, B, p->x_sol.sb, T, p->x_sol.st);
     if (dae) ok = ok && lg_make_map(&m_isol, p->i_sol.p, H, B, p->i_sol.sb, T, p->i_sol.st);
-    if (T > 1) ok = ok && lg_make_map(&m_dpde, dpre_de, H, B, H, T - 1, BH);
-    if (dae) ok = ok && lg_make_map(&m_dpae, dpre_ae, H, B, H, T, BH);
+    ok = ok && lg_make_map(&m_dpde, dpre_de, H, B, H, RC, BH);
+    if (dae) ok = ok && lg_make_map(&m_dpae, dpre_ae, H, B, H, RC + 1, BH);
     ok = ok && lg_make_map(&m_dpjde, w + L.dpj_de, H, B, H, E > 0 ? E : 1, BH) && lg_make_map(&m_dpjae, w + L.dpj_ae, H, B, H, E > 0 ? E : 1, BH);
-    ok = ok && lg_make_map(&m_zero, buf(BUF_DY1), H, B, H, 1, 0);
     if (!ok) return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (layer path, reverse)");
 
     auto gemm = [&](int which, int bidx, LgParams& q, const char* name) {      // B operand = work buffer `bidx`
@@ -1494,7 +1509,7 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
     auto ae_backward = [&](int j, int s) {
         LgParams q1 = c.base();                                                // h_j = ELU(A1x x_j + pre_ae[j])
         q1.mode = LG_HIDDEN;
-        q1.add1 = dpre_ae + (int64_t)j * BH;
+        q1.add1 = dpre_ae + (int64_t)(j - r0) * BH;
         q1.out = buf(L.ring_one(R_H, s));
         q1.b_r0 = j;
         c.launch(M_AE1X, m_xsol, m_xsol, q1, "psn_lg_gemm_kernel<bwd:ae1>");
@@ -1502,7 +1517,7 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
         q2.mode = LG_DELTA;
         q2.add1 = buf(L.ring_one(R_H, s));
         q2.out = buf(L.ring_one(R_DH, s));
-        q2.out2 = dpre_ae + (int64_t)j * BH; q2.out2_ld = H;
+        q2.out2 = dpre_ae + (int64_t)(j - r0) * BH; q2.out2_ld = H;
         q2.acc = buf(BUF_DCAE);
         gemm(M_T_AE2, L.ring_one(R_GI, s), q2, "psn_lg_gemm_kernel<bwd:ae2^T>");
         LgParams q3 = c.base();                                                // gx += A1x^T dh
@@ -1558,7 +1573,7 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
                                                          buf(BUF_ACCGI));
         psn_count_launch("psn_lg_bwd_init_kernel");
     }
-    for (int j = T - 1; j >= 0; j--) {
+    auto sweep_point = [&](int j) -> int {            // AE at grid point j, then (j >= 1) the reverse of step j
         const int s = j % ring;
         if (dae) ae_backward(j, s);
         if (j >= 1) {
@@ -1576,7 +1591,7 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
                     LgParams q = c.base();
                     q.mode = LG_HIDDEN;
                     gated(q, j - 1);
-                    q.add1_jump = w + L.pre_ae + (int64_t)T * BH; q.add1_jump_sr = BH;
+                    q.add1_jump = w + L.pj_ae; q.add1_jump_sr = BH;
                     q.out = buf(BUF_HEV);
                     gemm(M_AE1X, L.ring_y(s, 0), q, "psn_lg_gemm_kernel<bwd:ae1,event>");
                     LgParams q2 = c.base();
@@ -1592,8 +1607,8 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
             for (int e = 0; e < NS; e++) {
                 LgParams q1 = c.base();
                 q1.mode = LG_HIDDEN;
-                q1.add1 = w + L.pre_de + (int64_t)(j - 1) * BH;
-                if (E > 0) { q1.ev = p->event_idx; q1.ev_j = j - 1; q1.add1_jump = w + L.pre_de + jump_de; q1.add1_jump_sr = BH; }
+                q1.add1 = dpre_de + (int64_t)(j - 1 - r0) * BH;
+                if (E > 0) { q1.ev = p->event_idx; q1.ev_j = j - 1; q1.add1_jump = w + L.pj_de; q1.add1_jump_sr = BH; }
                 if (dae) q1.add2 = buf(BUF_G);
                 q1.out = buf(L.ring_a1(s, e));
                 gemm(M_DE1X, L.ring_y(s, e), q1, "psn_lg_gemm_kernel<bwd:de1>");
@@ -1665,10 +1680,89 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
         if (j >= 1) {
             const int sn = (j - 1) % ring;
             psn_lg_bwd_tail_kernel<<<nblk, 256, 0, stream>>>(B, H, E > 0 ? p->event_idx : nullptr, j - 1, buf(L.ring_one(R_DSUM, s)),
-                                                             dpre_de + (int64_t)(j - 1) * BH, w + L.dpj_de, BH, dae ? buf(BUF_GI0) : nullptr,
+                                                             dpre_de + (int64_t)(j - 1 - r0) * BH, w + L.dpj_de, BH, dae ? buf(BUF_GI0) : nullptr,
                                                              dae ? upi : nullptr, upi_sb, dae ? buf(L.ring_one(R_GI, sn)) : nullptr, buf(BUF_ACCGI));
             psn_count_launch("psn_lg_bwd_tail_kernel");
         }
+        return PSNODE_OK;
+    };
+    // the chunk's share of the hoisted gradients: input-series rows (d_z[r] += F_z^T d pre_de[r] and += A1z^T d pre_ae[r], the two halves of
+    // the [F_z^T | A1z^T] plane on their own because a row's two parts can belong to different chunks) and the weight gradients
+    // dF_z / dF_v += sum_r d pre_de[r] (x) z[r] / v[r],  dA1z / dA1v likewise
+    auto chunk_grads = [&](int de_rows, int ae_first, int ae_rows) -> int {    // DE rows r0 .. r0+de_rows-1; AE rows ae_first .. ae_first+ae_rows-1
+        // Order of the two parts of a row r: its DE part is always written first (same chunk, or -- for the chunk's top row -- by the
+        // later chunk that was swept earlier), so the DE part is a plain store and the AE part accumulates; only row T-1 has no DE part
+        auto series_part = [&](int which, const CUtensorMap& m_src, int src_row0, int rows, int grid_row0, int a_c0, bool accumulate, float* out,
+                               int64_t out_sr, int64_t out_sb, const char* name) {
+            if (!out || rows <= 0) return;
+            LgParams q = c.base();
+            q.R = rows; q.b_r0 = src_row0; q.a_c0 = a_c0;
+            q.out = out + (int64_t)grid_row0 * out_sr; q.out_sr = out_sr; q.out_ld = out_sb;
+            if (accumulate) { q.add1 = q.out; q.add1_sr = out_sr; q.add1_ld = out_sb; }
+            c.launch(which, m_src, m_src, q, name);
+        };
+        series_part(M_T_DZ, m_dpde, 0, de_rows, r0, 0, false, a->d_z.p, a->d_z.st, a->d_z.sb, "psn_lg_gemm_kernel<bwd:d_z,de>");
+        if (dae) {
+            series_part(M_T_DV, m_dpde, 0, de_rows, r0, 0, false, a->d_v.p, a->d_v.st, a->d_v.sb, "psn_lg_gemm_kernel<bwd:d_v,de>");
+            series_part(M_T_DZ, m_dpae, ae_first - r0, ae_rows, ae_first, H, true, a->d_z.p, a->d_z.st, a->d_z.sb, "psn_lg_gemm_kernel<bwd:d_z,ae>");
+            series_part(M_T_DV, m_dpae, ae_first - r0, ae_rows, ae_first, H, true, a->d_v.p, a->d_v.st, a->d_v.sb, "psn_lg_gemm_kernel<bwd:d_v,ae>");
+        }
+        int rc = PSNODE_OK;
+        if (de_rows > 0) {
+            rc = lg_wgrad(dpre_de, H, BH, H, p->z.p + (int64_t)r0 * p->z.st, p->z.sb, p->z.st, H, de_rows, B, th + o_W1 + 2 * S + X, 3 * S, 1, slabs, c.err,
+                          stream);
+            if (rc != PSNODE_OK) return rc;
+            if (dae) {
+                rc = lg_wgrad(dpre_de, H, BH, H, p->v.p + (int64_t)r0 * p->v.st, p->v.sb, p->v.st, H, de_rows, B, th + o_W1 + 2 * S + X + Z, 3 * S, 1, slabs,
+                              c.err, stream);
+                if (rc != PSNODE_OK) return rc;
+            }
+        }
+        if (dae && ae_rows > 0) {
+            const float* pp = dpre_ae + (int64_t)(ae_first - r0) * BH;
+            rc = lg_wgrad(pp, H, BH, H, p->z.p + (int64_t)ae_first * p->z.st, p->z.sb, p->z.st, H, ae_rows, B, th + o_A1 + S + X, lda, 1, slabs, c.err, stream);
+            if (rc != PSNODE_OK) return rc;
+            rc = lg_wgrad(pp, H, BH, H, p->v.p + (int64_t)ae_first * p->v.st, p->v.sb, p->v.st, H, ae_rows, B, th + o_A1 + S + X + Z, lda, 1, slabs, c.err,
+                          stream);
+            if (rc != PSNODE_OK) return rc;
+        }
+        return PSNODE_OK;
+    };
+    // the last grid row has no DE part (z[T-1] / v[T-1] only enter the AE): it starts at zero
+    if (a->d_z.p) {
+        psn_lg_zero_rows_kernel<<<nblk, 256, 0, stream>>>(1, B, H, a->d_z.p + (int64_t)(T - 1) * a->d_z.st, 0, a->d_z.sb);
+        psn_count_launch("psn_lg_zero_rows_kernel");
+    }
+    if (dae && a->d_v.p) {
+        psn_lg_zero_rows_kernel<<<nblk, 256, 0, stream>>>(1, B, H, a->d_v.p + (int64_t)(T - 1) * a->d_v.st, 0, a->d_v.sb);
+        psn_count_launch("psn_lg_zero_rows_kernel");
+    }
+    if (T == 1) {
+        if (dae) c.project(M_AE1ZV, c.m_z, c.m_v, 0, 1, w + L.c_ae, dpre_ae, "psn_lg_gemm_kernel<bwd:pre_ae>");
+        st = sweep_point(0);
+        if (st != PSNODE_OK) return st;
+        st = chunk_grads(0, 0, dae ? 1 : 0);
+        if (st != PSNODE_OK) return st;
+    }
+    for (int ck = T > 1 ? (T - 2) / RC : -1; ck >= 0; ck--) {
+        r0 = ck * RC;
+        const int r1 = r0 + RC < T - 1 ? r0 + RC : T - 1, n = r1 - r0;
+        c.project(M_DE1ZV, c.m_z, c.m_v, r0, n, w + L.c_de, dpre_de, "psn_lg_gemm_kernel<bwd:pre_de>");
+        if (dae) {
+            const int first = r0 == 0 ? 0 : r0 + 1;
+            c.project(M_AE1ZV, c.m_z, c.m_v, first, r1 - first + 1, w + L.c_ae, dpre_ae + (int64_t)(first - r0) * BH, "psn_lg_gemm_kernel<bwd:pre_ae>");
+        }
+        for (int j = r1; j > r0; j--) {
+            st = sweep_point(j);
+            if (st != PSNODE_OK) return st;
+        }
+        if (r0 == 0) {
+            st = sweep_point(0);
+            if (st != PSNODE_OK) return st;
+        }
+        const int ae_first = r0 == 0 ? 0 : r0 + 1;
+        st = chunk_grads(n, ae_first, dae ? r1 - ae_first + 1 : 0);
+        if (st != PSNODE_OK) return st;
     }
     PSN_CUDA(cudaGetLastError());
 
@@ -1677,27 +1771,7 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
         psn_lg_copy_rows_kernel<<<nblk, 256, 0, stream>>>(B, H, buf(BUF_GX), a->d_x0, a->d_x0_sb);
         psn_count_launch("psn_lg_copy_rows_kernel");
     }
-    // ---- input-series / jump gradients: d_z[r] = F_z^T d pre_de[r] + A1z^T d pre_ae[r]  (d pre_de[T-1] = 0: z[T-1] only enters the AE) ----
-    auto series_grad = [&](int which, float* out, int64_t out_sr, int64_t out_sb, const char* name) {
-        if (!out) return;
-        if (T > 1) {
-            LgParams q = c.base();
-            q.R = T - 1; q.nsrc = dae ? 2 : 1;
-            q.out = out; q.out_sr = out_sr; q.out_ld = out_sb;
-            c.launch(which, m_dpde, dae ? m_dpae : m_dpde, q, name);
-        }
-        if (dae) {                                                             // last grid row: the AE half only
-            LgParams q = c.base();
-            q.R = 1; q.nsrc = 2; q.b_r0 = 0;
-            q.out = out + (int64_t)(T - 1) * out_sr; q.out_sr = 0; q.out_ld = out_sb;
-            CUtensorMap m_last;
-            if (!lg_make_map(&m_last, dpre_ae + (int64_t)(T - 1) * BH, H, B, H, 1, 0)) return;
-            c.launch(which, m_zero, m_last, q, name);
-        } else {
-            psn_lg_zero_rows_kernel<<<nblk, 256, 0, stream>>>(1, B, H, out + (int64_t)(T - 1) * out_sr, 0, out_sb);
-            psn_count_launch("psn_lg_zero_rows_kernel");
-        }
-    };
+    // ---- jump-row gradients: d_zjump[k] = F_z^T d pre_de_jump[k] + A1z^T d pre_ae_jump[k], and their share of dF_z / dF_v / dA1z / dA1v ----
     auto jump_grad = [&](int which, float* out, int64_t out_se, int64_t out_sb, const char* name) {
         if (!out || E <= 0) return;
         LgParams q = c.base();
@@ -1705,36 +1779,14 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
         q.out = out; q.out_sr = out_se; q.out_ld = out_sb;
         c.launch(which, m_dpjde, dae ? m_dpjae : m_dpjde, q, name);
     };
-    // BUF_DY1 doubles as the zero operand of the last row: clear it (the sweep used it)
-    PSN_CUDA(cudaMemsetAsync(buf(BUF_DY1), 0, (size_t)BH * 4, stream));
-    series_grad(M_T_DZ, a->d_z.p, a->d_z.st, a->d_z.sb, "psn_lg_gemm_kernel<bwd:d_z>");
-    if (dae) series_grad(M_T_DV, a->d_v.p, a->d_v.st, a->d_v.sb, "psn_lg_gemm_kernel<bwd:d_v>");
     jump_grad(M_T_DZ, a->d_zjump, a->d_zj_se, a->d_zj_sb, "psn_lg_gemm_kernel<bwd:d_zjump>");
     if (dae) jump_grad(M_T_DV, a->d_vjump, a->d_vj_se, a->d_vj_sb, "psn_lg_gemm_kernel<bwd:d_vjump>");
-
-    // ---- hoisted weight gradients: dF_z, dF_v (and dA1z, dA1v) over the whole series and the jump rows ----
-    if (T > 1) {
-        st = lg_wgrad(dpre_de, H, BH, H, p->z.p, p->z.sb, p->z.st, H, T - 1, B, th + o_W1 + 2 * S + X, 3 * S, 1, slabs, c.err, stream);
-        if (st != PSNODE_OK) return st;
-        if (dae) {
-            st = lg_wgrad(dpre_de, H, BH, H, p->v.p, p->v.sb, p->v.st, H, T - 1, B, th + o_W1 + 2 * S + X + Z, 3 * S, 1, slabs, c.err, stream);
-            if (st != PSNODE_OK) return st;
-        }
-    }
     if (E > 0) {
         st = lg_wgrad(w + L.dpj_de, H, BH, H, p->z_jump, p->zj_sb, p->zj_se, H, E, B, th + o_W1 + 2 * S + X, 3 * S, 1, slabs, c.err, stream);
         if (st != PSNODE_OK) return st;
         if (dae) {
             st = lg_wgrad(w + L.dpj_de, H, BH, H, p->v_jump, p->vj_sb, p->vj_se, H, E, B, th + o_W1 + 2 * S + X + Z, 3 * S, 1, slabs, c.err, stream);
             if (st != PSNODE_OK) return st;
-        }
-    }
-    if (dae) {
-        st = lg_wgrad(dpre_ae, H, BH, H, p->z.p, p->z.sb, p->z.st, H, T, B, th + o_A1 + S + X, lda, 1, slabs, c.err, stream);
-        if (st != PSNODE_OK) return st;
-        st = lg_wgrad(dpre_ae, H, BH, H, p->v.p, p->v.sb, p->v.st, H, T, B, th + o_A1 + S + X + Z, lda, 1, slabs, c.err, stream);
-        if (st != PSNODE_OK) return st;
-        if (E > 0) {
             st = lg_wgrad(w + L.dpj_ae, H, BH, H, p->z_jump, p->zj_sb, p->zj_se, H, E, B, th + o_A1 + S + X, lda, 1, slabs, c.err, stream);
             if (st != PSNODE_OK) return st;
             st = lg_wgrad(w + L.dpj_ae, H, BH, H, p->v_jump, p->vj_sb, p->vj_se, H, E, B, th + o_A1 + S + X + Z, lda, 1, slabs, c.err, stream);

@@ -494,6 +494,9 @@ class _IntegrateLoss(torch.autograd.Function):
             if i_sol is not None and spec.target_i is not None:
                 num = num + masked_sse(i_sol, spec.target_i, spec.mask, spec.weight_i)
         ctx.tape, ctx.cfg, ctx.spec = tape, cfg, spec
+        # the trajectories are returned as non-differentiable by-products: without this autograd would hand backward() freshly
+        # zero-filled (T,B,X) / (T,B,I) gradients for them (2 x 15.6 GiB at the cfg5 shard)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(*[q for q in tens if q is not None], x_sol, *([i_sol] if i_sol is not None else []))
         ctx.present = [q is not None for q in tens]
         if i_sol is None:
@@ -511,6 +514,8 @@ class _IntegrateLoss(torch.autograd.Function):
         i_sol = next(it) if cfg.kind == N.DAE else None
         tape, ctx.tape = ctx.tape, None
         needs = ctx.needs_input_grad[2:]
+        if gnum is None:
+            return (None, None) + (None,) * len(ctx.present)
         scale = gnum.detach().to(torch.float32).reshape(1).contiguous()
         if isinstance(tape, TapeChunks):
             tape = None                     # chunked re-integration is not combined with loss fusion: recomputing sweep
