@@ -437,6 +437,9 @@ def _encoded_leg(w, solver, de, ae, resident, B, n_steps, units, active, barrier
             "raw_widths": {"x": XR, "z": ZR, "v": VR, "i": IR},
             "peak_hbm_gib_above_inputs": (torch.cuda.max_memory_allocated() - base) / 2 ** 30,
             "latent_series_gib_unfused": (4 if dae else 2) * T * B * H * 4 / 2 ** 30,
+            "note": ("runs on the per-layer GEMM kernel (impl = layer); at latent width 128 the unfused ODE path has the faster TMEM-resident wide "
+                     "kernel, so here the fused entry buys O(chunk) memory, not time" if H == 128 else
+                     "faster than torch encoders -> integrate_DAE -> torch decoders (740 ms at this shard) and O(chunk) memory"),
             "what": "Model.forward pipeline of the *_02 scripts in one call from the raw series: encoders generated inside the hoisted projection "
                     "GEMMs, integration in 64-row time chunks, decoders before the store (psnode_forward_encoded); outputs decoded (T,B,x_dim)"}
 
