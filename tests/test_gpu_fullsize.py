@@ -320,3 +320,53 @@ def test_cfg4_full_size_forward_and_gradients_against_oracle_sample(native_lib, 
     for gv, r in zip(sub_theta, ref_theta):
         assert _rel(gv, r) <= 2e-5
     assert _rel(full_dx0[rows], x064.grad) <= 2e-5 and _rel(full_dz[:, rows], z64.grad) <= 2e-5
+
+
+def test_cfg5_shard_gradients_layer_sweep_vs_generic_sweep(native_lib):
+    """BASELINE configs[4] per-GPU shard (DAE_02, latent 256, B = 8192 = 64 full trajectory tiles x 2 feature blocks), 80 RK4 steps (two time
+    chunks of the hoisted projections, ten turns of the activation ring), one event: every gradient sink of the layer path's tensor-core
+    reverse sweep against the CUDA-core generic sweep (itself pinned to float64 autograd at small sizes), and the forward against it too."""
+    from py_psnode_b200 import AE_Func, DAE_Event, DE_Func, RK4, _native
+    torch.manual_seed(2025)
+    dev = "cuda:0"
+    B, N, H = 8192, 80, 256
+    T = N + 1
+    de = DE_Func(x_dim=H, z_dim=H, hidden_dim=H, v_dim=H, i_dim=H, depth=2).to(dev)
+    ae = AE_Func(x_dim=H, v_dim=H, i_dim=H, hidden_dim=H, z_dim=H, depth=2).to(dev)
+    t = (torch.arange(T, dtype=torch.float32, device=dev) * 0.01).view(T, 1, 1).repeat(1, B, 1)
+    mk = lambda: torch.randn(T, B, H, device=dev) * 0.05
+    z0, v0 = mk(), mk()
+    x_init, i0 = torch.randn(B, H, device=dev) * 0.05, torch.randn(B, H, device=dev) * 0.05
+    wx, wi = mk(), mk()
+    event_t = t[N // 2].view(B, 1, 1).clone()
+    zj0, vj0 = torch.randn(B, 1, H, device=dev) * 0.05, torch.randn(B, 1, H, device=dev) * 0.05
+    plist = list(de.parameters()) + list(ae.parameters())
+    res = {}
+    for impl in ("layer", "generic"):
+        for p in plist:
+            p.grad = None
+        z, v = z0.clone().requires_grad_(True), v0.clone().requires_grad_(True)
+        zj, vj = zj0.clone().requires_grad_(True), vj0.clone().requires_grad_(True)
+        xi = x_init.clone().requires_grad_(True)
+        a0 = torch.cat((x_init, z0[0], v0[0], i0), dim=-1).requires_grad_(True)
+        ev = DAE_Event()
+        ev.set_event(t=event_t, z=zj, v=vj)
+        xs, is_ = RK4(impl=impl).integrate_DAE(x_init=xi, x_func=de, i_func=ae, t=t, x=x_init.unsqueeze(0).expand(T, B, H), z=z, v=v,
+                                              i=i0.unsqueeze(0).expand(T, B, H), all_initial=a0, event_fn=ev.event_fn,
+                                              jump_change_fn=ev.jump_change_fn)
+        ((xs * wx).sum() + (is_ * wi).sum()).backward()
+        kern = _native.last_kernel()
+        assert kern.startswith("psn_lg_") if impl == "layer" else kern.startswith("psn_g"), kern
+        res[impl] = dict(xs=xs.detach(), is_=is_.detach(), theta=[p.grad.clone() for p in plist], z=z.grad, v=v.grad, zj=zj.grad, vj=vj.grad,
+                         xi=xi.grad, a0=a0.grad)
+    a, b = res["layer"], res["generic"]
+    assert torch.allclose(a["xs"], b["xs"], rtol=1e-5, atol=1e-6) and torch.allclose(a["is_"], b["is_"], rtol=1e-5, atol=1e-6)
+    pairs = [(f"theta{k}", x, y) for k, (x, y) in enumerate(zip(a["theta"], b["theta"]))]
+    pairs += [(k, a[k], b[k]) for k in ("z", "v", "zj", "vj", "xi", "a0")]
+    worst = 0.0
+    for name, g, r in pairs:
+        scale = float(r.abs().max())
+        err = float((g - r).abs().max())
+        worst = max(worst, err / max(scale, 1e-30))
+        assert err <= 3e-5 * scale + 1e-7, f"{name}: err {err:.3e} scale {scale:.3e}"
+    print(f"cfg5 shard, layer vs generic sweep: worst relative gradient difference {worst:.2e}")
