@@ -908,11 +908,12 @@ struct LgCtx {
     void project(int which, const CUtensorMap& bz, const CUtensorMap& bv, int r_first, int R, const float* cadd, float* out, const char* name) const {
         if (R <= 0) return;
         LgParams q = base();
-        q.R = R; q.nsrc = dae ? 2 : 1; q.kchunks = H / 32;
+        const bool has_z = p->Z > 0;
+        q.R = R; q.nsrc = (dae && has_z) ? 2 : 1; q.kchunks = H / 32;
         q.b_r0 = r_first;
         q.add1 = cadd; q.add1_sr = 0; q.add1_ld = H;
         q.out = out; q.out_sr = BH; q.out_ld = H;
-        launch(which, bz, dae ? bv : bz, q, name);
+        launch(which, has_z ? bz : bv, dae ? bv : bz, q, name);
     }
 };
 
@@ -1000,13 +1001,13 @@ int lg_setup(LgCtx& c, const psnode_problem* p, int mode, void* ws, int64_t ws_b
     if (bwd) {
         c.prep(M_T_DE2, p->de.W[1], H, 0, -1, 0.0f, 1, H, H, 0);                      // W2^T
         c.prep(M_T_DE1X, W1, ld1, S, 2 * S, 1.0f, 1, H, H, 0);                        // F_x^T
-        c.prep(M_T_DZ, W1, ld1, S + X, 2 * S + X, 1.0f, 1, H, H, 0);                  // [F_z^T | A1z^T]
+        if (Z > 0) c.prep(M_T_DZ, W1, ld1, S + X, 2 * S + X, 1.0f, 1, H, H, 0);       // [F_z^T | A1z^T]
         c.prep(M_T_DA0, W1, ld1, 0, S, -1.0f, 1, S, H, 0);                            // [(W_a - W_b)^T | A1a^T]
         if (dae) {
             c.prep(M_T_DE1I, W1, ld1, S + X + Z + V, 2 * S + X + Z + V, 1.0f, 1, H, H, 0);
             c.prep(M_T_AE2, p->ae.W[1], H, 0, -1, 0.0f, 1, H, H, 0);
             c.prep(M_T_AE1X, A1, lda, S, -1, 0.0f, 1, H, H, 0);
-            c.prep(M_T_DZ, A1, lda, S + X, -1, 0.0f, 1, H, H, H);
+            if (Z > 0) c.prep(M_T_DZ, A1, lda, S + X, -1, 0.0f, 1, H, H, H);
             c.prep(M_T_DV, W1, ld1, S + X + Z, 2 * S + X + Z, 1.0f, 1, H, H, 0);      // [F_v^T | A1v^T]
             c.prep(M_T_DV, A1, lda, S + X + Z, -1, 0.0f, 1, H, H, H);
             c.prep(M_T_DA0, A1, lda, 0, -1, 0.0f, 1, S, H, H);
@@ -1022,10 +1023,10 @@ int lg_setup(LgCtx& c, const psnode_problem* p, int mode, void* ws, int64_t ws_b
              lg_make_map(&c.mw_lo[i], w + L.wts_lo[i], L.mcols[i], L.mrows[i], L.mcols[i], 1, 0);
     }
     if (!enc) {
-        ok = ok && lg_make_map(&c.m_z, p->z.p, H, B, p->z.sb, T, p->z.st);
+        if (Z > 0) ok = ok && lg_make_map(&c.m_z, p->z.p, H, B, p->z.sb, T, p->z.st);
         if (dae) ok = ok && lg_make_map(&c.m_v, p->v.p, H, B, p->v.sb, T, p->v.st);
         if (E > 0) {
-            ok = ok && lg_make_map(&c.m_zj, p->z_jump, H, B, p->zj_sb, E, p->zj_se);
+            if (Z > 0) ok = ok && lg_make_map(&c.m_zj, p->z_jump, H, B, p->zj_sb, E, p->zj_se);
             if (dae) ok = ok && lg_make_map(&c.m_vj, p->v_jump, H, B, p->vj_sb, E, p->vj_se);
         }
     }
@@ -1152,15 +1153,15 @@ bool psn_lg_supports(const psnode_problem* p) {
     const int H = p->X;
     if (H != 128 && H != 256) return false;
     const bool dae = p->kind == PSNODE_DAE;
-    if (p->Z != H) return false;                                   // (the z_dim == 0 script variant runs on the generic kernels)
+    if (p->Z != H && !(dae && p->Z == 0)) return false;            // Z = 0: the z_dim == 0 variant of DAE_02 (neural_01_DAE_02_direct_encode.py:73, :90)
     if (dae && (p->V != H || p->I != H)) return false;
     const int S = p->X + p->Z + p->V + p->I;
     if (p->de.n_layers != 2 || p->de.in_dim[0] != 3 * S || p->de.out_dim[0] != H || p->de.out_dim[1] != H) return false;
     if (dae && (p->ae.n_layers != 2 || p->ae.in_dim[0] != S + p->X + p->Z + p->V || p->ae.out_dim[0] != H || p->ae.out_dim[1] != H)) return false;
-    if (!view_ok(p->z.p, p->z.st, p->z.sb)) return false;
+    if (p->Z > 0 && !view_ok(p->z.p, p->z.st, p->z.sb)) return false;
     if (dae && !view_ok(p->v.p, p->v.st, p->v.sb)) return false;
     if (p->event_idx) {
-        if (!view_ok(p->z_jump, p->zj_sb, p->zj_se)) return false;
+        if (p->Z > 0 && !view_ok(p->z_jump, p->zj_sb, p->zj_se)) return false;
         if (dae && !view_ok(p->v_jump, p->vj_sb, p->vj_se)) return false;
     }
     if ((p->x_sol.sb & 3) || (p->x_sol.st & 3)) return false;
@@ -1701,17 +1702,19 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
             if (accumulate) { q.add1 = q.out; q.add1_sr = out_sr; q.add1_ld = out_sb; }
             c.launch(which, m_src, m_src, q, name);
         };
-        series_part(M_T_DZ, m_dpde, 0, de_rows, r0, 0, false, a->d_z.p, a->d_z.st, a->d_z.sb, "psn_lg_gemm_kernel<bwd:d_z,de>");
+        if (Z > 0) series_part(M_T_DZ, m_dpde, 0, de_rows, r0, 0, false, a->d_z.p, a->d_z.st, a->d_z.sb, "psn_lg_gemm_kernel<bwd:d_z,de>");
         if (dae) {
             series_part(M_T_DV, m_dpde, 0, de_rows, r0, 0, false, a->d_v.p, a->d_v.st, a->d_v.sb, "psn_lg_gemm_kernel<bwd:d_v,de>");
-            series_part(M_T_DZ, m_dpae, ae_first - r0, ae_rows, ae_first, H, true, a->d_z.p, a->d_z.st, a->d_z.sb, "psn_lg_gemm_kernel<bwd:d_z,ae>");
+            if (Z > 0) series_part(M_T_DZ, m_dpae, ae_first - r0, ae_rows, ae_first, H, true, a->d_z.p, a->d_z.st, a->d_z.sb, "psn_lg_gemm_kernel<bwd:d_z,ae>");
             series_part(M_T_DV, m_dpae, ae_first - r0, ae_rows, ae_first, H, true, a->d_v.p, a->d_v.st, a->d_v.sb, "psn_lg_gemm_kernel<bwd:d_v,ae>");
         }
         int rc = PSNODE_OK;
         if (de_rows > 0) {
-            rc = lg_wgrad(dpre_de, H, BH, H, p->z.p + (int64_t)r0 * p->z.st, p->z.sb, p->z.st, H, de_rows, B, th + o_W1 + 2 * S + X, 3 * S, 1, slabs, c.err,
-                          stream);
-            if (rc != PSNODE_OK) return rc;
+            if (Z > 0) {
+                rc = lg_wgrad(dpre_de, H, BH, H, p->z.p + (int64_t)r0 * p->z.st, p->z.sb, p->z.st, H, de_rows, B, th + o_W1 + 2 * S + X, 3 * S, 1, slabs,
+                              c.err, stream);
+                if (rc != PSNODE_OK) return rc;
+            }
             if (dae) {
                 rc = lg_wgrad(dpre_de, H, BH, H, p->v.p + (int64_t)r0 * p->v.st, p->v.sb, p->v.st, H, de_rows, B, th + o_W1 + 2 * S + X + Z, 3 * S, 1, slabs,
                               c.err, stream);
@@ -1720,8 +1723,11 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
         }
         if (dae && ae_rows > 0) {
             const float* pp = dpre_ae + (int64_t)(ae_first - r0) * BH;
-            rc = lg_wgrad(pp, H, BH, H, p->z.p + (int64_t)ae_first * p->z.st, p->z.sb, p->z.st, H, ae_rows, B, th + o_A1 + S + X, lda, 1, slabs, c.err, stream);
-            if (rc != PSNODE_OK) return rc;
+            if (Z > 0) {
+                rc = lg_wgrad(pp, H, BH, H, p->z.p + (int64_t)ae_first * p->z.st, p->z.sb, p->z.st, H, ae_rows, B, th + o_A1 + S + X, lda, 1, slabs, c.err,
+                              stream);
+                if (rc != PSNODE_OK) return rc;
+            }
             rc = lg_wgrad(pp, H, BH, H, p->v.p + (int64_t)ae_first * p->v.st, p->v.sb, p->v.st, H, ae_rows, B, th + o_A1 + S + X + Z, lda, 1, slabs, c.err,
                           stream);
             if (rc != PSNODE_OK) return rc;
@@ -1779,16 +1785,20 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
         q.out = out; q.out_sr = out_se; q.out_ld = out_sb;
         c.launch(which, m_dpjde, dae ? m_dpjae : m_dpjde, q, name);
     };
-    jump_grad(M_T_DZ, a->d_zjump, a->d_zj_se, a->d_zj_sb, "psn_lg_gemm_kernel<bwd:d_zjump>");
+    if (Z > 0) jump_grad(M_T_DZ, a->d_zjump, a->d_zj_se, a->d_zj_sb, "psn_lg_gemm_kernel<bwd:d_zjump>");
     if (dae) jump_grad(M_T_DV, a->d_vjump, a->d_vj_se, a->d_vj_sb, "psn_lg_gemm_kernel<bwd:d_vjump>");
     if (E > 0) {
-        st = lg_wgrad(w + L.dpj_de, H, BH, H, p->z_jump, p->zj_sb, p->zj_se, H, E, B, th + o_W1 + 2 * S + X, 3 * S, 1, slabs, c.err, stream);
-        if (st != PSNODE_OK) return st;
+        if (Z > 0) {
+            st = lg_wgrad(w + L.dpj_de, H, BH, H, p->z_jump, p->zj_sb, p->zj_se, H, E, B, th + o_W1 + 2 * S + X, 3 * S, 1, slabs, c.err, stream);
+            if (st != PSNODE_OK) return st;
+        }
         if (dae) {
             st = lg_wgrad(w + L.dpj_de, H, BH, H, p->v_jump, p->vj_sb, p->vj_se, H, E, B, th + o_W1 + 2 * S + X + Z, 3 * S, 1, slabs, c.err, stream);
             if (st != PSNODE_OK) return st;
-            st = lg_wgrad(w + L.dpj_ae, H, BH, H, p->z_jump, p->zj_sb, p->zj_se, H, E, B, th + o_A1 + S + X, lda, 1, slabs, c.err, stream);
-            if (st != PSNODE_OK) return st;
+            if (Z > 0) {
+                st = lg_wgrad(w + L.dpj_ae, H, BH, H, p->z_jump, p->zj_sb, p->zj_se, H, E, B, th + o_A1 + S + X, lda, 1, slabs, c.err, stream);
+                if (st != PSNODE_OK) return st;
+            }
             st = lg_wgrad(w + L.dpj_ae, H, BH, H, p->v_jump, p->vj_sb, p->vj_se, H, E, B, th + o_A1 + S + X + Z, lda, 1, slabs, c.err, stream);
             if (st != PSNODE_OK) return st;
         }

@@ -249,3 +249,64 @@ def test_layer_ode_h256_gradients_vs_fp64_autograd(native_lib, solver, events):
     if events:
         got["z_jump"], want["z_jump"] = zjd.grad, zj64.grad
     _compare_grads({k: g.detach().cpu() for k, g in got.items()}, want)
+
+
+@pytest.mark.parametrize("H,solver,events", [(128, "rk4", 1), (256, "euler", 0)])
+def test_layer_dae_without_z_inputs(native_lib, H, solver, events):
+    """The z_dim == 0 variant of DAE_02 (neural_01_DAE_02_direct_encode.py:73, :90: DE_Func 9H -> H -> H, AE_Func 5H -> H -> H, z of
+    width 0): forward against the oracle, every gradient against float64 autograd, on the layer path."""
+    from oracle import psnode_oracle as O
+    from py_psnode_b200 import AE_Func, DAE_Event, DE_Func, Euler, RK4, _native
+    torch.manual_seed(17 + H)
+    dev = "cuda:0"
+    B, N = 36, 10
+    T = N + 1
+    de = DE_Func(x_dim=H, z_dim=0, hidden_dim=H, v_dim=H, i_dim=H, depth=2)
+    ae = AE_Func(x_dim=H, v_dim=H, i_dim=H, hidden_dim=H, z_dim=0, depth=2)
+    t = (torch.arange(T, dtype=torch.float32) * 0.01).view(T, 1, 1).repeat(1, B, 1)
+    mk = lambda: torch.randn(T, B, H) * 0.05
+    x, v, i = mk(), mk(), mk()
+    z = torch.zeros(T, B, 0)
+    x_init = torch.randn(B, H) * 0.05
+    a0 = torch.cat((x_init, v[0], i[0]), dim=-1)
+    wx, wi = torch.randn(T, B, H) * 0.1, torch.randn(T, B, H) * 0.1
+    ev = None
+    if events:
+        ev = (t[N // 2].view(B, 1, 1).clone(), torch.zeros(B, 1, 0), torch.randn(B, 1, H) * 0.05)
+    # float64 autograd through the oracle
+    pd = [(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in _params(de.x_dot)]
+    pa = [(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in _params(ae.i_calculator)]
+    xi64, v64, a064 = x_init.double().requires_grad_(True), v.double().requires_grad_(True), a0.double().requires_grad_(True)
+    args = ("rk4" if solver == "rk4" else "euler", pd, pa, xi64, t.double(), x.double(), z.double(), v64, i.double(), a064)
+    vj64 = None
+    if ev:
+        vj64 = ev[2].double().requires_grad_(True)
+        sx, si = O.integrate_dae(*args, ev[0].double(), ev[1].double(), vj64)
+    else:
+        sx, si = O.integrate_dae(*args)
+    ((sx * wx.double()).sum() + (si * wi.double()).sum()).backward()
+    # layer path
+    de_d, ae_d = de.to(dev), ae.to(dev)
+    xid, vd, a0d = x_init.to(dev).requires_grad_(True), v.to(dev).requires_grad_(True), a0.to(dev).requires_grad_(True)
+    kw, vjd = {}, None
+    if ev:
+        vjd = ev[2].to(dev).requires_grad_(True)
+        e = DAE_Event()
+        e.set_event(t=ev[0].to(dev), z=ev[1].to(dev), v=vjd)
+        kw = dict(event_fn=e.event_fn, jump_change_fn=e.jump_change_fn)
+    S = RK4 if solver == "rk4" else Euler
+    gx, gi = S().integrate_DAE(x_init=xid, x_func=de_d, i_func=ae_d, t=t.to(dev), x=x.to(dev), z=z.to(dev), v=vd, i=i.to(dev), all_initial=a0d, **kw)
+    assert _native.last_kernel().startswith("psn_lg_gemm_kernel"), _native.last_kernel()
+    assert torch.allclose(gx.detach().cpu(), sx.detach().float(), rtol=RTOL, atol=ATOL), tol_report(gx.detach().cpu(), sx.detach().float())
+    assert torch.allclose(gi.detach().cpu(), si.detach().float(), rtol=RTOL, atol=ATOL), tol_report(gi.detach().cpu(), si.detach().float())
+    ((gx * wx.to(dev)).sum() + (gi * wi.to(dev)).sum()).backward()
+    assert _native.last_kernel().startswith("psn_lg_"), _native.last_kernel()
+    ld = [m for m in de_d.x_dot if isinstance(m, torch.nn.Linear)]
+    la = [m for m in ae_d.i_calculator if isinstance(m, torch.nn.Linear)]
+    got = {"W1": ld[0].weight.grad, "b1": ld[0].bias.grad, "W2": ld[1].weight.grad, "b2": ld[1].bias.grad, "A1": la[0].weight.grad,
+           "ab1": la[0].bias.grad, "A2": la[1].weight.grad, "ab2": la[1].bias.grad, "v": vd.grad, "x_init": xid.grad, "a0": a0d.grad}
+    want = {"W1": pd[0][0].grad, "b1": pd[0][1].grad, "W2": pd[1][0].grad, "b2": pd[1][1].grad, "A1": pa[0][0].grad, "ab1": pa[0][1].grad,
+            "A2": pa[1][0].grad, "ab2": pa[1][1].grad, "v": v64.grad, "x_init": xi64.grad, "a0": a064.grad}
+    if ev:
+        got["v_jump"], want["v_jump"] = vjd.grad, vj64.grad
+    _compare_grads({k: g.detach().cpu() for k, g in got.items()}, want)
