@@ -20,18 +20,21 @@ using namespace psn_tc;
 constexpr int H = PSW_H;
 constexpr int NSLOT = 3;                           // ring slots; a slot holds a PAIR of records
 constexpr int BLK_BYTES = PSW_BLOCK * 4;           // 8 KB
-constexpr int GRAD_THREADS = 512;
+constexpr int SPLIT_WARPS = 16;                    // splitter / drain warps (one float4 of a block per thread)
+constexpr int GRAD_THREADS = (SPLIT_WARPS + 2) * 32;   // + TMA producer warp + MMA issuer warp
 
-// One slot = two records: per-iteration fixed costs (mbarrier waits, proxy fence, CTA barrier, MMA issue, refill) are ~1400 cycles
-// whatever the amount of work, which held the one-record-per-iteration version at 3.3 TB/s (50 % of the copy bandwidth) with the
-// tensor pipe 29 % busy; a pair halves that overhead per byte.  The two records of a pair are one accumulation chain (12 MMAs).
+// One slot = two records: per-iteration fixed costs (mbarrier waits, proxy fence, MMA issue, refill) are ~1400 cycles whatever the
+// amount of work, which held the one-record-per-iteration version at 3.3 TB/s (50 % of the copy bandwidth) with the tensor pipe
+// 29 % busy; a pair halves that overhead per byte.  The two records of a pair are one accumulation chain (12 MMAs).
 struct __align__(128) Slot {
     float a_hi[2][PSW_BLOCK], a_lo[2][PSW_BLOCK], b_hi[2][PSW_BLOCK], b_lo[2][PSW_BLOCK];
 };
 struct __align__(128) GradSmem {
     Slot slot[NSLOT];
-    uint64_t full[NSLOT];
-    uint64_t done[NSLOT];
+    uint64_t full[NSLOT];          // producer -> splitters (transaction count)
+    uint64_t split[NSLOT];         // splitters -> issuer   (16 warp arrivals)
+    uint64_t done[NSLOT];          // issuer (tcgen05.commit) -> producer (slot free) and drainers (accumulator complete)
+    uint64_t drained[2];           // drainers -> issuer: accumulator buffer may be overwritten
     uint32_t tmem_base;
 };
 
@@ -46,12 +49,16 @@ struct GradParams {
     int* err;
 };
 
+// Warp roles (as psn_lg_gemm_kernel): warps 0..15 split the operand blocks and drain the accumulators, warp 16 is the TMA producer,
+// warp 17 the MMA issuer; every role waits only on the mbarrier of the role before it, so loads, splits, MMAs and drains of
+// different pairs overlap up to the depth of the ring.  (Version 1: one CTA barrier per pair and thread 0 refilling inside the loop,
+// 3.7 TB/s = 57 % of the copy bandwidth.)
 __global__ void __launch_bounds__(GRAD_THREADS, 1) psn_wide_grad_kernel(const __grid_constant__ GradParams q) {
     extern __shared__ unsigned char smem_raw[];
     GradSmem& sm = *reinterpret_cast<GradSmem*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
     const int tid = threadIdx.x, lane = tid & 31;
     const int cw = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int wq = cw & 3, cc = cw >> 2;
+    const int wq = cw & 3, cc = (cw >> 2) & 3;
     const int role = blockIdx.x >= q.cta0[2] ? 2 : (blockIdx.x >= q.cta0[1] ? 1 : 0);
     const int ncta = q.cta0[role + 1] - q.cta0[role], me = blockIdx.x - q.cta0[role];
     const int64_t per = (q.nrec[role] + ncta - 1) / ncta;
@@ -63,7 +70,8 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) psn_wide_grad_kernel(const __
     const int64_t astr = q.a_stride[role], bstr = q.b_stride[role];
 
     if (tid == 0) {
-        for (int s = 0; s < NSLOT; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.done[s], 1); }
+        for (int s = 0; s < NSLOT; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.split[s], SPLIT_WARPS); mbar_init(&sm.done[s], 1); }
+        mbar_init(&sm.drained[0], SPLIT_WARPS); mbar_init(&sm.drained[1], SPLIT_WARPS);
         fence_mbar_init();
     }
     if (cw == 0) tmem_alloc(&sm.tmem_base, 256);
@@ -73,52 +81,30 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) psn_wide_grad_kernel(const __
     const uint32_t tmem = sm.tmem_base;
     const uint32_t lane_base = (uint32_t)(32 * wq) << 16;
 
-    auto load_pair = [&](int i) {            // thread 0
-        const int s = i % NSLOT;
-        const int cnt = (2 * i + 1 < n) ? 2 : 1;
-        mbar_expect_tx(&sm.full[s], (uint32_t)(2 * cnt * BLK_BYTES));
-        for (int k = 0; k < cnt; k++) {
-            bulk_g2s(sm.slot[s].a_hi[k], abase + (r0 + 2 * i + k) * astr, BLK_BYTES, &sm.full[s]);
-            bulk_g2s(sm.slot[s].b_hi[k], bbase + (r0 + 2 * i + k) * bstr, BLK_BYTES, &sm.full[s]);
-        }
-    };
-    if (tid == 0)
-        for (int i = 0; i < NSLOT && i < np; i++) load_pair(i);
-
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; i++) acc[i] = 0.0f;
-    const uint32_t idesc = make_idesc_tf32(H, H);
-    // drain accumulator `buf` (this thread: lane m = 32 wq + lane, columns 32 cc .. 32 cc + 31) into the register sums
-    auto drain = [&](int buf) {
-        float v0[16], v1[16];
-        tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)(buf * H + 32 * cc), v0);
-        tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)(buf * H + 32 * cc + 16), v1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; i++) { acc[i] += v0[i]; acc[16 + i] += v1[i]; }
-    };
-
-    for (int i = 0; i < np; i++) {
-        const int s = i % NSLOT;
-        Slot& sl = sm.slot[s];
-        const int cnt = (2 * i + 1 < n) ? 2 : 1;
-        if (!mbar_wait(&sm.full[s], (uint32_t)((i / NSLOT) & 1))) { atomicExch(q.err, 6); __trap(); }
-        {   // tf32 hi (in place) / lo split: 512 float4 per block
-            for (int k = 0; k < cnt; k++) {
-                float4* ah = reinterpret_cast<float4*>(sl.a_hi[k]); float4* al = reinterpret_cast<float4*>(sl.a_lo[k]);
-                float4* bh = reinterpret_cast<float4*>(sl.b_hi[k]); float4* bl = reinterpret_cast<float4*>(sl.b_lo[k]);
-                float4 lo;
-                float4 hi = split4_hi(ah[tid], lo);
-                ah[tid] = hi; al[tid] = lo;
-                hi = split4_hi(bh[tid], lo);
-                bh[tid] = hi; bl[tid] = lo;
+    if (cw == SPLIT_WARPS) {
+        // ---- TMA producer ----
+        if (elect_one()) {
+            for (int i = 0; i < np; i++) {
+                const int s = i % NSLOT;
+                if (i >= NSLOT && !mbar_wait(&sm.done[s], (uint32_t)(((i - NSLOT) / NSLOT) & 1))) { atomicExch(q.err, 7); __trap(); }
+                const int cnt = (2 * i + 1 < n) ? 2 : 1;
+                mbar_expect_tx(&sm.full[s], (uint32_t)(2 * cnt * BLK_BYTES));
+                for (int k = 0; k < cnt; k++) {
+                    bulk_g2s(sm.slot[s].a_hi[k], abase + (r0 + 2 * i + k) * astr, BLK_BYTES, &sm.full[s]);
+                    bulk_g2s(sm.slot[s].b_hi[k], bbase + (r0 + 2 * i + k) * bstr, BLK_BYTES, &sm.full[s]);
+                }
             }
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (cw == 0) {
+        __syncwarp();
+    } else if (cw == SPLIT_WARPS + 1) {
+        // ---- MMA issuer ----
+        const uint32_t idesc = make_idesc_tf32(H, H);
+        for (int i = 0; i < np; i++) {
+            const int s = i % NSLOT;
+            Slot& sl = sm.slot[s];
+            const int cnt = (2 * i + 1 < n) ? 2 : 1;
+            if (i >= 2 && !mbar_wait(&sm.drained[i & 1], (uint32_t)(((i - 2) >> 1) & 1))) { atomicExch(q.err, 10); __trap(); }
+            if (!mbar_wait(&sm.split[s], (uint32_t)((i / NSLOT) & 1))) { atomicExch(q.err, 11); __trap(); }
             if (elect_one()) {
                 tc_fence_after();
                 const uint32_t d = tmem + (uint32_t)((i & 1) * H);
@@ -142,32 +128,51 @@ __global__ void __launch_bounds__(GRAD_THREADS, 1) psn_wide_grad_kernel(const __
             }
             __syncwarp();
         }
-        // refill the slot of pair i - 1 (its MMAs were issued one iteration ago) with pair i - 1 + NSLOT
-        if (tid == 0 && i >= 1 && i - 1 + NSLOT < np) {
-            const int sp = (i - 1) % NSLOT;
-            if (!mbar_wait(&sm.done[sp], (uint32_t)(((i - 1) / NSLOT) & 1))) { atomicExch(q.err, 7); __trap(); }
-            fence_async_smem();
-            load_pair(i - 1 + NSLOT);
-        }
-        // drain the PREVIOUS pair's accumulator (round-to-nearest adds in registers) while this pair's MMAs run
-        if (i >= 1) {
-            if (!mbar_wait(&sm.done[(i - 1) % NSLOT], (uint32_t)(((i - 1) / NSLOT) & 1))) { atomicExch(q.err, 8); __trap(); }
+    } else {
+        // ---- splitters / drainers ----
+        float acc[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) acc[i] = 0.0f;
+        // drain the accumulator of pair `pi` (this thread: lane m = 32 wq + lane, columns 32 cc .. 32 cc + 31) into the register sums
+        auto drain = [&](int pi) {
+            if (!mbar_wait(&sm.done[pi % NSLOT], (uint32_t)((pi / NSLOT) & 1))) { atomicExch(q.err, 8); __trap(); }
             tc_fence_after();
-            drain((i - 1) & 1);
+            const int buf = pi & 1;
+            float v0[16], v1[16];
+            tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)(buf * H + 32 * cc), v0);
+            tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)(buf * H + 32 * cc + 16), v1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; i++) { acc[i] += v0[i]; acc[16 + i] += v1[i]; }
             tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.drained[buf]);
+        };
+        for (int i = 0; i < np; i++) {
+            const int s = i % NSLOT;
+            Slot& sl = sm.slot[s];
+            const int cnt = (2 * i + 1 < n) ? 2 : 1;
+            if (!mbar_wait(&sm.full[s], (uint32_t)((i / NSLOT) & 1))) { atomicExch(q.err, 6); __trap(); }
+            for (int k = 0; k < cnt; k++) {          // tf32 hi (in place) / lo split: 512 float4 per block
+                float4* ah = reinterpret_cast<float4*>(sl.a_hi[k]); float4* al = reinterpret_cast<float4*>(sl.a_lo[k]);
+                float4* bh = reinterpret_cast<float4*>(sl.b_hi[k]); float4* bl = reinterpret_cast<float4*>(sl.b_lo[k]);
+                float4 lo;
+                float4 hi = split4_hi(ah[tid], lo);
+                ah[tid] = hi; al[tid] = lo;
+                hi = split4_hi(bh[tid], lo);
+                bh[tid] = hi; bl[tid] = lo;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.split[s]);
+            if (i >= 1) drain(i - 1);                // the previous pair's accumulator, while this pair's MMAs run
         }
-    }
-    if (np > 0) {
-        if (!mbar_wait(&sm.done[(np - 1) % NSLOT], (uint32_t)(((np - 1) / NSLOT) & 1))) { atomicExch(q.err, 9); __trap(); }
-        tc_fence_after();
-        drain((np - 1) & 1);
-        tc_fence_before();
-    }
-    {
+        if (np > 0) drain(np - 1);
         float* slab = q.slabs + (int64_t)blockIdx.x * H * H + (int64_t)(32 * wq + lane) * H + 32 * cc;
 #pragma unroll
         for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(slab + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
     }
+    tc_fence_before();
     __syncthreads();
     if (cw == 0) tmem_dealloc(tmem, 256);
 }
