@@ -26,14 +26,18 @@ constexpr int TB = 64;                       // trajectories per tile (MMA N)
 constexpr int NSTAGE = 3;
 constexpr int SLAB = TB * 128;               // bytes of one 32-feature slab: TB rows x 128 B
 constexpr int TILE_BYTES = 4 * SLAB;         // 32 KB
-constexpr int PROJ_THREADS = 256;
+constexpr int WORK_THREADS = 256;            // 8 warps: split the tiles, run the epilogue
+constexpr int PROJ_THREADS = WORK_THREADS + 64;   // + TMA producer warp + MMA issuer warp
+constexpr int NPP = 2;                       // K-partials per accumulator buffer (two buffers: the epilogue of tile i overlaps the MMAs of tile i + 1)
 constexpr int TM_A_HI = 0, TM_A_LO = 128, TM_ACC = 256;
 
 struct __align__(1024) ProjSmem {
     unsigned char hi[NSTAGE][TILE_BYTES];    // TMA destination (raw fp32), overwritten in place by the tf32 hi parts
     unsigned char lo[NSTAGE][TILE_BYTES];
-    uint64_t full[NSTAGE];
-    uint64_t mma_bar;
+    uint64_t full[NSTAGE];                   // producer -> workers (transaction count)
+    uint64_t split[NSTAGE];                  // workers -> issuer (8 warp arrivals)
+    uint64_t done[NSTAGE];                   // issuer (tcgen05.commit) -> producer (stage free) and workers (accumulator complete)
+    uint64_t drained[2];                     // workers -> issuer: accumulator buffer may be overwritten
     uint32_t tmem_base;
 };
 
@@ -45,18 +49,21 @@ struct ProjParams {
     int* err;
 };
 
+// Warp roles: warps 0..7 split the tiles and run the epilogue, warp 8 is the TMA producer, warp 9 the MMA issuer; each role waits
+// only on the mbarrier of the role before it.  (Version 1 ran load-wait -> split -> CTA barrier -> MMA -> wait -> epilogue -> CTA
+// barrier serially per tile: 36 % of the copy bandwidth.)
 __global__ void __launch_bounds__(PROJ_THREADS, 1) psn_wide_proj_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ProjParams q) {
     extern __shared__ unsigned char smem_raw[];
     ProjSmem& sm = *reinterpret_cast<ProjSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, lane = tid & 31;
     const int cw = __shfl_sync(0xffffffffu, tid >> 5, 0);
-    const int wq = cw & 3, hh = cw >> 2;
+    const int wq = cw & 3, hh = (cw >> 2) & 1;
     const int ntiles = q.R * q.nbt;
     const int my_n = blockIdx.x < ntiles ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; s++) mbar_init(&sm.full[s], 1);
-        mbar_init(&sm.mma_bar, 1);
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.split[s], WORK_THREADS / 32); mbar_init(&sm.done[s], 1); }
+        mbar_init(&sm.drained[0], WORK_THREADS / 32); mbar_init(&sm.drained[1], WORK_THREADS / 32);
         fence_mbar_init();
         prefetch_tmap(&tmap);
     }
@@ -67,19 +74,8 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) psn_wide_proj_kernel(const __
     const uint32_t tmem = sm.tmem_base;
     const uint32_t lane_base = (uint32_t)(32 * wq) << 16;
 
-    auto issue_tile_load = [&](int i) {         // thread 0 only
-        const int tile = blockIdx.x + i * gridDim.x;
-        const int r = tile / q.nbt, b0 = (tile - r * q.nbt) * TB;
-        const int s = i % NSTAGE;
-        mbar_expect_tx(&sm.full[s], TILE_BYTES);
-#pragma unroll
-        for (int cb = 0; cb < 4; cb++) tma_load_3d(sm.hi[s] + cb * SLAB, &tmap, cb * 32, b0, r, &sm.full[s]);
-    };
-    if (tid == 0)
-        for (int i = 0; i < NSTAGE && i < my_n; i++) issue_tile_load(i);
-
     // ---- A (hi, lo) -> TMEM: lane m = output feature, columns = reduction index -----------------------------------------
-    {
+    if (cw < WORK_THREADS / 32) {
         const int m = 32 * wq + lane;
         for (int ch = 0; ch < 8; ch++) {
             const int k0 = 64 * hh + 8 * ch;
@@ -101,88 +97,119 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) psn_wide_proj_kernel(const __
     __syncthreads();
     tc_fence_after();
 
-    const uint32_t idesc = make_idesc_tf32(128, TB);
-    for (int i = 0; i < my_n; i++) {
-        const int s = i % NSTAGE;
-        const int tile = blockIdx.x + i * gridDim.x;
-        const int r = tile / q.nbt, b0 = (tile - r * q.nbt) * TB;
-        // the per-trajectory constants of this thread's 32 outputs are fetched before anything is waited on (they were on the
-        // critical path of the epilogue: long_scoreboard 9.4 -> 1.5 warps per issue cycle, 2.09 -> 0.9 ms at the cfg4 shard)
-        float cadd[32];
+    if (cw == WORK_THREADS / 32) {
+        // ---- TMA producer ----
+        if (elect_one()) {
+            for (int i = 0; i < my_n; i++) {
+                const int s = i % NSTAGE;
+                if (i >= NSTAGE && !mbar_wait(&sm.done[s], (uint32_t)(((i - NSTAGE) / NSTAGE) & 1))) { atomicExch(q.err, 4); __trap(); }
+                const int tile = blockIdx.x + i * gridDim.x;
+                const int r = tile / q.nbt, b0 = (tile - r * q.nbt) * TB;
+                mbar_expect_tx(&sm.full[s], TILE_BYTES);
 #pragma unroll
-        for (int e = 0; e < 32; e++) {
-            const int b = min(b0 + 32 * hh + e, q.B - 1);
-            cadd[e] = q.add ? __ldg(q.add + (int64_t)b * q.add_sb + 32 * wq + lane) : 0.0f;
-        }
-        if (!mbar_wait(&sm.full[s], (uint32_t)((i / NSTAGE) & 1))) { atomicExch(q.err, 2); __trap(); }
-        // split the raw fp32 tile into tf32 hi (in place) and lo parts; elementwise, so the swizzled layout is preserved
-        {
-            float4* h4 = reinterpret_cast<float4*>(sm.hi[s]);
-            float4* l4 = reinterpret_cast<float4*>(sm.lo[s]);
-#pragma unroll
-            for (int e = 0; e < TILE_BYTES / 16 / PROJ_THREADS; e++) {
-                const int idx = tid + e * PROJ_THREADS;
-                float4 lo;
-                const float4 hi = split4_hi(h4[idx], lo);
-                h4[idx] = hi;
-                l4[idx] = lo;
+                for (int cb = 0; cb < 4; cb++) tma_load_3d(sm.hi[s] + cb * SLAB, &tmap, cb * 32, b0, r, &sm.full[s]);
             }
         }
-        fence_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        if (cw == 0) {
+        __syncwarp();
+    } else if (cw == WORK_THREADS / 32 + 1) {
+        // ---- MMA issuer: partial accumulator p of buffer (i & 1) <- K slabs 2p, 2p + 1 (32 features each) ----
+        const uint32_t idesc = make_idesc_tf32(128, TB);
+        for (int i = 0; i < my_n; i++) {
+            const int s = i % NSTAGE;
+            if (i >= 2 && !mbar_wait(&sm.drained[i & 1], (uint32_t)(((i - 2) >> 1) & 1))) { atomicExch(q.err, 5); __trap(); }
+            if (!mbar_wait(&sm.split[s], (uint32_t)((i / NSTAGE) & 1))) { atomicExch(q.err, 6); __trap(); }
             if (elect_one()) {
                 tc_fence_after();
                 const uint64_t d_hi = make_desc_sw128(smem_u32(sm.hi[s])), d_lo = make_desc_sw128(smem_u32(sm.lo[s]));
+                const uint32_t acc0 = tmem + TM_ACC + (uint32_t)((i & 1) * NPP * TB);
 #pragma unroll 1
-                for (int p = 0; p < 4; p++) {                     // partial accumulator p <- K slab p (32 features)
+                for (int p = 0; p < NPP; p++) {
                     uint32_t accumulate = 0;
 #pragma unroll
                     for (int term = 0; term < 3; term++) {        // small terms first
-                        const uint32_t a_col = (term == 0 ? TM_A_LO : TM_A_HI) + 32 * p;
-                        const uint64_t bd = (term == 1 ? d_lo : d_hi) + (uint64_t)((p * SLAB) >> 4);
 #pragma unroll
-                        for (int kk = 0; kk < 4; kk++) {
-                            mma_tf32_ts(tmem + TM_ACC + TB * p, tmem + a_col + 8 * kk, bd + (uint64_t)(2 * kk), idesc, accumulate);
-                            accumulate = 1;
+                        for (int sl = 0; sl < 2; sl++) {
+                            const int slab = 2 * p + sl;
+                            const uint32_t a_col = (term == 0 ? TM_A_LO : TM_A_HI) + 32 * slab;
+                            const uint64_t bd = (term == 1 ? d_lo : d_hi) + (uint64_t)((slab * SLAB) >> 4);
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++) {
+                                mma_tf32_ts(acc0 + TB * p, tmem + a_col + 8 * kk, bd + (uint64_t)(2 * kk), idesc, accumulate);
+                                accumulate = 1;
+                            }
                         }
                     }
                 }
-                mma_commit(&sm.mma_bar);
+                mma_commit(&sm.done[s]);
             }
             __syncwarp();
         }
-        if (!mbar_wait(&sm.mma_bar, (uint32_t)(i & 1))) { atomicExch(q.err, 3); __trap(); }
-        tc_fence_after();
-        if (tid == 0 && i + NSTAGE < my_n) { fence_async_smem(); issue_tile_load(i + NSTAGE); }   // stage s is free again
-        // ---- epilogue: sum the 4 partials, add the per-trajectory constant, store 128-byte lines ----------------------
-        {
-            const int m = 32 * wq + lane;
+    } else {
+        // ---- workers: split tile i, then the epilogue of tile i - 1 while the MMAs of tile i run ----
+        const int m = 32 * wq + lane;
+        float cadd_cur[32], cadd_prev[32];
+        int r_prev = 0, b0_prev = 0;
+        auto load_cadd = [&](int b0, float (&c)[32]) {
+#pragma unroll
+            for (int e = 0; e < 32; e++) {
+                const int b = min(b0 + 32 * hh + e, q.B - 1);
+                c[e] = q.add ? __ldg(q.add + (int64_t)b * q.add_sb + m) : 0.0f;
+            }
+        };
+        // sum the partials, add the per-trajectory constant, store 128-byte lines
+        auto epilogue = [&](int pi, int r, int b0, const float (&c)[32]) {
+            if (!mbar_wait(&sm.done[pi % NSTAGE], (uint32_t)((pi / NSTAGE) & 1))) { atomicExch(q.err, 3); __trap(); }
+            tc_fence_after();
+            const uint32_t acc0 = tmem + lane_base + TM_ACC + (uint32_t)((pi & 1) * NPP * TB);
 #pragma unroll
             for (int ch = 0; ch < 4; ch++) {
                 const int n0 = 32 * hh + 8 * ch;
-                float t0[8], t1[8], t2[8], t3[8];
-                const uint32_t a = tmem + lane_base + TM_ACC + n0;
-                tmem_ld_32x32b_x8(a, t0);
-                tmem_ld_32x32b_x8(a + TB, t1);
-                tmem_ld_32x32b_x8(a + 2 * TB, t2);
-                tmem_ld_32x32b_x8(a + 3 * TB, t3);
+                float t0[8], t1[8];
+                tmem_ld_32x32b_x8(acc0 + n0, t0);
+                tmem_ld_32x32b_x8(acc0 + TB + n0, t1);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i2 = 0; i2 < 8; i2++) {
                     const int b = b0 + n0 + i2;
-                    if (b < q.B) {
-                        const float v = ((t0[i2] + t1[i2]) + (t2[i2] + t3[i2])) + cadd[8 * ch + i2];
-                        q.out[(int64_t)r * q.out_sr + (int64_t)b * q.out_sb + m] = v;
-                    }
+                    if (b < q.B) q.out[(int64_t)r * q.out_sr + (int64_t)b * q.out_sb + m] = (t0[i2] + t1[i2]) + c[8 * ch + i2];
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.drained[pi & 1]);
+        };
+        for (int i = 0; i < my_n; i++) {
+            const int s = i % NSTAGE;
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int r = tile / q.nbt, b0 = (tile - r * q.nbt) * TB;
+            // the per-trajectory constants of this thread's 32 outputs are fetched before anything is waited on (they were on the
+            // critical path of the epilogue: long_scoreboard 9.4 -> 1.5 warps per issue cycle, 2.09 -> 0.9 ms at the cfg4 shard)
+            load_cadd(b0, cadd_cur);
+            if (!mbar_wait(&sm.full[s], (uint32_t)((i / NSTAGE) & 1))) { atomicExch(q.err, 2); __trap(); }
+            {   // raw fp32 tile -> tf32 hi (in place) and lo parts; elementwise, so the swizzled layout is preserved
+                float4* h4 = reinterpret_cast<float4*>(sm.hi[s]);
+                float4* l4 = reinterpret_cast<float4*>(sm.lo[s]);
+#pragma unroll
+                for (int e = 0; e < TILE_BYTES / 16 / WORK_THREADS; e++) {
+                    const int idx = tid + e * WORK_THREADS;
+                    float4 lo;
+                    const float4 hi = split4_hi(h4[idx], lo);
+                    h4[idx] = hi;
+                    l4[idx] = lo;
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.split[s]);
+            if (i >= 1) epilogue(i - 1, r_prev, b0_prev, cadd_prev);
+#pragma unroll
+            for (int e = 0; e < 32; e++) cadd_prev[e] = cadd_cur[e];
+            r_prev = r; b0_prev = b0;
         }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
+        if (my_n > 0) epilogue(my_n - 1, r_prev, b0_prev, cadd_prev);
     }
+    tc_fence_before();
+    __syncthreads();
     if (cw == 0) tmem_dealloc(tmem, 512);
 }
 
