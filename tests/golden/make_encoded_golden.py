@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Golden fixture for the fused encoder / decoder entry (`integrate_DAE_encoded`): the UNMODIFIED reference's
 `DAE_Model.forward` (neural_01_DAE_02_direct_encode.py:126-153) at hidden_dim = 128 -- the width the tensor-core layer path
-covers -- run on the CPU with Euler and RK4; forward outputs only (fp32 and an fp64 restatement through the same code).
+covers -- run on the CPU with Euler and RK4: forward outputs (fp32 and an fp64 restatement through the same code) and, for RK4, the
+script's training loss and every parameter gradient of the fp64 restatement (stored as fp32), so that the layer path's reverse sweep is
+checked inside the script's own pipeline against the reference's autograd (tests/test_gpu_real_scripts.py).
 The ODE counterpart is script_ode02.npz (hidden_dim = 128 already, make_script_golden.py).
 
     python tests/golden/make_encoded_golden.py        # build container only (needs oracle/_ref or /root/reference)
@@ -20,7 +22,8 @@ def main():
     import numpy as np
     import torch
     import ref_runner
-    from make_script_golden import make_inputs
+    import torch.nn.functional as F
+    from make_script_golden import make_inputs, script_loss
     torch.set_num_threads(1)
     nd, importlib = ref_runner.load_reference()
     mod = importlib.import_module("neural_01_DAE_02_direct_encode")
@@ -47,6 +50,15 @@ def main():
         for k in range(2):                        # x_pred, i_pred (the reconstruction outputs do not touch the solver)
             out[f"{sname}_pred{k}"] = preds[k].numpy().copy()
             out[f"{sname}_pred64_{k}"] = preds64[k].numpy().copy()
+    # training loss + gradients of the fp64 restatement (the arbiter), RK4
+    m64 = copy.deepcopy(base).double()
+    m64.solver = nd.RK4()
+    loss64, _ = script_loss("dae02", m64, {k: v.double() for k, v in d.items()}, F)
+    loss64.backward()
+    out["rk4_loss64"] = np.array(loss64.item(), dtype=np.float64)
+    for k, p in m64.named_parameters():
+        if p.grad is not None:
+            out[f"rk4_g64_{k}"] = p.grad.detach().numpy().astype(np.float32)
     path = os.path.join(HERE, "script_dae02_h128.npz")
     np.savez_compressed(path, **out)
     print(f"{path}: {len(out)} arrays, {os.path.getsize(path) / 1e3:.0f} KB")

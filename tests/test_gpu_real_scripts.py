@@ -97,3 +97,47 @@ def test_real_script_model_on_gpu(scripts, name, solver):
         big = torch.from_numpy(np.abs(g[gkey]) > 1e-6)
         assert torch.allclose(got[big], after[big], rtol=0, atol=2e-3 * LR), f"{name}/{solver} weights after Adam step: {pname}"
         assert float((got - before).abs().max()) <= 1.001 * LR + 1e-9
+
+
+def test_real_dae02_model_hidden128_trains_on_the_layer_path(scripts):
+    """The DAE_02 script's own `DAE_Model` at hidden_dim = 128 (the width of the tensor-core layer path; its `--hidden` default): forward,
+    the script's loss and EVERY parameter gradient -- through init_func, the five encoders / decoders, de_func and ae_func, i.e. the
+    layer path's reverse sweep incl. its latent-input, jump, x_init and all_initial gradients chained into torch autograd -- against the
+    float64 restatement the unmodified reference produced (tests/golden/make_encoded_golden.py)."""
+    import neural_dae
+    from make_script_golden import script_loss
+    from py_psnode_b200 import _native
+    mod = scripts["dae02"]
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "script_dae02_h128.npz"), allow_pickle=False))
+    kw = {str(k): int(v) for k, v in zip(g["kw_keys"], g["kw_vals"])}
+    dev = torch.device("cuda:0")
+    model = mod.DAE_Model(**kw)
+    model.load_state_dict({k[2:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("w_")})
+    model = model.to(dev)
+    model.solver = neural_dae.RK4()
+    d = {k[3:]: torch.from_numpy(v).to(dev) for k, v in g.items() if k.startswith("in_")}
+    model.train()
+    loss, preds = script_loss("dae02", model, d, torch.nn.functional)
+    fwd_kernel = _native.last_kernel()
+    assert fwd_kernel.startswith("psn_lg_gemm_kernel"), fwd_kernel
+    loss.backward()
+    assert _native.last_kernel().startswith("psn_lg_"), _native.last_kernel()
+    for k in range(2):
+        want, want64 = torch.from_numpy(g[f"rk4_pred{k}"]), torch.from_numpy(g[f"rk4_pred64_{k}"])
+        got = preds[k].detach().cpu()
+        assert torch.allclose(got, want, rtol=RTOL, atol=ATOL), f"output {k}: " + tol_report(got, want, want64)
+    assert abs(loss.item() - float(g["rk4_loss64"])) <= 1e-5 * abs(float(g["rk4_loss64"])) + 1e-7
+    report, bad = [], []
+    for pname, p in model.named_parameters():
+        key = f"rk4_g64_{pname}"
+        if key not in g:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, pname
+            continue
+        g64 = torch.from_numpy(g[key]).double()
+        got = p.grad.detach().cpu().double()
+        scale, err = float(g64.abs().max()), float((got - g64).abs().max())
+        report.append(f"{pname}: err {err:.2e} scale {scale:.2e} rel {err / max(scale, 1e-30):.1e}")
+        if not err <= 2e-5 * scale + 1e-8:
+            bad.append(report[-1])
+    print("dae02 hidden 128 / rk4 [" + fwd_kernel + "]\n  " + "\n  ".join(report))
+    assert not bad, bad
