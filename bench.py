@@ -469,13 +469,13 @@ def _encoded_leg(w, solver, de, ae, resident, B, n_steps, units, active, barrier
             "raw_widths": {"x": XR, "z": ZR, "v": VR, "i": IR},
             "peak_hbm_gib_above_inputs": peak_gib,
             "latent_series_gib_unfused": (4 if dae else 2) * T * B * H * 4 / 2 ** 30,
-            "note": ("runs on the per-layer GEMM kernel (impl = layer); device-resident, the unfused ODE path has the faster TMEM-resident wide "
-                     "kernel at latent width 128, but END TO END (host buffers) the fused entry wins: it moves the raw series and the decoded "
-                     "trajectories over PCIe instead of the 64x wider latent ones (compare `e2e` here with the workload's `e2e`)" if H == 128 else
+            "note": ("latent ODE_02 net: the wide kernels with the projection tiles generated from the raw series (psn_wide_forward_encoded) + the "
+                     "decoder over the latent scratch; END TO END it moves the raw series and the decoded trajectories over PCIe instead of the "
+                     "64x wider latent ones (compare `e2e` here with the workload's `e2e`)" if H == 128 else
                      "faster than torch encoders -> integrate_DAE -> torch decoders (740 ms at this shard), O(chunk) memory, and end to end it "
                      "covers ALL grid steps with 2.4 GB over PCIe (the unfused e2e leg needs 6.8 GB per 200 steps)"),
-            "what": "Model.forward pipeline of the *_02 scripts in one call from the raw series: encoders generated inside the hoisted projection "
-                    "GEMMs, integration in 64-row time chunks, decoders before the store (psnode_forward_encoded); outputs decoded (T,B,x_dim)"}
+            "what": "Model.forward pipeline of the *_02 scripts in one call from the raw series: encoder hidden layers generated inside the hoisted "
+                    "projection GEMMs, decoders before the store (psnode_forward_encoded); outputs decoded (T,B,x_dim)"}
 
 
 def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):

@@ -217,12 +217,14 @@ int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* work
 }
 
 int64_t psnode_forward_encoded_workspace(const psnode_problem* p, const psnode_codec* c) {
+    if (psn_wide_encoded_supports(p, c)) return psn_wide_encoded_workspace(p, c);
     if (!psn_lg_encoded_supports(p, c)) return 0;
     return psn_lg_encoded_workspace(p, c);
 }
 
 int psnode_forward_encoded(const psnode_problem* p, const psnode_codec* c, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!p || !c) return PSNODE_EINVAL;
+    if (psn_wide_encoded_supports(p, c)) return psn_wide_forward_encoded(p, c, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if (!psn_lg_encoded_supports(p, c)) return PSNODE_EUNSUPPORTED;
     return psn_lg_forward_encoded(p, c, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }

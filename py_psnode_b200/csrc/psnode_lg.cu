@@ -1423,6 +1423,66 @@ int psn_lg_forward_encoded(const psnode_problem* p, const psnode_codec* cd, void
     return PSNODE_OK;
 }
 
+// ---- decoder alone (used by the wide kernels' encoded entry): out[r] = D2 ELU(D1 src[r] + d1) + d2 over R contiguous (B, H) rows ----
+namespace {
+constexpr int DEC_RC = 64;           // latent rows per pass (the hidden layer of the decoder lives in an (rc, B, H) scratch)
+struct DecLayout { int64_t err, hi1, lo1, hi2, lo2, tmp, total; };
+DecLayout dec_layout(int B, int H) {
+    DecLayout L;
+    int64_t o = 64;
+    L.err = 0;
+    L.hi1 = o; o += al((int64_t)H * H); L.lo1 = o; o += al((int64_t)H * H);
+    L.hi2 = o; o += al((int64_t)128 * H); L.lo2 = o; o += al((int64_t)128 * H);
+    L.tmp = o; o += al((int64_t)DEC_RC * B * H);
+    L.total = o;
+    return L;
+}
+}  // namespace
+int64_t psn_lg_decode_workspace(int B, int H) { return dec_layout(B, H).total * 4; }
+
+int psn_lg_decode(const psnode_mlp* dec, int width, const float* src, int R, int B, int H, const psnode_series_out* out, void* ws, int64_t ws_bytes,
+                  cudaStream_t stream) {
+    const DecLayout L = dec_layout(B, H);
+    if (!ws || ws_bytes < L.total * 4) return PSNODE_EWORKSPACE;
+    if ((H != 128 && H != 256) || width < 1 || width > 128 || dec->n_layers != 2 || !lg_encode_fn()) return PSNODE_EUNSUPPORTED;
+    if (lg_prepare_kernels() != PSNODE_OK) return PSNODE_ECUDA;
+    float* w = static_cast<float*>(ws);
+    int* err = reinterpret_cast<int*>(w);
+    const int64_t BH = (int64_t)B * H;
+    PSN_CUDA(cudaMemsetAsync(err, 0, 256, stream));
+    PSN_CUDA(cudaMemsetAsync(w + L.hi2, 0, (size_t)128 * H * 4, stream));
+    PSN_CUDA(cudaMemsetAsync(w + L.lo2, 0, (size_t)128 * H * 4, stream));
+    psn_lg_prep2_kernel<<<(H * H + 255) / 256, 256, 0, stream>>>(dec->W[0], H, 0, -1, 0.0f, 0, H, H, H, w + L.hi1, w + L.lo1);
+    psn_lg_prep2_kernel<<<(width * H + 255) / 256, 256, 0, stream>>>(dec->W[1], H, 0, -1, 0.0f, 0, width, H, H, w + L.hi2, w + L.lo2);
+    psn_count_launch("psn_lg_prep_kernel"); psn_count_launch("psn_lg_prep_kernel");
+    CUtensorMap a1h, a1l, a2h, a2l, m_src, m_tmp;
+    bool ok = lg_make_map(&a1h, w + L.hi1, H, H, H, 1, 0) && lg_make_map(&a1l, w + L.lo1, H, H, H, 1, 0) && lg_make_map(&a2h, w + L.hi2, H, 128, H, 1, 0) &&
+              lg_make_map(&a2l, w + L.lo2, H, 128, H, 1, 0) && lg_make_map(&m_src, src, H, B, H, R, BH) && lg_make_map(&m_tmp, w + L.tmp, H, B, H, DEC_RC, BH);
+    if (!ok) return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (decoder)");
+    LgParams base;
+    std::memset(&base, 0, sizeof(base));
+    base.N = B; base.R = 1; base.nbt = (B + TN - 1) / TN; base.nsrc = 1; base.kchunks = H / 32; base.mode = LG_PLAIN;
+    base.add1_ld = H; base.add2_ld = H; base.out_ld = H; base.st_ld = H;
+    base.err = err; base.rotate = 1;
+    for (int r0 = 0; r0 < R; r0 += DEC_RC) {
+        const int n = r0 + DEC_RC < R ? DEC_RC : R - r0;
+        LgParams q = base;
+        q.mode = LG_HIDDEN;
+        q.R = n; q.b_r0 = r0;
+        q.bias = dec->b[0];
+        q.out = w + L.tmp; q.out_sr = BH;
+        lg_launch_gemm(a1h, a1l, m_src, m_src, q, H / TM, stream, "psn_lg_gemm_kernel<dec1>");
+        LgParams q2 = base;
+        q2.R = n;
+        q2.bias = dec->b[1];
+        q2.m_live = width;
+        q2.out = out->p + (int64_t)r0 * out->st; q2.out_sr = out->st; q2.out_ld = out->sb;
+        lg_launch_gemm(a2h, a2l, m_tmp, m_tmp, q2, 1, stream, "psn_lg_gemm_kernel<dec2>");
+    }
+    PSN_CUDA(cudaGetLastError());
+    return PSNODE_OK;
+}
+
 // ---- reverse sweep (discrete adjoint) on the same per-layer GEMM kernel --------------------------------------------------------
 // Exact reverse mode of the loop above (what loss.backward() replays in the reference, neural_01_DAE_02_direct_encode.py training
 // loop -> my_solvers.py:82-131).  Nothing of the forward pass is kept except the trajectory: x_sol / i_sol are the checkpoints, and

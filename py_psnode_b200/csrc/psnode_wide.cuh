@@ -66,6 +66,14 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
 bool psn_lg_encoded_supports(const psnode_problem* p, const psnode_codec* c);
 int64_t psn_lg_encoded_workspace(const psnode_problem* p, const psnode_codec* c);
 int psn_lg_forward_encoded(const psnode_problem* p, const psnode_codec* c, void* ws, int64_t ws_bytes, cudaStream_t stream);
+// the same entry for the latent ODE_02 net (X = Z = H = 128) on the wide kernels: generated projection tiles, TMEM-resident time loop
+bool psn_wide_encoded_supports(const psnode_problem* p, const psnode_codec* c);
+int64_t psn_wide_encoded_workspace(const psnode_problem* p, const psnode_codec* c);
+int psn_wide_forward_encoded(const psnode_problem* p, const psnode_codec* c, void* ws, int64_t ws_bytes, cudaStream_t stream);
+// decoder Linear(H -> H) . ELU . Linear(H -> width <= 128) over R contiguous latent rows (R, B, H) -> out rows (psnode_lg.cu)
+int64_t psn_lg_decode_workspace(int B, int H);
+int psn_lg_decode(const psnode_mlp* dec, int width, const float* src, int R, int B, int H, const psnode_series_out* out, void* ws, int64_t ws_bytes,
+                  cudaStream_t stream);
 
 // ---- row GEMM over a whole series (psnode_wide_proj.cu) ------------------------------------------------------------------
 // out[r][b][0:128] = A . in[r][b][0:128] (+ add[b][0:128]),  A[m][k] = W[m*ldw + k] or (transpose) W[k*ldw + m], optionally
@@ -77,6 +85,10 @@ struct PswProjJob {
     const float* add; int64_t add_sb;             // nullable
     float* out; int64_t out_sr, out_sb;
     int zero_rows_from;                           // rows r >= this are written as zeros (no GEMM); R if none
+    // encoder fusion (psnode_forward_encoded): `in` is not read; its tile is generated in shared memory as the hidden layer of the input
+    // encoder, in[r][b][k] = ELU(sum_c gen_W[k][c] * gen_raw[r][b][c] + gen_b[k]), from the raw (R, B, gen_w <= 8) series
+    const float* gen_raw = nullptr; int64_t gen_sr = 0, gen_sb = 0; int gen_w = 0;
+    const float* gen_W = nullptr; const float* gen_b = nullptr;
 };
 int psn_wide_proj(const PswProjJob& job, int* err_flag, cudaStream_t stream, const char* name);
 // c[b][m] = b1[m] + sum_k (W1[m][k] - W1[m][S + k]) * a0[b][k],  S = 256 (fp32 FMA; B x 128 outputs)

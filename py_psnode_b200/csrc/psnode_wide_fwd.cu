@@ -410,3 +410,132 @@ int psn_wide_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaSt
     }
 #undef PSW_FWD
 }
+
+// ---- encoded entry on the wide kernels (psnode_forward_encoded for the latent ODE_02 net, ODE_Model.forward,
+//      neural_00_ODE_02_direct_encode.py:75-89) ------------------------------------------------------------------------------------------
+// z_encoder = L(raw -> 128) . ELU . L(128 -> 128): its second Linear is folded into the hoisted half of layer 1 (A = F_z E2, constant
+// F_z e2 added to c), its hidden layer is generated inside the projection kernel's shared-memory tile from the raw (T, B, <= 8) series
+// (PswProjJob::gen_*), so the encoded series Zh never exists; the time loop is the TMEM-resident kernel above writing the latent
+// trajectory into workspace scratch, and x_decoder runs over that scratch 64 rows at a time (psn_lg_decode).
+namespace {
+// A[m][k] = sum_h F_z[m][h] E2[h][k],  F_z[m][h] = (W_b + W_c)[m][X + h];  cfold[m] = sum_h F_z[m][h] e2[h]
+__global__ void psn_wide_fold_enc_kernel(const float* __restrict__ W1, const float* __restrict__ E2, const float* __restrict__ e2,
+                                         float* __restrict__ A, float* __restrict__ cfold) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * H) return;
+    const int m = idx / H, k = idx - m * H;
+    float acc = 0.0f, accb = 0.0f;
+    for (int h = 0; h < H; h++) {
+        const float f = __ldg(W1 + (int64_t)m * (6 * H) + 3 * H + h) + __ldg(W1 + (int64_t)m * (6 * H) + 5 * H + h);
+        acc = fmaf(f, __ldg(E2 + h * H + k), acc);
+        if (k == 0) accb = fmaf(f, __ldg(e2 + h), accb);
+    }
+    A[idx] = acc;
+    if (k == 0) cfold[m] = accb;
+}
+__global__ void psn_wide_add_rowvec_kernel(float* __restrict__ c, const float* __restrict__ v, int64_t n) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) c[idx] += __ldg(v + (idx % H));
+}
+struct EncLayout { int64_t err, c, A, cfold, pre, xs, dec, total; };
+EncLayout enc_layout(const psnode_problem* p) {
+    EncLayout L;
+    const int E = p->event_idx ? p->E : 0;
+    auto al = [](int64_t f) { return (f + 63) & ~(int64_t)63; };
+    int64_t o = 64;
+    L.err = 0;
+    L.c = o; o += al(wide_c_floats(p->B));
+    L.A = o; o += al((int64_t)H * H);
+    L.cfold = o; o += al(H);
+    L.pre = o; o += al(psw_pre_floats(p->B, p->T, E) + PSW_BLOCK);
+    L.xs = o; o += al((int64_t)p->T * p->B * H);
+    L.dec = o; o += al(psn_lg_decode_workspace(p->B, H) / 4);
+    L.total = o;
+    return L;
+}
+}  // namespace
+
+bool psn_wide_encoded_supports(const psnode_problem* p, const psnode_codec* cd) {
+    if (!p || !cd || p->kind != PSNODE_ODE || p->teacher_x || p->X != H || p->Z != H || p->V || p->I) return false;
+    if (p->de.n_layers != 2 || p->de.in_dim[0] != 6 * H || p->de.out_dim[0] != H || p->de.out_dim[1] != H) return false;
+    const psnode_mlp& ze = cd->z_enc;
+    const psnode_mlp& xd = cd->x_dec;
+    if (ze.n_layers != 2 || cd->ZR < 1 || cd->ZR > 8 || ze.in_dim[0] != cd->ZR || ze.out_dim[0] != H || ze.in_dim[1] != H || ze.out_dim[1] != H) return false;
+    if (xd.n_layers != 2 || cd->XR < 1 || cd->XR > 128 || xd.in_dim[0] != H || xd.out_dim[0] != H || xd.in_dim[1] != H || xd.out_dim[1] != cd->XR) return false;
+    if (!cd->z_raw.p || !cd->x_out.p || !p->t.p || !p->a0 || !p->x.p) return false;
+    if (p->event_idx && (p->E < 1 || !cd->zj_raw)) return false;
+    static const bool off = std::getenv("PSNODE_ENCODED_WIDE") && std::atoi(std::getenv("PSNODE_ENCODED_WIDE")) == 0;
+    return !off;
+}
+
+int64_t psn_wide_encoded_workspace(const psnode_problem* p, const psnode_codec* cd) {
+    (void)cd;
+    return enc_layout(p).total * 4;
+}
+
+int psn_wide_forward_encoded(const psnode_problem* p, const psnode_codec* cd, void* ws, int64_t ws_bytes, cudaStream_t stream) {
+    const EncLayout L = enc_layout(p);
+    if (ws == nullptr || ws_bytes < L.total * 4) return PSNODE_EWORKSPACE;
+    float* w = static_cast<float*>(ws);
+    int* err = reinterpret_cast<int*>(w);
+    const int E = p->event_idx ? p->E : 0;
+    const int T = p->T, B = p->B;
+    const int64_t bpad = psw_bpad(B);
+    float* c = w + L.c;
+    float* pre = w + L.pre;
+    float* xs = w + L.xs;
+    PSN_CUDA(cudaMemsetAsync(err, 0, 256, stream));
+    const float* W1 = p->de.W[0];
+    if (T > 1) {
+        int st = psn_wide_const(W1, p->de.b[0], p->a0, p->a0_sb, B, c, stream);
+        if (st != PSNODE_OK) return st;
+        psn_wide_fold_enc_kernel<<<(H * H + 255) / 256, 256, 0, stream>>>(W1, cd->z_enc.W[1], cd->z_enc.b[1], w + L.A, w + L.cfold);
+        psn_count_launch("psn_wide_fold_enc_kernel");
+        psn_wide_add_rowvec_kernel<<<(int)(((int64_t)B * H + 255) / 256), 256, 0, stream>>>(c, w + L.cfold, (int64_t)B * H);
+        psn_count_launch("psn_wide_add_rowvec_kernel");
+        PswProjJob job;
+        job.in = nullptr; job.in_sr = 0; job.in_sb = 0;
+        job.R = T - 1; job.B = B;
+        job.W = w + L.A; job.W2 = nullptr; job.ldw = H; job.transpose = 0;
+        job.add = c; job.add_sb = H;
+        job.out = pre; job.out_sr = bpad * H; job.out_sb = H;
+        job.zero_rows_from = job.R;
+        job.gen_raw = cd->z_raw.p; job.gen_sr = cd->z_raw.st; job.gen_sb = cd->z_raw.sb; job.gen_w = cd->ZR;
+        job.gen_W = cd->z_enc.W[0]; job.gen_b = cd->z_enc.b[0];
+        st = psn_wide_proj(job, err, stream, "psn_wide_proj_kernel<pre,enc>");
+        if (st != PSNODE_OK) return st;
+        if (E > 0) {
+            job.R = E;
+            job.out = pre + (int64_t)(T - 1) * bpad * H;
+            job.gen_raw = cd->zj_raw; job.gen_sr = cd->zjr_se; job.gen_sb = cd->zjr_sb;
+            st = psn_wide_proj(job, err, stream, "psn_wide_proj_kernel<pre_jump,enc>");
+            if (st != PSNODE_OK) return st;
+        }
+    }
+    WideFwdParams q;
+    q.B = B; q.T = T; q.ngroups = psw_ngroups(B);
+    q.t = p->t; q.x = p->x;
+    q.event_idx = p->event_idx;
+    q.pre = pre; q.pre_sr = bpad * H;
+    q.W1 = W1; q.W2 = p->de.W[1]; q.b2 = p->de.b[1];
+    q.x_sol.p = xs; q.x_sol.st = (int64_t)B * H; q.x_sol.sb = H;
+    q.tape = nullptr;
+    q.err = err;
+    const int grid = (q.ngroups + PSW_GROUPS_PER_CTA - 1) / PSW_GROUPS_PER_CTA;
+    const int smem = (int)sizeof(CtaSmem) + 128;
+    auto launch = [&](auto kern, const char* name) -> int {
+        PSN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, PSW_GROUPS_PER_CTA * GROUP_THREADS, smem, stream>>>(q);
+        psn_count_launch(name);
+        PSN_CUDA(cudaGetLastError());
+        return PSNODE_OK;
+    };
+    int st;
+    switch (p->method) {
+        case PSNODE_EULER: st = launch(psn_wide_fwd_kernel<PSNODE_EULER, false, 4>, "psn_wide_fwd_kernel<euler>"); break;
+        case PSNODE_MIDPOINT: st = launch(psn_wide_fwd_kernel<PSNODE_MIDPOINT, false, 4>, "psn_wide_fwd_kernel<midpoint>"); break;
+        default: st = launch(psn_wide_fwd_kernel<PSNODE_RK4, false, 4>, "psn_wide_fwd_kernel<rk4>"); break;
+    }
+    if (st != PSNODE_OK) return st;
+    return psn_lg_decode(&cd->x_dec, cd->XR, xs, T, B, H, &cd->x_out, w + L.dec, psn_lg_decode_workspace(B, H), stream);
+}

@@ -46,6 +46,8 @@ struct ProjParams {
     const float* W; const float* W2; int ldw; int transpose;
     const float* add; int64_t add_sb;
     float* out; int64_t out_sr, out_sb;
+    const float* gen_raw; int64_t gen_sr, gen_sb; int gen_w;     // generated tiles (encoder fusion); gen_raw == NULL: TMA tiles
+    const float* gen_W; const float* gen_b;
     int* err;
 };
 
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) psn_wide_proj_kernel(const __
         for (int s = 0; s < NSTAGE; s++) { mbar_init(&sm.full[s], 1); mbar_init(&sm.split[s], WORK_THREADS / 32); mbar_init(&sm.done[s], 1); }
         mbar_init(&sm.drained[0], WORK_THREADS / 32); mbar_init(&sm.drained[1], WORK_THREADS / 32);
         fence_mbar_init();
-        prefetch_tmap(&tmap);
+        if (!q.gen_raw) prefetch_tmap(&tmap);
     }
     if (cw == 0) tmem_alloc(&sm.tmem_base, 512);
     tc_fence_before();
@@ -98,8 +100,8 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) psn_wide_proj_kernel(const __
     tc_fence_after();
 
     if (cw == WORK_THREADS / 32) {
-        // ---- TMA producer ----
-        if (elect_one()) {
+        // ---- TMA producer (idle when the tiles are generated) ----
+        if (!q.gen_raw && elect_one()) {
             for (int i = 0; i < my_n; i++) {
                 const int s = i % NSTAGE;
                 if (i >= NSTAGE && !mbar_wait(&sm.done[s], (uint32_t)(((i - NSTAGE) / NSTAGE) & 1))) { atomicExch(q.err, 4); __trap(); }
@@ -185,6 +187,38 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) psn_wide_proj_kernel(const __
             // the per-trajectory constants of this thread's 32 outputs are fetched before anything is waited on (they were on the
             // critical path of the epilogue: long_scoreboard 9.4 -> 1.5 warps per issue cycle, 2.09 -> 0.9 ms at the cfg4 shard)
             load_cadd(b0, cadd_cur);
+            if (q.gen_raw) {
+                // Encoder fusion: the tile is computed here instead of fetched, in the layout TMA delivers (slab cb = features 32 cb ..,
+                // 128-byte row n, 16-byte unit u at position u ^ (n & 7)).  Stage s is free: every warp ran the epilogue of tile i - NSTAGE,
+                // i.e. saw its MMAs complete, two iterations ago.
+                float4* h4 = reinterpret_cast<float4*>(sm.hi[s]);
+                float4* l4 = reinterpret_cast<float4*>(sm.lo[s]);
+                float raw[2][8];
+#pragma unroll
+                for (int hf = 0; hf < 2; hf++) {
+                    const int b = min(b0 + (tid >> 3) + 32 * hf, q.B - 1);
+#pragma unroll
+                    for (int cc = 0; cc < 8; cc++) raw[hf][cc] = cc < q.gen_w ? __ldg(q.gen_raw + (int64_t)r * q.gen_sr + (int64_t)b * q.gen_sb + cc) : 0.0f;
+                }
+#pragma unroll
+                for (int e = 0; e < TILE_BYTES / 16 / WORK_THREADS; e++) {
+                    const int idx = tid + e * WORK_THREADS;
+                    const int cb = idx >> 9, n = (idx & 511) >> 3, k0 = 32 * cb + (((idx & 7) ^ (n & 7)) << 2);
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        float pre = __ldg(q.gen_b + k0 + u);
+#pragma unroll
+                        for (int cc = 0; cc < 8; cc++)
+                            if (cc < q.gen_w) pre = fmaf(__ldg(q.gen_W + (k0 + u) * q.gen_w + cc), raw[e & 1][cc], pre);
+                        v[u] = psn_elu(pre);
+                    }
+                    float4 lo;
+                    const float4 hi = split4_hi(make_float4(v[0], v[1], v[2], v[3]), lo);
+                    h4[idx] = hi;
+                    l4[idx] = lo;
+                }
+            } else {
             if (!mbar_wait(&sm.full[s], (uint32_t)((i / NSTAGE) & 1))) { atomicExch(q.err, 2); __trap(); }
             {   // raw fp32 tile -> tf32 hi (in place) and lo parts; elementwise, so the swizzled layout is preserved
                 float4* h4 = reinterpret_cast<float4*>(sm.hi[s]);
@@ -197,6 +231,7 @@ __global__ void __launch_bounds__(PROJ_THREADS, 1) psn_wide_proj_kernel(const __
                     h4[idx] = hi;
                     l4[idx] = lo;
                 }
+            }
             }
             fence_async_smem();
             __syncwarp();
@@ -314,11 +349,12 @@ int psn_wide_proj(const PswProjJob& job, int* err_flag, cudaStream_t stream, con
     q.W = job.W; q.W2 = job.W2; q.ldw = job.ldw; q.transpose = job.transpose;
     q.add = job.add; q.add_sb = job.add_sb;
     q.out = job.out; q.out_sr = job.out_sr; q.out_sb = job.out_sb;
+    q.gen_raw = job.gen_raw; q.gen_sr = job.gen_sr; q.gen_sb = job.gen_sb; q.gen_w = job.gen_w; q.gen_W = job.gen_W; q.gen_b = job.gen_b;
     q.err = err_flag;
     int dev = 0, sms = 148;
     PSN_CUDA(cudaGetDevice(&dev));
     PSN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    if (use_simple_proj() || !psn_wide_proj_view_ok(job.in, job.in_sr, job.in_sb) || encode_fn() == nullptr) {
+    if (!job.gen_raw && (use_simple_proj() || !psn_wide_proj_view_ok(job.in, job.in_sr, job.in_sb) || encode_fn() == nullptr)) {
         const int smem = (128 * 128 + 16 * 128) * 4;
         PSN_CUDA(cudaFuncSetAttribute(psn_wide_proj_simple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         psn_wide_proj_simple_kernel<<<sms * 2, 128, smem, stream>>>(job.in, job.in_sr, job.in_sb, q);
@@ -327,6 +363,8 @@ int psn_wide_proj(const PswProjJob& job, int* err_flag, cudaStream_t stream, con
         return PSNODE_OK;
     }
     CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof(tmap));
+    if (!job.gen_raw) {
     const cuuint64_t gdim[3] = {128, (cuuint64_t)job.B, (cuuint64_t)job.R};
     const cuuint64_t gstr[2] = {(cuuint64_t)job.in_sb * 4, (cuuint64_t)job.in_sr * 4};
     const cuuint32_t box[3] = {32, TB, 1};
@@ -335,6 +373,7 @@ int psn_wide_proj(const PswProjJob& job, int* err_flag, cudaStream_t stream, con
                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled");
+    }
     const int ntiles = q.R * q.nbt;
     const int grid = ntiles < sms ? ntiles : sms;
     const int smem = (int)sizeof(ProjSmem) + 1024;

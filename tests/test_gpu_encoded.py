@@ -137,10 +137,12 @@ def test_encoded_dae_vs_unfused_pipeline(native_lib, H, solver, B, N, chunk, eve
     assert torch.equal(again_x, got_x), "deterministic"
 
 
-def test_encoded_ode_h256_vs_unfused_pipeline(native_lib):
+@pytest.mark.parametrize("H,B", [(256, 130), (128, 130), (128, 1000)])
+def test_encoded_ode_vs_unfused_pipeline(native_lib, H, B):
+    """H = 256: per-layer GEMM kernel; H = 128: the wide kernels (projection tiles generated from the raw series, TMEM-resident time loop)."""
     from py_psnode_b200 import DE_Func, ODE_Event, RK4
     torch.manual_seed(95)
-    B, N, H, XR, ZR = 130, 20, 256, 8, 2
+    N, XR, ZR = 20, 8, 2
     T = N + 1
     de = DE_Func(x_dim=H, z_dim=H, hidden_dim=H, depth=2).to(DEV)
     z_enc, x_dec = _codec(ZR, H, H).to(DEV), _codec(H, H, XR).to(DEV)
@@ -154,8 +156,8 @@ def test_encoded_ode_h256_vs_unfused_pipeline(native_lib):
         a0 = torch.cat((x0, Zh[0]), dim=-1)
         ev = ODE_Event()
         ev.set_event(t=event_t, z=z_enc(zj))
-        xs = RK4(impl="layer").integrate_ODE(x_func=de, t=t, x=x0.unsqueeze(0).expand(T, B, H), z=Zh, all_initial=a0, event_fn=ev.event_fn,
-                                             jump_change_fn=ev.jump_change_fn)
+        xs = RK4().integrate_ODE(x_func=de, t=t, x=x0.unsqueeze(0).expand(T, B, H), z=Zh, all_initial=a0, event_fn=ev.event_fn,
+                                 jump_change_fn=ev.jump_change_fn)
         want = x_dec(xs)
         got = RK4().integrate_ODE_encoded(x_func=de, t=t, x0=x0, z=z, all_initial=a0, z_encoder=z_enc, x_decoder=x_dec, event_t=event_t,
                                           z_jump=zj, chunk_rows=6)
