@@ -29,11 +29,35 @@
 namespace {
 using namespace psn_tc;
 
+// hi / lo split of the streamed operand.  The tensor core TRUNCATES a tf32 operand to 10 mantissa bits; with PSN_LG_ROUND_LO the lo part is
+// rounded to nearest here first (2 integer instructions per element), which halves its error and removes the truncation's sign dependence
+__device__ __forceinline__ float4 lg_split4(const float4 v, float4& lo) {
+    float4 hi = split4_hi(v, lo);
+#if PSN_LG_ROUND_LO
+    lo.x = __uint_as_float((__float_as_uint(lo.x) + 0x1000u) & 0xFFFFE000u); lo.y = __uint_as_float((__float_as_uint(lo.y) + 0x1000u) & 0xFFFFE000u);
+    lo.z = __uint_as_float((__float_as_uint(lo.z) + 0x1000u) & 0xFFFFE000u); lo.w = __uint_as_float((__float_as_uint(lo.w) + 0x1000u) & 0xFFFFE000u);
+#endif
+    return hi;
+}
+
 constexpr int TM = 128, TN = 128;
 constexpr int NST = 3;
 constexpr int SLAB = TN * 128;          // 16 KB: 128 rows x 32 fp32
 constexpr int LG_THREADS = 320;         // 8 split / epilogue warps + TMA producer warp + MMA issuer warp
-constexpr int NPART = 2;                // K-partials (truncating fp32 accumulate: short chains)
+#ifndef PSN_LG_NPART
+#define PSN_LG_NPART 2
+#endif
+#ifndef PSN_LG_CLASS_SPLIT
+#define PSN_LG_CLASS_SPLIT 1            // partial accumulators by term class (small cross terms | big term), see the issuer loop; 0: by K range
+#endif
+#ifndef PSN_LG_ROUND_LO
+#define PSN_LG_ROUND_LO 0
+#endif
+// Partial accumulators (the tensor core's fp32 accumulation truncates: chains must stay short).  Measured on a 2000-step cfg5-width run
+// against the float64 oracle (tests/test_gpu_layer.py::test_layer_dae_full_length_drift; the reference's own fp32 run: 5.6e-6 off):
+//   2 partials by K range 1.65e-5 | 2 by term class 1.37e-5 (same speed, the default) | 4 by K range 9.8e-6 (-7 % speed) |
+//   4 by class x K half 8.0e-6 (-7.5 %: -DPSN_LG_NPART=4) | rounding the streamed operand's lo part to nearest first: no effect
+constexpr int NPART = PSN_LG_NPART;
 constexpr int GEN_W = 8;                // widest raw input of a generated B source
 
 enum { LG_PLAIN = 0, LG_HIDDEN = 1, LG_RK = 2, LG_DELTA = 3, LG_BRK = 4 };      // LG_BRK: LgParams::stage = the EPI_B* kind
@@ -174,6 +198,23 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                 tc_fence_after();
                 const uint64_t da_hi = make_desc_sw128(smem_u32(sm.a_hi[s])), da_lo = make_desc_sw128(smem_u32(sm.a_lo[s]));
                 const uint64_t db_hi = make_desc_sw128(smem_u32(sm.b_hi[s])), db_lo = make_desc_sw128(smem_u32(sm.b_lo[s]));
+#if PSN_LG_CLASS_SPLIT
+                // partial accumulators by TERM CLASS: the two small cross terms (A_lo.B_hi, A_hi.B_lo: 2^-11 of the result) go to their own
+                // accumulator, the big term A_hi.B_hi to another (x K-halves when NPART = 4): the truncating fp32 accumulation of the tensor
+                // core then only sees chains of nchunk * 4 / (NPART / 2) same-magnitude MMAs, and the small terms lose nothing to a large sum
+                constexpr int KH = NPART / 2;
+                const int kh = (c * KH) / nchunk;
+                const bool first = c == (kh * nchunk + KH - 1) / KH;               // first chunk of this K-half
+#pragma unroll
+                for (int term = 0; term < 3; term++) {
+                    const uint64_t ad = term == 0 ? da_lo : da_hi;
+                    const uint64_t bd = term == 1 ? db_lo : db_hi;
+                    const uint32_t acc = tmem + (uint32_t)(((term == 2 ? 1 : 0) * KH + kh) * TN);
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)
+                        mma_tf32(acc, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc, (first && kk == 0 && term != 1) ? 0u : 1u);
+                }
+#else
                 const int part = (c * NPART) / nchunk;
                 const bool first = c == (part * nchunk + NPART - 1) / NPART;       // first chunk of this partial
                 uint32_t accumulate = first ? 0u : 1u;
@@ -187,6 +228,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                         accumulate = 1;
                     }
                 }
+#endif
                 mma_commit(&sm.done[s]);
             }
             __syncwarp();
@@ -222,7 +264,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                         v[u] = psn_elu(pre);
                     }
                     float4 lo;
-                    const float4 hi = split4_hi(make_float4(v[0], v[1], v[2], v[3]), lo);
+                    const float4 hi = lg_split4(make_float4(v[0], v[1], v[2], v[3]), lo);
                     h4[idx] = hi;
                     l4[idx] = lo;
                 }
@@ -231,7 +273,7 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                 for (int e = 0; e < SLAB / 16 / 256; e++) {
                     const int idx = tid + e * 256;
                     float4 lo;
-                    const float4 hi = split4_hi(h4[idx], lo);
+                    const float4 hi = lg_split4(h4[idx], lo);
                     h4[idx] = hi;
                     l4[idx] = lo;
                 }
@@ -318,7 +360,19 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
             float t0[16], t1[16];
             tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)n0, t0);
             tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)(TN + n0), t1);
-            tmem_ld_wait();
+            if constexpr (NPART == 4) {          // two register arrays only: fold the partials pairwise as they arrive
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i++) t0[i] += t1[i];
+                tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)(2 * TN + n0), t1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i++) t0[i] += t1[i];
+                tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)(3 * TN + n0), t1);
+                tmem_ld_wait();
+            } else {
+                tmem_ld_wait();
+            }
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const int c = 16 * bt + i;
