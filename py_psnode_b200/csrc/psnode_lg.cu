@@ -700,7 +700,7 @@ int64_t lg_wgrad_slab_floats(int M, int K) { return (int64_t)WG_NSPLIT_MAX * (M 
 
 // out[M x K] (+)= sum over slots and rows of P^T Q.  P: (nslots, N, M) with strides (p_ss, p_sn, 1); Q: (nslots, N, K) likewise.
 int lg_wgrad(const float* P, int64_t p_sn, int64_t p_ss, int M, const float* Q, int64_t q_sn, int64_t q_ss, int K, int nslots, int N, float* out,
-             int64_t out_ld, int accumulate, float* slabs, int* err, cudaStream_t stream, const int32_t* ev = nullptr, int ev_j = 0) {
+             int64_t out_ld, int accumulate, float* slabs, int* err, cudaStream_t stream, const int32_t* ev = nullptr, int ev_j = 0, int max_ctas = 148) {
     CUtensorMap mp, mq;
     if (!lg_make_map32(&mp, P, M, N, p_sn, nslots, p_ss) || !lg_make_map32(&mq, Q, K, N, q_sn, nslots, q_ss))
         return psn_cuda_fail(cudaErrorInvalidValue, "cuTensorMapEncodeTiled (layer weight gradients)");
@@ -709,7 +709,7 @@ int lg_wgrad(const float* P, int64_t p_sn, int64_t p_ss, int M, const float* Q, 
     q.mblks = M / TM; q.kblks = K / TN;
     const int ntiles = q.mblks * q.kblks;
     const int64_t total = (int64_t)nslots * ((N + 31) / 32);
-    int nsplit = 148 / ntiles;
+    int nsplit = max_ctas / ntiles;
     if (nsplit > WG_NSPLIT_MAX) nsplit = WG_NSPLIT_MAX;
     if (nsplit > total) nsplit = (int)total;
     if (nsplit < 1) nsplit = 1;
@@ -808,17 +808,40 @@ struct LgLayout {
     // reverse pass
     int ring, nst, nbufs;
     int64_t dpj_de, dpj_ae, bufs, slabs;
-    int ring_y(int s, int e) const { return BUF_SINGLES + (0 * ring + s) * nst + e; }
-    int ring_a1(int s, int e) const { return BUF_SINGLES + (1 * ring + s) * nst + e; }
-    int ring_dk(int s, int e) const { return BUF_SINGLES + (2 * ring + s) * nst + e; }
-    int ring_d1(int s, int e) const { return BUF_SINGLES + (3 * ring + s) * nst + e; }
-    int ring_one(int kind, int s) const { return BUF_SINGLES + 4 * ring * nst + kind * ring + s; }      // kind: 0 i0, 1 dsum, 2 gi, 3 h, 4 dh
+    // `ring` = steps per weight-gradient batch, `depth` = physical slots (2 * ring when the batch GEMMs overlap the next batch's sweep)
+    int depth;
+    int64_t slabs2;
+    int ring_y(int s, int e) const { return BUF_SINGLES + (0 * depth + s) * nst + e; }
+    int ring_a1(int s, int e) const { return BUF_SINGLES + (1 * depth + s) * nst + e; }
+    int ring_dk(int s, int e) const { return BUF_SINGLES + (2 * depth + s) * nst + e; }
+    int ring_d1(int s, int e) const { return BUF_SINGLES + (3 * depth + s) * nst + e; }
+    int ring_one(int kind, int s) const { return BUF_SINGLES + 4 * depth * nst + kind * depth + s; }      // kind: 0 i0, 1 dsum, 2 gi, 3 h, 4 dh
 };
 enum { R_I0 = 0, R_DSUM, R_GI, R_H, R_DH };
 
 int lg_chunk_rows() {
     static const int v = std::getenv("PSNODE_LG_CHUNK") ? std::atoi(std::getenv("PSNODE_LG_CHUNK")) : 64;
     return v < 1 ? 1 : v;
+}
+// SMs a layer launch of this problem leaves idle (its grid is one CTA per 128 x 128 output tile)
+int lg_idle_sms(const psnode_problem* p) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const int grid = ((p->B + TN - 1) / TN) * (p->X / TM);
+    return grid >= sms ? 0 : sms - grid;
+}
+// When a layer launch leaves a large part of the chip idle (H = 128: 64 CTAs at B = 8192; small batches), the ring-batch weight-gradient
+// GEMMs of the reverse sweep run on a side stream on those SMs, capped at their number, one batch behind the sweep (measured at
+// B = 8192: H = 128, 84 idle SMs: 404 -> 337 us per step; H = 256, 20 idle SMs: 569 -> 636 us, the side stream becomes the critical
+// path -- so only with >= 48 idle SMs).  PSNODE_LG_OVERLAP=0 switches it off.  Not with events: their gated per-step weight-gradient
+// launches accumulate into the same blocks and would race with the side stream.
+bool lg_overlap_wgrad(const psnode_problem* p) {
+    static const bool on = !(std::getenv("PSNODE_LG_OVERLAP") && std::atoi(std::getenv("PSNODE_LG_OVERLAP")) == 0);
+    return on && !(p->event_idx && p->E > 0) && lg_idle_sms(p) >= 48;
 }
 int lg_ring_depth() {
     static const int v = std::getenv("PSNODE_LG_RING") ? std::atoi(std::getenv("PSNODE_LG_RING")) : 8;
@@ -878,11 +901,13 @@ LgLayout lg_layout(const psnode_problem* p, int mode, int chunk_rows = 0) {
         L.ring = lg_ring_depth();
         if (p->T - 1 < L.ring) L.ring = p->T > 1 ? p->T - 1 : 1;
         L.nst = psw_nstages(p->method);
-        L.nbufs = BUF_SINGLES + L.ring * (4 * L.nst + 5);
+        L.depth = lg_overlap_wgrad(p) ? 2 * L.ring : L.ring;
+        L.nbufs = BUF_SINGLES + L.depth * (4 * L.nst + 5);
         L.dpj_de = o; o += al((int64_t)(E > 0 ? E : 1) * BH);
         L.dpj_ae = o; o += al((int64_t)(E > 0 ? E : 1) * BH);
         L.bufs = o; o += (int64_t)L.nbufs * al(BH);
         L.slabs = o; o += al(lg_wgrad_slab_floats(H, L.S));
+        L.slabs2 = o; o += al(lg_wgrad_slab_floats(H, H));
     }
     L.total = o;
     return L;
@@ -1577,7 +1602,8 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
     const int H = c.H, B = c.B, T = c.T, E = c.E, S = c.S, NS = c.nstages;
     const int X = p->X, Z = p->Z, V = p->V;
     const int64_t BH = c.BH, BHa = al(BH);
-    const int ring = L.ring;
+    const int ring = L.ring, depth = L.depth;
+    const bool overlap = depth > ring;
     const int nblk = (int)((BH + 255) / 256);
     auto buf = [&](int i) { return w + L.bufs + (int64_t)i * BHa; };
     float* slabs = w + L.slabs;
@@ -1640,29 +1666,68 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
         q3.out = buf(BUF_GX);
         gemm(M_T_AE1X, L.ring_one(R_DH, s), q3, "psn_lg_gemm_kernel<bwd:ae1x^T>");
     };
+    // Side stream for the batch weight-gradient GEMMs (see lg_overlap_wgrad): capped at the SMs a layer launch leaves free, they run one
+    // batch behind the sweep on the other half of the (double-depth) ring.
+    static cudaStream_t side = nullptr;
+    static cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    static int side_dev = -1;
+    int cur_dev = 0;
+    PSN_CUDA(cudaGetDevice(&cur_dev));
+    if (overlap && (!side || side_dev != cur_dev)) {        // (one process per GPU: created once; re-created if the device changed)
+        side_dev = cur_dev;
+        int lo = 0, hi = 0;
+        PSN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PSN_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, lo));
+        for (int i = 0; i < 2; i++) {
+            PSN_CUDA(cudaEventCreateWithFlags(&ev_ready[i], cudaEventDisableTiming));
+            PSN_CUDA(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    bool done_pending[2] = {false, false};
+    if (overlap) {                                           // the side stream starts behind everything already queued on `stream`
+        PSN_CUDA(cudaEventRecord(ev_ready[0], stream));
+        PSN_CUDA(cudaStreamWaitEvent(side, ev_ready[0], 0));
+    }
     // weight-gradient products of the steps / grid points of one ring batch: grid points [j_lo, j_hi)
     auto flush = [&](int j_lo, int j_hi) -> int {
         const int de_lo = j_lo < 1 ? 1 : j_lo, n_de = j_hi - de_lo;            // DE steps in the batch
+        const int half = (j_lo / ring) & 1;
+        cudaStream_t ws_stream = overlap ? side : stream;
+        float* wslabs = overlap ? w + L.slabs2 : slabs;
+        const int cap = overlap ? lg_idle_sms(p) : 148;
+        if (overlap) {
+            PSN_CUDA(cudaEventRecord(ev_ready[half], stream));
+            PSN_CUDA(cudaStreamWaitEvent(side, ev_ready[half], 0));
+        }
         int rc = PSNODE_OK;
         if (n_de > 0) {
-            const int s0 = de_lo % ring;
-            rc = lg_wgrad(buf(L.ring_dk(s0, 0)), H, BHa, H, buf(L.ring_a1(s0, 0)), H, BHa, H, n_de * NS, B, th + o_W2, H, 1, slabs, c.err, stream);
+            const int s0 = de_lo % depth;
+            rc = lg_wgrad(buf(L.ring_dk(s0, 0)), H, BHa, H, buf(L.ring_a1(s0, 0)), H, BHa, H, n_de * NS, B, th + o_W2, H, 1, wslabs, c.err, ws_stream, nullptr, 0,
+                          cap);
             if (rc != PSNODE_OK) return rc;
-            rc = lg_wgrad(buf(L.ring_d1(s0, 0)), H, BHa, H, buf(L.ring_y(s0, 0)), H, BHa, H, n_de * NS, B, th + o_W1 + 2 * S, 3 * S, 1, slabs, c.err, stream);
+            rc = lg_wgrad(buf(L.ring_d1(s0, 0)), H, BHa, H, buf(L.ring_y(s0, 0)), H, BHa, H, n_de * NS, B, th + o_W1 + 2 * S, 3 * S, 1, wslabs, c.err, ws_stream,
+                          nullptr, 0, cap);
             if (rc != PSNODE_OK) return rc;
             if (dae) {
                 rc = lg_wgrad(buf(L.ring_one(R_DSUM, s0)), H, BHa, H, buf(L.ring_one(R_I0, s0)), H, BHa, H, n_de, B, th + o_W1 + 2 * S + X + Z + V, 3 * S, 1,
-                              slabs, c.err, stream);
+                              wslabs, c.err, ws_stream, nullptr, 0, cap);
                 if (rc != PSNODE_OK) return rc;
             }
         }
         if (dae && j_hi > j_lo) {
-            const int s0 = j_lo % ring, n = j_hi - j_lo;
-            rc = lg_wgrad(buf(L.ring_one(R_GI, s0)), H, BHa, H, buf(L.ring_one(R_H, s0)), H, BHa, H, n, B, th + o_A2, H, 1, slabs, c.err, stream);
+            const int s0 = j_lo % depth, n = j_hi - j_lo;
+            rc = lg_wgrad(buf(L.ring_one(R_GI, s0)), H, BHa, H, buf(L.ring_one(R_H, s0)), H, BHa, H, n, B, th + o_A2, H, 1, wslabs, c.err, ws_stream, nullptr, 0,
+                          cap);
             if (rc != PSNODE_OK) return rc;
             rc = lg_wgrad(buf(L.ring_one(R_DH, s0)), H, BHa, H, p->x_sol.p + (int64_t)j_lo * p->x_sol.st, p->x_sol.sb, p->x_sol.st, H, n, B,
-                          th + o_A1 + S, lda, 1, slabs, c.err, stream);
+                          th + o_A1 + S, lda, 1, wslabs, c.err, ws_stream, nullptr, 0, cap);
             if (rc != PSNODE_OK) return rc;
+        }
+        if (overlap) {
+            PSN_CUDA(cudaEventRecord(ev_done[half], side));
+            done_pending[half] = true;
+            // the sweep now moves on to the batch below, which lives in the OTHER half of the ring: that half must have been consumed
+            if (done_pending[half ^ 1]) { PSN_CUDA(cudaStreamWaitEvent(stream, ev_done[half ^ 1], 0)); done_pending[half ^ 1] = false; }
         }
         return PSNODE_OK;
     };
@@ -1682,14 +1747,14 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
     };
     // ---- start: adjoints of the last grid point ----
     {
-        const int s = (T - 1) % ring;
+        const int s = (T - 1) % depth;
         upstream_row(T - 1);
         psn_lg_bwd_init_kernel<<<nblk, 256, 0, stream>>>(B, H, upx, upx_sb, dae ? upi : nullptr, upi_sb, buf(BUF_GX), buf(L.ring_one(R_GI, s)),
                                                          buf(BUF_ACCGI));
         psn_count_launch("psn_lg_bwd_init_kernel");
     }
     auto sweep_point = [&](int j) -> int {            // AE at grid point j, then (j >= 1) the reverse of step j
-        const int s = j % ring;
+        const int s = j % depth;
         if (dae) ae_backward(j, s);
         if (j >= 1) {
             upstream_row(j - 1);
@@ -1793,7 +1858,7 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
             if (st != PSNODE_OK) return st;
         }
         if (j >= 1) {
-            const int sn = (j - 1) % ring;
+            const int sn = (j - 1) % depth;
             psn_lg_bwd_tail_kernel<<<nblk, 256, 0, stream>>>(B, H, E > 0 ? p->event_idx : nullptr, j - 1, buf(L.ring_one(R_DSUM, s)),
                                                              dpre_de + (int64_t)(j - 1 - r0) * BH, w + L.dpj_de, BH, dae ? buf(BUF_GI0) : nullptr,
                                                              dae ? upi : nullptr, upi_sb, dae ? buf(L.ring_one(R_GI, sn)) : nullptr, buf(BUF_ACCGI));
@@ -1885,6 +1950,8 @@ int psn_lg_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, 
         if (st != PSNODE_OK) return st;
     }
     PSN_CUDA(cudaGetLastError());
+    for (int i = 0; i < 2; i++)
+        if (done_pending[i]) { PSN_CUDA(cudaStreamWaitEvent(stream, ev_done[i], 0)); done_pending[i] = false; }
 
     // ---- gradient of the initial state ----
     if (a->d_x0) {

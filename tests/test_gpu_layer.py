@@ -190,11 +190,13 @@ def test_layer_dae_gradients_vs_fp64_autograd(native_lib, H, solver, events, B, 
     _compare_grads(got, want)
 
 
-def test_layer_dae_gradients_vs_generic_sweep(native_lib):
+@pytest.mark.parametrize("events", [1, 0])
+def test_layer_dae_gradients_vs_generic_sweep(native_lib, events):
     """Same sweep against the CUDA-core generic reverse sweep (itself pinned to the reference's autograd goldens) at a batch of
-    several n-tiles and more steps than the ring holds; deterministic across two runs."""
+    several n-tiles and more steps than the ring holds; deterministic across two runs.  Without events the ring-batch weight-gradient
+    GEMMs run on the side stream, one batch behind the sweep (lg_overlap_wgrad); with events in line."""
     B, N, H = 300, 21, 256
-    de, ae, d, ev = _dae_problem(B=B, N=N, H=H, seed=77, events=1)
+    de, ae, d, ev = _dae_problem(B=B, N=N, H=H, seed=77, events=events)
     torch.manual_seed(6)
     wx, wi = torch.randn(N + 1, B, H) * 0.1, torch.randn(N + 1, B, H) * 0.1
     got, fk, bk = _dae_grads_gpu("rk4", de, ae, d, ev, wx, wi, "layer")
