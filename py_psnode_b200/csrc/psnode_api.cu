@@ -2,6 +2,7 @@
 // the device-side event table, launch accounting and the host-buffer convenience entry.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include "psnode_internal.cuh"
@@ -63,6 +64,14 @@ int validate(const psnode_problem* p) {
     return PSNODE_OK;
 }
 
+}  // namespace
+// generic kernels: prefer the 2-trajectories-per-CTA build when 8 per CTA would leave most of the chip idle (PSNODE_GENERIC_TB2=0/1 forces)
+bool psn_prefer_tb2(const psnode_problem* p) {
+    static const int forced = std::getenv("PSNODE_GENERIC_TB2") ? std::atoi(std::getenv("PSNODE_GENERIC_TB2")) : -1;
+    if (forced >= 0) return forced != 0;
+    return p->B <= 8 * 37;          // <= 37 CTAs of 8 trajectories: a quarter of the 148 SMs
+}
+namespace {
 __global__ void psn_event_table_kernel(const float* __restrict__ t0, int64_t t_st, int T, const float* __restrict__ ev0,
                                        int64_t ev_se, int E, int* __restrict__ event_idx, int* __restrict__ err) {
     if (blockIdx.x == 0 && threadIdx.x == 0) err[0] = 0;
@@ -173,6 +182,11 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
     if (p->impl == PSNODE_IMPL_AUTO && psn_wide_supports(p)) return psn_wide_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_lg_supports(p)) return psn_lg_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_fused_supports(p)) return psn_fused_forward(p, workspace, workspace_bytes, s);
+    // small batches: 2 trajectories per CTA instead of 8 puts 4 x as many SMs to work (the kernels are latency-bound per CTA)
+    if (psn_prefer_tb2(p)) {
+        const int t2 = psn_generic_forward_tb2(p, workspace, workspace_bytes, s);
+        if (t2 != PSNODE_EUNSUPPORTED) return t2;
+    }
     const int gst = psn_generic_forward(p, workspace, workspace_bytes, s);
     if (gst != PSNODE_EUNSUPPORTED) return gst;
     return psn_generic_forward_tb2(p, workspace, workspace_bytes, s);      // per-trajectory vectors too wide for 8 trajectories per CTA
@@ -211,6 +225,10 @@ int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* work
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_LAYER) && psn_lg_bwd_supports(p, a))
         return psn_lg_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if (a->fuse_x.target.p || a->fuse_i.target.p) return PSNODE_EUNSUPPORTED;      // the generic recomputing sweeps take gx / gi only
+    if (psn_prefer_tb2(p)) {
+        const int t2 = psn_generic_backward_tb2(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+        if (t2 != PSNODE_EUNSUPPORTED) return t2;
+    }
     const int gst = psn_generic_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if (gst != PSNODE_EUNSUPPORTED) return gst;
     return psn_generic_backward_tb2(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));

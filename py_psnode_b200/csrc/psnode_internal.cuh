@@ -50,6 +50,8 @@ int64_t psn_generic_forward_workspace_tb2(const psnode_problem* p);
 int psn_generic_backward_tb2(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
 int64_t psn_generic_backward_workspace_tb2(const psnode_problem* p, const psnode_adjoint* a);
 
+bool psn_prefer_tb2(const psnode_problem* p);      // psnode_api.cu
+
 bool psn_fused_supports(const psnode_problem* p);
 int psn_fused_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream);
 int64_t psn_fused_forward_workspace(const psnode_problem* p);
