@@ -126,6 +126,11 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                                                                    const __grid_constant__ LgParams q) {
     // programmatic dependent launch: everything above the first read of the previous launch's output may overlap its tail
     if (q.trace >= 0 && threadIdx.x == 0) atomicMin(&g_lg_tmin[q.trace][0], lg_gtime());
+    if (threadIdx.x == 0) {               // the descriptors are kernel parameters: fetch them while the previous launch is still running
+        prefetch_tmap(&map_a_hi); prefetch_tmap(&map_a_lo);
+        if (!(q.gen & 1)) prefetch_tmap(&map_b0);
+        if (q.nsrc > 1 && !(q.gen & 2)) prefetch_tmap(&map_b1);
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (q.trace >= 0 && threadIdx.x == 0) { const unsigned long long tt = lg_gtime(); atomicMin(&g_lg_tmin[q.trace][1], tt); atomicMax(&g_lg_tmax[q.trace][1], tt); }
     int evk = -1;
