@@ -172,3 +172,33 @@ def test_blackwell_native_sass_of_the_latent_width_kernels(native_lib):
         txt = subprocess.run(["cuobjdump", "-sass", obj], stdout=subprocess.PIPE, text=True, check=True).stdout
         for mn in mnemonics:
             assert mn in txt, f"{unit}: no {mn} in the SASS"
+
+
+def test_round2_entries_have_no_cpu_path():
+    """The fused model-pipeline entries (encoders / decoders, Init_Func) are CUDA-only like the rest of the path: CPU tensors raise."""
+    import torch.nn as nn
+    from py_psnode_b200 import AE_Func, DE_Func, RK4
+    H, B, T = 128, 3, 4
+    codec = lambda i, o: nn.Sequential(nn.Linear(i, H), nn.ELU(), nn.Linear(H, o))
+    de = DE_Func(x_dim=H, z_dim=H, hidden_dim=H, depth=2)
+    t = torch.zeros(T, B, 1)
+    with pytest.raises((RuntimeError, TypeError), match="CUDA|cuda"):
+        RK4().integrate_ODE_encoded(x_func=de, t=t, x0=torch.zeros(B, H), z=torch.zeros(T, B, 2), all_initial=torch.zeros(B, 2 * H),
+                                    z_encoder=codec(2, H), x_decoder=codec(H, 3))
+    init = nn.Module()
+    init.init_fun = nn.Sequential(nn.Linear(5, 8), nn.ELU(), nn.Linear(8, 4))
+    init.forward = lambda z0, v0, i0: init.init_fun(torch.cat([z0, v0, i0], dim=-1))
+    with pytest.raises((RuntimeError, TypeError), match="CUDA|cuda"):
+        RK4.init_state(init, torch.zeros(B, 1), torch.zeros(B, 2), torch.zeros(B, 2))
+
+
+def test_codec_modules_are_pattern_checked():
+    """Encoders / decoders must be nn.Sequential(Linear, ELU, Linear); anything else is rejected before any kernel runs."""
+    import torch.nn as nn
+    from py_psnode_b200 import pattern
+    ok = nn.Sequential(nn.Linear(2, 8), nn.ELU(), nn.Linear(8, 8))
+    assert len(pattern.codec_chain(ok, "z_encoder")) == 2
+    for bad in (nn.Sequential(nn.Linear(2, 8), nn.ReLU(), nn.Linear(8, 8)), nn.Sequential(nn.Linear(2, 8)), nn.Linear(2, 8),
+                nn.Sequential(nn.Linear(2, 8), nn.ELU(), nn.Linear(8, 8), nn.ELU(), nn.Linear(8, 8))):
+        with pytest.raises(pattern.UnsupportedModuleError):
+            pattern.codec_chain(bad, "z_encoder")
