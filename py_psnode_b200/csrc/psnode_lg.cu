@@ -429,14 +429,17 @@ __global__ void __launch_bounds__(LG_THREADS, 1) psn_lg_gemm_kernel(const __grid
                 }
             }
         };
+        // A warp whose 64 columns all lie beyond a ragged batch (B = 5: warps 4..7 of the only tile) has nothing to fetch or store; its
+        // operand addresses would be out of bounds (compute-sanitizer memcheck), so it only keeps the barriers company.
+        const bool warp_live = full_tile || nlive > 0;
         Buf cur, nxt;
-        fetch(0, cur);                      // issued BEFORE the wait for the last MMAs: the first operand batch's L2 / HBM latency hides under them
+        if (warp_live) fetch(0, cur);       // issued BEFORE the wait for the last MMAs: the first operand batch's L2 / HBM latency hides under them
         if (!mbar_wait(&sm.done[(nchunk - 1) % NST], (uint32_t)(((nchunk - 1) / NST) & 1))) { atomicExch(q.err, 13); __trap(); }
         tc_fence_after();
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the next layer's grid may be set up while this epilogue runs
         stamp();
 #pragma unroll 1
-        for (int bt = 0; bt < 4; bt++) {
+        for (int bt = 0; bt < 4 && warp_live; bt++) {
             if (bt + 1 < 4) fetch(bt + 1, nxt);
             finish(bt, cur);
             cur = nxt;
