@@ -151,6 +151,7 @@ int64_t psnode_forward_workspace(const psnode_problem* p) {
     if (f > g) g = f;
     if (psn_wide_supports(p)) { const int64_t w = psn_wide_forward_workspace(p); if (w > g) g = w; }
     if (psn_lg_supports(p)) { const int64_t w = psn_lg_forward_workspace(p); if (w > g) g = w; }
+    if (psn_wide4_supports(p)) { const int64_t w = psn_wide4_forward_workspace(p); if (w > g) g = w; }
     return g > t ? g : t;
 }
 
@@ -171,8 +172,9 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
         return psn_fused_forward(p, workspace, workspace_bytes, s);
     }
     if (p->impl == PSNODE_IMPL_WIDE) {
-        if (!psn_wide_supports(p)) return PSNODE_EUNSUPPORTED;
-        return psn_wide_forward(p, workspace, workspace_bytes, s);
+        if (psn_wide_supports(p)) return psn_wide_forward(p, workspace, workspace_bytes, s);
+        if (psn_wide4_supports(p)) return psn_wide4_forward(p, workspace, workspace_bytes, s);
+        return PSNODE_EUNSUPPORTED;
     }
     if (p->impl == PSNODE_IMPL_LAYER) {
         if (!psn_lg_supports(p)) return PSNODE_EUNSUPPORTED;
@@ -181,6 +183,7 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
     if (p->impl == PSNODE_IMPL_AUTO && psn_tc_supports(p)) return psn_tc8_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_wide_supports(p)) return psn_wide_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_lg_supports(p)) return psn_lg_forward(p, workspace, workspace_bytes, s);
+    if (p->impl == PSNODE_IMPL_AUTO && psn_wide4_auto() && psn_wide4_supports(p)) return psn_wide4_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_fused_supports(p)) return psn_fused_forward(p, workspace, workspace_bytes, s);
     // small batches: 2 trajectories per CTA instead of 8 puts 4 x as many SMs to work (the kernels are latency-bound per CTA)
     if (psn_prefer_tb2(p)) {

@@ -53,6 +53,11 @@ int psn_wide_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaSt
 bool psn_wide_bwd_supports(const psnode_problem* p, const psnode_adjoint* a);
 int64_t psn_wide_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);
 int psn_wide_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
+// the 4-layer ODE_01 net at hidden 128 (X <= 16, Z <= 8) on the same machinery, forward only (psnode_wide4_fwd.cu)
+bool psn_wide4_supports(const psnode_problem* p);
+bool psn_wide4_auto();
+int64_t psn_wide4_forward_workspace(const psnode_problem* p);
+int psn_wide4_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream);
 
 // per-layer tcgen05 GEMM launches for the latent nets that do not fit one SM (psnode_lg.cu: DAE_02 / ODE_02 with H = 128 / 256)
 bool psn_lg_supports(const psnode_problem* p);
