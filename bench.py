@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- RK4 trajectory-steps/s of the fused integrator on BASELINE.json's configs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5] [--no-others]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5|ode01_h128] [--no-others]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 The JSON line's top level is BASELINE.json's headline: configs[1] ("cfg2": RK4, ODE_01 DE_Func X=16 Z=2 H=64, B = 4096 x 1000
@@ -52,6 +52,12 @@ WORKLOADS = {
     "cfg5": dict(kind="dae", net="02", X=256, Z=256, V=256, I=256, H=256, B=65536, N=2000, scaling="strong", quoted_gpus=8,
                  bytes_per_unit=4100, flop_per_unit=7864320, aux_steps=200, train_steps=2000,
                  desc="RK4 fixed-step, DAE_02 latent DE_Func 3072-256-256 + AE_Func 1792-256-256, global batch 65536 x 2000 steps"),
+    # not a BASELINE config: cfg2 at the training script's argparse default --hidden 128 (neural_00_ODE_01_no_encode.py:245-247;
+    # VERDICT r01 item 9): forward on psn_wide4_fwd_kernel, reverse sweep on the generic recomputing kernels
+    "ode01_h128": dict(kind="ode", net="01", X=16, Z=2, V=0, I=0, H=128, B=4096, N=1000, scaling="weak", bytes_per_unit=76,
+                       flop_per_unit=333824,
+                       desc="RK4 fixed-step, ODE_01 DE_Func 54-128-128-128-16 (the script's default --hidden 128; not a BASELINE config) "
+                            "+ external input z(t), batch 4096 x 1000 steps"),
 }
 FP32_PEAK_TFLOPS = 74.4     # nominal: 148 SM x 128 lanes x 2 x 1.965 GHz; measured 72.1 by bench_micro/micro.cu
 
@@ -231,7 +237,7 @@ def cpu_leg(w, B, sample_steps, repeats):
 def cpu_sample_plan(name, w):
     """(B, steps, note) of the CPU sample per workload: the full job where it costs seconds, >= the stated number of steps at
     full batch otherwise (the loop has no step-dependent state: per-step cost is constant)."""
-    if name in ("cfg2", "cfg3"):
+    if name in ("cfg2", "cfg3", "ode01_h128"):
         return w["B"], w["N"], f"the whole job: B={w['B']} x {w['N']} RK4 steps"
     if name == "cfg4":
         return w["B"], 50, f"B={w['B']} (full batch) x 50 of {w['N']} RK4 steps, scaled linearly"

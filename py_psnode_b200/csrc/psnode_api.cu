@@ -183,7 +183,7 @@ int psnode_forward(const psnode_problem* p, void* workspace, int64_t workspace_b
     if (p->impl == PSNODE_IMPL_AUTO && psn_tc_supports(p)) return psn_tc8_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_wide_supports(p)) return psn_wide_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_lg_supports(p)) return psn_lg_forward(p, workspace, workspace_bytes, s);
-    if (p->impl == PSNODE_IMPL_AUTO && psn_wide4_auto() && psn_wide4_supports(p)) return psn_wide4_forward(p, workspace, workspace_bytes, s);
+    if (p->impl == PSNODE_IMPL_AUTO && psn_wide4_supports(p) && psn_wide4_auto(p)) return psn_wide4_forward(p, workspace, workspace_bytes, s);
     if (p->impl == PSNODE_IMPL_AUTO && psn_fused_supports(p)) return psn_fused_forward(p, workspace, workspace_bytes, s);
     // small batches: 2 trajectories per CTA instead of 8 puts 4 x as many SMs to work (the kernels are latency-bound per CTA)
     if (psn_prefer_tb2(p)) {

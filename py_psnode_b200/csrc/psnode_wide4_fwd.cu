@@ -1,6 +1,7 @@
 // psnode_wide4_fwd.cu -- tensor-core forward integrator for the 4-layer ODE_01 DE_Func at hidden width 128, the argparse default
 // of the reference's training script (neural_00_ODE_01_no_encode.py:245-247 `--hidden 128`; net :61-68:
-// L(3S -> 128) . ELU . L(128 -> 128) . ELU . L(128 -> 128) . ELU . L(128 -> X), S = X + Z, X <= 16, Z <= 8).
+// L(3S -> 128) . ELU . L(128 -> 128) . ELU . L(128 -> 128) . ELU . L(128 -> X), S = X + Z, X <= 16, Z <= 8).  Any hidden width up to 128
+// runs here zero-padded to 128 neurons (a padded neuron has zero weights and bias, ELU(0) = 0: exact); `impl = auto` sends 64 < H <= 128.
 // FixedGridODESolver.integrate_ODE (neural_dae/my_solvers.py:52-80) with Euler / Midpoint / RK4-3/8 steps
 // (neural_dae/my_fixed_grid.py:15-59), events as neural_base.py:52-65.  Same machinery as psnode_wide_fwd.cu:
 // M = 128 neurons = TMEM lanes, N = 16 trajectories per group, two groups of 8 warps per CTA, 3xTF32 products, 4 K-partials.
@@ -40,7 +41,7 @@ constexpr int GROUP_THREADS = PSW_GROUP_THREADS;
 constexpr int NP = 4, KPI = 16 / NP;              // K-partials (one issuing warp each), K-steps of 8 per issuer
 
 struct Wide4Params {
-    int B, T, ngroups, X, Z;
+    int B, T, ngroups, X, Z, Hh;                  // Hh: the net's hidden width (<= 128; narrower nets are zero-padded to 128 neurons)
     psnode_series t, x, z;
     const int32_t* event_idx;
     const float* z_jump; int64_t zj_sb, zj_se;
@@ -85,12 +86,13 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
     const int g = cw >> 3, wk = cw & 7, wq = wk & 3, h = wk >> 2;
     const bool issuer = h == 0;                                // warps 0..3 of a group: one K-partial each
     GroupSmem& gs = sm.g[g];
-    const int B = q.B, T = q.T, X = q.X, Z = q.Z, S = q.X + q.Z;
+    const int B = q.B, T = q.T, X = q.X, Z = q.Z, S = q.X + q.Z, Hh = q.Hh;
     const int gid = blockIdx.x * PSW_GROUPS_PER_CTA + g;
     const int b0 = gid * TN;
     const bool live = gid < q.ngroups;
     const int m = 32 * wq + lane;                              // the neuron (and, below 16, the state row) this thread owns
-    const float* w1row = q.W1 + (int64_t)m * (3 * S);          // W1 = [W_a | W_b | W_c], blocks of S columns
+    const bool mh = m < Hh;                                    // a real neuron (padded ones have zero weights and biases: ELU(0) = 0)
+    const float* w1row = q.W1 + (int64_t)(mh ? m : 0) * (3 * S);   // W1 = [W_a | W_b | W_c], blocks of S columns
 
     // ---- one-time setup ---------------------------------------------------------------------------------------------
     if (tid == 0) {
@@ -114,13 +116,14 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int k = k0 + i;
-                split_tf32(__ldg(q.W2 + m * H + k), w2h[i], w2l[i]);
+                const bool in = mh && k < Hh;
+                split_tf32(in ? __ldg(q.W2 + m * Hh + k) : 0.0f, w2h[i], w2l[i]);
                 float lo;
-                split_tf32(__ldg(q.W3 + m * H + k), w3h[i], lo);
+                split_tf32(in ? __ldg(q.W3 + m * Hh + k) : 0.0f, w3h[i], lo);
                 sm.w3lo[tile_byte(m, k, LBO_W, SBO_W) >> 2] = lo;
                 if (m < M4) {                                   // warp-uniform (wq < 2): output layer, rows >= X are zero
                     float v4h, v4l;
-                    split_tf32(m < X ? __ldg(q.W4 + m * H + k) : 0.0f, v4h, v4l);
+                    split_tf32(m < X && k < Hh ? __ldg(q.W4 + m * Hh + k) : 0.0f, v4h, v4l);
                     sm.w4hi[tile_byte(m, k, LBO_W, SBO_W) >> 2] = v4h;
                     sm.w4lo[tile_byte(m, k, LBO_W, SBO_W) >> 2] = v4l;
                 }
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
         if (cc == 0) {                                          // folded layer 1, state part: (W_b + W_c)[m][k], k < X, zero-padded to 16
             for (int k = 0; k < XP; k++) {
                 float fh, fl;
-                split_tf32(k < X ? __ldg(w1row + S + k) + __ldg(w1row + 2 * S + k) : 0.0f, fh, fl);
+                split_tf32(mh && k < X ? __ldg(w1row + S + k) + __ldg(w1row + 2 * S + k) : 0.0f, fh, fl);
                 sm.fxhi[tile_byte(m, k, LBO_W, SBO_F) >> 2] = fh;
                 sm.fxlo[tile_byte(m, k, LBO_W, SBO_F) >> 2] = fl;
             }
@@ -145,20 +148,20 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
     tc_fence_after();
 
     if (live) {
-        const float bias2 = __ldg(q.b2 + m), bias3 = __ldg(q.b3 + m);
+        const float bias2 = mh ? __ldg(q.b2 + m) : 0.0f, bias3 = mh ? __ldg(q.b3 + m) : 0.0f;
         const bool state_row = m < XP;                          // lanes 0..15 of the sub-partition-0 warps (both column halves)
         const bool live_x = m < X;
         const float bias4 = live_x ? __ldg(q.b4 + m) : 0.0f;
         // held-input half of the folded layer 1 and the per-trajectory constant (fp32 FMA, once per call)
         float fz[ZMAX], cst[8];
 #pragma unroll
-        for (int k = 0; k < ZMAX; k++) fz[k] = k < Z ? __ldg(w1row + S + X + k) + __ldg(w1row + 2 * S + X + k) : 0.0f;
+        for (int k = 0; k < ZMAX; k++) fz[k] = mh && k < Z ? __ldg(w1row + S + X + k) + __ldg(w1row + 2 * S + X + k) : 0.0f;
         {
-            const float b1m = __ldg(q.b1 + m);
+            const float b1m = mh ? __ldg(q.b1 + m) : 0.0f;
 #pragma unroll
             for (int i = 0; i < 8; i++) cst[i] = b1m;
             for (int k = 0; k < S; k++) {
-                const float wd = __ldg(w1row + k) - __ldg(w1row + S + k);
+                const float wd = mh ? __ldg(w1row + k) - __ldg(w1row + S + k) : 0.0f;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
                     const int bb = min(b0 + 8 * h + i, B - 1);
@@ -459,12 +462,12 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
 }  // namespace
 
 // PSNODE_WIDE4=0 keeps `impl = auto` off this kernel (the generic CUDA-core kernel takes the shape); `impl = wide` always reaches it
-bool psn_wide4_auto() {
+bool psn_wide4_auto(const psnode_problem* p) {
     static const bool on = [] {
         const char* e = getenv("PSNODE_WIDE4");
         return !(e && e[0] == '0');
     }();
-    return on;
+    return on && p->de.out_dim[0] > 64;      // narrower nets cost the same 128-neuron time here: they stay on the CUDA-core kernels
 }
 
 bool psn_wide4_supports(const psnode_problem* p) {
@@ -472,8 +475,10 @@ bool psn_wide4_supports(const psnode_problem* p) {
     if (p->X < 1 || p->X > XP || p->Z < 0 || p->Z > ZMAX || p->V != 0 || p->I != 0) return false;
     const psnode_mlp& n = p->de;
     if (n.n_layers != 4 || n.in_dim[0] != 3 * (p->X + p->Z) || n.out_dim[3] != p->X) return false;
+    const int hh = n.out_dim[0];
+    if (hh < 1 || hh > H) return false;
     for (int l = 0; l < 3; l++)
-        if (n.out_dim[l] != H || n.in_dim[l + 1] != H) return false;
+        if (n.out_dim[l] != hh || n.in_dim[l + 1] != hh) return false;
     if (p->event_idx && p->Z > 0 && !p->z_jump) return false;
     return true;
 }
@@ -485,7 +490,7 @@ int psn_wide4_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaS
     int* err = static_cast<int*>(ws);
     PSN_CUDA(cudaMemsetAsync(err, 0, 256, stream));
     Wide4Params q;
-    q.B = p->B; q.T = p->T; q.ngroups = psw_ngroups(p->B); q.X = p->X; q.Z = p->Z;
+    q.B = p->B; q.T = p->T; q.ngroups = psw_ngroups(p->B); q.X = p->X; q.Z = p->Z; q.Hh = p->de.out_dim[0];
     q.t = p->t; q.x = p->x; q.z = p->z;
     q.event_idx = p->event_idx;
     q.z_jump = p->z_jump; q.zj_sb = p->zj_sb; q.zj_se = p->zj_se;

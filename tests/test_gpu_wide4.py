@@ -17,11 +17,11 @@ def _params(mod):
     return [(m.weight.detach().cpu(), m.bias.detach().cpu()) for m in mod if isinstance(m, torch.nn.Linear)]
 
 
-def _problem(B, N, seed, X=16, Z=2, events=0, scale=0.1):
+def _problem(B, N, seed, X=16, Z=2, events=0, scale=0.1, hidden=H):
     from py_psnode_b200 import DE_Func
     torch.manual_seed(seed)
     T = N + 1
-    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H)
+    de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=hidden)
     t = (torch.arange(T, dtype=torch.float32) * 0.01).view(T, 1, 1).repeat(1, B, 1)
     x = torch.randn(T, B, X) * scale
     z = torch.randn(T, B, Z) * scale
@@ -78,6 +78,18 @@ def test_wide4_forward_narrow_widths_ragged_batch_events_batch_major(native_lib,
     assert torch.allclose(got, want, rtol=RTOL, atol=ATOL), tol_report(got, want)
     no_ev = _oracle("rk4", de, t, x, z, a0, None)
     assert not torch.allclose(no_ev, want, rtol=1e-3, atol=1e-4), "the events must change the trajectory"
+
+
+@pytest.mark.parametrize("hidden,impl", [(96, "auto"), (100, "auto"), (72, "wide"), (40, "wide"), (64, "wide")])
+def test_wide4_forward_padded_hidden_widths(native_lib, hidden, impl):
+    """Hidden widths below 128 run zero-padded to 128 neurons (exact: a padded neuron has zero weights and bias, ELU(0) = 0);
+    impl = auto sends 64 < H <= 128 here (H = 64 has its own kernel, narrower nets stay on the CUDA cores), impl = wide any H <= 128."""
+    de, t, x, z, a0, ev = _problem(B=21, N=20, seed=70 + hidden, events=1, hidden=hidden)
+    want = _oracle("rk4", de, t, x, z, a0, ev)
+    got, kern = _run("rk4", de, t, x, z, a0, ev, impl)
+    if impl == "wide" or not os.environ.get("PSNODE_WIDE4", "1").startswith("0"):
+        assert kern.startswith("psn_wide4_fwd_kernel"), kern
+    assert torch.allclose(got, want, rtol=RTOL, atol=ATOL), tol_report(got, want)
 
 
 def test_wide4_forward_vs_generic_many_ctas(native_lib):

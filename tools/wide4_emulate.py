@@ -69,24 +69,26 @@ def emulate_group(method, W, b, t, x, z, a0, event_idx, z_jump, b0):
     S = X + Z
     nst = {"euler": 1, "midpoint": 2, "rk4": 4}[method]
     W1, W2, W3, W4 = W
+    Hh = W2.shape[0]                # the net's hidden width; neurons Hh..127 are zero padding
     tmem = np.full((128, 512), np.nan, dtype=np.float64)
     w3lo, w4hi, w4lo = Smem(H * H * 4), Smem(M4 * H * 4), Smem(M4 * H * 4)
     fxhi, fxlo = Smem(H * XP * 4), Smem(H * XP * 4)
     act_hi, act_lo = Smem(ACT_TILE), Smem(ACT_TILE)
     for m in range(H):
         for k in range(H):
-            h2, l2 = split(W2[m, k]); tmem[m, TM_W2_HI + k] = h2; tmem[m, TM_W2_LO + k] = l2
-            h3, l3 = split(W3[m, k]); tmem[m, TM_W3_HI + k] = h3
+            inb = m < Hh and k < Hh
+            h2, l2 = split(W2[m, k] if inb else 0.0); tmem[m, TM_W2_HI + k] = h2; tmem[m, TM_W2_LO + k] = l2
+            h3, l3 = split(W3[m, k] if inb else 0.0); tmem[m, TM_W3_HI + k] = h3
             w3lo.st(tile_byte(m, k, LBO_W, SBO_W), l3)
             if m < M4:
-                h4, l4 = split(W4[m, k] if m < X else 0.0)
+                h4, l4 = split(W4[m, k] if (m < X and k < Hh) else 0.0)
                 w4hi.st(tile_byte(m, k, LBO_W, SBO_W), h4); w4lo.st(tile_byte(m, k, LBO_W, SBO_W), l4)
         for k in range(XP):
-            fh, fl = split(np.float32(W1[m, S + k]) + np.float32(W1[m, 2 * S + k]) if k < X else 0.0)
+            fh, fl = split(np.float32(W1[m, S + k]) + np.float32(W1[m, 2 * S + k]) if (m < Hh and k < X) else 0.0)
             fxhi.st(tile_byte(m, k, LBO_W, SBO_F), fh); fxlo.st(tile_byte(m, k, LBO_W, SBO_F), fl)
     bb = [min(b0 + n, B - 1) for n in range(TN)]
     fz = np.zeros((H, ZMAX)); cst = np.zeros((H, TN))
-    for m in range(H):
+    for m in range(Hh):
         for k in range(Z):
             fz[m, k] = np.float32(W1[m, S + X + k]) + np.float32(W1[m, 2 * S + X + k])
         for n in range(TN):
@@ -160,7 +162,7 @@ def emulate_group(method, W, b, t, x, z, a0, event_idx, z_jump, b0):
                 for n in range(TN):
                     store_tile(m, n, a[m, n])
             for kind, bias in ((2, b[1]), (3, b[2])):
-                layer(kind); a = elu(collect(4) + bias[:, None])
+                layer(kind); a = elu(collect(4) + np.concatenate([bias, np.zeros(H - Hh)])[:, None])
                 for m in range(H):
                     for n in range(TN):
                         store_tile(m, n, a[m, n])
@@ -189,10 +191,10 @@ def emulate_group(method, W, b, t, x, z, a0, event_idx, z_jump, b0):
 def main():
     from py_psnode_b200.neural_base import DE_Func
     worst = 0.0
-    for method, X, Z, B, N, events in (("rk4", 16, 2, 16, 3, 0), ("midpoint", 5, 3, 21, 4, 1), ("euler", 16, 8, 7, 3, 1)):
+    for method, X, Z, B, N, events, Hn in (("rk4", 16, 2, 16, 3, 0, 128), ("midpoint", 5, 3, 21, 4, 1, 100), ("euler", 16, 8, 7, 3, 1, 72)):
         torch.manual_seed(3)
         T = N + 1
-        de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H)
+        de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=Hn)
         params = [(m.weight.detach(), m.bias.detach()) for m in de.x_dot if isinstance(m, torch.nn.Linear)]
         t = (torch.arange(T, dtype=torch.float32) * 0.01).view(T, 1, 1).repeat(1, B, 1)
         x = torch.randn(T, B, X) * 0.1
@@ -214,7 +216,7 @@ def main():
             err = np.abs(got[:, :nlive] - want[:, b0:b0 + nlive]).max()
             assert np.isfinite(got[:, :nlive]).all(), "a never-written operand was read"
             worst = max(worst, err)
-            print(f"{method} X={X} Z={Z} B={B} group@{b0}: max|emulated - oracle| = {err:.2e}", flush=True)
+            print(f"{method} X={X} Z={Z} H={Hn} B={B} group@{b0}: max|emulated - oracle| = {err:.2e}", flush=True)
     assert worst < 2e-6, worst
     print("ok")
 
