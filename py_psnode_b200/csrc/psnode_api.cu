@@ -135,6 +135,10 @@ int64_t psnode_tape_floats(const psnode_problem* p) {
     if (validate(p) != PSNODE_OK) return 0;
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_WIDE) && psn_wide_supports(p) && !psn_tc_supports(p))
         return psw_tape_floats(p->B, p->T, p->method);
+    // the 4-layer ODE_01 net on the wide4 kernels: a tape only when its tensor-core reverse sweep is enabled and the forward dispatch lands there
+    if (psn_wide4_bwd_enabled() && psn_wide4_supports(p) && !psn_tc_supports(p) &&
+        (p->impl == PSNODE_IMPL_WIDE || (p->impl == PSNODE_IMPL_AUTO && psn_wide4_auto(p))))
+        return psw4_tape_floats(p->B, p->T, p->method);
     if (p->impl != PSNODE_IMPL_AUTO && p->impl != PSNODE_IMPL_TC && p->impl != PSNODE_IMPL_TC8) return 0;
     if (!psn_tc_supports(p)) return 0;
     if (p->kind == PSNODE_DAE)      // only the 8-warp forward kernel records the DAE tape
@@ -201,6 +205,7 @@ int psnode_sweep_fuses_loss(const psnode_problem* p, const psnode_adjoint* a) {
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC || p->impl == PSNODE_IMPL_TC8) && psn_tc_bwd_supports(p, a)) return 1;
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_TC8) && psn_tc_dae_bwd_supports(p, a)) return 1;
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_LAYER) && psn_lg_bwd_supports(p, a)) return 1;
+    if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_WIDE) && psn_wide4_bwd_supports(p, a)) return 1;
     return 0;
 }
 
@@ -211,6 +216,7 @@ int64_t psnode_backward_workspace(const psnode_problem* p, const psnode_adjoint*
     const int64_t t = !psn_tc_supports(p) ? 0 : (p->kind == PSNODE_ODE ? psn_tc_backward_workspace(p, a) : psn_tc_dae_backward_workspace(p, a));
     if (psn_wide_bwd_supports(p, a)) { const int64_t w = psn_wide_backward_workspace(p, a); if (w > g) g = w; }
     if (psn_lg_bwd_supports(p, a)) { const int64_t w = psn_lg_backward_workspace(p, a); if (w > g) g = w; }
+    if (psn_wide4_bwd_supports(p, a)) { const int64_t w = psn_wide4_backward_workspace(p, a); if (w > g) g = w; }
     return g > t ? g : t;
 }
 
@@ -227,6 +233,8 @@ int psnode_backward(const psnode_problem* p, const psnode_adjoint* a, void* work
         return psn_tc_dae_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_LAYER) && psn_lg_bwd_supports(p, a))
         return psn_lg_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    if ((p->impl == PSNODE_IMPL_AUTO || p->impl == PSNODE_IMPL_WIDE) && psn_wide4_bwd_supports(p, a))
+        return psn_wide4_backward(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
     if (a->fuse_x.target.p || a->fuse_i.target.p) return PSNODE_EUNSUPPORTED;      // the generic recomputing sweeps take gx / gi only
     if (psn_prefer_tb2(p)) {
         const int t2 = psn_generic_backward_tb2(p, a, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));

@@ -45,6 +45,15 @@ static inline int64_t psw_tape_floats(int B, int T, int method) {
     return (int64_t)psw_ngroups(B) * (T > 1 ? T - 1 : 0) * psw_nstages(method) * PSW_FWD_REC;
 }
 
+// 4-layer ODE_01 net (psnode_wide4_fwd.cu / psnode_wide4_bwd.cu): forward tape record per (group, step, stage) = a1 | a2 | a3 blocks +
+// the stage input y as [16 trajectories][16 state rows]; reverse tape record = delta2 | delta3 blocks
+constexpr int PSW4_YBLK = PSW_N * 16;
+constexpr int PSW4_FWD_REC = 3 * PSW_BLOCK + PSW4_YBLK;
+constexpr int PSW4_BWD_REC = 2 * PSW_BLOCK;
+static inline int64_t psw4_tape_floats(int B, int T, int method) {
+    return (int64_t)psw_ngroups(B) * (T > 1 ? T - 1 : 0) * psw_nstages(method) * PSW4_FWD_REC;
+}
+
 __host__ __device__ __forceinline__ int psw_block_off(int m, int n) { return (m >> 3) * 128 + (n >> 2) * 32 + (m & 7) * 4 + (n & 3); }
 
 bool psn_wide_supports(const psnode_problem* p);
@@ -58,6 +67,13 @@ bool psn_wide4_supports(const psnode_problem* p);
 bool psn_wide4_auto(const psnode_problem* p);
 int64_t psn_wide4_forward_workspace(const psnode_problem* p);
 int psn_wide4_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaStream_t stream);
+// its tape-based tensor-core reverse sweep (psnode_wide4_bwd.cu): parameter, x[0] and all_initial gradients
+bool psn_wide4_bwd_enabled();
+bool psn_wide4_bwd_supports(const psnode_problem* p, const psnode_adjoint* a);
+int64_t psn_wide4_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);
+int psn_wide4_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
+int psn_wide_grad_pairs(const float* a0, int64_t a0_stride, const float* b0, int64_t b0_stride, const float* a1, int64_t a1_stride,
+                        const float* b1, int64_t b1_stride, int64_t nrec, int ncta, float* slabs, int* err, int cta0[3], cudaStream_t stream);
 
 // per-layer tcgen05 GEMM launches for the latent nets that do not fit one SM (psnode_lg.cu: DAE_02 / ODE_02 with H = 128 / 256)
 bool psn_lg_supports(const psnode_problem* p);

@@ -51,6 +51,7 @@ struct Wide4Params {
     const float* W3; const float* b3;
     const float* W4; const float* b4;
     psnode_series_out x_sol;
+    float* tape;                                  // psw4_tape_floats(B, T, method) floats, or NULL
     int* err;
 };
 
@@ -76,7 +77,7 @@ static_assert(sizeof(CtaSmem) + 128 <= 227 * 1024, "one CTA per SM: the tiles mu
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(GROUP_THREADS) : "memory"); }
 __device__ __forceinline__ void st_f32(unsigned char* base, int off, float v) { *reinterpret_cast<float*>(base + off) = v; }
 
-template <int METHOD>
+template <int METHOD, bool TAPE>
 __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wide4_fwd_kernel(const __grid_constant__ Wide4Params q) {
     constexpr int NST = METHOD == PSNODE_EULER ? 1 : (METHOD == PSNODE_MIDPOINT ? 2 : 4);
     extern __shared__ unsigned char smem_raw[];
@@ -309,7 +310,12 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
             }
         };
         // hidden-layer epilogue: a = ELU(acc + bias) -> the next layer's operand tile
-        auto hidden_epilogue = [&](const float (&d)[8], float bias) {
+        const int toff = psw_block_off(m, 8 * h);                          // tape block: float4 at toff, float4 at toff + 32
+        auto tape_block = [&](float* blk, const float (&a)[8]) {
+            __stcs(reinterpret_cast<float4*>(blk + toff), make_float4(a[0], a[1], a[2], a[3]));
+            __stcs(reinterpret_cast<float4*>(blk + toff + 32), make_float4(a[4], a[5], a[6], a[7]));
+        };
+        auto hidden_epilogue = [&](const float (&d)[8], float bias, float* trec_blk) {
             float a[8];
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
@@ -319,6 +325,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                 psn_elu2(v0, v1, a[i], a[i + 1]);
             }
             store_tile(a);
+            if (TAPE && trec_blk) tape_block(trec_blk, a);
         };
         auto event_of_step = [&](int j) { return q.event_idx ? __ldg(q.event_idx + (j - 1)) : -1; };
         // one warp, one step ahead: the held input of step j (z[j-1], or z_jump[:, k] when event k fires at t[j-1]:
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
         };
 
         // ---- initial state ------------------------------------------------------------------------------------------
-        float x0[8], k1[8], k2[8], k3[8];
+        float x0[8], k1[8], k2[8], k3[8], ycur[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             x0[i] = 0.0f;
@@ -359,6 +366,10 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
             }
             store_tile(x0);
         }
+#pragma unroll
+        for (int i = 0; i < 8; i++) ycur[i] = x0[i];
+        // tape record per (group, step, stage): a1 | a2 | a3 as 128 x 16 blocks, then the stage input y as [trajectory][16 state rows]
+        float* trec = (TAPE && q.tape) ? q.tape + (int64_t)gid * (T - 1) * NST * PSW4_FWD_REC : nullptr;
         if (T > 1) {
             if (wk == 4) stage_held(1);
             if (wk == 5) stage_dt(1);
@@ -382,6 +393,10 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
             for (int e = 0; e < NST; e++) {
                 float d[8];
                 issue_l1();
+                if (TAPE && trec && state_row) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) trec[3 * PSW_BLOCK + (8 * h + i) * XP + m] = ycur[i];
+                }
                 if (e == 0 && j + 1 < T) {                                         // next step's inputs, one step ahead
                     if (wk == 4) stage_held(j + 1);
                     if (wk == 5) stage_dt(j + 1);
@@ -398,16 +413,17 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                         psn_elu2(v0, v1, a[i], a[i + 1]);
                     }
                     store_tile(a);
+                    if (TAPE && trec) tape_block(trec, a);
                 }
                 publish();
                 // ---- layers 2 and 3 ----
                 issue_l2();
                 collect4(d);
-                hidden_epilogue(d, bias2);
+                hidden_epilogue(d, bias2, trec ? trec + PSW_BLOCK : nullptr);
                 publish();
                 issue_l3();
                 collect4(d);
-                hidden_epilogue(d, bias3);
+                hidden_epilogue(d, bias3, trec ? trec + 2 * PSW_BLOCK : nullptr);
                 publish();
                 // ---- layer 4 + stage algebra (reference operation order, my_fixed_grid.py:15-59) on the 16 state rows ----
                 issue_l4();
@@ -440,6 +456,8 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                         if (!live_x) xn[i] = 0.0f;                                   // padded state rows stay exactly zero
                     }
                     store_tile(xn);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) ycur[i] = xn[i];
                     if (last) {
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
@@ -449,6 +467,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                         }
                     }
                 }
+                if (TAPE && trec) trec += PSW4_FWD_REC;
                 publish();
             }
         }
@@ -500,6 +519,7 @@ int psn_wide4_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaS
     q.W3 = p->de.W[2]; q.b3 = p->de.b[2];
     q.W4 = p->de.W[3]; q.b4 = p->de.b[3];
     q.x_sol = p->x_sol;
+    q.tape = (p->tape && p->tape_floats >= psw4_tape_floats(p->B, p->T, p->method)) ? p->tape : nullptr;
     q.err = err;
     const int grid = (q.ngroups + PSW_GROUPS_PER_CTA - 1) / PSW_GROUPS_PER_CTA;
     const int smem = (int)sizeof(CtaSmem) + 128;
@@ -510,9 +530,16 @@ int psn_wide4_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaS
         PSN_CUDA(cudaGetLastError());
         return PSNODE_OK;
     };
+    if (q.tape) {
+        switch (p->method) {
+            case PSNODE_EULER: return launch(psn_wide4_fwd_kernel<PSNODE_EULER, true>, "psn_wide4_fwd_kernel<euler,tape>");
+            case PSNODE_MIDPOINT: return launch(psn_wide4_fwd_kernel<PSNODE_MIDPOINT, true>, "psn_wide4_fwd_kernel<midpoint,tape>");
+            default: return launch(psn_wide4_fwd_kernel<PSNODE_RK4, true>, "psn_wide4_fwd_kernel<rk4,tape>");
+        }
+    }
     switch (p->method) {
-        case PSNODE_EULER: return launch(psn_wide4_fwd_kernel<PSNODE_EULER>, "psn_wide4_fwd_kernel<euler>");
-        case PSNODE_MIDPOINT: return launch(psn_wide4_fwd_kernel<PSNODE_MIDPOINT>, "psn_wide4_fwd_kernel<midpoint>");
-        default: return launch(psn_wide4_fwd_kernel<PSNODE_RK4>, "psn_wide4_fwd_kernel<rk4>");
+        case PSNODE_EULER: return launch(psn_wide4_fwd_kernel<PSNODE_EULER, false>, "psn_wide4_fwd_kernel<euler>");
+        case PSNODE_MIDPOINT: return launch(psn_wide4_fwd_kernel<PSNODE_MIDPOINT, false>, "psn_wide4_fwd_kernel<midpoint>");
+        default: return launch(psn_wide4_fwd_kernel<PSNODE_RK4, false>, "psn_wide4_fwd_kernel<rk4>");
     }
 }

@@ -377,3 +377,25 @@ int psn_wide_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws
     PSN_CUDA(cudaGetLastError());
     return PSNODE_OK;
 }
+
+// Two big-K products D_r = sum_rec A_r[rec] . B_r[rec]^T (128 x 128, 128 x 16 blocks) with the kernel above, half of the CTAs each: per-CTA slabs
+// [0, cta0[1]) belong to product 0, [cta0[1], cta0[2]) to product 1 (psnode_wide4_bwd.cu: dW2 and dW3 of the 4-layer net)
+int psn_wide_grad_pairs(const float* a0, int64_t a0_stride, const float* b0, int64_t b0_stride, const float* a1, int64_t a1_stride,
+                        const float* b1, int64_t b1_stride, int64_t nrec, int ncta, float* slabs, int* err, int cta0[3], cudaStream_t stream) {
+    GradParams g;
+    g.a_base[0] = a0; g.b_base[0] = b0; g.a_stride[0] = a0_stride; g.b_stride[0] = b0_stride;
+    g.a_base[1] = a1; g.b_base[1] = b1; g.a_stride[1] = a1_stride; g.b_stride[1] = b1_stride;
+    g.a_base[2] = a1; g.b_base[2] = b1; g.a_stride[2] = a1_stride; g.b_stride[2] = b1_stride;
+    g.nrec[0] = g.nrec[1] = nrec; g.nrec[2] = 0;
+    if (ncta < 2) return PSNODE_EINVAL;
+    g.cta0[0] = 0; g.cta0[1] = ncta / 2; g.cta0[2] = ncta; g.cta0[3] = ncta;
+    g.slabs = slabs;
+    g.err = err;
+    cta0[0] = 0; cta0[1] = g.cta0[1]; cta0[2] = ncta;
+    const int smem = (int)sizeof(GradSmem) + 128;
+    PSN_CUDA(cudaFuncSetAttribute(psn_wide_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    psn_wide_grad_kernel<<<ncta, GRAD_THREADS, smem, stream>>>(g);
+    psn_count_launch("psn_wide_grad_kernel");
+    PSN_CUDA(cudaGetLastError());
+    return PSNODE_OK;
+}

@@ -127,3 +127,89 @@ def test_wide4_is_what_auto_picks_and_training_still_matches(native_lib):
     for p, g in zip(de.parameters(), ref):
         err = (p.grad.double().cpu() - g).abs().max().item()
         assert err <= 2e-5 * max(g.abs().max().item(), 1e-3), (tuple(p.shape), err, g.abs().max().item())
+
+
+# ---- tensor-core reverse sweep of the same shape (psn_wide4_bwd_kernel + psn_wide_grad_kernel + psn_wide4_assemble_kernel) -------------
+def _wide4_bwd_default_on():
+    return os.environ.get("PSNODE_WIDE4_BWD", "0")[:1] != "0"
+
+
+@pytest.mark.parametrize("solver,X,Z,hidden,B,events", [("rk4", 16, 2, 128, 40, 1), ("euler", 16, 2, 128, 16, 0), ("midpoint", 5, 3, 96, 37, 2),
+                                                        ("rk4", 12, 8, 128, 21, 0), ("rk4", 1, 1, 72, 5, 1)])
+def test_wide4_gradients_vs_fp64_autograd(native_lib, monkeypatch, solver, X, Z, hidden, B, events):
+    """Discrete adjoint on the tensor cores for the 4-layer net: every parameter gradient, dL/dx[0] and dL/d all_initial against float64
+    autograd through the oracle (the switch is read per call: PSNODE_WIDE4_BWD)."""
+    from oracle import psnode_oracle as O
+    from py_psnode_b200 import Euler, Midpoint, ODE_Event, RK4, _native
+    monkeypatch.setenv("PSNODE_WIDE4_BWD", "1")
+    dev = "cuda:0"
+    N = 14
+    de, t, x, z, a0, ev = _problem(B=B, N=N, seed=80 + X + B, X=X, Z=Z, events=events, hidden=hidden)
+    T = N + 1
+    w = torch.randn(T, B, X) * 0.1
+    p64 = [(W.double().requires_grad_(True), b.double().requires_grad_(True)) for W, b in _params(de.x_dot)]
+    x64 = x.double().requires_grad_(True)
+    a064 = a0.double().requires_grad_(True)
+    args = (ev[0].double(), ev[1].double()) if ev else ()
+    sol64 = O.integrate_ode(solver, p64, t.double(), x64, z.double(), a064, *args)
+    (sol64 * w.double()).sum().backward()
+    de_d = de.to(dev)
+    xd = x.to(dev).requires_grad_(True)
+    a0d = a0.to(dev).requires_grad_(True)
+    kw = {}
+    if ev:
+        e = ODE_Event()
+        e.set_event(t=ev[0].to(dev), z=ev[1].to(dev))
+        kw = dict(event_fn=e.event_fn, jump_change_fn=e.jump_change_fn)
+    S = {"euler": Euler, "midpoint": Midpoint, "rk4": RK4}[solver]
+    sol = S(impl="wide").integrate_ODE(x_func=de_d, t=t.to(dev), x=xd, z=z.to(dev), all_initial=a0d, **kw)
+    assert _native.last_kernel().startswith("psn_wide4_fwd_kernel") and "tape" in _native.last_kernel(), _native.last_kernel()
+    assert torch.allclose(sol.detach().cpu(), sol64.detach().float(), rtol=RTOL, atol=ATOL)
+    (sol * w.to(dev)).sum().backward()
+    assert _native.last_kernel().startswith("psn_wide4_assemble_kernel"), _native.last_kernel()
+    lin = [m for m in de_d.x_dot if isinstance(m, torch.nn.Linear)]
+    pairs = [(f"{n}{k + 1}", getattr(lin[k], a).grad, p64[k][i].grad) for k in range(4) for n, a, i in (("W", "weight", 0), ("b", "bias", 1))]
+    pairs += [("x", xd.grad, x64.grad), ("all_initial", a0d.grad, a064.grad)]
+    bad = []
+    for name, g, g64 in pairs:
+        scale = float(g64.abs().max())
+        err = float((g.cpu().double() - g64).abs().max())
+        print(f"grad {name}: max err {err:.3e} scale {scale:.3e} rel {err / max(scale, 1e-30):.2e}")
+        if not err <= 2e-5 * scale + 1e-7:
+            bad.append((name, err, scale))
+    assert not bad, bad
+
+
+def test_wide4_fused_loss_sweep_matches_generic_sweep_many_ctas(native_lib, monkeypatch):
+    """B = 2500 (157 groups, 79 CTAs of the sweep; 148 CTAs of the block-GEMM pass), 40 RK4 steps, one event, masked-MSE loss fused into the
+    sweep: parameter gradients against the generic recomputing sweep of the same problem, twice for determinism."""
+    from py_psnode_b200 import ODE_Event, RK4, _native
+    dev = "cuda:0"
+    B, N = 2500, 40
+    de, t, x, z, a0, ev = _problem(B=B, N=N, seed=91, events=1)
+    T = N + 1
+    target = (torch.randn(T, B, 16) * 0.1).to(dev)
+    mask = (torch.rand(T, B, 1) > 0.3).float().to(dev)
+    de_d = de.to(dev)
+    e = ODE_Event()
+    e.set_event(t=ev[0].to(dev), z=ev[1].to(dev))
+
+    def grads(flag, impl):
+        monkeypatch.setenv("PSNODE_WIDE4_BWD", flag)
+        for p in de_d.parameters():
+            p.grad = None
+        num, _ = RK4(impl=impl).integrate_ODE_loss(x_func=de_d, t=t.to(dev), x=x.to(dev), z=z.to(dev), all_initial=a0.to(dev), target=target,
+                                                   mask=mask, event_fn=e.event_fn, jump_change_fn=e.jump_change_fn)
+        (num / mask.sum()).backward()
+        return [p.grad.clone() for p in de_d.parameters()], _native.last_kernel()
+
+    ref, k0 = grads("0", "wide")
+    got, k1 = grads("1", "wide")
+    again, _ = grads("1", "auto")
+    assert k0.startswith("psn_grad_reduce_kernel") or "generic" in k0, k0
+    assert k1.startswith("psn_wide4_assemble_kernel"), k1
+    for p, a, b, c in zip(de_d.parameters(), ref, got, again):
+        scale = float(a.abs().max())
+        err = float((a - b).abs().max())
+        assert err <= 2e-5 * scale + 1e-9, (tuple(p.shape), err, scale)
+        assert torch.equal(b, c), "the sweep must be deterministic"
