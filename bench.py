@@ -53,7 +53,7 @@ WORKLOADS = {
                  bytes_per_unit=4100, flop_per_unit=7864320, aux_steps=200, train_steps=2000,
                  desc="RK4 fixed-step, DAE_02 latent DE_Func 3072-256-256 + AE_Func 1792-256-256, global batch 65536 x 2000 steps"),
     # not a BASELINE config: cfg2 at the training script's argparse default --hidden 128 (neural_00_ODE_01_no_encode.py:245-247;
-    # VERDICT r01 item 9): forward on psn_wide4_fwd_kernel, reverse sweep on the generic recomputing kernels
+    # VERDICT r01 item 9): forward on psn_wide4_fwd_kernel, tape-based reverse sweep on psn_wide4_bwd_kernel + psn_wide_grad_kernel
     "ode01_h128": dict(kind="ode", net="01", X=16, Z=2, V=0, I=0, H=128, B=4096, N=1000, scaling="weak", bytes_per_unit=76,
                        flop_per_unit=333824,
                        desc="RK4 fixed-step, ODE_01 DE_Func 54-128-128-128-16 (the script's default --hidden 128; not a BASELINE config) "

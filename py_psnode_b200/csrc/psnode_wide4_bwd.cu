@@ -605,7 +605,7 @@ Bwd4Layout bwd4_layout(const psnode_problem* p) {
 // PSNODE_WIDE4_BWD=0 keeps the generic recomputing sweep for this shape (and no tape is recorded)
 bool psn_wide4_bwd_enabled() {
     const char* e = getenv("PSNODE_WIDE4_BWD");
-    return e ? e[0] != '0' : false;
+    return e ? e[0] != '0' : true;
 }
 
 bool psn_wide4_bwd_supports(const psnode_problem* p, const psnode_adjoint* a) {

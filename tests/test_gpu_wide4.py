@@ -105,8 +105,8 @@ def test_wide4_forward_vs_generic_many_ctas(native_lib):
 
 
 def test_wide4_is_what_auto_picks_and_training_still_matches(native_lib):
-    """impl = auto reaches the kernel (unless PSNODE_WIDE4=0), and a training step through it -- tensor-core forward, generic
-    recomputing reverse sweep from the stored trajectory -- gives the parameter gradients of float64 autograd through the oracle."""
+    """impl = auto reaches the kernel (unless PSNODE_WIDE4=0), and a training step through it with the switches at their defaults
+    (tensor-core forward with tape + tensor-core reverse sweep) gives the parameter gradients of float64 autograd through the oracle."""
     from oracle import psnode_oracle as O
     from py_psnode_b200 import RK4, _native
     dev = "cuda:0"
@@ -124,16 +124,14 @@ def test_wide4_is_what_auto_picks_and_training_still_matches(native_lib):
         p.grad = None
     out = RK4().integrate_ODE(x_func=de, t=t.to(dev), x=x.to(dev), z=z.to(dev), all_initial=a0.to(dev))
     out.square().sum().backward()
+    if os.environ.get("PSNODE_WIDE4", "1")[:1] != "0" and os.environ.get("PSNODE_WIDE4_BWD", "1")[:1] != "0":
+        assert _native.last_kernel().startswith("psn_wide4_assemble_kernel"), _native.last_kernel()
     for p, g in zip(de.parameters(), ref):
         err = (p.grad.double().cpu() - g).abs().max().item()
         assert err <= 2e-5 * max(g.abs().max().item(), 1e-3), (tuple(p.shape), err, g.abs().max().item())
 
 
 # ---- tensor-core reverse sweep of the same shape (psn_wide4_bwd_kernel + psn_wide_grad_kernel + psn_wide4_assemble_kernel) -------------
-def _wide4_bwd_default_on():
-    return os.environ.get("PSNODE_WIDE4_BWD", "0")[:1] != "0"
-
-
 @pytest.mark.parametrize("solver,X,Z,hidden,B,events", [("rk4", 16, 2, 128, 40, 1), ("euler", 16, 2, 128, 16, 0), ("midpoint", 5, 3, 96, 37, 2),
                                                         ("rk4", 12, 8, 128, 21, 0), ("rk4", 1, 1, 72, 5, 1)])
 def test_wide4_gradients_vs_fp64_autograd(native_lib, monkeypatch, solver, X, Z, hidden, B, events):
