@@ -48,6 +48,7 @@ struct Wide4BwdParams {
     float* slabs;                                 // [2 * ngroups][SLAB_FIELDS][128]
     float* d_x0; int64_t d_x0_sb;
     float* d_a0; int64_t d_a0_sb;
+    int pf;                                       // stage y one stage ahead with cp.async + L2-prefetch the next record (PSNODE_WIDE4_PF)
     int* err;
 };
 
@@ -55,7 +56,7 @@ struct __align__(128) GroupSmem {
     unsigned char act_hi[ACT_TILE];
     unsigned char act_lo[ACT_TILE];
     float dkt[TN * XP];                           // dk_e of the stage, fp32, [trajectory][state row]
-    float yt[TN * XP];                            // stage input y_e, fp32, same layout (from the forward tape)
+    float yt[2][TN * XP];                         // stage input y_e, fp32, same layout (from the forward tape); double-buffered by stage
     float rk[4][TN * XP];                         // state threads' private adjoint state: lambda | dyA | dyB | sum_e dy_e, same layout
     float zh[2][TN * ZMAX];
     float dts[2][TN];
@@ -76,6 +77,11 @@ static_assert(ACT_TILE >= TN * H * 4, "the activation tile doubles as the dc scr
 
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(GROUP_THREADS) : "memory"); }
 __device__ __forceinline__ void st_f32(unsigned char* base, int off, float v) { *reinterpret_cast<float*>(base + off) = v; }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int METHOD>
 __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wide4_bwd_kernel(const __grid_constant__ Wide4BwdParams q) {
@@ -345,8 +351,20 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
             if (wk == 5) stage_dt(T - 1);
             if (wk == 6) stage_held(T - 1);
         }
-        publish();
         const int64_t grec = (int64_t)gid * (T - 1);
+        const bool pf = q.pf != 0;
+        // one warp: the 1 KB stage-input block of a record -> yt[buf], asynchronously (no registers, nothing on the state threads' path)
+        auto stage_y = [&](const float* rec, int buf) {
+            const float* src = rec + 3 * PSW_BLOCK;
+            cp_async16(&gs.yt[buf][4 * lane], src + 4 * lane);
+            cp_async16(&gs.yt[buf][128 + 4 * lane], src + 128 + 4 * lane);
+        };
+        if (pf && T > 1 && wk == 7) {
+            stage_y(q.tape + ((grec + (T - 2)) * NST + (NST - 1)) * PSW4_FWD_REC, 0);
+            cp_async_wait_all();
+        }
+        publish();
+        int sc = 0;                                             // stage counter: yt[sc & 1] is this stage's buffer
 
         for (int j = T - 1; j >= 1; j--) {
             const float* frec = q.tape + (grec + (j - 1)) * NST * PSW4_FWD_REC;
@@ -383,7 +401,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                         }
                         db4 += dk[i];
                         gs.dkt[(8 * h + i) * XP + m] = dk[i];
-                        gs.yt[(8 * h + i) * XP + m] = __ldcs(fr + 3 * PSW_BLOCK + (8 * h + i) * XP + m);
+                        if (!pf) gs.yt[sc & 1][(8 * h + i) * XP + m] = __ldcs(fr + 3 * PSW_BLOCK + (8 * h + i) * XP + m);
                     }
                     store_tile(dk);
                 }
@@ -391,6 +409,16 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                 // the next step's held inputs: only now, behind a group barrier, has every thread finished reading this buffer at the end
                 // of step j + 1 (the step sizes are read at stage tops only, so they are staged at the top of the step)
                 if (e == NST - 1 && j > 1 && wk == 6) stage_held(j - 1);
+                const bool has_next = !(j == 1 && e == 0);      // the next stage's record is the one right below this one
+                if (pf && has_next) {
+                    const float* nx = fr - PSW4_FWD_REC;
+                    if (wk == 7) stage_y(nx, (sc + 1) & 1);     // last read two barriers before the previous stage ended
+#pragma unroll
+                    for (int blk = 0; blk < 3; blk++) {
+                        prefetch_l2(nx + blk * PSW_BLOCK + toff);
+                        prefetch_l2(nx + blk * PSW_BLOCK + toff + 32);
+                    }
+                }
                 // ---- delta3 = (W4^T dk) * ELU'(a3);  dW4 += dk . a3^T ----
                 issue_w4t();
                 load_block(fr + 2 * PSW_BLOCK, a);
@@ -425,6 +453,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                 }
                 store_tile(d);
                 tape_block(br, d);
+                if (pf && wk == 7) cp_async_wait_all();           // the next stage's y block has landed: visible behind this barrier
                 publish();
                 // ---- delta1 = (W2^T delta2) * ELU'(a1);  dF_x += delta1 . y^T ----
                 issue_w2t();
@@ -436,7 +465,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                     sum1[i] += d[i];
 #pragma unroll
                     for (int kq = 0; kq < XP / 4; kq++) {
-                        const float4 v = *reinterpret_cast<const float4*>(&gs.yt[(8 * h + i) * XP + 4 * kq]);
+                        const float4 v = *reinterpret_cast<const float4*>(&gs.yt[sc & 1][(8 * h + i) * XP + 4 * kq]);
                         dfx[4 * kq + 0] = fmaf(v.x, d[i], dfx[4 * kq + 0]);
                         dfx[4 * kq + 1] = fmaf(v.y, d[i], dfx[4 * kq + 1]);
                         dfx[4 * kq + 2] = fmaf(v.z, d[i], dfx[4 * kq + 2]);
@@ -460,6 +489,7 @@ __global__ void __launch_bounds__(PSW_GROUPS_PER_CTA * GROUP_THREADS, 1) psn_wid
                         }
                     }
                 }
+                sc++;
             }
             // ---- end of step j: held-input and constant gradients of the folded layer 1, lambda_{j-1} ----
 #pragma unroll
@@ -645,6 +675,7 @@ int psn_wide4_backward(const psnode_problem* p, const psnode_adjoint* a, void* w
     q.slabs = w + L.slabs;
     q.d_x0 = a->d_x0; q.d_x0_sb = a->d_x0_sb;
     q.d_a0 = a->d_a0; q.d_a0_sb = a->d_a0_sb;
+    { const char* e = getenv("PSNODE_WIDE4_PF"); q.pf = e ? (e[0] != '0') : 0; }
     q.err = err;
     {
         const int grid = (int)((ng + PSW_GROUPS_PER_CTA - 1) / PSW_GROUPS_PER_CTA);

@@ -11,7 +11,7 @@ dev = "cuda:0"
 torch.manual_seed(0)
 X, Z, H = 16, 2, 128
 B = 4096
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+N = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1000
 T = N + 1
 de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=H).to(dev)
 t = (torch.arange(T, dtype=torch.float32, device=dev) * 0.01).view(T, 1, 1).repeat(1, B, 1)
@@ -32,8 +32,12 @@ def step():
 
 
 res = {}
-for flag in ("0", "1"):
+modes = (("0", "0"), ("1", "0"), ("1", "1"))         # (PSNODE_WIDE4_BWD, PSNODE_WIDE4_PF)
+if "fast" in sys.argv:
+    modes = modes[1:]
+for flag, pfl in modes:
     os.environ["PSNODE_WIDE4_BWD"] = flag
+    os.environ["PSNODE_WIDE4_PF"] = pfl
     engine.release_tape_pool()
     torch.cuda.empty_cache()
     torch.cuda.reset_peak_memory_stats()
@@ -44,8 +48,10 @@ for flag in ("0", "1"):
         step()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 2
-    res[flag] = [p.grad.clone() for p in plist]
-    print(f"PSNODE_WIDE4_BWD={flag}: training step {ms:.1f} ms = {B * N / ms / 1e3:.1f} M traj-steps/s, peak {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB, "
+    res[flag + pfl] = [p.grad.clone() for p in plist]
+    print(f"PSNODE_WIDE4_BWD={flag} PSNODE_WIDE4_PF={pfl}: training step {ms:.1f} ms = {B * N / ms / 1e3:.1f} M traj-steps/s, peak {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB, "
           f"last kernel {_native.last_kernel()}", flush=True)
-for p, a, b in zip(plist, res["0"], res["1"]):
-    print(f"   {tuple(p.shape)}: max|tensor-core sweep - generic sweep| = {(a - b).abs().max().item():.3e} (scale {a.abs().max().item():.3e})", flush=True)
+base = "00" if "00" in res else "10"
+for p, a, b, c in zip(plist, res[base], res["10"], res["11"]):
+    print(f"   {tuple(p.shape)}: max|tensor-core sweep - {'generic' if base == '00' else 'itself'}| = {(a - b).abs().max().item():.3e}, "
+          f"prefetch variant bit-identical: {torch.equal(b, c)} (scale {a.abs().max().item():.3e})", flush=True)
