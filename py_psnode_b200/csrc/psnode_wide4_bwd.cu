@@ -48,7 +48,7 @@ struct Wide4BwdParams {
     float* slabs;                                 // [2 * ngroups][SLAB_FIELDS][128]
     float* d_x0; int64_t d_x0_sb;
     float* d_a0; int64_t d_a0_sb;
-    int pf;                                       // stage y one stage ahead with cp.async + L2-prefetch the next record (PSNODE_WIDE4_PF)
+    int pf;                                       // stage y one stage ahead with cp.async + L2-prefetch the next record (PSNODE_WIDE4_PF=0: off)
     int* err;
 };
 
@@ -675,7 +675,7 @@ int psn_wide4_backward(const psnode_problem* p, const psnode_adjoint* a, void* w
     q.slabs = w + L.slabs;
     q.d_x0 = a->d_x0; q.d_x0_sb = a->d_x0_sb;
     q.d_a0 = a->d_a0; q.d_a0_sb = a->d_a0_sb;
-    { const char* e = getenv("PSNODE_WIDE4_PF"); q.pf = e ? (e[0] != '0') : 0; }
+    { const char* e = getenv("PSNODE_WIDE4_PF"); q.pf = e ? (e[0] != '0') : 1; }      // A/B at the cfg2 batch: 68.5 -> 57.2 ms per training step
     q.err = err;
     {
         const int grid = (int)((ng + PSW_GROUPS_PER_CTA - 1) / PSW_GROUPS_PER_CTA);
