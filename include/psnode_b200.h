@@ -56,7 +56,7 @@ extern "C" {
 #define PSNODE_IMPL_TC8 4      /* same, 8 warps per 16-trajectory group (4 accumulator elements per thread) */
 #define PSNODE_IMPL_WIDE 5     /* tcgen05 kernels for the latent `*_02_direct_encode` nets (X = Z = H = 128, 2 layers): TMA-staged
                                   input series, hoisted input GEMM, both weight matrices resident in TMEM; also the 4-layer ODE_01 net
-                                  at hidden <= 128 (X <= 16, Z <= 8; forward only, AUTO takes it for hidden 65..128) */
+                                  at hidden <= 128 (X <= 16, Z <= 8; forward and tape-based reverse sweep, AUTO takes it for hidden 65..128) */
 
 #define PSNODE_IMPL_LAYER 6    /* latent nets too wide for one SM (DAE_02 / ODE_02, X = Z (= V = I) = H = 128 or 256): one tcgen05 GEMM
                                   launch per layer over the whole batch shard, TMA-streamed operands, fused epilogues */

@@ -19,7 +19,7 @@
 // The state tile (K = 16 rows) shares the activation tile: rows 0..15 are rewritten with the next stage input after layer 4 and
 // layer 1 reads K-steps 0..1 only.  Thread (lane m, half h) owns neuron m of 8 trajectories; threads m < 16 also own state row m.
 // Bound: tensor pipe / dependent-layer latency (4 layers x stages x steps); HBM traffic (X + Z + 1) x 4 B read, X x 4 B written per
-// trajectory-step.  Forward / evaluation only: the reverse sweep of this shape is the generic recomputing one (no tape is offered).
+// trajectory-step.  The `tape` instantiation records a1 | a2 | a3 and the stage input of every stage for the reverse sweep (psnode_wide4_bwd.cu).
 #include <cstddef>
 #include <cstdlib>
 #include "psnode_wide.cuh"
