@@ -1,6 +1,6 @@
 """The four scripts at their argparse defaults (--batch 64, --hidden 128; solver Euler as hard-coded in the models, and RK4): time of one
 integrate call and of one forward + backward on the GPU, next to the oracle port on the host cores (same sizes, all threads).
-    gpurun -- python tools/script_default_probe.py [steps]"""
+    gpurun -- python tests/probe_script_default.py [steps]"""
 import sys, time, torch
 sys.path.insert(0, '.')
 from py_psnode_b200 import DE_Func, AE_Func, Euler, RK4, _native

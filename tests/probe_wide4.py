@@ -1,8 +1,8 @@
 """The ODE_01 net at the scripts' argparse default --hidden 128 (neural_00_ODE_01_no_encode.py:245-247; DE_Func 54-128-128-128-16) at the
 cfg2 batch (B = 4096 x 1000 RK4 steps) and at the scripts' default batch (64): tensor-core kernel (impl = wide -> psn_wide4_fwd_kernel)
 against the CUDA-core generic kernel, device-timed, with the error of both against the oracle's float64 run on the first 32 trajectories.
-    gpurun -- python tools/wide4_probe.py            # timing + accuracy table
-    gpurun -- python tools/wide4_probe.py one 200    # one forward call of N steps (for ncu captures)"""
+    gpurun -- python tests/probe_wide4.py            # timing + accuracy table
+    gpurun -- python tests/probe_wide4.py one 200    # one forward call of N steps (for ncu captures)"""
 import sys
 import torch
 sys.path.insert(0, '.')

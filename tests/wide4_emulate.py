@@ -3,7 +3,7 @@ TMEM as a (128 lanes x 512 columns) array, tcgen05.mma as `D[lane(r)][d + n] (+)
 canonical no-swizzle K-major operand addressing of psnode_tc.cuh, one group of 16 trajectories at a time.  It checks the folding, the
 weight-tile / descriptor pairs, the K-partial bookkeeping, the M = 64 row -> lane map of the output layer and the held-input / event
 staging against the oracle WITHOUT a GPU (the hardware semantics it assumes are the ones the shipped wide / tc8 kernels rely on).
-    python tools/wide4_emulate.py"""
+    python tests/wide4_emulate.py"""
 import os
 import sys
 
@@ -370,9 +370,13 @@ def assemble(slabs, g2, g3, X, Z, Hh):
     return out
 
 
-def main_bwd():
+BWD_CASES = (("rk4", 16, 2, 16, 3, 0, 128), ("midpoint", 5, 3, 21, 3, 1, 100), ("euler", 16, 8, 7, 3, 1, 72))
+FWD_CASES = (("rk4", 16, 2, 16, 3, 0, 128), ("midpoint", 5, 3, 21, 4, 1, 100), ("euler", 16, 8, 7, 3, 1, 72))
+
+
+def main_bwd(cases=BWD_CASES):
     from py_psnode_b200.neural_base import DE_Func
-    for method, X, Z, B, N, events, Hn in (("rk4", 16, 2, 16, 3, 0, 128), ("midpoint", 5, 3, 21, 3, 1, 100), ("euler", 16, 8, 7, 3, 1, 72)):
+    for method, X, Z, B, N, events, Hn in cases:
         torch.manual_seed(5)
         T = N + 1
         de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=Hn)
@@ -424,10 +428,10 @@ def main_bwd():
     print("bwd ok")
 
 
-def main():
+def main(cases=None):
     from py_psnode_b200.neural_base import DE_Func
     worst = 0.0
-    for method, X, Z, B, N, events, Hn in (("rk4", 16, 2, 16, 3, 0, 128), ("midpoint", 5, 3, 21, 4, 1, 100), ("euler", 16, 8, 7, 3, 1, 72)):
+    for method, X, Z, B, N, events, Hn in (FWD_CASES if cases is None else cases):
         torch.manual_seed(3)
         T = N + 1
         de = DE_Func(x_dim=X, z_dim=Z, hidden_dim=Hn)
