@@ -62,6 +62,15 @@ WORKLOADS = {
 FP32_PEAK_TFLOPS = 74.4     # nominal: 148 SM x 128 lanes x 2 x 1.965 GHz; measured 72.1 by bench_micro/micro.cu
 
 
+def line_config(name, w, world):
+    """The `config` object of the JSON line: the workload only, nothing arm-specific -- both arms print the same one."""
+    B = rank_batch(w, world)
+    return {"workload": name + ": " + w["desc"], "batch_per_gpu": B,
+            "global_batch": B * world if w["scaling"] == "weak" else w["B"],
+            "grid_steps": w["N"], "state_dim": w["X"], "hidden": w["H"], "parallelism": f"batch-shard x{world}",
+            "l2": "working set per call (cfg2: inputs 49 MB + trajectory 262 MB) exceeds the 126 MB L2"}
+
+
 def rank_batch(w, world):
     """Trajectories one rank integrates: weak workloads keep B per GPU, strong ones shard the global batch (cfg5 never
     fewer than 8 ways: one 1/8 shard per rank is what fits and what BASELINE quotes)."""
@@ -264,7 +273,7 @@ def run_reference_arm(args, name, w, rank):
     line = {"impl": "reference", "metric": "rk4_traj_steps_per_sec", "value": value, "unit": "traj-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name + ": " + w["desc"], "sample": sample},
+            "config": line_config(name, w, max(args.gpus, 1)),
             "cpu_baseline": {"value": value, "unit": "traj-steps/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "traj-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -784,11 +793,8 @@ def main():
             "metric": "rk4_traj_steps_per_sec", "value": res["value"], "unit": "traj-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": w["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": res["workload"], "batch_per_gpu": B,
-                       "global_batch": B * world if w["scaling"] == "weak" else w["B"],
-                       "grid_steps": res["grid_steps"], "state_dim": w["X"], "hidden": w["H"], "parallelism": f"batch-shard x{world}",
-                       "kernel": res["kernel"],
-                       "l2": "working set per call (cfg2: inputs 49 MB + trajectory 262 MB) exceeds the 126 MB L2"},
+            "config": line_config(args.workload, w, world),
+            "kernel": res["kernel"],
             "roofline": res["roofline"], "roofline_hbm": res["roofline_hbm"], "fp32": res["fp32"],
             "kernel_ms": res["kernel_ms"], "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
             "host_affinity": affinity,
