@@ -723,6 +723,26 @@ def run_workload(name, w, args, ctx, steps, warmup, legs, main_line):
     return res
 
 
+def assemble_line(args, w, world, res, others, affinity):
+    """The ONE JSON line of our arm from a run_workload() result (kept apart from main() so the contract's keys are testable on the CPU)."""
+    line = {
+        "metric": "rk4_traj_steps_per_sec", "value": res["value"], "unit": "traj-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": w["scaling"],
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": line_config(args.workload, w, world),
+        "kernel": res["kernel"],
+        "roofline": res["roofline"], "roofline_hbm": res["roofline_hbm"], "fp32": res["fp32"],
+        "kernel_ms": res["kernel_ms"], "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
+        "host_affinity": affinity,
+    }
+    for k in ("e2e", "train", "encoded", "cpu_baseline", "sample", "note"):
+        if k in res:
+            line[k] = res[k]
+    if others:
+        line["others"] = others
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -788,23 +808,7 @@ def main():
                 others[name] = o
 
     if rank == 0:
-        B = res["batch_per_gpu"]
-        line = {
-            "metric": "rk4_traj_steps_per_sec", "value": res["value"], "unit": "traj-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": w["scaling"],
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": line_config(args.workload, w, world),
-            "kernel": res["kernel"],
-            "roofline": res["roofline"], "roofline_hbm": res["roofline_hbm"], "fp32": res["fp32"],
-            "kernel_ms": res["kernel_ms"], "gpu_launches": res["gpu_launches"], "clocks": res["clocks"],
-            "host_affinity": affinity,
-        }
-        for k in ("e2e", "train", "encoded", "cpu_baseline", "sample", "note"):
-            if k in res:
-                line[k] = res[k]
-        if others:
-            line["others"] = others
-        print(json.dumps(line), flush=True)
+        print(json.dumps(assemble_line(args, w, world, res, others, affinity)), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
