@@ -302,7 +302,7 @@ class _Integrate(torch.autograd.Function):
         if isinstance(tape, TapeChunks):
             grads = _backward_chunked(cfg, tens, gx, gi if cfg.kind == N.DAE else None, needs, tape.rows)
         else:
-            grads = backward_raw(cfg, tens, x_sol, i_sol, gx, gi if cfg.kind == N.DAE else None, needs, tape)
+            grads = _backward_or_recompute(cfg, tens, x_sol, i_sol, gx, gi if cfg.kind == N.DAE else None, needs, tape)
             _give_tape(tape)
         return (None, *grads)
 
@@ -346,7 +346,7 @@ def _backward_chunked(cfg: Config, tens, gx, gi, needs, rows: int) -> List[Optio
             xs, _is, tape = forward_raw(cfg, sub, want_tape=False)
         if isinstance(tape, TapeChunks):
             tape = None
-        g = backward_raw(cfg, sub, xs, _is, gx[:, b0:b1], gi[:, b0:b1] if gi is not None else None, needs, tape)
+        g = _backward_or_recompute(cfg, sub, xs, _is, gx[:, b0:b1], gi[:, b0:b1] if gi is not None else None, needs, tape)
         _give_tape(tape)
         for k, gk in enumerate(g):
             if gk is None:
@@ -478,6 +478,19 @@ def backward_raw(cfg: Config, tens, x_sol, i_sol, gx, gi, needs, tape=None, fuse
     return out
 
 
+def _backward_or_recompute(cfg: Config, tens, x_sol, i_sol, gx, gi, needs, tape, **kw) -> List[Optional[torch.Tensor]]:
+    """backward_raw on the tape; if the tape-based sweep's own workspace (delta records of the latent / hidden-128 paths: up to the
+    size of the tape again) does not fit next to the tape, drop the tape and run the recomputing sweep instead of failing the step."""
+    if tape is None:
+        return backward_raw(cfg, tens, x_sol, i_sol, gx, gi, needs, None, **kw)
+    try:
+        return backward_raw(cfg, tens, x_sol, i_sol, gx, gi, needs, tape, **kw)
+    except torch.cuda.OutOfMemoryError:
+        release_tape_pool()
+        torch.cuda.empty_cache()
+        return backward_raw(cfg, tens, x_sol, i_sol, gx, gi, needs, None, **kw)
+
+
 class _IntegrateLoss(torch.autograd.Function):
     """num, x_sol, i_sol = integrate_loss(cfg, spec, t, x, ...): the integration fused with the masked squared-error
     numerator of the scripts' loss.  Only `num` is differentiable; its backward runs the reverse sweep with the loss gradient
@@ -519,7 +532,7 @@ class _IntegrateLoss(torch.autograd.Function):
         scale = gnum.detach().to(torch.float32).reshape(1).contiguous()
         if isinstance(tape, TapeChunks):
             tape = None                     # chunked re-integration is not combined with loss fusion: recomputing sweep
-        grads = backward_raw(cfg, tens, x_sol, i_sol, None, None, needs, tape, fuse=ctx.spec, fuse_scale=scale)
+        grads = _backward_or_recompute(cfg, tens, x_sol, i_sol, None, None, needs, tape, fuse=ctx.spec, fuse_scale=scale)
         _give_tape(tape)
         return (None, None, *grads)
 
