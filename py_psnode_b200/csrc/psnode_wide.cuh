@@ -62,7 +62,7 @@ int psn_wide_forward(const psnode_problem* p, void* ws, int64_t ws_bytes, cudaSt
 bool psn_wide_bwd_supports(const psnode_problem* p, const psnode_adjoint* a);
 int64_t psn_wide_backward_workspace(const psnode_problem* p, const psnode_adjoint* a);
 int psn_wide_backward(const psnode_problem* p, const psnode_adjoint* a, void* ws, int64_t ws_bytes, cudaStream_t stream);
-// the 4-layer ODE_01 net at hidden 128 (X <= 16, Z <= 8) on the same machinery, forward only (psnode_wide4_fwd.cu)
+// the 4-layer ODE_01 net at hidden <= 128 (X <= 16, Z <= 8) on the same machinery (psnode_wide4_fwd.cu; `tape` instantiation for the sweep below)
 bool psn_wide4_supports(const psnode_problem* p);
 bool psn_wide4_auto(const psnode_problem* p);
 int64_t psn_wide4_forward_workspace(const psnode_problem* p);
